@@ -1,0 +1,169 @@
+/*
+ * mpc_b200.h -- C ABI of the B200-native batched NMPC solver that drops in
+ * behind mpc_ros's MPC::Solve hot path.
+ *
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the OkDoky/mpc_ros tree).  Plain C: pointers and sizes only, no C++ or
+ * torch types.  All batch buffers are SoA, component-major with the problem
+ * index fastest: element (c, i) of a "C x batch" buffer is buf[c*batch + i].
+ * Buffers may live in host or device memory (auto-detected per pointer; host
+ * buffers are staged through the handle's pinned memory).
+ *
+ * There is no CPU fallback: every solve runs the sm_100a CUDA kernels and the
+ * calls fail with MPC_B200_ERR_CUDA when no usable device is present.
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_B200_VERSION 100
+
+/* ---- error codes (return values) ---- */
+enum {
+    MPC_B200_OK = 0,
+    MPC_B200_ERR_INVALID = -1,      /* bad argument (NULL, batch > max_batch, ...) */
+    MPC_B200_ERR_CUDA = -2,         /* CUDA runtime error / no device; see mpc_b200_last_cuda_error */
+    MPC_B200_ERR_UNSUPPORTED = -3,  /* parameter combination outside the GPU path */
+    MPC_B200_ERR_IO = -4,           /* params file unreadable */
+    MPC_B200_ERR_NOMEM = -5
+};
+
+/* ---- per-problem status: numeric values of CppAD::ipopt::solve_result<>::status_type
+ *      (mpc_ros/include/cppad/ipopt/solve_result.hpp:30-46), which MPC::Solve reads at
+ *      mpc_ros/src/mpc_planner.cpp:378 ---- */
+enum {
+    MPC_B200_STATUS_NOT_DEFINED = 0,
+    MPC_B200_STATUS_SUCCESS = 1,
+    MPC_B200_STATUS_MAXITER_EXCEEDED = 2,
+    MPC_B200_STATUS_STOP_AT_TINY_STEP = 3,
+    MPC_B200_STATUS_STOP_AT_ACCEPTABLE_POINT = 4,
+    MPC_B200_STATUS_LOCAL_INFEASIBILITY = 5,
+    MPC_B200_STATUS_RESTORATION_FAILURE = 9,
+    MPC_B200_STATUS_ERROR_IN_STEP_COMPUTATION = 10,
+    MPC_B200_STATUS_INVALID_NUMBER_DETECTED = 11
+};
+
+/*
+ * Parameters of one MPC instance.  Replaces the string-keyed map of
+ * MPC::LoadParams / FG_eval::LoadParams (mpc_ros/src/mpc_planner.cpp:71-97,
+ * :243-262; keys written at mpc_ros/src/driving_state.cpp:65-79) and the
+ * mpc_* keys of mpc_ros/params/mpc_params.yaml:12-25.
+ */
+typedef struct mpc_b200_params {
+    int32_t mpc_steps;      /* STEPS  / mpc_steps        (horizon N) */
+    double dt;              /* DT     / 1/controller_freq */
+    double ref_cte;         /* REF_CTE    / mpc_ref_cte   */
+    double ref_etheta;      /* REF_ETHETA / mpc_ref_etheta */
+    double ref_vel;         /* REF_V      / mpc_ref_vel   */
+    double w_cte;           /* W_CTE      / mpc_w_cte     */
+    double w_etheta;        /* W_EPSI     / mpc_w_etheta  */
+    double w_vel;           /* W_V        / mpc_w_vel     */
+    double w_angvel;        /* W_ANGVEL   / mpc_w_angvel  */
+    double w_accel;         /* W_A        / mpc_w_accel   */
+    double w_angvel_d;      /* W_DANGVEL  / mpc_w_angvel_d */
+    double w_accel_d;       /* W_DA       / mpc_w_accel_d */
+    double max_angvel;      /* ANGVEL     / mpc_max_angvel */
+    double max_throttle;    /* MAXTHR     / mpc_max_throttle */
+    double bound_value;     /* BOUND      / mpc_bound_value */
+    /* solver controls; the reference leaves these at Ipopt's defaults
+     * (only print_level and max_cpu_time are set, mpc_planner.cpp:358,368) */
+    double tol;             /* Ipopt tol, 1e-8 */
+    int32_t max_iter;       /* iteration cap per problem (Ipopt: 3000; default here 200) */
+    /* non-solver keys of mpc_params.yaml:2-9, carried for the callers above MPC::Solve */
+    int32_t delay_mode;     /* delay_mode */
+    double max_speed;       /* max_speed */
+    double path_length;     /* path_length */
+    double waypoints_dist;  /* waypoints_dist */
+    double goal_radius;     /* goal_radius */
+    double controller_freq; /* controller_freq */
+} mpc_b200_params;
+
+/* Defaults = the constructor defaults of MPC::MPC (mpc_planner.cpp:223-241) and
+ * FG_eval::FG_eval (:42-68) as MPC::Solve sees them before any LoadParams. */
+void mpc_b200_params_default(mpc_b200_params *p);
+/* The values of mpc_ros/params/mpc_params.yaml:1-25 (the benchmark configuration). */
+void mpc_b200_params_yaml_default(mpc_b200_params *p);
+/* Parse a flat "key: value" YAML file with the keys of mpc_params.yaml; unknown keys are
+ * ignored, missing keys keep the value already in *p.  Returns MPC_B200_OK / _ERR_IO. */
+int mpc_b200_params_from_yaml(const char *path, mpc_b200_params *p);
+/* One key of the LoadParams map (DT STEPS REF_CTE REF_ETHETA REF_V W_CTE W_EPSI W_V W_ANGVEL
+ * W_A W_DANGVEL W_DA ANGVEL MAXTHR BOUND).  Unknown key: MPC_B200_ERR_INVALID, *p untouched. */
+int mpc_b200_params_set(mpc_b200_params *p, const char *key, double value);
+
+typedef struct mpc_b200_handle mpc_b200_handle;
+
+/* Creates a solver bound to one CUDA device with scratch for max_batch problems.
+ * One handle per host thread / per GPU; a handle is not re-entrant. */
+int mpc_b200_create(mpc_b200_handle **h, const mpc_b200_params *p, int32_t max_batch, int32_t device);
+void mpc_b200_destroy(mpc_b200_handle *h);
+/* Replaces MPC::LoadParams between solves (mpc_planner.cpp:243; called per tick from
+ * Tracking::deceleration, driving_state.cpp:121-141).  Cheap: no rebuild. */
+int mpc_b200_set_params(mpc_b200_handle *h, const mpc_b200_params *p);
+int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p);
+
+/* Size in doubles of one problem's warm-start record: primal (8N-2, the reference's variable
+ * layout, mpc_planner.cpp:232-239) + equality multipliers (6N) + control-bound multipliers
+ * zL, zU (2(N-1) each). */
+int32_t mpc_b200_warm_size(int32_t mpc_steps);
+
+/*
+ * Batched MPC::Solve (mpc_ros/src/mpc_planner.cpp:265-402): `batch` independent problems.
+ *   state    6 x batch   [x, y, theta, v, cte, etheta]        (:270-275)
+ *   coeffs   4 x batch   cubic reference-path coefficients    (:186-190; driving_state.cpp:210)
+ *   ref_vel  batch       optional per-problem REF_V override (NULL = params.ref_vel); the reference
+ *                        rewrites REF_V per tick (driving_state.cpp:127-139)
+ *   warm_in  warm_size x batch, optional (NULL = the reference's cold start, :288-300)
+ *   u0       2 x batch   {w_0, throttle_0} = MPC::Solve's return value (:398-401)
+ *   pred     3N x batch  mpc_x, mpc_y, mpc_theta (:388-396)
+ *   obj      batch       objective value (solution.obj_value, :381), optional
+ *   status   batch       per-problem status (:378), optional
+ *   iters    batch       interior-point iterations, optional
+ *   kkt_res  batch       final scaled optimality error E_0 (Ipopt's `tol` measure), optional
+ *   warm_out warm_size x batch, optional
+ *   stream   cudaStream_t, or NULL for the handle's own stream.  The call returns after the
+ *            results are in the caller's buffers (synchronous, like MPC::Solve) unless every
+ *            buffer is device memory AND a stream is given, in which case it only enqueues.
+ */
+int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
+                         const double *state, const double *coeffs, const double *ref_vel,
+                         const double *warm_in,
+                         double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
+                         double *kkt_res, double *warm_out, void *stream);
+
+/*
+ * Batched waypoint transform + cubic polyfit + (cte, etheta): the reference pre-step
+ * Tracking::findBestPath (mpc_ros/src/driving_state.cpp:196-235) with polyfit (:283-300).
+ *   wx, wy   M x batch   waypoints in the global frame
+ *   pose     3 x batch   px, py, theta
+ *   coeffs_out      4 x batch
+ *   cte_etheta_out  2 x batch (cte = c[0], :211; etheta by the atan2 rule, :215-235), optional
+ */
+int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                           const double *wx, const double *wy, const double *pose,
+                           double *coeffs_out, double *cte_etheta_out, void *stream);
+
+/* Seconds spent on the device by the last solve_batch / polyfit_batch on this handle
+ * (CUDA events on the launching stream around the kernel only; no copies). */
+double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h);
+/* Number of kernels this handle has launched so far. */
+int64_t mpc_b200_launch_count(const mpc_b200_handle *h);
+
+const char *mpc_b200_strerror(int code);
+const char *mpc_b200_last_cuda_error(const mpc_b200_handle *h);
+int mpc_b200_version(void);
+/* Number of usable CUDA devices (0 when none / no driver). */
+int mpc_b200_device_count(void);
+
+/* FP64 FMA microbenchmark used to fix the roofline denominator (MEASURED_PEAKS.json has
+ * no FP64 entry): independent DFMA chains on every SM.  Returns measured TFLOP/s, <0 on error. */
+double mpc_b200_measure_fp64_peak(int32_t device, int32_t iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */

@@ -1,0 +1,215 @@
+"""mpc_ros_b200/capi.py -- ctypes view of the C ABI in include/mpc_b200.h.
+
+This is harness plumbing for tests/ and bench.py (the product's host side is C++:
+mpc_ros_b200/include/mpc_planner.h).  It never computes anything itself and has no fallback:
+every solve goes through libmpc_b200.so's CUDA kernels, and loading fails loudly when the
+library has not been built (python -c "import __graft_entry__ as g; g.build()").
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(_HERE, "lib", "libmpc_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class Params(C.Structure):
+    """mirror of struct mpc_b200_params"""
+    _fields_ = [
+        ("mpc_steps", C.c_int32),
+        ("dt", C.c_double), ("ref_cte", C.c_double), ("ref_etheta", C.c_double), ("ref_vel", C.c_double),
+        ("w_cte", C.c_double), ("w_etheta", C.c_double), ("w_vel", C.c_double), ("w_angvel", C.c_double),
+        ("w_accel", C.c_double), ("w_angvel_d", C.c_double), ("w_accel_d", C.c_double),
+        ("max_angvel", C.c_double), ("max_throttle", C.c_double), ("bound_value", C.c_double),
+        ("tol", C.c_double), ("max_iter", C.c_int32),
+        ("delay_mode", C.c_int32), ("max_speed", C.c_double), ("path_length", C.c_double),
+        ("waypoints_dist", C.c_double), ("goal_radius", C.c_double), ("controller_freq", C.c_double),
+    ]
+
+
+# every symbol include/mpc_b200.h declares
+EXPORTS = [
+    "mpc_b200_params_default", "mpc_b200_params_yaml_default", "mpc_b200_params_from_yaml",
+    "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
+    "mpc_b200_get_params", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
+    "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
+    "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
+]
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libmpc_b200.so is not built (%s); run __graft_entry__.build(). "
+                           "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.mpc_b200_params_default.argtypes = [C.POINTER(Params)]
+    L.mpc_b200_params_yaml_default.argtypes = [C.POINTER(Params)]
+    L.mpc_b200_params_from_yaml.argtypes = [C.c_char_p, C.POINTER(Params)]
+    L.mpc_b200_params_from_yaml.restype = C.c_int
+    L.mpc_b200_params_set.argtypes = [C.POINTER(Params), C.c_char_p, C.c_double]
+    L.mpc_b200_params_set.restype = C.c_int
+    L.mpc_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.c_int32, C.c_int32]
+    L.mpc_b200_create.restype = C.c_int
+    L.mpc_b200_destroy.argtypes = [C.c_void_p]
+    L.mpc_b200_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.mpc_b200_set_params.restype = C.c_int
+    L.mpc_b200_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.mpc_b200_get_params.restype = C.c_int
+    L.mpc_b200_warm_size.argtypes = [C.c_int32]
+    L.mpc_b200_warm_size.restype = C.c_int32
+    L.mpc_b200_solve_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 12
+    L.mpc_b200_solve_batch.restype = C.c_int
+    L.mpc_b200_polyfit_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    L.mpc_b200_polyfit_batch.restype = C.c_int
+    L.mpc_b200_last_kernel_seconds.argtypes = [C.c_void_p]
+    L.mpc_b200_last_kernel_seconds.restype = C.c_double
+    L.mpc_b200_launch_count.argtypes = [C.c_void_p]
+    L.mpc_b200_launch_count.restype = C.c_int64
+    L.mpc_b200_strerror.argtypes = [C.c_int]
+    L.mpc_b200_strerror.restype = C.c_char_p
+    L.mpc_b200_last_cuda_error.argtypes = [C.c_void_p]
+    L.mpc_b200_last_cuda_error.restype = C.c_char_p
+    L.mpc_b200_version.restype = C.c_int
+    L.mpc_b200_device_count.restype = C.c_int
+    L.mpc_b200_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32]
+    L.mpc_b200_measure_fp64_peak.restype = C.c_double
+    if hasattr(L, "mpc_b200_debug_profile"):
+        L.mpc_b200_debug_profile.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.mpc_b200_debug_profile.restype = C.c_int
+    if hasattr(L, "mpc_b200_debug_fp64_probe"):
+        L.mpc_b200_debug_fp64_probe.argtypes = [C.c_int32] * 4
+        L.mpc_b200_debug_fp64_probe.restype = C.c_double
+    _LIB = L
+    return L
+
+
+class MpcError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = lib().mpc_b200_strerror(code).decode()
+        RuntimeError.__init__(self, "mpc_b200 error %d: %s %s" % (code, msg, detail))
+
+
+def yaml_default_params():
+    p = Params()
+    lib().mpc_b200_params_yaml_default(C.byref(p))
+    return p
+
+
+def default_params():
+    p = Params()
+    lib().mpc_b200_params_default(C.byref(p))
+    return p
+
+
+def params_from_yaml(path, base=None):
+    p = base if base is not None else default_params()
+    rc = lib().mpc_b200_params_from_yaml(path.encode(), C.byref(p))
+    if rc != 0:
+        raise MpcError(rc, path)
+    return p
+
+
+def params_from_map(pm, base=None):
+    """pm: the reference's LoadParams map (DT, STEPS, REF_V, ...)."""
+    p = base if base is not None else default_params()
+    for k, v in pm.items():
+        rc = lib().mpc_b200_params_set(C.byref(p), k.encode(), float(v))
+        if rc != 0:
+            raise MpcError(rc, k)
+    return p
+
+
+def _addr(x):
+    """host numpy array or anything with data_ptr() (a device tensor) -> integer address"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()
+
+
+class Solver:
+    """Owns one mpc_b200_handle."""
+
+    def __init__(self, params, max_batch, device=0):
+        self._h = C.c_void_p()
+        self.max_batch = max_batch
+        rc = lib().mpc_b200_create(C.byref(self._h), C.byref(params), max_batch, device)
+        if rc != 0:
+            self._h = None
+            raise MpcError(rc)
+        self.N = params.mpc_steps
+
+    def close(self):
+        if self._h:
+            lib().mpc_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        rc = lib().mpc_b200_set_params(self._h, C.byref(params))
+        if rc != 0:
+            raise MpcError(rc)
+        self.N = params.mpc_steps
+
+    def solve_raw(self, batch, state, coeffs, u0, pred, ref_vel=None, warm_in=None, obj=None, status=None,
+                  iters=None, kkt=None, warm_out=None, stream=None):
+        rc = lib().mpc_b200_solve_batch(self._h, batch, _addr(state), _addr(coeffs), _addr(ref_vel), _addr(warm_in),
+                                        _addr(u0), _addr(pred), _addr(obj), _addr(status), _addr(iters), _addr(kkt),
+                                        _addr(warm_out), stream)
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def solve(self, state, coeffs, ref_vel=None):
+        """Host numpy in/out.  state 6 x B, coeffs 4 x B."""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        B = state.shape[1]
+        N = self.N
+        out = dict(u0=np.zeros((2, B)), pred=np.zeros((3 * N, B)), obj=np.zeros(B),
+                   status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32), kkt=np.zeros(B))
+        if ref_vel is not None:
+            ref_vel = np.ascontiguousarray(ref_vel, dtype=np.float64)
+        self.solve_raw(B, state, coeffs, out["u0"], out["pred"], ref_vel=ref_vel, obj=out["obj"],
+                       status=out["status"], iters=out["iters"], kkt=out["kkt"])
+        return out
+
+    def polyfit(self, wx, wy, pose):
+        wx = np.ascontiguousarray(wx, dtype=np.float64)
+        wy = np.ascontiguousarray(wy, dtype=np.float64)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        M, B = wx.shape
+        coeffs = np.zeros((4, B)); ce = np.zeros((2, B))
+        rc = lib().mpc_b200_polyfit_batch(self._h, B, M, _addr(wx), _addr(wy), _addr(pose), _addr(coeffs), _addr(ce), None)
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+        return coeffs, ce[0], ce[1]
+
+    def polyfit_raw(self, batch, M, wx, wy, pose, coeffs, cte_etheta=None, stream=None):
+        rc = lib().mpc_b200_polyfit_batch(self._h, batch, M, _addr(wx), _addr(wy), _addr(pose), _addr(coeffs),
+                                          _addr(cte_etheta), stream)
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    @property
+    def last_kernel_seconds(self):
+        return lib().mpc_b200_last_kernel_seconds(self._h)
+
+    @property
+    def launch_count(self):
+        return lib().mpc_b200_launch_count(self._h)

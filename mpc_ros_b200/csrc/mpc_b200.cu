@@ -1,0 +1,530 @@
+// mpc_b200.cu -- C ABI (include/mpc_b200.h) + kernel launches.  sm_100a only; no CPU path.
+#include "../../include/mpc_b200.h"
+#include "nmpc_kernel.cuh"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <string>
+
+using nmpc::SolveArgs;
+
+#define MAX_WAYPOINTS 64
+
+// ================================================================ K1: transform + polyfit
+// Reference: Tracking::findBestPath, mpc_ros/src/driving_state.cpp:196-235, polyfit :283-300
+// (Vandermonde by running products + unpivoted Householder QR, what Eigen's
+// householderQr().solve() does).  One thread per problem: M ~ 11 waypoints, a 11x4 QR.
+__global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, const double *__restrict__ wy,
+                               const double *__restrict__ pose, double *__restrict__ coeffs_out,
+                               double *__restrict__ cte_eth_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const double px = pose[i], py = pose[(size_t)batch + i], th = pose[2 * (size_t)batch + i];
+    double st, ct;
+    sincos(th, &st, &ct);
+    double A[MAX_WAYPOINTS][4];
+    double b[MAX_WAYPOINTS];
+    for (int j = 0; j < M; j++) {
+        const double dx = wx[(size_t)j * batch + i] - px, dy = wy[(size_t)j * batch + i] - py;
+        const double xv = dx * ct + dy * st;      // driving_state.cpp:205
+        b[j] = dy * ct - dx * st;                 // :206
+        A[j][0] = 1.0;
+        A[j][1] = A[j][0] * xv; A[j][2] = A[j][1] * xv; A[j][3] = A[j][2] * xv;   // :292-296
+    }
+    double c[4];
+    bool ok = true;
+    for (int k = 0; k < 4; k++) {
+        double nrm = 0.0;
+        for (int r = k; r < M; r++) nrm += A[r][k] * A[r][k];
+        nrm = sqrt(nrm);
+        if (nrm == 0.0) { ok = false; break; }
+        const double alpha = (A[k][k] > 0.0) ? -nrm : nrm;
+        A[k][k] -= alpha;
+        double vtv = 0.0;
+        for (int r = k; r < M; r++) vtv += A[r][k] * A[r][k];
+        const double beta = 2.0 / vtv;
+        for (int j = k + 1; j < 4; j++) {
+            double s = 0.0;
+            for (int r = k; r < M; r++) s += A[r][k] * A[r][j];
+            s *= beta;
+            for (int r = k; r < M; r++) A[r][j] -= s * A[r][k];
+        }
+        double s = 0.0;
+        for (int r = k; r < M; r++) s += A[r][k] * b[r];
+        s *= beta;
+        for (int r = k; r < M; r++) b[r] -= s * A[r][k];
+        A[k][k] = alpha;
+    }
+    if (ok) {
+        for (int k = 3; k >= 0; k--) {
+            double s = b[k];
+            for (int j = k + 1; j < 4; j++) s -= A[k][j] * c[j];
+            c[k] = s / A[k][k];
+        }
+    } else {
+        const double nanv = nan("");
+        c[0] = c[1] = c[2] = c[3] = nanv;
+    }
+    for (int k = 0; k < 4; k++) coeffs_out[(size_t)k * batch + i] = c[k];
+    if (cte_eth_out) {
+        // cte = polyeval(coeffs, 0) = c[0] (:211); etheta by the reference's atan2 rule (:215-235)
+        double gx = 0.0, gy = 0.0;
+        const int ns = (int)(M * 0.3);
+        for (int j = 1; j < ns; j++) {
+            gx += wx[(size_t)j * batch + i] - wx[(size_t)(j - 1) * batch + i];
+            gy += wy[(size_t)j * batch + i] - wy[(size_t)(j - 1) * batch + i];
+        }
+        double tt = th;
+        const double traj = atan2(gy, gx);
+        const double PI = 3.14159265358979323846;
+        if (tt <= -PI + traj) tt += 2.0 * PI;
+        double eth;
+        if (gx != 0.0 && gy != 0.0 && tt - traj < 1.8 * PI) eth = tt - traj; else eth = 0.0;
+        cte_eth_out[i] = c[0];
+        cte_eth_out[(size_t)batch + i] = eth;
+    }
+}
+
+// ================================================================ FP64 probes
+// mode 0: throughput -- 8 independent DFMA chains per thread, every SM busy
+// mode 1..: single-warp issue/latency probes (see mpc_b200_debug_fp64_probe)
+template <int ILP>
+__global__ void dfma_kernel(double *out, int iters, int active_lanes, long long *cycles)
+{
+    double acc[ILP];
+    const double a = 1.0000001, b = 1e-9;
+#pragma unroll
+    for (int j = 0; j < ILP; j++) acc[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+    const bool act = (threadIdx.x & 31) < active_lanes;
+    long long t0 = clock64();
+    if (act) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int j = 0; j < ILP; j++) acc[j] = fma(acc[j], a, b);
+        }
+    }
+    long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < ILP; j++) s += acc[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (cycles && threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// ================================================================ handle
+struct mpc_b200_handle {
+    mpc_b200_params params;
+    int device;
+    int max_batch;
+    int num_sms;
+    size_t smem_optin;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    // device scratch
+    double *d_state, *d_coeffs, *d_refv, *d_u0, *d_pred, *d_obj, *d_kkt, *d_warm_out;
+    int *d_status, *d_iters;
+    double *d_wx, *d_wy, *d_pose, *d_cte;
+    // pinned staging
+    double *h_in, *h_out;
+    size_t h_in_bytes, h_out_bytes;
+    int pred_steps;        // horizon the scratch was sized for
+    double last_kernel_s;
+    long long launches;
+    long long *d_prof;
+    std::string last_err;
+};
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static int cuda_fail(mpc_b200_handle *h, cudaError_t e, const char *what)
+{
+    if (h) h->last_err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return MPC_B200_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); } while (0)
+
+static void free_scratch(mpc_b200_handle *h)
+{
+    cudaFree(h->d_state); cudaFree(h->d_coeffs); cudaFree(h->d_refv); cudaFree(h->d_u0); cudaFree(h->d_pred);
+    cudaFree(h->d_obj); cudaFree(h->d_kkt); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_warm_out);
+    cudaFree(h->d_wx); cudaFree(h->d_wy); cudaFree(h->d_pose); cudaFree(h->d_cte);
+    cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
+    if (h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
+    h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
+    h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = NULL;
+    h->h_in = h->h_out = NULL;
+}
+
+static int alloc_scratch(mpc_b200_handle *h)
+{
+    const size_t B = (size_t)h->max_batch, N = (size_t)h->params.mpc_steps;
+    h->pred_steps = (int)N;
+    CK(cudaMalloc(&h->d_state, sizeof(double) * 6 * B));
+    CK(cudaMalloc(&h->d_coeffs, sizeof(double) * 4 * B));
+    CK(cudaMalloc(&h->d_refv, sizeof(double) * B));
+    CK(cudaMalloc(&h->d_u0, sizeof(double) * 2 * B));
+    CK(cudaMalloc(&h->d_pred, sizeof(double) * 3 * N * B));
+    CK(cudaMalloc(&h->d_obj, sizeof(double) * B));
+    CK(cudaMalloc(&h->d_kkt, sizeof(double) * B));
+    CK(cudaMalloc(&h->d_status, sizeof(int) * B));
+    CK(cudaMalloc(&h->d_iters, sizeof(int) * B));
+    CK(cudaMalloc(&h->d_wx, sizeof(double) * MAX_WAYPOINTS * B));
+    CK(cudaMalloc(&h->d_wy, sizeof(double) * MAX_WAYPOINTS * B));
+    CK(cudaMalloc(&h->d_pose, sizeof(double) * 3 * B));
+    CK(cudaMalloc(&h->d_cte, sizeof(double) * 2 * B));
+    h->d_warm_out = NULL;
+    h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
+    h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 1 + 6) * B;
+    CK(cudaMallocHost(&h->h_in, h->h_in_bytes));
+    CK(cudaMallocHost(&h->h_out, h->h_out_bytes));
+    return MPC_B200_OK;
+}
+
+static int check_params(const mpc_b200_params *p)
+{
+    if (!p) return MPC_B200_ERR_INVALID;
+    if (p->mpc_steps < 2 || p->mpc_steps > 640) return MPC_B200_ERR_INVALID;
+    if (!(p->dt > 0.0) || !(p->max_angvel > 0.0) || !(p->max_throttle > 0.0)) return MPC_B200_ERR_INVALID;
+    // rate penalties couple u_k and u_{k+1} (mpc_planner.cpp:144-147): needs the augmented-state
+    // Riccati variant; not on the GPU path yet.
+    if (p->w_angvel_d != 0.0 || p->w_accel_d != 0.0) return MPC_B200_ERR_UNSUPPORTED;
+    return MPC_B200_OK;
+}
+
+extern "C" {
+
+int mpc_b200_version(void) { return MPC_B200_VERSION; }
+
+int mpc_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *mpc_b200_strerror(int code)
+{
+    switch (code) {
+        case MPC_B200_OK: return "ok";
+        case MPC_B200_ERR_INVALID: return "invalid argument";
+        case MPC_B200_ERR_CUDA: return "CUDA error or no usable device (this library has no CPU path)";
+        case MPC_B200_ERR_UNSUPPORTED: return "parameter combination not supported by the GPU path";
+        case MPC_B200_ERR_IO: return "cannot read parameter file";
+        case MPC_B200_ERR_NOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+const char *mpc_b200_last_cuda_error(const mpc_b200_handle *h) { return h ? h->last_err.c_str() : ""; }
+
+int32_t mpc_b200_warm_size(int32_t N) { return (8 * N - 2) + 6 * N + 4 * (N - 1); }
+
+int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max_batch, int32_t device)
+{
+    if (!out || max_batch < 1) return MPC_B200_ERR_INVALID;
+    *out = NULL;
+    int rc = check_params(p);
+    if (rc != MPC_B200_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return MPC_B200_ERR_CUDA;
+    }
+    mpc_b200_handle *h = new (std::nothrow) mpc_b200_handle();
+    if (!h) return MPC_B200_ERR_NOMEM;
+    h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0;
+    h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
+    h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = NULL; h->h_in = h->h_out = NULL;
+    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    int sms = 0, optin = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
+    h->num_sms = sms; h->smem_optin = (size_t)optin;
+    e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
+    rc = alloc_scratch(h);
+    if (rc != MPC_B200_OK) { free_scratch(h); delete h; return rc; }
+    *out = h;
+    return MPC_B200_OK;
+}
+
+void mpc_b200_destroy(mpc_b200_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_scratch(h);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int mpc_b200_set_params(mpc_b200_handle *h, const mpc_b200_params *p)
+{
+    if (!h) return MPC_B200_ERR_INVALID;
+    int rc = check_params(p);
+    if (rc != MPC_B200_OK) return rc;
+    const bool regrow = p->mpc_steps > h->pred_steps;
+    h->params = *p;
+    if (regrow) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        free_scratch(h);
+        return alloc_scratch(h);
+    }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p)
+{
+    if (!h || !p) return MPC_B200_ERR_INVALID;
+    *p = h->params;
+    return MPC_B200_OK;
+}
+
+double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h) { return h ? h->last_kernel_s : 0.0; }
+int64_t mpc_b200_launch_count(const mpc_b200_handle *h) { return h ? h->launches : 0; }
+
+// Problems per CTA: as many as shared memory and the thread budget allow, but spread a small
+// batch over all SMs (the CTA's latency does not depend on how many lanes are active).
+static int choose_pb(const mpc_b200_handle *h, int N, int batch)
+{
+    const int NG = (N + 1) / 2;
+    int pb = 32;
+    if (pb > 320 / NG) pb = 320 / NG;
+    while (pb > 1 && nmpc::smem_bytes(N, pb) > h->smem_optin) pb--;
+    const int spread = (batch + h->num_sms - 1) / h->num_sms;
+    if (spread < pb) pb = spread < 1 ? 1 : spread;
+    return pb;
+}
+
+int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
+                         const double *state, const double *coeffs, const double *ref_vel,
+                         const double *warm_in,
+                         double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
+                         double *kkt_res, double *warm_out, void *stream_v)
+{
+    if (!h || batch < 0 || batch > h->max_batch || !state || !coeffs || !u0 || !pred) return MPC_B200_ERR_INVALID;
+    if (warm_in) return MPC_B200_ERR_UNSUPPORTED;   // warm start lands with the closed-loop row
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const mpc_b200_params &P = h->params;
+    const int N = P.mpc_steps;
+    const size_t B = (size_t)batch;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+
+    const bool dev_in = is_device_ptr(state);
+    const bool dev_out = is_device_ptr(u0);
+    if (is_device_ptr(coeffs) != dev_in || (ref_vel && is_device_ptr(ref_vel) != dev_in)) return MPC_B200_ERR_INVALID;
+    if (is_device_ptr(pred) != dev_out || (obj && is_device_ptr(obj) != dev_out) ||
+        (status && is_device_ptr(status) != dev_out) || (iters && is_device_ptr(iters) != dev_out) ||
+        (kkt_res && is_device_ptr(kkt_res) != dev_out) || (warm_out && is_device_ptr(warm_out) != dev_out))
+        return MPC_B200_ERR_INVALID;
+
+    SolveArgs a;
+    a.prm.N = N; a.prm.dt = P.dt; a.prm.ref_cte = P.ref_cte; a.prm.ref_etheta = P.ref_etheta; a.prm.ref_vel = P.ref_vel;
+    a.prm.w_cte = P.w_cte; a.prm.w_etheta = P.w_etheta; a.prm.w_vel = P.w_vel; a.prm.w_angvel = P.w_angvel;
+    a.prm.w_accel = P.w_accel; a.prm.max_angvel = P.max_angvel; a.prm.max_throttle = P.max_throttle;
+    a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
+    a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 200;
+    a.batch = batch;
+    a.PB = choose_pb(h, N, batch);
+    a.prof = h->d_prof;
+
+    if (dev_in) {
+        a.state = state; a.coeffs = coeffs; a.ref_vel = ref_vel;
+    } else {
+        double *hi = h->h_in;
+        memcpy(hi, state, sizeof(double) * 6 * B);
+        memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B);
+        if (ref_vel) memcpy(hi + 10 * B, ref_vel, sizeof(double) * B);
+        // state and coeffs scratch are separate allocations: two copies (three with ref_vel)
+        CK(cudaMemcpyAsync(h->d_state, hi, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_coeffs, hi + 6 * B, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, st));
+        if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, hi + 10 * B, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+        a.state = h->d_state; a.coeffs = h->d_coeffs; a.ref_vel = ref_vel ? h->d_refv : NULL;
+    }
+    if (warm_out && !dev_out) return MPC_B200_ERR_UNSUPPORTED;  // host warm_out staging not wired yet
+    if (dev_out) {
+        a.u0 = u0; a.pred = pred; a.obj = obj; a.status = status; a.iters = iters; a.kkt = kkt_res; a.warm_out = warm_out;
+    } else {
+        a.u0 = h->d_u0; a.pred = h->d_pred; a.obj = h->d_obj; a.status = h->d_status; a.iters = h->d_iters;
+        a.kkt = h->d_kkt; a.warm_out = NULL;
+    }
+
+    const int NG = (N + 1) / 2;
+    const int stage_threads = ((NG * a.PB + 31) / 32) * 32;
+    const int threads = 32 + stage_threads;
+    const int grid = (batch + a.PB - 1) / a.PB;
+    const size_t smem = nmpc::smem_bytes(N, a.PB);
+    CK(cudaEventRecord(h->ev0, st));
+    nmpc::nmpc_solve_kernel<2><<<grid, threads, smem, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    h->launches++;
+
+    if (!dev_out) {
+        double *ho = h->h_out;
+        double *ho_u0 = ho, *ho_pred = ho + 2 * B, *ho_obj = ho_pred + 3 * (size_t)N * B, *ho_kkt = ho_obj + B;
+        int *ho_status = reinterpret_cast<int *>(ho_kkt + B), *ho_iters = ho_status + B;
+        CK(cudaMemcpyAsync(ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
+        if (obj) CK(cudaMemcpyAsync(ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        if (kkt_res) CK(cudaMemcpyAsync(ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        if (status) CK(cudaMemcpyAsync(ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        if (iters) CK(cudaMemcpyAsync(ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(u0, ho_u0, sizeof(double) * 2 * B);
+        memcpy(pred, ho_pred, sizeof(double) * 3 * N * B);
+        if (obj) memcpy(obj, ho_obj, sizeof(double) * B);
+        if (kkt_res) memcpy(kkt_res, ho_kkt, sizeof(double) * B);
+        if (status) memcpy(status, ho_status, sizeof(int) * B);
+        if (iters) memcpy(iters, ho_iters, sizeof(int) * B);
+    } else if (!(dev_in && stream_v)) {
+        CK(cudaStreamSynchronize(st));
+    }
+    if (!(dev_in && dev_out && stream_v)) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
+    }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                           const double *wx, const double *wy, const double *pose,
+                           double *coeffs_out, double *cte_etheta_out, void *stream_v)
+{
+    if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !coeffs_out) return MPC_B200_ERR_INVALID;
+    if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;   // polyfit asserts order <= M-1 (driving_state.cpp:286)
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t B = (size_t)batch;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    const bool dev_in = is_device_ptr(wx), dev_out = is_device_ptr(coeffs_out);
+    if (is_device_ptr(wy) != dev_in || is_device_ptr(pose) != dev_in) return MPC_B200_ERR_INVALID;
+    if (cte_etheta_out && is_device_ptr(cte_etheta_out) != dev_out) return MPC_B200_ERR_INVALID;
+    const double *dwx = wx, *dwy = wy, *dpose = pose;
+    if (!dev_in) {
+        double *hi = h->h_in;
+        memcpy(hi, wx, sizeof(double) * M * B);
+        memcpy(hi + (size_t)M * B, wy, sizeof(double) * M * B);
+        memcpy(hi + 2 * (size_t)M * B, pose, sizeof(double) * 3 * B);
+        CK(cudaMemcpyAsync(h->d_wx, hi, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_wy, hi + (size_t)M * B, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_pose, hi + 2 * (size_t)M * B, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
+        dwx = h->d_wx; dwy = h->d_wy; dpose = h->d_pose;
+    }
+    double *dco = dev_out ? coeffs_out : h->d_coeffs;
+    double *dce = cte_etheta_out ? (dev_out ? cte_etheta_out : h->d_cte) : NULL;
+    CK(cudaEventRecord(h->ev0, st));
+    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, dce);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    h->launches++;
+    if (!dev_out) {
+        double *ho = h->h_out;
+        CK(cudaMemcpyAsync(ho, dco, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
+        if (dce) CK(cudaMemcpyAsync(ho + 4 * B, dce, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(coeffs_out, ho, sizeof(double) * 4 * B);
+        if (dce) memcpy(cte_etheta_out, ho + 4 * B, sizeof(double) * 2 * B);
+    } else if (!(dev_in && stream_v)) {
+        CK(cudaStreamSynchronize(st));
+    }
+    if (!(dev_in && dev_out && stream_v)) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
+    }
+    return MPC_B200_OK;
+}
+
+double mpc_b200_measure_fp64_peak(int32_t device, int32_t iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256;
+    double *out = NULL;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_kernel<8><<<blocks, threads>>>(out, 64, 32, NULL);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        dfma_kernel<8><<<blocks, threads>>>(out, iters, 32, NULL);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double tf = flops / (1e-3 * ms) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    return best;
+}
+
+// NMPC_PROFILE builds: per-phase SM-cycle counters of CTA 0's control thread for the last solve
+// (0 residual phase, 1 check, 2 coeff phase, 3 backward sweep, 4 forward sweep, 5 step phase,
+//  6 ctrl_step + adjoint, 7 trial phase, 8 line-search decision, 9 accept phase).  Returns 0 if
+// the library was built without NMPC_PROFILE.
+int mpc_b200_debug_profile(mpc_b200_handle *h, long long *out12)
+{
+#ifdef NMPC_PROFILE
+    if (!h) return 0;
+    if (!h->d_prof) {
+        if (cudaMalloc(&h->d_prof, sizeof(long long) * 12) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cudaMemset(h->d_prof, 0, sizeof(long long) * 12);
+        return 1;
+    }
+    if (out12) cudaMemcpy(out12, h->d_prof, sizeof(long long) * 12, cudaMemcpyDeviceToHost);
+    return 1;
+#else
+    (void)h; (void)out12;
+    return 0;
+#endif
+}
+
+// Single-warp DFMA probe: returns SM cycles per warp-level DFMA instruction for `ilp`
+// independent chains (1, 2, 4 or 8) with `active_lanes` lanes enabled.
+double mpc_b200_debug_fp64_probe(int32_t device, int32_t ilp, int32_t active_lanes, int32_t iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    double *out = NULL; long long *cyc = NULL;
+    cudaMalloc(&out, sizeof(double) * 32); cudaMalloc(&cyc, sizeof(long long));
+    for (int rep = 0; rep < 2; rep++) {
+        if (ilp == 1) dfma_kernel<1><<<1, 32>>>(out, iters, active_lanes, cyc);
+        else if (ilp == 2) dfma_kernel<2><<<1, 32>>>(out, iters, active_lanes, cyc);
+        else if (ilp == 4) dfma_kernel<4><<<1, 32>>>(out, iters, active_lanes, cyc);
+        else dfma_kernel<8><<<1, 32>>>(out, iters, active_lanes, cyc);
+    }
+    long long c = 0;
+    cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
+    cudaFree(out); cudaFree(cyc);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    const int chains = (ilp == 1 || ilp == 2 || ilp == 4) ? ilp : 8;
+    return (double)c / ((double)iters * chains);
+}
+
+}  // extern "C"

@@ -1,0 +1,819 @@
+// nmpc_phases.cuh -- the per-(problem, stage) and per-problem phases of the batched
+// structure-exploiting interior-point NMPC solver.
+//
+// What it replaces in the reference (OkDoky/mpc_ros):
+//   * FG_eval's CppAD-taped cost / dynamics and taped Jacobian / Hessian
+//     (mpc_ros/src/mpc_planner.cpp:102-217, cppad/ipopt/solve_callback.hpp:625-1020)
+//     -> closed-form stage derivatives (stage_eval / stage_coeffs below);
+//   * Ipopt's primal-dual interior-point loop (call site cppad/ipopt/solve.hpp:586)
+//     -> the same published algorithm (Waechter & Biegler 2006, Ipopt 3.12 defaults: monotone
+//     barrier, filter line search, inertia-correcting regularisation) with the stage-wise
+//     block-tridiagonal KKT system solved by a sparsity-exploiting Riccati recursion.
+//
+// Execution model (see nmpc_kernel.cu): a CTA owns PB problems.  "Stage threads" own one
+// (problem, stage) pair each in the stage-parallel phases; one "control thread" per problem
+// (lane == problem in warp 0) runs the per-problem logic and the serial Riccati sweeps.  All
+// cross-thread data goes through the CTA's shared-memory block, indexed
+// [stage][slot][problem] so that a warp touches 32 consecutive doubles.  Phases are separated
+// by CTA barriers, which is also what lets tests/emu run the identical phase functions
+// sequentially on the host as a logic check (test-only; the product has no CPU path).
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD inline
+#endif
+
+namespace nmpc {
+
+// ---------------------------------------------------------------- shared-memory layout
+enum Slot {
+    S_X = 0, S_Y, S_T, S_V, S_C, S_E,          // state s_k = [x y theta v cte etheta]
+    L_X, L_Y, L_T, L_V, L_C, L_E,              // lambda_{k+1}: multiplier of  s_{k+1} - phi(s_k,u_k) = 0
+    A_13, A_14, A_23, A_24, A_51, A_54, A_56,  // non-trivial entries of A_k = d phi / d s
+    D_X, D_Y, D_T, D_V, D_C, D_E,              // d_k = -(s_{k+1} - phi_k); after the forward sweep: ds_{k+1}
+    W_0, W_1, W_2, W_3, W_4, W_5, W_6, W_7, W_8, W_9, W_10, W_11,  // work slots (see phases)
+    NSLOTS
+};
+
+// per-problem scalars shared between the control thread and the stage threads
+enum PSlot {
+    PS_MU = 0, PS_TAU, PS_SF, PS_REFV, PS_ALPHA, PS_ALPHA_Z, PS_DW,
+    PS_L0X, PS_L0Y, PS_L0T, PS_L0V, PS_L0C, PS_L0E,       // lambda_0 (initial-condition rows)
+    PS_N0X, PS_N0Y, PS_N0T, PS_N0V, PS_N0C, PS_N0E,       // its Newton target lambda_0^+
+    NPS
+};
+enum PISlot {
+    PI_MODE = 0,   // what the stage threads do next (see Mode)
+    PI_STATUS,     // 0 while running, else final status
+    PI_LSQ,        // 1 during the first cycle: least-squares multiplier start (W&B eq. (36))
+    NPI
+};
+
+// Per-problem phase, written by the control thread, read by the stage threads.
+enum Mode {
+    MODE_IDLE = 0,      // problem finished / lane unused
+    MODE_RESID,         // evaluate residuals at the iterate (stage_residuals), then ctrl_check
+    MODE_COEF,          // write Newton-system coefficients (stage_coeffs), then the Riccati sweeps
+    MODE_STEP,          // sweeps succeeded: stage_step, then ctrl_step
+    MODE_TRIAL,         // line search: stage_trial at PS_ALPHA, then ctrl_linesearch
+    MODE_ACCEPT         // stage_accept; doubles as MODE_RESID for the next iteration
+};
+
+struct Params {
+    int N;
+    double dt, ref_cte, ref_etheta, ref_vel;
+    double w_cte, w_etheta, w_vel, w_angvel, w_accel;
+    double max_angvel, max_throttle;
+    double tol;
+    int max_iter;
+};
+
+struct Smem {
+    double *st;   // [N][NSLOTS][PB]
+    double *ps;   // [NPS][PB]
+    int *pi;      // [NPI][PB]
+    int PB;
+    MPC_HD double &at(int k, int slot, int p) const { return st[(k * NSLOTS + slot) * PB + p]; }
+    MPC_HD double &P(int slot, int p) const { return ps[slot * PB + p]; }
+    MPC_HD int &I(int slot, int p) const { return pi[slot * PB + p]; }
+};
+
+MPC_HD size_t smem_bytes(int N, int PB)
+{
+    return sizeof(double) * ((size_t)N * NSLOTS * PB + (size_t)NPS * PB) + sizeof(int) * (size_t)NPI * PB;
+}
+
+// Ipopt 3.12 default constants (Waechter & Biegler 2006)
+#define NMPC_KAPPA_EPS 10.0
+#define NMPC_KAPPA_MU 0.2
+#define NMPC_THETA_MU 1.5
+#define NMPC_TAU_MIN 0.99
+#define NMPC_S_MAX 100.0
+#define NMPC_GAMMA_THETA 1e-5
+#define NMPC_GAMMA_PHI 1e-8
+#define NMPC_S_THETA 1.1
+#define NMPC_S_PHI 2.3
+#define NMPC_ETA_PHI 1e-8
+#define NMPC_GAMMA_ALPHA 0.05
+#define NMPC_KAPPA_SIGMA 1e10
+#define NMPC_MU_INIT 0.1
+#define NMPC_BOUND_RELAX 1e-8
+#define NMPC_LAM_MAX 1e3
+#define NMPC_DW_MIN 1e-20
+#define NMPC_DW_0 1e-4
+#define NMPC_DW_MAX 1e40
+#define NMPC_KW_MINUS (1.0 / 3.0)
+#define NMPC_KW_PLUS 8.0
+#define NMPC_KW_PLUS_BAR 100.0
+#define NMPC_EPS_MACH 2.220446049250313e-16
+#define NMPC_MAX_FILTER 12
+
+// ---------------------------------------------------------------- per-(problem, stage) registers
+struct StageRegs {
+    double uw, ua;              // controls of this stage (k <= N-2)
+    double zlw, zuw, zla, zua;  // bound multipliers of the controls (scaled problem)
+    double sn, cs, se, ce;      // sin/cos(theta_k), sin/cos(etheta_k) at the current iterate
+    double tsn, tcs, tse, tce;  // the same at the last trial point
+    double qv, qc, qe;          // objective gradient wrt (v, cte, etheta) at the current iterate
+    double hxx, htt, htv, hee, hev;  // Lagrangian-Hessian entries of this stage
+    double duw, dua;            // Newton step of the controls
+    double c0, c1, c2, c3;      // path polynomial coefficients
+};
+
+MPC_HD double fmax2(double a, double b) { return a > b ? a : b; }
+MPC_HD double fmin2(double a, double b) { return a < b ? a : b; }
+
+MPC_HD void sincos_d(double a, double *s, double *c)
+{
+#if defined(__CUDA_ARCH__)
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+
+// relaxed control bounds (Ipopt bound_relax_factor, W&B Sec. 3.5)
+MPC_HD double relaxed(double b) { return b + NMPC_BOUND_RELAX * fmax2(1.0, b); }
+
+// ---------------------------------------------------------------- init
+// Reference cold start (mpc_planner.cpp:288-300): zeros except stage 0 = state.
+MPC_HD void stage_init(const Params &prm, const Smem &sm, StageRegs &r, int k, int p,
+                       const double *state6, const double *coef4)
+{
+    for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
+    for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = 0.0;
+    r.uw = 0.0; r.ua = 0.0;
+    r.zlw = r.zuw = r.zla = r.zua = 1.0;      // bound_mult_init_val
+    r.c0 = coef4[0]; r.c1 = coef4[1]; r.c2 = coef4[2]; r.c3 = coef4[3];
+    sincos_d(sm.at(k, S_T, p), &r.sn, &r.cs);
+    sincos_d(sm.at(k, S_E, p), &r.se, &r.ce);
+    r.duw = r.dua = 0.0;
+    r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
+    r.qv = r.qc = r.qe = 0.0;
+    r.tsn = r.sn; r.tcs = r.cs; r.tse = r.se; r.tce = r.ce;
+    (void)prm;
+}
+
+// ---------------------------------------------------------------- phase A1: residuals at the iterate
+// Writes the stage's partial sums for the control thread into W_0..W_8:
+//   W_0 max|c|, W_1 sum|c|, W_2 max|dual residual|, W_3 max compl product, W_4 min compl product,
+//   W_5 sum|lambda|, W_6 sum|z|, W_7 scaled objective part, W_8 sum of log-barrier arguments.
+// Also leaves d_k = -c_{k+1} in the D slots and the objective gradient in r.q*.
+MPC_HD void stage_residuals(const Params &prm, const Smem &sm, StageRegs &r, int k, int p)
+{
+    const int N = prm.N;
+    const double sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
+    const double x = sm.at(k, S_X, p), y = sm.at(k, S_Y, p), th = sm.at(k, S_T, p);
+    const double v = sm.at(k, S_V, p), ct = sm.at(k, S_C, p), e = sm.at(k, S_E, p);
+    (void)th;
+    // objective part of this stage (mpc_planner.cpp:122-140)
+    const double ec = ct - prm.ref_cte, ee = e - prm.ref_etheta, ev = v - refv;
+    double f = prm.w_cte * ec * ec + prm.w_etheta * ee * ee + prm.w_vel * ev * ev;
+    r.qv = 2.0 * sf * prm.w_vel * ev;
+    r.qc = 2.0 * sf * prm.w_cte * ec;
+    r.qe = 2.0 * sf * prm.w_etheta * ee;
+    double prinf = 0.0, pr1 = 0.0, duinf = 0.0, vmax = -1e300, vmin = 1e300, l1 = 0.0, z1 = 0.0, lnsum = 0.0;
+    // lambda_k (multiplier of the constraint that defines s_k) lives in stage k-1's L slots
+    double lkx, lky, lkt, lkv, lkc, lke;
+    if (k == 0) {
+        lkx = sm.P(PS_L0X, p); lky = sm.P(PS_L0Y, p); lkt = sm.P(PS_L0T, p);
+        lkv = sm.P(PS_L0V, p); lkc = sm.P(PS_L0C, p); lke = sm.P(PS_L0E, p);
+        l1 += fabs(lkx) + fabs(lky) + fabs(lkt) + fabs(lkv) + fabs(lkc) + fabs(lke);
+    } else {
+        lkx = sm.at(k - 1, L_X, p); lky = sm.at(k - 1, L_Y, p); lkt = sm.at(k - 1, L_T, p);
+        lkv = sm.at(k - 1, L_V, p); lkc = sm.at(k - 1, L_C, p); lke = sm.at(k - 1, L_E, p);
+    }
+    if (k < N - 1) {
+        f += prm.w_angvel * r.uw * r.uw + prm.w_accel * r.ua * r.ua;
+        const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
+        const double dpoly = r.c1 + x * (2.0 * r.c2 + 3.0 * r.c3 * x);
+        // defect of the dynamics interval k -> k+1 (mpc_planner.cpp:208-215)
+        const double cx = sm.at(k + 1, S_X, p) - (x + v * r.cs * dt);
+        const double cy = sm.at(k + 1, S_Y, p) - (y + v * r.sn * dt);
+        const double cth = sm.at(k + 1, S_T, p) - (th + r.uw * dt);
+        const double cv = sm.at(k + 1, S_V, p) - (v + r.ua * dt);
+        const double cc = sm.at(k + 1, S_C, p) - ((poly - y) + v * r.se * dt);
+        const double ce_ = sm.at(k + 1, S_E, p) - (e + r.uw * dt);
+        sm.at(k, D_X, p) = -cx; sm.at(k, D_Y, p) = -cy; sm.at(k, D_T, p) = -cth;
+        sm.at(k, D_V, p) = -cv; sm.at(k, D_C, p) = -cc; sm.at(k, D_E, p) = -ce_;
+        prinf = fmax2(fmax2(fmax2(fabs(cx), fabs(cy)), fmax2(fabs(cth), fabs(cv))), fmax2(fabs(cc), fabs(ce_)));
+        pr1 = fabs(cx) + fabs(cy) + fabs(cth) + fabs(cv) + fabs(cc) + fabs(ce_);
+        // stationarity wrt s_k:  grad f + lambda_k - A_k^T lambda_{k+1}
+        const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mt = sm.at(k, L_T, p);
+        const double mv = sm.at(k, L_V, p), mc = sm.at(k, L_C, p), me = sm.at(k, L_E, p);
+        const double a13 = -v * r.sn * dt, a14 = r.cs * dt, a23 = v * r.cs * dt, a24 = r.sn * dt;
+        const double a51 = dpoly, a54 = r.se * dt, a56 = v * r.ce * dt;
+        const double rx = lkx - (mx + a51 * mc);
+        const double ry = lky - (my - mc);
+        const double rt = lkt - (a13 * mx + a23 * my + mt);
+        const double rv = r.qv + lkv - (a14 * mx + a24 * my + mv + a54 * mc);
+        const double rc = r.qc + lkc;
+        const double re = r.qe + lke - (a56 * mc + me);
+        // stationarity wrt u_k:  grad f - B^T lambda_{k+1} - zL + zU
+        const double rw = 2.0 * sf * prm.w_angvel * r.uw - dt * (mt + me) - r.zlw + r.zuw;
+        const double ra = 2.0 * sf * prm.w_accel * r.ua - dt * mv - r.zla + r.zua;
+        duinf = fmax2(fmax2(fmax2(fabs(rx), fabs(ry)), fmax2(fabs(rt), fabs(rv))),
+                      fmax2(fmax2(fabs(rc), fabs(re)), fmax2(fabs(rw), fabs(ra))));
+        l1 += fabs(mx) + fabs(my) + fabs(mt) + fabs(mv) + fabs(mc) + fabs(me);
+        z1 = r.zlw + r.zuw + r.zla + r.zua;
+        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+        const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
+        const double p1 = slw * r.zlw, p2 = suw * r.zuw, p3 = sla * r.zla, p4 = sua * r.zua;
+        vmax = fmax2(fmax2(p1, p2), fmax2(p3, p4));
+        vmin = fmin2(fmin2(p1, p2), fmin2(p3, p4));
+        lnsum = log(slw) + log(suw) + log(sla) + log(sua);
+    } else {
+        // last stage: no dynamics, no control
+        const double rx = lkx, ry = lky, rt = lkt, rv = r.qv + lkv, rc = r.qc + lkc, re = r.qe + lke;
+        duinf = fmax2(fmax2(fmax2(fabs(rx), fabs(ry)), fmax2(fabs(rt), fabs(rv))), fmax2(fabs(rc), fabs(re)));
+    }
+    sm.at(k, W_0, p) = prinf; sm.at(k, W_1, p) = pr1; sm.at(k, W_2, p) = duinf;
+    sm.at(k, W_3, p) = vmax; sm.at(k, W_4, p) = vmin; sm.at(k, W_5, p) = l1;
+    sm.at(k, W_6, p) = z1; sm.at(k, W_7, p) = sf * f; sm.at(k, W_8, p) = lnsum;
+}
+
+// ---------------------------------------------------------------- phase A2: Newton-system coefficients
+// Writes A_k and the work slots  W_0 qv, W_1 qc, W_2 qe, W_3 qw, W_4 qa, W_5 hxx, W_6 htt,
+// W_7 htv, W_8 hee, W_9 hev, W_10 rw, W_11 ra  for the Riccati sweep.
+// lsq != 0: the least-squares multiplier system (identity Hessian, zero defect).
+MPC_HD void stage_coeffs(const Params &prm, const Smem &sm, StageRegs &r, int k, int p, int lsq)
+{
+    const int N = prm.N;
+    const double sf = sm.P(PS_SF, p), mu = sm.P(PS_MU, p), dt = prm.dt;
+    const double x = sm.at(k, S_X, p), v = sm.at(k, S_V, p);
+    if (k < N - 1) {
+        const double dpoly = r.c1 + x * (2.0 * r.c2 + 3.0 * r.c3 * x);
+        const double ddpoly = 2.0 * r.c2 + 6.0 * r.c3 * x;
+        sm.at(k, A_13, p) = -v * r.sn * dt; sm.at(k, A_14, p) = r.cs * dt;
+        sm.at(k, A_23, p) = v * r.cs * dt;  sm.at(k, A_24, p) = r.sn * dt;
+        sm.at(k, A_51, p) = dpoly; sm.at(k, A_54, p) = r.se * dt; sm.at(k, A_56, p) = v * r.ce * dt;
+        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+        const double ilw = 1.0 / (r.uw + Uw), iuw = 1.0 / (Uw - r.uw);
+        const double ila = 1.0 / (r.ua + Ua), iua = 1.0 / (Ua - r.ua);
+        const double gw = 2.0 * sf * prm.w_angvel * r.uw, ga = 2.0 * sf * prm.w_accel * r.ua;
+        if (lsq) {
+            r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
+            sm.at(k, W_3, p) = gw - r.zlw + r.zuw;
+            sm.at(k, W_4, p) = ga - r.zla + r.zua;
+            sm.at(k, W_10, p) = 1.0; sm.at(k, W_11, p) = 1.0;
+            for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
+        } else {
+            const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mc = sm.at(k, L_C, p);
+            // second derivatives of the constraint rows weighted by lambda_{k+1}
+            r.hxx = -mc * ddpoly;
+            r.htt = (mx * r.cs + my * r.sn) * v * dt;
+            r.htv = (mx * r.sn - my * r.cs) * dt;
+            r.hee = mc * v * r.se * dt;
+            r.hev = -mc * r.ce * dt;
+            sm.at(k, W_3, p) = gw - mu * ilw + mu * iuw;     // gradient of the barrier objective
+            sm.at(k, W_4, p) = ga - mu * ila + mu * iua;
+            sm.at(k, W_10, p) = 2.0 * sf * prm.w_angvel + r.zlw * ilw + r.zuw * iuw;   // R + Sigma
+            sm.at(k, W_11, p) = 2.0 * sf * prm.w_accel + r.zla * ila + r.zua * iua;
+        }
+        sm.at(k, W_5, p) = r.hxx; sm.at(k, W_6, p) = r.htt; sm.at(k, W_7, p) = r.htv;
+        sm.at(k, W_8, p) = r.hee; sm.at(k, W_9, p) = r.hev;
+    }
+    sm.at(k, W_0, p) = r.qv; sm.at(k, W_1, p) = r.qc; sm.at(k, W_2, p) = r.qe;
+}
+
+// ---------------------------------------------------------------- Riccati sweeps (control thread)
+// Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}.
+struct HessDiag { double dx, dy, dt_, dv, dc, de, du; };
+
+// Backward sweep over stages N-1 .. 0.  5x5 value matrix over (x,y,theta,v,etheta); the cte
+// row/column of A is zero, so cte only contributes a rank-one term.  Returns 0 if some
+// R~_k is not positive definite (wrong KKT inertia), else 1.  Overwrites W_0..W_11 of each
+// stage k <= N-2 with the gains K (2x5) and k_ff (2).
+MPC_HD int riccati_backward(const Params &prm, const Smem &sm, int p, const HessDiag &hd)
+{
+    const int N = prm.N;
+    const double dt = prm.dt, dt2 = dt * dt;
+    // terminal stage
+    double Pxx = hd.dx, Pxy = 0, Pxt = 0, Pxv = 0, Pxe = 0, Pyy = hd.dy, Pyt = 0, Pyv = 0, Pye = 0;
+    double Ptt = hd.dt_, Ptv = 0, Pte = 0, Pvv = hd.dv, Pve = 0, Pee = hd.de;
+    double px = 0, py = 0, pt = 0, pv = sm.at(N - 1, W_0, p), pe = sm.at(N - 1, W_2, p);
+    double qc_next = sm.at(N - 1, W_1, p);
+    const double gam = hd.dc;
+    int ok = 1;
+    for (int k = N - 2; k >= 0; k--) {
+        const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
+                     a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
+                     a56 = sm.at(k, A_56, p);
+        const double dx = sm.at(k, D_X, p), dy = sm.at(k, D_Y, p), dth = sm.at(k, D_T, p),
+                     dv = sm.at(k, D_V, p), dc = sm.at(k, D_C, p), de = sm.at(k, D_E, p);
+        const double qv = sm.at(k, W_0, p), qc = sm.at(k, W_1, p), qe = sm.at(k, W_2, p),
+                     qw = sm.at(k, W_3, p), qa = sm.at(k, W_4, p);
+        const double hxx = sm.at(k, W_5, p), htt = sm.at(k, W_6, p), htv = sm.at(k, W_7, p),
+                     hee = sm.at(k, W_8, p), hev = sm.at(k, W_9, p);
+        const double rw = sm.at(k, W_10, p), ra = sm.at(k, W_11, p);
+
+        // ---- vector part first (uses P_{k+1}):  pt~ = P d + p,  pi_c = gam d_c + q_c,k+1
+        const double tx = Pxx * dx + Pxy * dy + Pxt * dth + Pxv * dv + Pxe * de + px;
+        const double ty = Pxy * dx + Pyy * dy + Pyt * dth + Pyv * dv + Pye * de + py;
+        const double tt = Pxt * dx + Pyt * dy + Ptt * dth + Ptv * dv + Pte * de + pt;
+        const double tv = Pxv * dx + Pyv * dy + Ptv * dth + Pvv * dv + Pve * de + pv;
+        const double te = Pxe * dx + Pye * dy + Pte * dth + Pve * dv + Pee * de + pe;
+        const double pic = gam * dc + qc_next;
+
+        // ---- W = P A5 (columns theta, v change), M = A5^T W
+        const double Mxt = Pxt + a13 * Pxx + a23 * Pxy;
+        const double Myt = Pyt + a13 * Pxy + a23 * Pyy;
+        const double Met = Pte + a13 * Pxe + a23 * Pye;
+        const double Mxv = Pxv + a14 * Pxx + a24 * Pxy;
+        const double Myv = Pyv + a14 * Pxy + a24 * Pyy;
+        const double Mev = Pve + a14 * Pxe + a24 * Pye;
+        const double Wtt = Ptt + a13 * Pxt + a23 * Pyt;
+        const double Wtv = Ptv + a14 * Pxt + a24 * Pyt;   // W[theta][v]
+        const double Wvt = Ptv + a13 * Pxv + a23 * Pyv;   // W[v][theta]
+        const double Wvv = Pvv + a14 * Pxv + a24 * Pyv;
+        const double Mtt = Wtt + a13 * Mxt + a23 * Myt;
+        const double Mtv = Wtv + a13 * Mxv + a23 * Myv;
+        const double Mvv = Wvv + a14 * Mxv + a24 * Myv;
+
+        // ---- S~ = B^T W  (B = dt [e_theta + e_etheta | e_v]),  R~ = R + B^T P B
+        const double Swx = dt * (Pxt + Pxe), Swy = dt * (Pyt + Pye), Swt = dt * (Wtt + Met),
+                     Swv = dt * (Wtv + Mev), Swe = dt * (Pte + Pee);
+        const double Sax = dt * Pxv, Say = dt * Pyv, Sat = dt * Wvt, Sav = dt * Wvv, Sae = dt * Pve;
+        const double Rww = rw + hd.du + dt2 * (Ptt + 2.0 * Pte + Pee);
+        const double Rwa = dt2 * (Ptv + Pve);
+        const double Raa = ra + hd.du + dt2 * Pvv;
+        const double det = Rww * Raa - Rwa * Rwa;
+        if (!(Rww > 0.0) || !(det > 0.0)) ok = 0;
+        const double idet = 1.0 / det;
+        const double i11 = Raa * idet, i12 = -Rwa * idet, i22 = Rww * idet;
+
+        // ---- Q~ = Q + M + gam a_c a_c^T   (a_c = [a51, -1, 0, a54, a56] over x,y,theta,v,etheta)
+        const double g1 = gam * a51, g4 = gam * a54, g6 = gam * a56;
+        const double Qxx = Pxx + g1 * a51 + hxx + hd.dx;
+        const double Qxy = Pxy - g1;
+        const double Qxt = Mxt;
+        const double Qxv = Mxv + g1 * a54;
+        const double Qxe = Pxe + g1 * a56;
+        const double Qyy = Pyy + gam + hd.dy;
+        const double Qyt = Myt;
+        const double Qyv = Myv - g4;
+        const double Qye = Pye - g6;
+        const double Qtt = Mtt + htt + hd.dt_;
+        const double Qtv = Mtv + htv;
+        const double Qte = Met;
+        const double Qvv = Mvv + g4 * a54 + hd.dv;
+        const double Qve = Mev + g4 * a56 + hev;
+        const double Qee = Pee + g6 * a56 + hee + hd.de;
+
+        // ---- gains  K = -R~^{-1} S~
+        const double Kwx = -(i11 * Swx + i12 * Sax), Kax = -(i12 * Swx + i22 * Sax);
+        const double Kwy = -(i11 * Swy + i12 * Say), Kay = -(i12 * Swy + i22 * Say);
+        const double Kwt = -(i11 * Swt + i12 * Sat), Kat = -(i12 * Swt + i22 * Sat);
+        const double Kwv = -(i11 * Swv + i12 * Sav), Kav = -(i12 * Swv + i22 * Sav);
+        const double Kwe = -(i11 * Swe + i12 * Sae), Kae = -(i12 * Swe + i22 * Sae);
+        // ---- feed-forward
+        const double ruw = qw + dt * (tt + te), rua = qa + dt * tv;
+        const double kfw = -(i11 * ruw + i12 * rua), kfa = -(i12 * ruw + i22 * rua);
+
+        // ---- P_k = Q~ + S~^T K
+        Pxx = Qxx + Swx * Kwx + Sax * Kax;
+        Pxy = Qxy + Swx * Kwy + Sax * Kay;
+        Pxt = Qxt + Swx * Kwt + Sax * Kat;
+        Pxv = Qxv + Swx * Kwv + Sax * Kav;
+        Pxe = Qxe + Swx * Kwe + Sax * Kae;
+        Pyy = Qyy + Swy * Kwy + Say * Kay;
+        Pyt = Qyt + Swy * Kwt + Say * Kat;
+        Pyv = Qyv + Swy * Kwv + Say * Kav;
+        Pye = Qye + Swy * Kwe + Say * Kae;
+        Ptt = Qtt + Swt * Kwt + Sat * Kat;
+        Ptv = Qtv + Swt * Kwv + Sat * Kav;
+        Pte = Qte + Swt * Kwe + Sat * Kae;
+        Pvv = Qvv + Swv * Kwv + Sav * Kav;
+        Pve = Qve + Swv * Kwe + Sav * Kae;
+        Pee = Qee + Swe * Kwe + Sae * Kae;
+        // ---- p_k = q_s + A^T p~ + S~^T k_ff
+        px = tx + a51 * pic + Swx * kfw + Sax * kfa;
+        py = ty - pic + Swy * kfw + Say * kfa;
+        pt = tt + a13 * tx + a23 * ty + Swt * kfw + Sat * kfa;
+        pv = qv + tv + a14 * tx + a24 * ty + a54 * pic + Swv * kfw + Sav * kfa;
+        pe = qe + te + a56 * pic + Swe * kfw + Sae * kfa;
+        qc_next = qc;
+
+        sm.at(k, W_0, p) = Kwx; sm.at(k, W_1, p) = Kwy; sm.at(k, W_2, p) = Kwt; sm.at(k, W_3, p) = Kwv;
+        sm.at(k, W_4, p) = Kwe; sm.at(k, W_5, p) = Kax; sm.at(k, W_6, p) = Kay; sm.at(k, W_7, p) = Kat;
+        sm.at(k, W_8, p) = Kav; sm.at(k, W_9, p) = Kae; sm.at(k, W_10, p) = kfw; sm.at(k, W_11, p) = kfa;
+    }
+    return ok;
+}
+
+// Forward sweep: ds_0 = 0 (the initial-condition rows stay satisfied).  Leaves du_k in
+// W_10/W_11 of stage k and ds_{k+1} in the D slots of stage k.
+MPC_HD void riccati_forward(const Params &prm, const Smem &sm, int p)
+{
+    const int N = prm.N;
+    const double dt = prm.dt;
+    double sx = 0, sy = 0, st = 0, sv = 0, sc = 0, se = 0;
+    (void)sc;
+    for (int k = 0; k < N - 1; k++) {
+        const double duw = sm.at(k, W_0, p) * sx + sm.at(k, W_1, p) * sy + sm.at(k, W_2, p) * st +
+                           sm.at(k, W_3, p) * sv + sm.at(k, W_4, p) * se + sm.at(k, W_10, p);
+        const double dua = sm.at(k, W_5, p) * sx + sm.at(k, W_6, p) * sy + sm.at(k, W_7, p) * st +
+                           sm.at(k, W_8, p) * sv + sm.at(k, W_9, p) * se + sm.at(k, W_11, p);
+        const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
+                     a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
+                     a56 = sm.at(k, A_56, p);
+        const double nx = sx + a13 * st + a14 * sv + sm.at(k, D_X, p);
+        const double ny = sy + a23 * st + a24 * sv + sm.at(k, D_Y, p);
+        const double nt = st + dt * duw + sm.at(k, D_T, p);
+        const double nv = sv + dt * dua + sm.at(k, D_V, p);
+        const double nc = a51 * sx - sy + a54 * sv + a56 * se + sm.at(k, D_C, p);
+        const double ne = se + dt * duw + sm.at(k, D_E, p);
+        sm.at(k, W_10, p) = duw; sm.at(k, W_11, p) = dua;
+        sm.at(k, D_X, p) = nx; sm.at(k, D_Y, p) = ny; sm.at(k, D_T, p) = nt;
+        sm.at(k, D_V, p) = nv; sm.at(k, D_C, p) = nc; sm.at(k, D_E, p) = ne;
+        sx = nx; sy = ny; st = nt; sv = nv; sc = nc; se = ne;
+    }
+}
+
+// ---------------------------------------------------------------- phase C: step-dependent stage work
+// Reads ds_k, du_k; writes g_k = q_s + Q_k ds_k into W_0..W_5 and the partials
+// W_6 primal fraction-to-boundary limit, W_7 dual limit, W_8 grad(phi_mu)^T d.
+MPC_HD void stage_step(const Params &prm, const Smem &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq)
+{
+    const int N = prm.N;
+    const double mu = sm.P(PS_MU, p), tau = sm.P(PS_TAU, p), sf = sm.P(PS_SF, p);
+    double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
+    if (k > 0) {
+        dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
+        dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
+    }
+    double amax = 1.0, az = 1.0, gd = r.qv * dsv + r.qc * dsc + r.qe * dse;
+    if (k < N - 1) {
+        r.duw = sm.at(k, W_10, p); r.dua = sm.at(k, W_11, p);
+        if (!lsq) {
+            const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+            const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
+            // fraction to the boundary (W&B eq. (15))
+            if (r.duw < 0.0) amax = fmin2(amax, -tau * slw / r.duw);
+            if (r.duw > 0.0) amax = fmin2(amax, tau * suw / r.duw);
+            if (r.dua < 0.0) amax = fmin2(amax, -tau * sla / r.dua);
+            if (r.dua > 0.0) amax = fmin2(amax, tau * sua / r.dua);
+            const double dzlw = mu / slw - r.zlw - r.zlw / slw * r.duw;
+            const double dzuw = mu / suw - r.zuw + r.zuw / suw * r.duw;
+            const double dzla = mu / sla - r.zla - r.zla / sla * r.dua;
+            const double dzua = mu / sua - r.zua + r.zua / sua * r.dua;
+            if (dzlw < 0.0) az = fmin2(az, -tau * r.zlw / dzlw);
+            if (dzuw < 0.0) az = fmin2(az, -tau * r.zuw / dzuw);
+            if (dzla < 0.0) az = fmin2(az, -tau * r.zla / dzla);
+            if (dzua < 0.0) az = fmin2(az, -tau * r.zua / dzua);
+            const double gw = 2.0 * sf * prm.w_angvel * r.uw - mu / slw + mu / suw;
+            const double ga = 2.0 * sf * prm.w_accel * r.ua - mu / sla + mu / sua;
+            gd += gw * r.duw + ga * r.dua;
+        }
+    }
+    // g_k = q_s,k + Q_k ds_k  (Q_k = diag + the five lambda-weighted entries)
+    sm.at(k, W_0, p) = (hd.dx + r.hxx) * dsx;
+    sm.at(k, W_1, p) = hd.dy * dsy;
+    sm.at(k, W_2, p) = (hd.dt_ + r.htt) * dst + r.htv * dsv;
+    sm.at(k, W_3, p) = r.qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
+    sm.at(k, W_4, p) = r.qc + hd.dc * dsc;
+    sm.at(k, W_5, p) = r.qe + r.hev * dsv + (hd.de + r.hee) * dse;
+    sm.at(k, W_6, p) = amax; sm.at(k, W_7, p) = az; sm.at(k, W_8, p) = gd;
+}
+
+// Adjoint sweep (control thread): lambda_k^+ = A_k^T lambda_{k+1}^+ - g_k, k = N-1 .. 0.
+// lambda_{k+1}^+ is left in W_6..W_11 of stage k; lambda_0^+ in PS_N0*.
+MPC_HD void adjoint_sweep(const Params &prm, const Smem &sm, int p)
+{
+    const int N = prm.N;
+    double lx = -sm.at(N - 1, W_0, p), ly = -sm.at(N - 1, W_1, p), lt = -sm.at(N - 1, W_2, p);
+    double lv = -sm.at(N - 1, W_3, p), lc = -sm.at(N - 1, W_4, p), le = -sm.at(N - 1, W_5, p);
+    for (int k = N - 2; k >= 0; k--) {
+        sm.at(k, W_6, p) = lx; sm.at(k, W_7, p) = ly; sm.at(k, W_8, p) = lt;
+        sm.at(k, W_9, p) = lv; sm.at(k, W_10, p) = lc; sm.at(k, W_11, p) = le;
+        const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
+                     a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
+                     a56 = sm.at(k, A_56, p);
+        const double nx = lx + a51 * lc - sm.at(k, W_0, p);
+        const double ny = ly - lc - sm.at(k, W_1, p);
+        const double nt = a13 * lx + a23 * ly + lt - sm.at(k, W_2, p);
+        const double nv = a14 * lx + a24 * ly + lv + a54 * lc - sm.at(k, W_3, p);
+        const double nc = -sm.at(k, W_4, p);
+        const double ne = a56 * lc + le - sm.at(k, W_5, p);
+        lx = nx; ly = ny; lt = nt; lv = nv; lc = nc; le = ne;
+    }
+    sm.P(PS_N0X, p) = lx; sm.P(PS_N0Y, p) = ly; sm.P(PS_N0T, p) = lt;
+    sm.P(PS_N0V, p) = lv; sm.P(PS_N0C, p) = lc; sm.P(PS_N0E, p) = le;
+}
+
+// ---------------------------------------------------------------- phase E1: trial point
+// Evaluates the trial iterate s + alpha ds, u + alpha du; writes W_0 sum|c|, W_1 scaled
+// objective part, W_2 sum of log-barrier arguments (or a huge negative flag if outside).
+MPC_HD void stage_trial(const Params &prm, const Smem &sm, StageRegs &r, int k, int p)
+{
+    const int N = prm.N;
+    const double alpha = sm.P(PS_ALPHA, p), sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
+    double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
+    if (k > 0) {
+        dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
+        dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
+    }
+    const double x = sm.at(k, S_X, p) + alpha * dsx, y = sm.at(k, S_Y, p) + alpha * dsy;
+    const double th = sm.at(k, S_T, p) + alpha * dst, v = sm.at(k, S_V, p) + alpha * dsv;
+    const double ct = sm.at(k, S_C, p) + alpha * dsc, e = sm.at(k, S_E, p) + alpha * dse;
+    sincos_d(th, &r.tsn, &r.tcs);
+    sincos_d(e, &r.tse, &r.tce);
+    const double ec = ct - prm.ref_cte, ee = e - prm.ref_etheta, ev = v - refv;
+    double f = prm.w_cte * ec * ec + prm.w_etheta * ee * ee + prm.w_vel * ev * ev;
+    double pr1 = 0.0, lnsum = 0.0;
+    if (k < N - 1) {
+        const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
+        f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
+        const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
+        const double nx = sm.at(k + 1, S_X, p) + alpha * sm.at(k, D_X, p);
+        const double ny = sm.at(k + 1, S_Y, p) + alpha * sm.at(k, D_Y, p);
+        const double nt = sm.at(k + 1, S_T, p) + alpha * sm.at(k, D_T, p);
+        const double nv = sm.at(k + 1, S_V, p) + alpha * sm.at(k, D_V, p);
+        const double nc = sm.at(k + 1, S_C, p) + alpha * sm.at(k, D_C, p);
+        const double ne = sm.at(k + 1, S_E, p) + alpha * sm.at(k, D_E, p);
+        const double cx = nx - (x + v * r.tcs * dt);
+        const double cy = ny - (y + v * r.tsn * dt);
+        const double cth = nt - (th + uw * dt);
+        const double cv = nv - (v + ua * dt);
+        const double cc = nc - ((poly - y) + v * r.tse * dt);
+        const double ce_ = ne - (e + uw * dt);
+        pr1 = fabs(cx) + fabs(cy) + fabs(cth) + fabs(cv) + fabs(cc) + fabs(ce_);
+        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+        const double slw = uw + Uw, suw = Uw - uw, sla = ua + Ua, sua = Ua - ua;
+        if (slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0)
+            lnsum = log(slw) + log(suw) + log(sla) + log(sua);
+        else
+            lnsum = -1e300;
+    }
+    sm.at(k, W_0, p) = pr1; sm.at(k, W_1, p) = sf * f; sm.at(k, W_2, p) = lnsum;
+}
+
+// ---------------------------------------------------------------- phase F: accept the step
+MPC_HD void stage_accept(const Params &prm, const Smem &sm, StageRegs &r, int k, int p, int lsq)
+{
+    const int N = prm.N;
+    if (lsq) {
+        // adopt the least-squares multipliers (or zero if too large; decided by the control thread
+        // through PS_ALPHA = 1 / 0)
+        const double keep = sm.P(PS_ALPHA, p);
+        if (k < N - 1)
+            for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = (keep != 0.0) ? sm.at(k, W_6 + c, p) : 0.0;
+        return;
+    }
+    const double alpha = sm.P(PS_ALPHA, p), az = sm.P(PS_ALPHA_Z, p), mu = sm.P(PS_MU, p);
+    if (k > 0)
+        for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) += alpha * sm.at(k - 1, D_X + c, p);
+    if (k < N - 1) {
+        for (int c = 0; c < 6; c++) {
+            const double l = sm.at(k, L_X + c, p);
+            sm.at(k, L_X + c, p) = l + alpha * (sm.at(k, W_6 + c, p) - l);
+        }
+        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+        {
+            const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
+            r.zlw += az * (mu / slw - r.zlw - r.zlw / slw * r.duw);
+            r.zuw += az * (mu / suw - r.zuw + r.zuw / suw * r.duw);
+            r.zla += az * (mu / sla - r.zla - r.zla / sla * r.dua);
+            r.zua += az * (mu / sua - r.zua + r.zua / sua * r.dua);
+        }
+        r.uw += alpha * r.duw; r.ua += alpha * r.dua;
+        {
+            // keep the multipliers within kappa_Sigma of mu / slack (W&B eq. (16))
+            const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
+            r.zlw = fmax2(fmin2(r.zlw, NMPC_KAPPA_SIGMA * mu / slw), mu / (NMPC_KAPPA_SIGMA * slw));
+            r.zuw = fmax2(fmin2(r.zuw, NMPC_KAPPA_SIGMA * mu / suw), mu / (NMPC_KAPPA_SIGMA * suw));
+            r.zla = fmax2(fmin2(r.zla, NMPC_KAPPA_SIGMA * mu / sla), mu / (NMPC_KAPPA_SIGMA * sla));
+            r.zua = fmax2(fmin2(r.zua, NMPC_KAPPA_SIGMA * mu / sua), mu / (NMPC_KAPPA_SIGMA * sua));
+        }
+    }
+    r.sn = r.tsn; r.cs = r.tcs; r.se = r.tse; r.ce = r.tce;
+}
+
+// ---------------------------------------------------------------- control thread state + logic
+struct Ctrl {
+    int iter;
+    int status;
+    int n_accept;          // consecutive "acceptable" iterations
+    int nfilt;
+    int armijo;            // the pending accepted step is an Armijo (f-type) step
+    int ls_first;
+    int lsq_pending;
+    double dw_last;
+    double theta0, theta_min, theta_max;
+    double theta, phi, gd;          // at the current iterate, for the line search
+    double alpha_min;
+    double E0, obj;
+    double fth[NMPC_MAX_FILTER], fph[NMPC_MAX_FILTER];
+};
+
+MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
+{
+    HessDiag h;
+    if (lsq) { h.dx = h.dy = h.dt_ = h.dv = h.dc = h.de = 1.0; h.du = 0.0; return h; }
+    h.dx = dw; h.dy = dw; h.dt_ = dw; h.du = dw;
+    h.dv = 2.0 * sf * prm.w_vel + dw;
+    h.dc = 2.0 * sf * prm.w_cte + dw;
+    h.de = 2.0 * sf * prm.w_etheta + dw;
+    return h;
+}
+
+// Gradient-based objective scaling at the start point (Ipopt nlp_scaling_max_gradient = 100).
+MPC_HD double objective_scaling(const Params &prm, const double *state6, double refv)
+{
+    double g = fabs(2.0 * prm.w_cte * (state6[4] - prm.ref_cte));
+    g = fmax2(g, fabs(2.0 * prm.w_etheta * (state6[5] - prm.ref_etheta)));
+    g = fmax2(g, fabs(2.0 * prm.w_vel * (state6[3] - refv)));
+    if (prm.N > 1) {
+        g = fmax2(g, fabs(2.0 * prm.w_cte * prm.ref_cte));
+        g = fmax2(g, fabs(2.0 * prm.w_etheta * prm.ref_etheta));
+        g = fmax2(g, fabs(2.0 * prm.w_vel * refv));
+    }
+    return g > 100.0 ? 100.0 / g : 1.0;
+}
+
+MPC_HD void ctrl_init(const Params &prm, const Smem &sm, Ctrl &c, int p, const double *state6, double refv)
+{
+    c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.armijo = 0; c.ls_first = 1; c.lsq_pending = 1;
+    c.dw_last = 0.0; c.theta0 = 0.0; c.theta_min = 0.0; c.theta_max = 0.0; c.theta = 0.0; c.phi = 0.0; c.gd = 0.0;
+    c.alpha_min = 0.0; c.E0 = 1e300; c.obj = 0.0;
+    sm.P(PS_MU, p) = NMPC_MU_INIT;
+    sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - NMPC_MU_INIT);
+    sm.P(PS_SF, p) = objective_scaling(prm, state6, refv);
+    sm.P(PS_REFV, p) = refv;
+    sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; sm.P(PS_DW, p) = 0.0;
+    for (int i = 0; i < 6; i++) { sm.P(PS_L0X + i, p) = 0.0; sm.P(PS_N0X + i, p) = 0.0; }
+    sm.I(PI_MODE, p) = MODE_RESID;
+    sm.I(PI_STATUS, p) = 0;
+    sm.I(PI_LSQ, p) = 1;
+}
+
+MPC_HD int filter_acceptable(const Ctrl &c, double theta, double phi)
+{
+    if (!(theta < c.theta_max)) return 0;
+    for (int i = 0; i < c.nfilt; i++)
+        if (theta >= c.fth[i] && phi >= c.fph[i]) return 0;
+    return 1;
+}
+
+MPC_HD void filter_add(Ctrl &c, double theta, double phi)
+{
+    const double th = (1.0 - NMPC_GAMMA_THETA) * theta, ph = phi - NMPC_GAMMA_PHI * theta;
+    if (c.nfilt < NMPC_MAX_FILTER) { c.fth[c.nfilt] = th; c.fph[c.nfilt] = ph; c.nfilt++; }
+    else {
+        // full: overwrite the entry that dominates least (largest theta)
+        int j = 0;
+        for (int i = 1; i < NMPC_MAX_FILTER; i++) if (c.fth[i] > c.fth[j]) j = i;
+        c.fth[j] = th; c.fph[j] = ph;
+    }
+}
+
+// Phase B: reduce the residual partials, test convergence, update mu.  Returns 1 when the problem
+// continues with a Newton step, 0 when it has terminated (status set).
+MPC_HD int ctrl_check(const Params &prm, const Smem &sm, Ctrl &c, int p)
+{
+    const int N = prm.N;
+    double prinf = 0, pr1 = 0, duinf = 0, vmax = -1e300, vmin = 1e300, l1 = 0, z1 = 0, f = 0, lnsum = 0;
+    for (int k = 0; k < N; k++) {
+        prinf = fmax2(prinf, sm.at(k, W_0, p)); pr1 += sm.at(k, W_1, p);
+        duinf = fmax2(duinf, sm.at(k, W_2, p));
+        vmax = fmax2(vmax, sm.at(k, W_3, p)); vmin = fmin2(vmin, sm.at(k, W_4, p));
+        l1 += sm.at(k, W_5, p); z1 += sm.at(k, W_6, p); f += sm.at(k, W_7, p); lnsum += sm.at(k, W_8, p);
+    }
+    double mu = sm.P(PS_MU, p);
+    const double sf = sm.P(PS_SF, p);
+    const int m = 6 * N, nb = 4 * (N - 1);
+    const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) / NMPC_S_MAX;
+    const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) / NMPC_S_MAX;
+    const double compl0 = fmax2(fabs(vmax), fabs(vmin));
+    const double E0 = fmax2(fmax2(duinf / s_d, prinf), compl0 / s_c);
+    c.E0 = E0; c.obj = f / sf;
+    if (!(E0 == E0) || !(f == f)) { c.status = 11; return 0; }
+    if (E0 <= prm.tol && duinf / sf <= 1.0 && prinf <= 1e-4 && compl0 / sf <= 1e-4) { c.status = 1; return 0; }
+    if (E0 <= 1e-6 && prinf <= 1e-2 && compl0 / sf <= 1e-2) c.n_accept++; else c.n_accept = 0;
+    if (c.n_accept >= 15) { c.status = 4; return 0; }
+    if (c.iter >= prm.max_iter) { c.status = 2; return 0; }
+    // monotone barrier update (W&B eq. (7)); repeated while the barrier problem is already solved
+    int changed = 0;
+    for (;;) {
+        const double cmu = fmax2(fabs(vmax - mu), fabs(vmin - mu));
+        const double Emu = fmax2(fmax2(duinf / s_d, prinf), cmu / s_c);
+        if (!(Emu <= NMPC_KAPPA_EPS * mu)) break;
+        const double floor_ = fmin2(prm.tol, 1e-4) / (NMPC_KAPPA_EPS + 1.0);
+        const double mun = fmax2(floor_, fmin2(NMPC_KAPPA_MU * mu, pow(mu, NMPC_THETA_MU)));
+        if (!(mun < mu)) break;
+        mu = mun; changed = 1;
+    }
+    if (changed) {
+        c.nfilt = 0;
+        sm.P(PS_MU, p) = mu;
+        sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - mu);
+    }
+    c.theta = pr1;
+    c.phi = f - mu * lnsum;
+    if (c.iter == 0 && c.theta_max == 0.0) {
+        c.theta0 = pr1;
+        c.theta_max = 1e4 * fmax2(1.0, pr1);
+        c.theta_min = 1e-4 * fmax2(1.0, pr1);
+    }
+    return 1;
+}
+
+// Next regularisation value of the inertia-correction sequence (W&B Algorithm IC).
+MPC_HD double next_dw(const Ctrl &c, double dw)
+{
+    if (dw == 0.0) return (c.dw_last == 0.0) ? NMPC_DW_0 : fmax2(NMPC_DW_MIN, NMPC_KW_MINUS * c.dw_last);
+    return (c.dw_last == 0.0) ? NMPC_KW_PLUS_BAR * dw : NMPC_KW_PLUS * dw;
+}
+
+// Phase D: after the step is known.  Reduces the step partials, runs the adjoint sweep, sets
+// up the line search.  Leaves PS_ALPHA (first trial) and PS_ALPHA_Z.
+MPC_HD void ctrl_step(const Params &prm, const Smem &sm, Ctrl &c, int p)
+{
+    const int N = prm.N;
+    double amax = 1.0, az = 1.0, gd = 0.0;
+    for (int k = 0; k < N; k++) {
+        amax = fmin2(amax, sm.at(k, W_6, p)); az = fmin2(az, sm.at(k, W_7, p)); gd += sm.at(k, W_8, p);
+    }
+    adjoint_sweep(prm, sm, p);
+    c.gd = gd;
+    const double th = c.theta;
+    if (gd < 0.0 && th <= c.theta_min)
+        c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd)),
+                                               pow(th, NMPC_S_THETA) / pow(-gd, NMPC_S_PHI));
+    else if (gd < 0.0)
+        c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd));
+    else
+        c.alpha_min = NMPC_GAMMA_ALPHA * NMPC_GAMMA_THETA;
+    c.ls_first = 1;
+    sm.P(PS_ALPHA, p) = amax;
+    sm.P(PS_ALPHA_Z, p) = az;
+}
+
+// Phase E2: filter line-search decision for the trial just evaluated (W&B A-5).
+// Returns 1 accepted, 0 backtrack (PS_ALPHA halved), -1 failed (alpha < alpha_min).
+MPC_HD int ctrl_linesearch(const Params &prm, const Smem &sm, Ctrl &c, int p)
+{
+    const int N = prm.N;
+    double th_t = 0.0, f_t = 0.0, ln_t = 0.0;
+    int inside = 1;
+    for (int k = 0; k < N; k++) {
+        th_t += sm.at(k, W_0, p); f_t += sm.at(k, W_1, p);
+        const double l = sm.at(k, W_2, p);
+        if (l <= -1e299) inside = 0; else ln_t += l;
+    }
+    const double mu = sm.P(PS_MU, p), alpha = sm.P(PS_ALPHA, p);
+    const double phi_t = f_t - mu * ln_t;
+    const double th = c.theta, phi = c.phi, gd = c.gd;
+    int ok = inside && (th_t == th_t) && (phi_t == phi_t);
+    int acc = 0;
+    if (ok && filter_acceptable(c, th_t, phi_t)) {
+        const int sw = (gd < 0.0) && (alpha * pow(-gd, NMPC_S_PHI) > pow(th, NMPC_S_THETA));
+        if (th <= c.theta_min && sw) {
+            if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; c.armijo = 1; }
+        } else {
+            if (th_t <= (1.0 - NMPC_GAMMA_THETA) * th ||
+                phi_t - 10.0 * NMPC_EPS_MACH * fabs(phi) <= phi - NMPC_GAMMA_PHI * th) { acc = 1; c.armijo = 0; }
+        }
+    }
+    if (acc) {
+        if (!c.armijo) filter_add(c, th, phi);
+        return 1;
+    }
+    c.ls_first = 0;
+    const double a2 = 0.5 * alpha;
+    if (a2 < c.alpha_min) return -1;
+    sm.P(PS_ALPHA, p) = a2;
+    return 0;
+}
+
+// LSQ multiplier start: keep the least-squares multipliers unless they are huge (W&B Sec. 3.6).
+MPC_HD void ctrl_lsq_finish(const Params &prm, const Smem &sm, Ctrl &c, int p)
+{
+    const int N = prm.N;
+    adjoint_sweep(prm, sm, p);
+    double lmax = 0.0;
+    for (int k = 0; k < N - 1; k++)
+        for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.at(k, W_6 + i, p)));
+    for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.P(PS_N0X + i, p)));
+    const double keep = (lmax <= NMPC_LAM_MAX) ? 1.0 : 0.0;   // NaN compares false -> 0
+    sm.P(PS_ALPHA, p) = keep;
+    for (int i = 0; i < 6; i++) sm.P(PS_L0X + i, p) = (keep != 0.0) ? sm.P(PS_N0X + i, p) : 0.0;
+    c.lsq_pending = 0;
+}
+
+// Control-thread part of accepting a step: lambda_0 and the iteration counter.
+MPC_HD void ctrl_accept(const Smem &sm, Ctrl &c, int p)
+{
+    const double alpha = sm.P(PS_ALPHA, p);
+    for (int i = 0; i < 6; i++) {
+        const double l = sm.P(PS_L0X + i, p);
+        sm.P(PS_L0X + i, p) = l + alpha * (sm.P(PS_N0X + i, p) - l);
+    }
+    c.iter++;
+}
+
+}  // namespace nmpc

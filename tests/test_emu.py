@@ -1,0 +1,108 @@
+"""CPU tier: the solver's phase functions (the code the CUDA kernel runs, nmpc_phases.cuh) executed
+by the test-only host emulator, against the oracle.  Checks the LOGIC of the structure-exploiting
+interior-point method here where there is no GPU; the -m gpu tier checks the kernel itself."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from oracle.oracle_py import YAML_DEFAULT, CFG_DEFAULT
+from tests.problems import mild, generated
+
+_EMU = None
+
+
+def emu_solve(pm, state, coeffs, PB=4, tol=1e-8, max_iter=200, ref_vel=None):
+    global _EMU
+    if _EMU is None:
+        _EMU = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libnmpc_emu.so"))
+    dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
+    N = int(pm["STEPS"]); B = state.shape[1]
+    prm = np.array([pm["DT"], pm["REF_CTE"], pm["REF_ETHETA"], pm["REF_V"], pm["W_CTE"], pm["W_EPSI"], pm["W_V"],
+                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], 0, 0, 0], dtype=np.float64)
+    state = np.ascontiguousarray(state, dtype=np.float64); coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    u0 = np.zeros((2, B)); pred = np.zeros((3 * N, B)); obj = np.zeros(B); kkt = np.zeros(B); lam = np.zeros((6 * N, B))
+    st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32); nreg = np.zeros(B, dtype=np.int32)
+    rv = None if ref_vel is None else np.ascontiguousarray(ref_vel, dtype=np.float64).ctypes.data_as(dp)
+    P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    _EMU.nmpc_emu_solve(C.c_int(N), P(prm), C.c_double(tol), C.c_int(max_iter), C.c_int(PB), C.c_int(B), P(state),
+                        P(coeffs), rv, P(u0), P(pred), P(obj), st.ctypes.data_as(ip), it.ctypes.data_as(ip), P(kkt),
+                        P(lam), nreg.ctypes.data_as(ip))
+    return dict(u0=u0, pred=pred, obj=obj, status=st, iters=it, kkt=kkt, lam=lam, nreg=nreg)
+
+
+def test_emu_matches_oracle_mild(oracle):
+    state, coeffs = mild(21, 24)
+    r = emu_solve(YAML_DEFAULT, state, coeffs, PB=5)
+    nobound = dict(YAML_DEFAULT, BOUND=1e19)
+    for i in range(24):
+        o = oracle.solve(YAML_DEFAULT, state[:, i], coeffs[:, i])
+        assert r["status"][i] == 1 and o["status"] == 1
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5            # north-star tolerance
+        assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"])
+        assert r["kkt"][i] <= 1e-8
+        # same algorithm, same iterates: against the oracle without the (inactive) state bounds the
+        # Riccati solver reproduces iteration count, controls and multipliers to rounding
+        o2 = oracle.solve(nobound, state[:, i], coeffs[:, i])
+        assert r["iters"][i] == o2["iters"]
+        assert np.abs(r["u0"][:, i] - o2["u0"]).max() <= 1e-10
+        assert np.abs(r["lam"][:, i] - o2["lam"]).max() <= 1e-8 * max(1.0, np.abs(o2["lam"]).max())
+        assert np.abs(r["pred"][:, i].reshape(3, -1) - o["pred"]).max() <= 1e-6
+
+
+def test_emu_matches_oracle_generated(oracle):
+    g, state, coeffs = generated(20261020, 150, oracle)
+    r = emu_solve(YAML_DEFAULT, state, coeffs, PB=32)
+    both = 0; close = 0
+    for i in range(150):
+        o = oracle.solve(YAML_DEFAULT, state[:, i], coeffs[:, i])
+        if o["status"] == 1 and r["status"][i] == 1:
+            both += 1
+            if np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5 and abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"]):
+                close += 1
+    assert both >= 147
+    assert close >= both - 1       # a non-convex corner case may settle in another local minimum
+
+
+def test_emu_cfg_weights(oracle):
+    pm = dict(CFG_DEFAULT, W_DA=0.0)
+    state, coeffs = mild(22, 8)
+    r = emu_solve(pm, state, coeffs, PB=3)
+    for i in range(8):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert r["status"][i] == 1 and o["status"] == 1
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5
+        assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"])
+
+
+def test_emu_long_horizon(oracle):
+    pm = dict(YAML_DEFAULT, STEPS=100)
+    state, coeffs = mild(23, 2)
+    coeffs[2:] *= 0.1      # keep a 10 s horizon on a sane path
+    r = emu_solve(pm, state, coeffs, PB=2)
+    for i in range(2):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert r["status"][i] == 1 and o["status"] == 1
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5
+        assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"])
+
+
+def test_emu_lane_independence():
+    """A problem's result must not depend on which CTA lane it lands in or on its neighbours."""
+    state, coeffs = mild(24, 13)
+    a = emu_solve(YAML_DEFAULT, state, coeffs, PB=1)
+    b = emu_solve(YAML_DEFAULT, state, coeffs, PB=32)
+    perm = np.random.default_rng(0).permutation(13)
+    c = emu_solve(YAML_DEFAULT, state[:, perm], coeffs[:, perm], PB=4)
+    np.testing.assert_array_equal(a["u0"], b["u0"])
+    np.testing.assert_array_equal(a["u0"][:, perm], c["u0"])
+    np.testing.assert_array_equal(a["iters"][perm], c["iters"])
+
+
+def test_emu_ref_vel_override(oracle):
+    state, coeffs = mild(25, 4)
+    rv = np.array([0.2, 0.5, 0.8, 0.05])
+    r = emu_solve(YAML_DEFAULT, state, coeffs, PB=4, ref_vel=rv)
+    for i in range(4):
+        o = oracle.solve(dict(YAML_DEFAULT, REF_V=rv[i]), state[:, i], coeffs[:, i])
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5

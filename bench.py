@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- converged NMPC solves/sec (N = 20) of the hot path on N B200 GPUs of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W           # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W   # the reference's CPU MPC::Solve
+
+A "step" is one pass of the hot path over one batch of synthetic problems: the reference pre-step
+(waypoint transform + cubic polyfit + state assembly, driving_state.cpp:196-256) followed by the
+batched MPC::Solve, i.e. mpc_b200_prestep_batch + mpc_b200_solve_batch on BASELINE config 2
+(4,096 independent N = 20 problems on random poses along the infinity / epitrochoid / square tracks,
+mpc_params.yaml weights).  For N > 1 every rank owns its own 4,096-problem slice (weak scaling, no
+collective on the solve path); the timed region is bracketed by a barrier + synchronize and the
+slowest rank's device time is used.
+
+`value`   : inputs already resident in HBM, device-pointer C-ABI calls on one stream.
+`e2e`     : the same steps through the C ABI with HOST buffers (pinned staging, H2D + D2H inside
+            the timed region).
+`roofline`: FP64 pipe.  achieved = algorithmic flops of the solve kernel (SURVEY section 8d:
+            27,879 flop per interior-point iteration at N = 20, times the iterations actually
+            taken) / its CUDA-event duration on the launching stream; peak = DFMA-chain peak
+            measured live (MEASURED_PEAKS.json has no FP64 entry).
+`cpu_baseline`: oracle/_ref (the reference's unmodified mpc_planner.cpp + CppAD; solver inside is
+            the repo's Ipopt stand-in, Ipopt itself is not installed) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "converged_nmpc_solves_per_sec_N20"
+UNIT = "solves/s"
+BATCH = 4096                 # BASELINE config 2
+SEED = 20261018 + 2          # seed = 20261018 + config#
+FLOP_PER_ITER_N20 = 27879.0  # SURVEY 8d algorithmic flops per interior-point iteration, N = 20
+WORKLOAD = ("config2: batch of 4096 independent N=20 diff-drive NMPC problems per GPU, random poses on "
+            "infinity/epitrochoid/square tracks, mpc_params.yaml weights, cold start; step = prestep "
+            "(transform+polyfit+state) + solve")
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index; self.rows = []; self.proc = None; self.thr = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def rd():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thr = threading.Thread(target=rd, daemon=True); self.thr.start()
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = []; smax = None; reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+def _ref_worker(args):
+    seed, count, offset = args
+    from oracle.oracle_py import Oracle, Reference, YAML_DEFAULT, ref_available
+    from bench import gen_py
+    g = gen_py.problems(seed, offset + count)
+    orc = Oracle()
+    use_ref = ref_available()
+    if use_ref:
+        R = Reference(YAML_DEFAULT)
+    conv = 0; iters = 0
+    t0 = time.perf_counter()
+    for i in range(offset, offset + count):
+        c, cte, eth = orc.prestep(g["wx"][:, i], g["wy"][:, i], *g["pose"][:, i])
+        st = np.array([0.0, 0.0, 0.0, g["vel"][0, i], cte, eth])
+        r = R.solve(st, c) if use_ref else orc.solve(YAML_DEFAULT, st, c)
+        conv += int(r["status"] == 1); iters += r["iters"]
+    return conv, iters, time.perf_counter() - t0, use_ref
+
+
+def cpu_reference_rate(per_core, cores=None):
+    """Times the reference's MPC::Solve (oracle/_ref) on `cores` processes, per_core problems each."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    jobs = [(SEED, per_core, k * per_core) for k in range(cores)]
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    conv = sum(r[0] for r in res); iters = sum(r[1] for r in res)
+    busy = max(r[2] for r in res)
+    kind = "reference" if res[0][3] else "port"
+    return dict(value=conv / busy, unit=UNIT, cores=cores, kind=kind,
+                sample="%d problems (%d per core x %d processes) of the config-2 generator, seed %d; %d converged; "
+                       "mean %.1f iterations; solver inside: oracle/ipm.c stand-in for Ipopt 3.12.8"
+                       % (per_core * cores, per_core, cores, SEED, conv, iters / max(1, per_core * cores)),
+                wall_s=wall)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample per step so that the whole run stays within a few minutes whatever K is
+    per_core = max(8, min(a.ref_per_core, 10000 // max(1, a.steps)))
+    for _ in range(a.warmup):
+        cpu_reference_rate(max(1, per_core // 8))
+    vals = []; last = None
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        last = cpu_reference_rate(per_core)
+        vals.append(last["value"])
+    ms = (time.perf_counter() - t0) * 1e3 / max(1, a.steps)
+    v = float(np.mean(vals))
+    last["value"] = v
+    print(json.dumps(dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps,
+                          warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                          dtype="f64", data="synthetic", config=dict(workload=WORKLOAD),
+                          cpu_baseline=last,
+                          e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+# ------------------------------------------------------------------ our arm (CUDA)
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from mpc_ros_b200 import capi
+    from bench import gen_py
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if capi.lib().mpc_b200_device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; the solver has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.batch; N = 20
+    prm = capi.yaml_default_params()
+    prm.delay_mode = 0                       # configs 2-4 use the plain state
+    prm.max_iter = a.max_iter
+    solver = capi.Solver(prm, B, local)
+    L = capi.lib()
+
+    # ---- synthetic inputs: R distinct batches, more than L2 in total with their outputs
+    R = a.sets
+    M = gen_py._lib().mpcgen_num_waypoints(5.0)
+    g = gen_py.problems(SEED + 1000 * rank, B * R)
+    def split(x):   # (C, B*R) -> R contiguous (C, B) device tensors
+        return [torch.from_numpy(np.ascontiguousarray(x[:, j * B:(j + 1) * B])).to(dev) for j in range(R)]
+    d_wx = split(g["wx"]); d_wy = split(g["wy"]); d_pose = split(g["pose"]); d_vel = split(g["vel"])
+    f64 = dict(dtype=torch.float64, device=dev); i32 = dict(dtype=torch.int32, device=dev)
+    d_coef = [torch.zeros((4, B), **f64) for _ in range(R)]; d_state = [torch.zeros((6, B), **f64) for _ in range(R)]
+    d_u0 = [torch.zeros((2, B), **f64) for _ in range(R)]; d_pred = [torch.zeros((3 * N, B), **f64) for _ in range(R)]
+    d_obj = [torch.zeros(B, **f64) for _ in range(R)]; d_kkt = [torch.zeros(B, **f64) for _ in range(R)]
+    d_stat = [torch.zeros(B, **i32) for _ in range(R)]; d_it = [torch.zeros(B, **i32) for _ in range(R)]
+    in_bytes = (2 * M + 6) * B * 8
+    out_bytes = (2 + 3 * N + 2) * B * 8 + 2 * B * 4
+    set_bytes = in_bytes + out_bytes + 10 * B * 8
+    flush = torch.empty(256 * 1024 * 1024 // 8, **f64)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev(j, ev=None):
+        j %= R
+        solver.prestep_raw(B, M, d_wx[j], d_wy[j], d_pose[j], d_vel[j], d_coef[j], d_state[j], stream=stream)
+        if ev is not None:
+            ev[0].record()
+        solver.solve_raw(B, d_state[j], d_coef[j], d_u0[j], d_pred[j], obj=d_obj[j], status=d_stat[j], iters=d_it[j],
+                         kkt=d_kkt[j], stream=stream)
+        if ev is not None:
+            ev[1].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = L.mpc_b200_measure_fp64_peak(local, 100000)   # also brings the clocks up
+    for j in range(a.warmup):
+        step_dev(j)
+    flush.fill_(1.0)                        # one L2 flush; the timed steps then rotate over > L2 of data
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    n0 = solver.launch_count
+    e0.record()
+    for j in range(a.steps):
+        step_dev(a.warmup + j, evs[j])
+    e1.record()
+    barrier()
+    launches = solver.launch_count - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    # converged problems and iterations actually taken in the timed steps (results are deterministic per set)
+    conv_steps = 0; iter_steps = 0.0; per_set = {}
+    for j in range(a.steps):
+        s = (a.warmup + j) % R
+        if s not in per_set:
+            st = d_stat[s].cpu().numpy(); kk = d_kkt[s].cpu().numpy(); it = d_it[s].cpu().numpy()
+            ok = (st == 1) & (kk <= 1e-8)
+            per_set[s] = (int(ok.sum()), float(it.sum()), float(it[ok].mean()) if ok.any() else 0.0, int(it.max()))
+        conv_steps += per_set[s][0]; iter_steps += per_set[s][1]
+    cnt = torch.tensor([conv_steps, iter_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    conv_total = float(cnt[0].item())
+    value = conv_total / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (the solve kernel), this rank
+    flops_per_launch = FLOP_PER_ITER_N20 * iter_steps / a.steps
+    achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12
+    roofline = dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak,
+                    traffic=None, kernel="nmpc_solve_kernel", kernel_ms=kern_ms,
+                    flops_per_launch=flops_per_launch,
+                    peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak; "
+                                "MEASURED_PEAKS.json has no FP64 entry")
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    def pinned(shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype).pin_memory()
+    Rh = min(R, 8)
+    h_wx = [pinned((M, B)) for _ in range(Rh)]; h_wy = [pinned((M, B)) for _ in range(Rh)]
+    h_pose = [pinned((3, B)) for _ in range(Rh)]; h_vel = [pinned((3, B)) for _ in range(Rh)]
+    for j in range(Rh):
+        h_wx[j].copy_(d_wx[j]); h_wy[j].copy_(d_wy[j]); h_pose[j].copy_(d_pose[j]); h_vel[j].copy_(d_vel[j])
+    h_coef = pinned((4, B)); h_state = pinned((6, B)); h_u0 = pinned((2, B)); h_pred = pinned((3 * N, B))
+    h_obj = pinned(B); h_kkt = pinned(B); h_stat = pinned(B, torch.int32); h_it = pinned(B, torch.int32)
+
+    def step_host(j):
+        j %= Rh
+        # the pre-step result stays on the device; only the raw inputs go up and the solve outputs come down
+        solver.prestep_raw(B, M, h_wx[j].numpy(), h_wy[j].numpy(), h_pose[j].numpy(), h_vel[j].numpy(),
+                           h_coef.numpy(), h_state.numpy())
+        solver.solve_raw(B, h_state.numpy(), h_coef.numpy(), h_u0.numpy(), h_pred.numpy(), obj=h_obj.numpy(),
+                         status=h_stat.numpy(), iters=h_it.numpy(), kkt=h_kkt.numpy())
+        return int(((h_stat.numpy() == 1) & (h_kkt.numpy() <= 1e-8)).sum())
+
+    e2e_steps = max(3, min(a.steps, a.e2e_steps))
+    for j in range(3):
+        step_host(j)
+    barrier()
+    t0 = time.perf_counter(); conv_h = 0
+    for j in range(e2e_steps):
+        conv_h += step_host(j)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev); ce = torch.tensor([float(conv_h)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    h2d = (2 * M + 6) * B * 8 + 10 * B * 8          # prestep inputs + (state, coeffs) re-sent to the solve call
+    d2h = 10 * B * 8 + (2 + 3 * N + 2) * B * 8 + 2 * B * 4
+    e2e = dict(value=float(ce.item()) / float(te.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+               steps=e2e_steps, note="synchronous C-ABI calls with host buffers, one handle, one stream")
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            cpu = cpu_reference_rate(a.ref_per_core)
+        it_mean = float(np.mean([v[2] for v in per_set.values()])); it_max = int(max(v[3] for v in per_set.values()))
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=ms_total / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload=WORKLOAD, batch_per_gpu=B, mpc_steps=N, max_iter=a.max_iter,
+                                l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one "
+                                   "L2 flush" % (R, R * set_bytes / 1e6),
+                                converged_fraction=conv_total / (B * a.steps * world), mean_iters_converged=it_mean,
+                                max_iters=it_max),
+                    clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    solver.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--sets", type=int, default=48)
+    ap.add_argument("--max-iter", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--ref-per-core", type=int, default=160)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,17 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                            const double *wx, const double *wy, const double *pose,
                            double *coeffs_out, double *cte_etheta_out, void *stream);
 
+/*
+ * The whole reference pre-step in one call: polyfit_batch plus the 6-state assembly of
+ * Tracking::findBestPath (mpc_ros/src/driving_state.cpp:242-256), including the delay-compensated
+ * state when params.delay_mode is set (:243-254).
+ *   vel        3 x batch   v (feedback_vel.linear.x, :191), previous w (:192), previous throttle (:193)
+ *   state_out  6 x batch   ready for mpc_b200_solve_batch
+ */
+int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                           const double *wx, const double *wy, const double *pose, const double *vel,
+                           double *coeffs_out, double *state_out, void *stream);
+
 /* Seconds spent on the device by the last solve_batch / polyfit_batch on this handle
  * (CUDA events on the launching stream around the kernel only; no copies). */
 double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h);

@@ -36,6 +36,7 @@ EXPORTS = [
     "mpc_b200_params_default", "mpc_b200_params_yaml_default", "mpc_b200_params_from_yaml",
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
     "mpc_b200_get_params", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
+    "mpc_b200_prestep_batch",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
 ]
@@ -70,6 +71,8 @@ def lib():
     L.mpc_b200_solve_batch.restype = C.c_int
     L.mpc_b200_polyfit_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6
     L.mpc_b200_polyfit_batch.restype = C.c_int
+    L.mpc_b200_prestep_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
+    L.mpc_b200_prestep_batch.restype = C.c_int
     L.mpc_b200_last_kernel_seconds.argtypes = [C.c_void_p]
     L.mpc_b200_last_kernel_seconds.restype = C.c_double
     L.mpc_b200_launch_count.argtypes = [C.c_void_p]
@@ -205,6 +208,20 @@ class Solver:
                                           _addr(cte_etheta), stream)
         if rc != 0:
             raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def prestep_raw(self, batch, M, wx, wy, pose, vel, coeffs, state, stream=None):
+        rc = lib().mpc_b200_prestep_batch(self._h, batch, M, _addr(wx), _addr(wy), _addr(pose), _addr(vel),
+                                          _addr(coeffs), _addr(state), stream)
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def prestep(self, wx, wy, pose, vel):
+        wx = np.ascontiguousarray(wx, dtype=np.float64); wy = np.ascontiguousarray(wy, dtype=np.float64)
+        pose = np.ascontiguousarray(pose, dtype=np.float64); vel = np.ascontiguousarray(vel, dtype=np.float64)
+        M, B = wx.shape
+        coeffs = np.zeros((4, B)); state = np.zeros((6, B))
+        self.prestep_raw(B, M, wx, wy, pose, vel, coeffs, state)
+        return coeffs, state
 
     @property
     def last_kernel_seconds(self):

@@ -20,7 +20,8 @@ using nmpc::SolveArgs;
 // householderQr().solve() does).  One thread per problem: M ~ 11 waypoints, a 11x4 QR.
 __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, const double *__restrict__ wy,
                                const double *__restrict__ pose, double *__restrict__ coeffs_out,
-                               double *__restrict__ cte_eth_out)
+                               double *__restrict__ cte_eth_out, const double *__restrict__ vel,
+                               double *__restrict__ state_out, int delay_mode, double dt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
@@ -71,7 +72,7 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
         c[0] = c[1] = c[2] = c[3] = nanv;
     }
     for (int k = 0; k < 4; k++) coeffs_out[(size_t)k * batch + i] = c[k];
-    if (cte_eth_out) {
+    if (cte_eth_out || state_out) {
         // cte = polyeval(coeffs, 0) = c[0] (:211); etheta by the reference's atan2 rule (:215-235)
         double gx = 0.0, gy = 0.0;
         const int ns = (int)(M * 0.3);
@@ -85,8 +86,27 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
         if (tt <= -PI + traj) tt += 2.0 * PI;
         double eth;
         if (gx != 0.0 && gy != 0.0 && tt - traj < 1.8 * PI) eth = tt - traj; else eth = 0.0;
-        cte_eth_out[i] = c[0];
-        cte_eth_out[(size_t)batch + i] = eth;
+        if (cte_eth_out) {
+            cte_eth_out[i] = c[0];
+            cte_eth_out[(size_t)batch + i] = eth;
+        }
+        if (state_out) {
+            // state assembly, driving_state.cpp:242-256
+            const double v = vel[i];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = v, s4 = c[0], s5 = eth;
+            if (delay_mode) {
+                const double w = vel[(size_t)batch + i], thr = vel[2 * (size_t)batch + i];
+                s0 = v * dt;                       // px_act   (:245)
+                s1 = 0.0;                          // py_act   (:246)
+                s2 = w * dt;                       // theta_act (:247)
+                s3 = v + thr * dt;                 // v_act    (:248)
+                s4 = c[0] + v * sin(eth) * dt;     // cte_act  (:250)
+                s5 = eth - s2;                     // etheta_act (:251)
+            }
+            state_out[i] = s0; state_out[(size_t)batch + i] = s1; state_out[2 * (size_t)batch + i] = s2;
+            state_out[3 * (size_t)batch + i] = s3; state_out[4 * (size_t)batch + i] = s4;
+            state_out[5 * (size_t)batch + i] = s5;
+        }
     }
 }
 
@@ -128,7 +148,7 @@ struct mpc_b200_handle {
     // device scratch
     double *d_state, *d_coeffs, *d_refv, *d_u0, *d_pred, *d_obj, *d_kkt, *d_warm_out;
     int *d_status, *d_iters;
-    double *d_wx, *d_wy, *d_pose, *d_cte;
+    double *d_wx, *d_wy, *d_pose, *d_cte, *d_vel;
     // pinned staging
     double *h_in, *h_out;
     size_t h_in_bytes, h_out_bytes;
@@ -159,11 +179,11 @@ static void free_scratch(mpc_b200_handle *h)
 {
     cudaFree(h->d_state); cudaFree(h->d_coeffs); cudaFree(h->d_refv); cudaFree(h->d_u0); cudaFree(h->d_pred);
     cudaFree(h->d_obj); cudaFree(h->d_kkt); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_warm_out);
-    cudaFree(h->d_wx); cudaFree(h->d_wy); cudaFree(h->d_pose); cudaFree(h->d_cte);
+    cudaFree(h->d_wx); cudaFree(h->d_wy); cudaFree(h->d_pose); cudaFree(h->d_cte); cudaFree(h->d_vel);
     cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
     if (h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
-    h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = NULL;
+    h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL;
     h->h_in = h->h_out = NULL;
 }
 
@@ -184,6 +204,7 @@ static int alloc_scratch(mpc_b200_handle *h)
     CK(cudaMalloc(&h->d_wy, sizeof(double) * MAX_WAYPOINTS * B));
     CK(cudaMalloc(&h->d_pose, sizeof(double) * 3 * B));
     CK(cudaMalloc(&h->d_cte, sizeof(double) * 2 * B));
+    CK(cudaMalloc(&h->d_vel, sizeof(double) * 3 * B));
     h->d_warm_out = NULL;
     h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
     h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 1 + 6) * B;
@@ -246,7 +267,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     if (!h) return MPC_B200_ERR_NOMEM;
     h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
-    h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = NULL; h->h_in = h->h_out = NULL;
+    h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
     h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -257,7 +278,8 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     h->num_sms = sms; h->smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
     if (rc != MPC_B200_OK) { free_scratch(h); delete h; return rc; }
@@ -345,6 +367,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.prm.w_accel = P.w_accel; a.prm.max_angvel = P.max_angvel; a.prm.max_throttle = P.max_throttle;
     a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
     a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 200;
+    a.prm.grp = 2;   // = SPT of the kernel instantiation
     a.batch = batch;
     a.PB = choose_pb(h, N, batch);
     a.prof = h->d_prof;
@@ -376,7 +399,8 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     const int grid = (batch + a.PB - 1) / a.PB;
     const size_t smem = nmpc::smem_bytes(N, a.PB);
     CK(cudaEventRecord(h->ev0, st));
-    nmpc::nmpc_solve_kernel<2><<<grid, threads, smem, st>>>(a);
+    if (a.PB == 32) nmpc::nmpc_solve_kernel<2, 32><<<grid, threads, smem, st>>>(a);
+    else nmpc::nmpc_solve_kernel<2, 0><<<grid, threads, smem, st>>>(a);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++;
@@ -435,7 +459,7 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
     double *dco = dev_out ? coeffs_out : h->d_coeffs;
     double *dce = cte_etheta_out ? (dev_out ? cte_etheta_out : h->d_cte) : NULL;
     CK(cudaEventRecord(h->ev0, st));
-    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, dce);
+    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, dce, NULL, NULL, 0, 0.0);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++;
@@ -446,6 +470,58 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
         CK(cudaStreamSynchronize(st));
         memcpy(coeffs_out, ho, sizeof(double) * 4 * B);
         if (dce) memcpy(cte_etheta_out, ho + 4 * B, sizeof(double) * 2 * B);
+    } else if (!(dev_in && stream_v)) {
+        CK(cudaStreamSynchronize(st));
+    }
+    if (!(dev_in && dev_out && stream_v)) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
+    }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                           const double *wx, const double *wy, const double *pose, const double *vel,
+                           double *coeffs_out, double *state_out, void *stream_v)
+{
+    if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !vel || !coeffs_out || !state_out)
+        return MPC_B200_ERR_INVALID;
+    if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t B = (size_t)batch;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    const bool dev_in = is_device_ptr(wx), dev_out = is_device_ptr(coeffs_out);
+    if (is_device_ptr(wy) != dev_in || is_device_ptr(pose) != dev_in || is_device_ptr(vel) != dev_in) return MPC_B200_ERR_INVALID;
+    if (is_device_ptr(state_out) != dev_out) return MPC_B200_ERR_INVALID;
+    const double *dwx = wx, *dwy = wy, *dpose = pose, *dvel = vel;
+    if (!dev_in) {
+        double *hi = h->h_in;
+        memcpy(hi, wx, sizeof(double) * M * B);
+        memcpy(hi + (size_t)M * B, wy, sizeof(double) * M * B);
+        memcpy(hi + 2 * (size_t)M * B, pose, sizeof(double) * 3 * B);
+        memcpy(hi + 2 * (size_t)M * B + 3 * B, vel, sizeof(double) * 3 * B);
+        CK(cudaMemcpyAsync(h->d_wx, hi, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_wy, hi + (size_t)M * B, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_pose, hi + 2 * (size_t)M * B, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_vel, hi + 2 * (size_t)M * B + 3 * B, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
+        dwx = h->d_wx; dwy = h->d_wy; dpose = h->d_pose; dvel = h->d_vel;
+    }
+    double *dco = dev_out ? coeffs_out : h->d_coeffs;
+    double *dso = dev_out ? state_out : h->d_state;
+    CK(cudaEventRecord(h->ev0, st));
+    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, NULL, dvel, dso,
+                                                         h->params.delay_mode, h->params.dt);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    h->launches++;
+    if (!dev_out) {
+        double *ho = h->h_out;
+        CK(cudaMemcpyAsync(ho, dco, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ho + 4 * B, dso, sizeof(double) * 6 * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(coeffs_out, ho, sizeof(double) * 4 * B);
+        memcpy(state_out, ho + 4 * B, sizeof(double) * 6 * B);
     } else if (!(dev_in && stream_v)) {
         CK(cudaStreamSynchronize(st));
     }

@@ -42,13 +42,13 @@ struct SolveArgs {
 #define PROF_FLUSH()
 #endif
 
-template <int SPT>
+template <int SPT, int CPB>
 __global__ void __launch_bounds__(352, 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;
-    const int N = prm.N, PB = a.PB, batch = a.batch;
-    Smem sm;
+    const int N = prm.N, PB = (CPB > 0) ? CPB : a.PB, batch = a.batch;
+    SmemT<CPB> sm;
     sm.st = smem_raw;
     sm.ps = smem_raw + (size_t)N * NSLOTS * PB;
     sm.pi = reinterpret_cast<int *>(sm.ps + (size_t)NPS * PB);
@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(352, 1) nmpc_solve_kernel(const SolveArgs a)
             if (have) {
                 const int md = sm.I(PI_MODE, p);
                 if (md == MODE_RESID || md == MODE_ACCEPT) {
+                    ResidPart acc;
+                    part_reset(acc);
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_residuals(prm, sm, r[j], k0 + j, p);
+                        if (k0 + j < N) stage_residuals(prm, sm, r[j], k0 + j, p, acc);
+                    part_store(sm, k0, p, acc);
                 }
             }
             __syncthreads();  // B1
@@ -185,17 +188,23 @@ __global__ void __launch_bounds__(352, 1) nmpc_solve_kernel(const SolveArgs a)
             if (have && sm.I(PI_MODE, p) == MODE_STEP) {
                 const int lsq = sm.I(PI_LSQ, p);
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
+                StepPart acc;
+                part_reset(acc);
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_step(prm, sm, r[j], k0 + j, p, hd, lsq);
+                    if (k0 + j < N) stage_step(prm, sm, r[j], k0 + j, p, hd, lsq, acc);
+                part_store(sm, k0, p, acc);
             }
             __syncthreads();  // B5
             __syncthreads();  // B6
             for (;;) {
                 if (have && sm.I(PI_MODE, p) == MODE_TRIAL) {
+                    TrialPart acc;
+                    part_reset(acc);
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_trial(prm, sm, r[j], k0 + j, p);
+                        if (k0 + j < N) stage_trial(prm, sm, r[j], k0 + j, p, acc);
+                    part_store(sm, k0, p, acc);
                 }
                 __syncthreads();  // B7
                 if (!__syncthreads_or(0)) break;  // B8

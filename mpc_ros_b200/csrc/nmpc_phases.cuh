@@ -70,17 +70,23 @@ struct Params {
     double max_angvel, max_throttle;
     double tol;
     int max_iter;
+    int grp;      // stages per stage thread: partial sums are pre-reduced over groups of grp stages
 };
 
-struct Smem {
+// View of the CTA's shared-memory block.  CPB > 0 fixes the problems-per-CTA at compile time so
+// that every access is base + lane*8 + immediate (no index arithmetic in the sweeps).
+template <int CPB>
+struct SmemT {
     double *st;   // [N][NSLOTS][PB]
     double *ps;   // [NPS][PB]
     int *pi;      // [NPI][PB]
     int PB;
-    MPC_HD double &at(int k, int slot, int p) const { return st[(k * NSLOTS + slot) * PB + p]; }
-    MPC_HD double &P(int slot, int p) const { return ps[slot * PB + p]; }
-    MPC_HD int &I(int slot, int p) const { return pi[slot * PB + p]; }
+    MPC_HD int pb() const { return CPB > 0 ? CPB : PB; }
+    MPC_HD double &at(int k, int slot, int p) const { return st[(k * NSLOTS + slot) * pb() + p]; }
+    MPC_HD double &P(int slot, int p) const { return ps[slot * pb() + p]; }
+    MPC_HD int &I(int slot, int p) const { return pi[slot * pb() + p]; }
 };
+typedef SmemT<0> Smem;
 
 MPC_HD size_t smem_bytes(int N, int PB)
 {
@@ -136,12 +142,51 @@ MPC_HD void sincos_d(double a, double *s, double *c)
 #endif
 }
 
+// Reciprocal for the 2x2 Riccati pivot: hardware seed + Newton steps (no special-case branch; the
+// caller has already checked the argument is a positive finite number).
+MPC_HD double fast_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0); y = fma(y, e, y);
+    e = fma(-x, y, 1.0); y = fma(y, e, y);
+    e = fma(-x, y, 1.0); y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// Partial sums a stage thread accumulates over its group of stages before one shared-memory write.
+struct ResidPart { double prinf, pr1, duinf, vmax, vmin, l1, z1, f, lnsum; };
+struct StepPart { double amax, az, gd; };
+struct TrialPart { double pr1, f, lnsum; int inside; };
+MPC_HD void part_reset(ResidPart &a) { a.prinf = 0; a.pr1 = 0; a.duinf = 0; a.vmax = -1e300; a.vmin = 1e300; a.l1 = 0; a.z1 = 0; a.f = 0; a.lnsum = 0; }
+MPC_HD void part_reset(StepPart &a) { a.amax = 1.0; a.az = 1.0; a.gd = 0.0; }
+MPC_HD void part_reset(TrialPart &a) { a.pr1 = 0; a.f = 0; a.lnsum = 0; a.inside = 1; }
+template <class SM> MPC_HD void part_store(const SM &sm, int k0, int p, const ResidPart &a)
+{
+    sm.at(k0, W_0, p) = a.prinf; sm.at(k0, W_1, p) = a.pr1; sm.at(k0, W_2, p) = a.duinf;
+    sm.at(k0, W_3, p) = a.vmax; sm.at(k0, W_4, p) = a.vmin; sm.at(k0, W_5, p) = a.l1;
+    sm.at(k0, W_6, p) = a.z1; sm.at(k0, W_7, p) = a.f; sm.at(k0, W_8, p) = a.lnsum;
+}
+template <class SM> MPC_HD void part_store(const SM &sm, int k0, int p, const StepPart &a)
+{
+    sm.at(k0, W_6, p) = a.amax; sm.at(k0, W_7, p) = a.az; sm.at(k0, W_8, p) = a.gd;
+}
+template <class SM> MPC_HD void part_store(const SM &sm, int k0, int p, const TrialPart &a)
+{
+    sm.at(k0, W_0, p) = a.pr1; sm.at(k0, W_1, p) = a.f; sm.at(k0, W_2, p) = a.inside ? a.lnsum : -1e300;
+}
+
 // relaxed control bounds (Ipopt bound_relax_factor, W&B Sec. 3.5)
 MPC_HD double relaxed(double b) { return b + NMPC_BOUND_RELAX * fmax2(1.0, b); }
 
 // ---------------------------------------------------------------- init
 // Reference cold start (mpc_planner.cpp:288-300): zeros except stage 0 = state.
-MPC_HD void stage_init(const Params &prm, const Smem &sm, StageRegs &r, int k, int p,
+template <class SM>
+MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int p,
                        const double *state6, const double *coef4)
 {
     for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
@@ -159,11 +204,12 @@ MPC_HD void stage_init(const Params &prm, const Smem &sm, StageRegs &r, int k, i
 }
 
 // ---------------------------------------------------------------- phase A1: residuals at the iterate
-// Writes the stage's partial sums for the control thread into W_0..W_8:
-//   W_0 max|c|, W_1 sum|c|, W_2 max|dual residual|, W_3 max compl product, W_4 min compl product,
-//   W_5 sum|lambda|, W_6 sum|z|, W_7 scaled objective part, W_8 sum of log-barrier arguments.
+// Accumulates the stage's partial sums into `acc` (stored by part_store into W_0..W_8 of the group's
+// first stage): max|c|, sum|c|, max|dual residual|, max / min complementarity product, sum|lambda|,
+// sum|z|, scaled objective part, sum of the logs of the bound slacks.
 // Also leaves d_k = -c_{k+1} in the D slots and the objective gradient in r.q*.
-MPC_HD void stage_residuals(const Params &prm, const Smem &sm, StageRegs &r, int k, int p)
+template <class SM>
+MPC_HD void stage_residuals(const Params &prm, const SM &sm, StageRegs &r, int k, int p, ResidPart &acc)
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
@@ -225,22 +271,23 @@ MPC_HD void stage_residuals(const Params &prm, const Smem &sm, StageRegs &r, int
         const double p1 = slw * r.zlw, p2 = suw * r.zuw, p3 = sla * r.zla, p4 = sua * r.zua;
         vmax = fmax2(fmax2(p1, p2), fmax2(p3, p4));
         vmin = fmin2(fmin2(p1, p2), fmin2(p3, p4));
-        lnsum = log(slw) + log(suw) + log(sla) + log(sua);
+        lnsum = log((slw * suw) * (sla * sua));
     } else {
         // last stage: no dynamics, no control
         const double rx = lkx, ry = lky, rt = lkt, rv = r.qv + lkv, rc = r.qc + lkc, re = r.qe + lke;
         duinf = fmax2(fmax2(fmax2(fabs(rx), fabs(ry)), fmax2(fabs(rt), fabs(rv))), fmax2(fabs(rc), fabs(re)));
     }
-    sm.at(k, W_0, p) = prinf; sm.at(k, W_1, p) = pr1; sm.at(k, W_2, p) = duinf;
-    sm.at(k, W_3, p) = vmax; sm.at(k, W_4, p) = vmin; sm.at(k, W_5, p) = l1;
-    sm.at(k, W_6, p) = z1; sm.at(k, W_7, p) = sf * f; sm.at(k, W_8, p) = lnsum;
+    acc.prinf = fmax2(acc.prinf, prinf); acc.pr1 += pr1; acc.duinf = fmax2(acc.duinf, duinf);
+    acc.vmax = fmax2(acc.vmax, vmax); acc.vmin = fmin2(acc.vmin, vmin); acc.l1 += l1;
+    acc.z1 += z1; acc.f += sf * f; acc.lnsum += lnsum;
 }
 
 // ---------------------------------------------------------------- phase A2: Newton-system coefficients
 // Writes A_k and the work slots  W_0 qv, W_1 qc, W_2 qe, W_3 qw, W_4 qa, W_5 hxx, W_6 htt,
 // W_7 htv, W_8 hee, W_9 hev, W_10 rw, W_11 ra  for the Riccati sweep.
 // lsq != 0: the least-squares multiplier system (identity Hessian, zero defect).
-MPC_HD void stage_coeffs(const Params &prm, const Smem &sm, StageRegs &r, int k, int p, int lsq)
+template <class SM>
+MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq)
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), mu = sm.P(PS_MU, p), dt = prm.dt;
@@ -284,11 +331,36 @@ MPC_HD void stage_coeffs(const Params &prm, const Smem &sm, StageRegs &r, int k,
 // Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}.
 struct HessDiag { double dx, dy, dt_, dv, dc, de, du; };
 
+// Coefficients of one stage as the backward sweep consumes them.
+struct StageCoef {
+    double a13, a14, a23, a24, a51, a54, a56;
+    double dx, dy, dth, dv, dc, de;
+    double qv, qc, qe, qw, qa;
+    double hxx, htt, htv, hee, hev;
+    double rw, ra;
+};
+template <class SM>
+MPC_HD void load_coef(const SM &sm, int k, int p, StageCoef &c)
+{
+    c.a13 = sm.at(k, A_13, p); c.a14 = sm.at(k, A_14, p); c.a23 = sm.at(k, A_23, p); c.a24 = sm.at(k, A_24, p);
+    c.a51 = sm.at(k, A_51, p); c.a54 = sm.at(k, A_54, p); c.a56 = sm.at(k, A_56, p);
+    c.dx = sm.at(k, D_X, p); c.dy = sm.at(k, D_Y, p); c.dth = sm.at(k, D_T, p);
+    c.dv = sm.at(k, D_V, p); c.dc = sm.at(k, D_C, p); c.de = sm.at(k, D_E, p);
+    c.qv = sm.at(k, W_0, p); c.qc = sm.at(k, W_1, p); c.qe = sm.at(k, W_2, p);
+    c.qw = sm.at(k, W_3, p); c.qa = sm.at(k, W_4, p);
+    c.hxx = sm.at(k, W_5, p); c.htt = sm.at(k, W_6, p); c.htv = sm.at(k, W_7, p);
+    c.hee = sm.at(k, W_8, p); c.hev = sm.at(k, W_9, p);
+    c.rw = sm.at(k, W_10, p); c.ra = sm.at(k, W_11, p);
+}
+
 // Backward sweep over stages N-1 .. 0.  5x5 value matrix over (x,y,theta,v,etheta); the cte
 // row/column of A is zero, so cte only contributes a rank-one term.  Returns 0 if some
 // R~_k is not positive definite (wrong KKT inertia), else 1.  Overwrites W_0..W_11 of each
-// stage k <= N-2 with the gains K (2x5) and k_ff (2).
-MPC_HD int riccati_backward(const Params &prm, const Smem &sm, int p, const HessDiag &hd)
+// stage k <= N-2 with the gains K (2x5) and k_ff (2).  The next stage's coefficients are
+// loaded while the current stage computes (the sweep is one long dependency chain through
+// P; everything that does not depend on P is kept off that chain).
+template <class SM>
+MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
     const int N = prm.N;
     const double dt = prm.dt, dt2 = dt * dt;
@@ -299,70 +371,65 @@ MPC_HD int riccati_backward(const Params &prm, const Smem &sm, int p, const Hess
     double qc_next = sm.at(N - 1, W_1, p);
     const double gam = hd.dc;
     int ok = 1;
+    StageCoef c, nx;
+    load_coef(sm, N - 2, p, c);
+    nx = c;
+#pragma unroll 1
     for (int k = N - 2; k >= 0; k--) {
-        const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
-                     a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
-                     a56 = sm.at(k, A_56, p);
-        const double dx = sm.at(k, D_X, p), dy = sm.at(k, D_Y, p), dth = sm.at(k, D_T, p),
-                     dv = sm.at(k, D_V, p), dc = sm.at(k, D_C, p), de = sm.at(k, D_E, p);
-        const double qv = sm.at(k, W_0, p), qc = sm.at(k, W_1, p), qe = sm.at(k, W_2, p),
-                     qw = sm.at(k, W_3, p), qa = sm.at(k, W_4, p);
-        const double hxx = sm.at(k, W_5, p), htt = sm.at(k, W_6, p), htv = sm.at(k, W_7, p),
-                     hee = sm.at(k, W_8, p), hev = sm.at(k, W_9, p);
-        const double rw = sm.at(k, W_10, p), ra = sm.at(k, W_11, p);
+        if (k > 0) load_coef(sm, k - 1, p, nx);
 
-        // ---- vector part first (uses P_{k+1}):  pt~ = P d + p,  pi_c = gam d_c + q_c,k+1
-        const double tx = Pxx * dx + Pxy * dy + Pxt * dth + Pxv * dv + Pxe * de + px;
-        const double ty = Pxy * dx + Pyy * dy + Pyt * dth + Pyv * dv + Pye * de + py;
-        const double tt = Pxt * dx + Pyt * dy + Ptt * dth + Ptv * dv + Pte * de + pt;
-        const double tv = Pxv * dx + Pyv * dy + Ptv * dth + Pvv * dv + Pve * de + pv;
-        const double te = Pxe * dx + Pye * dy + Pte * dth + Pve * dv + Pee * de + pe;
-        const double pic = gam * dc + qc_next;
+        // ---- R~ = R + B^T P B  (B = dt [e_theta + e_etheta | e_v]) and its inverse: the head of the
+        //      critical chain, needs only P_{k+1}
+        const double Rww = c.rw + hd.du + dt2 * ((Ptt + Pee) + 2.0 * Pte);
+        const double Rwa = dt2 * (Ptv + Pve);
+        const double Raa = c.ra + hd.du + dt2 * Pvv;
+        const double det = Rww * Raa - Rwa * Rwa;
+        if (!(Rww > 0.0) || !(det > 0.0)) ok = 0;
+        const double idet = fast_rcp(det);
+        const double i11 = Raa * idet, i12 = -Rwa * idet, i22 = Rww * idet;
 
         // ---- W = P A5 (columns theta, v change), M = A5^T W
-        const double Mxt = Pxt + a13 * Pxx + a23 * Pxy;
-        const double Myt = Pyt + a13 * Pxy + a23 * Pyy;
-        const double Met = Pte + a13 * Pxe + a23 * Pye;
-        const double Mxv = Pxv + a14 * Pxx + a24 * Pxy;
-        const double Myv = Pyv + a14 * Pxy + a24 * Pyy;
-        const double Mev = Pve + a14 * Pxe + a24 * Pye;
-        const double Wtt = Ptt + a13 * Pxt + a23 * Pyt;
-        const double Wtv = Ptv + a14 * Pxt + a24 * Pyt;   // W[theta][v]
-        const double Wvt = Ptv + a13 * Pxv + a23 * Pyv;   // W[v][theta]
-        const double Wvv = Pvv + a14 * Pxv + a24 * Pyv;
-        const double Mtt = Wtt + a13 * Mxt + a23 * Myt;
-        const double Mtv = Wtv + a13 * Mxv + a23 * Myv;
-        const double Mvv = Wvv + a14 * Mxv + a24 * Myv;
+        const double Mxt = Pxt + c.a13 * Pxx + c.a23 * Pxy;
+        const double Myt = Pyt + c.a13 * Pxy + c.a23 * Pyy;
+        const double Met = Pte + c.a13 * Pxe + c.a23 * Pye;
+        const double Mxv = Pxv + c.a14 * Pxx + c.a24 * Pxy;
+        const double Myv = Pyv + c.a14 * Pxy + c.a24 * Pyy;
+        const double Mev = Pve + c.a14 * Pxe + c.a24 * Pye;
+        const double Wtt = Ptt + c.a13 * Pxt + c.a23 * Pyt;
+        const double Wtv = Ptv + c.a14 * Pxt + c.a24 * Pyt;   // W[theta][v]
+        const double Wvt = Ptv + c.a13 * Pxv + c.a23 * Pyv;   // W[v][theta]
+        const double Wvv = Pvv + c.a14 * Pxv + c.a24 * Pyv;
+        const double Mtt = Wtt + c.a13 * Mxt + c.a23 * Myt;
+        const double Mtv = Wtv + c.a13 * Mxv + c.a23 * Myv;
+        const double Mvv = Wvv + c.a14 * Mxv + c.a24 * Myv;
 
-        // ---- S~ = B^T W  (B = dt [e_theta + e_etheta | e_v]),  R~ = R + B^T P B
+        // ---- S~ = B^T W
         const double Swx = dt * (Pxt + Pxe), Swy = dt * (Pyt + Pye), Swt = dt * (Wtt + Met),
                      Swv = dt * (Wtv + Mev), Swe = dt * (Pte + Pee);
         const double Sax = dt * Pxv, Say = dt * Pyv, Sat = dt * Wvt, Sav = dt * Wvv, Sae = dt * Pve;
-        const double Rww = rw + hd.du + dt2 * (Ptt + 2.0 * Pte + Pee);
-        const double Rwa = dt2 * (Ptv + Pve);
-        const double Raa = ra + hd.du + dt2 * Pvv;
-        const double det = Rww * Raa - Rwa * Rwa;
-        if (!(Rww > 0.0) || !(det > 0.0)) ok = 0;
-        const double idet = 1.0 / det;
-        const double i11 = Raa * idet, i12 = -Rwa * idet, i22 = Rww * idet;
+
+        // ---- vector part (uses P_{k+1}):  p~ = P d + p,  pi_c = gam d_c + q_c,k+1
+        const double tx = (Pxx * c.dx + Pxy * c.dy) + (Pxt * c.dth + Pxv * c.dv) + (Pxe * c.de + px);
+        const double ty = (Pxy * c.dx + Pyy * c.dy) + (Pyt * c.dth + Pyv * c.dv) + (Pye * c.de + py);
+        const double tt = (Pxt * c.dx + Pyt * c.dy) + (Ptt * c.dth + Ptv * c.dv) + (Pte * c.de + pt);
+        const double tv = (Pxv * c.dx + Pyv * c.dy) + (Ptv * c.dth + Pvv * c.dv) + (Pve * c.de + pv);
+        const double te = (Pxe * c.dx + Pye * c.dy) + (Pte * c.dth + Pve * c.dv) + (Pee * c.de + pe);
+        const double pic = gam * c.dc + qc_next;
 
         // ---- Q~ = Q + M + gam a_c a_c^T   (a_c = [a51, -1, 0, a54, a56] over x,y,theta,v,etheta)
-        const double g1 = gam * a51, g4 = gam * a54, g6 = gam * a56;
-        const double Qxx = Pxx + g1 * a51 + hxx + hd.dx;
+        const double g1 = gam * c.a51, g4 = gam * c.a54, g6 = gam * c.a56;
+        const double Qxx = Pxx + (g1 * c.a51 + (c.hxx + hd.dx));
         const double Qxy = Pxy - g1;
-        const double Qxt = Mxt;
-        const double Qxv = Mxv + g1 * a54;
-        const double Qxe = Pxe + g1 * a56;
-        const double Qyy = Pyy + gam + hd.dy;
-        const double Qyt = Myt;
+        const double Qxv = Mxv + g1 * c.a54;
+        const double Qxe = Pxe + g1 * c.a56;
+        const double Qyy = Pyy + (gam + hd.dy);
         const double Qyv = Myv - g4;
         const double Qye = Pye - g6;
-        const double Qtt = Mtt + htt + hd.dt_;
-        const double Qtv = Mtv + htv;
-        const double Qte = Met;
-        const double Qvv = Mvv + g4 * a54 + hd.dv;
-        const double Qve = Mev + g4 * a56 + hev;
-        const double Qee = Pee + g6 * a56 + hee + hd.de;
+        const double Qtt = Mtt + (c.htt + hd.dt_);
+        const double Qtv = Mtv + c.htv;
+        const double Qvv = Mvv + (g4 * c.a54 + hd.dv);
+        const double Qve = Mev + (g4 * c.a56 + c.hev);
+        const double Qee = Pee + (g6 * c.a56 + (c.hee + hd.de));
 
         // ---- gains  K = -R~^{-1} S~
         const double Kwx = -(i11 * Swx + i12 * Sax), Kax = -(i12 * Swx + i22 * Sax);
@@ -371,43 +438,45 @@ MPC_HD int riccati_backward(const Params &prm, const Smem &sm, int p, const Hess
         const double Kwv = -(i11 * Swv + i12 * Sav), Kav = -(i12 * Swv + i22 * Sav);
         const double Kwe = -(i11 * Swe + i12 * Sae), Kae = -(i12 * Swe + i22 * Sae);
         // ---- feed-forward
-        const double ruw = qw + dt * (tt + te), rua = qa + dt * tv;
+        const double ruw = c.qw + dt * (tt + te), rua = c.qa + dt * tv;
         const double kfw = -(i11 * ruw + i12 * rua), kfa = -(i12 * ruw + i22 * rua);
-
-        // ---- P_k = Q~ + S~^T K
-        Pxx = Qxx + Swx * Kwx + Sax * Kax;
-        Pxy = Qxy + Swx * Kwy + Sax * Kay;
-        Pxt = Qxt + Swx * Kwt + Sax * Kat;
-        Pxv = Qxv + Swx * Kwv + Sax * Kav;
-        Pxe = Qxe + Swx * Kwe + Sax * Kae;
-        Pyy = Qyy + Swy * Kwy + Say * Kay;
-        Pyt = Qyt + Swy * Kwt + Say * Kat;
-        Pyv = Qyv + Swy * Kwv + Say * Kav;
-        Pye = Qye + Swy * Kwe + Say * Kae;
-        Ptt = Qtt + Swt * Kwt + Sat * Kat;
-        Ptv = Qtv + Swt * Kwv + Sat * Kav;
-        Pte = Qte + Swt * Kwe + Sat * Kae;
-        Pvv = Qvv + Swv * Kwv + Sav * Kav;
-        Pve = Qve + Swv * Kwe + Sav * Kae;
-        Pee = Qee + Swe * Kwe + Sae * Kae;
-        // ---- p_k = q_s + A^T p~ + S~^T k_ff
-        px = tx + a51 * pic + Swx * kfw + Sax * kfa;
-        py = ty - pic + Swy * kfw + Say * kfa;
-        pt = tt + a13 * tx + a23 * ty + Swt * kfw + Sat * kfa;
-        pv = qv + tv + a14 * tx + a24 * ty + a54 * pic + Swv * kfw + Sav * kfa;
-        pe = qe + te + a56 * pic + Swe * kfw + Sae * kfa;
-        qc_next = qc;
 
         sm.at(k, W_0, p) = Kwx; sm.at(k, W_1, p) = Kwy; sm.at(k, W_2, p) = Kwt; sm.at(k, W_3, p) = Kwv;
         sm.at(k, W_4, p) = Kwe; sm.at(k, W_5, p) = Kax; sm.at(k, W_6, p) = Kay; sm.at(k, W_7, p) = Kat;
         sm.at(k, W_8, p) = Kav; sm.at(k, W_9, p) = Kae; sm.at(k, W_10, p) = kfw; sm.at(k, W_11, p) = kfa;
+
+        // ---- P_k = Q~ + S~^T K
+        Pxx = Qxx + (Swx * Kwx + Sax * Kax);
+        Pxy = Qxy + (Swx * Kwy + Sax * Kay);
+        Pxt = Mxt + (Swx * Kwt + Sax * Kat);
+        Pxv = Qxv + (Swx * Kwv + Sax * Kav);
+        Pxe = Qxe + (Swx * Kwe + Sax * Kae);
+        Pyy = Qyy + (Swy * Kwy + Say * Kay);
+        Pyt = Myt + (Swy * Kwt + Say * Kat);
+        Pyv = Qyv + (Swy * Kwv + Say * Kav);
+        Pye = Qye + (Swy * Kwe + Say * Kae);
+        Ptt = Qtt + (Swt * Kwt + Sat * Kat);
+        Ptv = Qtv + (Swt * Kwv + Sat * Kav);
+        Pte = Met + (Swt * Kwe + Sat * Kae);
+        Pvv = Qvv + (Swv * Kwv + Sav * Kav);
+        Pve = Qve + (Swv * Kwe + Sav * Kae);
+        Pee = Qee + (Swe * Kwe + Sae * Kae);
+        // ---- p_k = q_s + A^T p~ + S~^T k_ff
+        px = (tx + c.a51 * pic) + (Swx * kfw + Sax * kfa);
+        py = (ty - pic) + (Swy * kfw + Say * kfa);
+        pt = (tt + c.a13 * tx + c.a23 * ty) + (Swt * kfw + Sat * kfa);
+        pv = ((c.qv + tv) + (c.a14 * tx + c.a24 * ty)) + (c.a54 * pic + (Swv * kfw + Sav * kfa));
+        pe = ((c.qe + te) + c.a56 * pic) + (Swe * kfw + Sae * kfa);
+        qc_next = c.qc;
+        c = nx;
     }
     return ok;
 }
 
 // Forward sweep: ds_0 = 0 (the initial-condition rows stay satisfied).  Leaves du_k in
 // W_10/W_11 of stage k and ds_{k+1} in the D slots of stage k.
-MPC_HD void riccati_forward(const Params &prm, const Smem &sm, int p)
+template <class SM>
+MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p)
 {
     const int N = prm.N;
     const double dt = prm.dt;
@@ -435,9 +504,12 @@ MPC_HD void riccati_forward(const Params &prm, const Smem &sm, int p)
 }
 
 // ---------------------------------------------------------------- phase C: step-dependent stage work
-// Reads ds_k, du_k; writes g_k = q_s + Q_k ds_k into W_0..W_5 and the partials
-// W_6 primal fraction-to-boundary limit, W_7 dual limit, W_8 grad(phi_mu)^T d.
-MPC_HD void stage_step(const Params &prm, const Smem &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq)
+// Reads ds_k, du_k; writes g_k = q_s + Q_k ds_k into W_0..W_5 and accumulates the partials
+// (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`
+// (stored by part_store into W_6..W_8 of the group's first stage AFTER all of the group's g_k).
+template <class SM>
+MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq,
+                       StepPart &acc)
 {
     const int N = prm.N;
     const double mu = sm.P(PS_MU, p), tau = sm.P(PS_TAU, p), sf = sm.P(PS_SF, p);
@@ -477,12 +549,13 @@ MPC_HD void stage_step(const Params &prm, const Smem &sm, StageRegs &r, int k, i
     sm.at(k, W_3, p) = r.qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
     sm.at(k, W_4, p) = r.qc + hd.dc * dsc;
     sm.at(k, W_5, p) = r.qe + r.hev * dsv + (hd.de + r.hee) * dse;
-    sm.at(k, W_6, p) = amax; sm.at(k, W_7, p) = az; sm.at(k, W_8, p) = gd;
+    acc.amax = fmin2(acc.amax, amax); acc.az = fmin2(acc.az, az); acc.gd += gd;
 }
 
 // Adjoint sweep (control thread): lambda_k^+ = A_k^T lambda_{k+1}^+ - g_k, k = N-1 .. 0.
 // lambda_{k+1}^+ is left in W_6..W_11 of stage k; lambda_0^+ in PS_N0*.
-MPC_HD void adjoint_sweep(const Params &prm, const Smem &sm, int p)
+template <class SM>
+MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
 {
     const int N = prm.N;
     double lx = -sm.at(N - 1, W_0, p), ly = -sm.at(N - 1, W_1, p), lt = -sm.at(N - 1, W_2, p);
@@ -506,9 +579,10 @@ MPC_HD void adjoint_sweep(const Params &prm, const Smem &sm, int p)
 }
 
 // ---------------------------------------------------------------- phase E1: trial point
-// Evaluates the trial iterate s + alpha ds, u + alpha du; writes W_0 sum|c|, W_1 scaled
-// objective part, W_2 sum of log-barrier arguments (or a huge negative flag if outside).
-MPC_HD void stage_trial(const Params &prm, const Smem &sm, StageRegs &r, int k, int p)
+// Evaluates the trial iterate s + alpha ds, u + alpha du; accumulates sum|c|, the scaled objective
+// part and the sum of the logs of the bound slacks (flag `inside` cleared if a bound is crossed).
+template <class SM>
+MPC_HD void stage_trial(const Params &prm, const SM &sm, StageRegs &r, int k, int p, TrialPart &acc)
 {
     const int N = prm.N;
     const double alpha = sm.P(PS_ALPHA, p), sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
@@ -545,15 +619,16 @@ MPC_HD void stage_trial(const Params &prm, const Smem &sm, StageRegs &r, int k, 
         const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
         const double slw = uw + Uw, suw = Uw - uw, sla = ua + Ua, sua = Ua - ua;
         if (slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0)
-            lnsum = log(slw) + log(suw) + log(sla) + log(sua);
+            lnsum = log((slw * suw) * (sla * sua));
         else
-            lnsum = -1e300;
+            acc.inside = 0;
     }
-    sm.at(k, W_0, p) = pr1; sm.at(k, W_1, p) = sf * f; sm.at(k, W_2, p) = lnsum;
+    acc.pr1 += pr1; acc.f += sf * f; acc.lnsum += lnsum;
 }
 
 // ---------------------------------------------------------------- phase F: accept the step
-MPC_HD void stage_accept(const Params &prm, const Smem &sm, StageRegs &r, int k, int p, int lsq)
+template <class SM>
+MPC_HD void stage_accept(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq)
 {
     const int N = prm.N;
     if (lsq) {
@@ -605,7 +680,7 @@ struct Ctrl {
     double dw_last;
     double theta0, theta_min, theta_max;
     double theta, phi, gd;          // at the current iterate, for the line search
-    double alpha_min;
+    double alpha_min, sw_log;
     double E0, obj;
     double fth[NMPC_MAX_FILTER], fph[NMPC_MAX_FILTER];
 };
@@ -635,11 +710,12 @@ MPC_HD double objective_scaling(const Params &prm, const double *state6, double 
     return g > 100.0 ? 100.0 / g : 1.0;
 }
 
-MPC_HD void ctrl_init(const Params &prm, const Smem &sm, Ctrl &c, int p, const double *state6, double refv)
+template <class SM>
+MPC_HD void ctrl_init(const Params &prm, const SM &sm, Ctrl &c, int p, const double *state6, double refv)
 {
     c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.armijo = 0; c.ls_first = 1; c.lsq_pending = 1;
     c.dw_last = 0.0; c.theta0 = 0.0; c.theta_min = 0.0; c.theta_max = 0.0; c.theta = 0.0; c.phi = 0.0; c.gd = 0.0;
-    c.alpha_min = 0.0; c.E0 = 1e300; c.obj = 0.0;
+    c.alpha_min = 0.0; c.sw_log = 0.0; c.E0 = 1e300; c.obj = 0.0;
     sm.P(PS_MU, p) = NMPC_MU_INIT;
     sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - NMPC_MU_INIT);
     sm.P(PS_SF, p) = objective_scaling(prm, state6, refv);
@@ -673,11 +749,12 @@ MPC_HD void filter_add(Ctrl &c, double theta, double phi)
 
 // Phase B: reduce the residual partials, test convergence, update mu.  Returns 1 when the problem
 // continues with a Newton step, 0 when it has terminated (status set).
-MPC_HD int ctrl_check(const Params &prm, const Smem &sm, Ctrl &c, int p)
+template <class SM>
+MPC_HD int ctrl_check(const Params &prm, const SM &sm, Ctrl &c, int p)
 {
     const int N = prm.N;
     double prinf = 0, pr1 = 0, duinf = 0, vmax = -1e300, vmin = 1e300, l1 = 0, z1 = 0, f = 0, lnsum = 0;
-    for (int k = 0; k < N; k++) {
+    for (int k = 0; k < N; k += prm.grp) {
         prinf = fmax2(prinf, sm.at(k, W_0, p)); pr1 += sm.at(k, W_1, p);
         duinf = fmax2(duinf, sm.at(k, W_2, p));
         vmax = fmax2(vmax, sm.at(k, W_3, p)); vmin = fmin2(vmin, sm.at(k, W_4, p));
@@ -703,7 +780,7 @@ MPC_HD int ctrl_check(const Params &prm, const Smem &sm, Ctrl &c, int p)
         const double Emu = fmax2(fmax2(duinf / s_d, prinf), cmu / s_c);
         if (!(Emu <= NMPC_KAPPA_EPS * mu)) break;
         const double floor_ = fmin2(prm.tol, 1e-4) / (NMPC_KAPPA_EPS + 1.0);
-        const double mun = fmax2(floor_, fmin2(NMPC_KAPPA_MU * mu, pow(mu, NMPC_THETA_MU)));
+        const double mun = fmax2(floor_, fmin2(NMPC_KAPPA_MU * mu, mu * sqrt(mu)));   // theta_mu = 1.5
         if (!(mun < mu)) break;
         mu = mun; changed = 1;
     }
@@ -731,20 +808,23 @@ MPC_HD double next_dw(const Ctrl &c, double dw)
 
 // Phase D: after the step is known.  Reduces the step partials, runs the adjoint sweep, sets
 // up the line search.  Leaves PS_ALPHA (first trial) and PS_ALPHA_Z.
-MPC_HD void ctrl_step(const Params &prm, const Smem &sm, Ctrl &c, int p)
+template <class SM>
+MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p)
 {
     const int N = prm.N;
     double amax = 1.0, az = 1.0, gd = 0.0;
-    for (int k = 0; k < N; k++) {
+    for (int k = 0; k < N; k += prm.grp) {
         amax = fmin2(amax, sm.at(k, W_6, p)); az = fmin2(az, sm.at(k, W_7, p)); gd += sm.at(k, W_8, p);
     }
     adjoint_sweep(prm, sm, p);
     c.gd = gd;
     const double th = c.theta;
-    if (gd < 0.0 && th <= c.theta_min)
-        c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd)),
-                                               pow(th, NMPC_S_THETA) / pow(-gd, NMPC_S_PHI));
-    else if (gd < 0.0)
+    // switching condition (W&B eq. (19)) in log form:  log alpha + s_phi log(-gd) > s_theta log theta
+    c.sw_log = 0.0;
+    if (gd < 0.0 && th <= c.theta_min) {
+        c.sw_log = NMPC_S_THETA * log(th) - NMPC_S_PHI * log(-gd);      // -inf when theta == 0
+        c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd)), exp(c.sw_log));
+    } else if (gd < 0.0)
         c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd));
     else
         c.alpha_min = NMPC_GAMMA_ALPHA * NMPC_GAMMA_THETA;
@@ -755,12 +835,13 @@ MPC_HD void ctrl_step(const Params &prm, const Smem &sm, Ctrl &c, int p)
 
 // Phase E2: filter line-search decision for the trial just evaluated (W&B A-5).
 // Returns 1 accepted, 0 backtrack (PS_ALPHA halved), -1 failed (alpha < alpha_min).
-MPC_HD int ctrl_linesearch(const Params &prm, const Smem &sm, Ctrl &c, int p)
+template <class SM>
+MPC_HD int ctrl_linesearch(const Params &prm, const SM &sm, Ctrl &c, int p)
 {
     const int N = prm.N;
     double th_t = 0.0, f_t = 0.0, ln_t = 0.0;
     int inside = 1;
-    for (int k = 0; k < N; k++) {
+    for (int k = 0; k < N; k += prm.grp) {
         th_t += sm.at(k, W_0, p); f_t += sm.at(k, W_1, p);
         const double l = sm.at(k, W_2, p);
         if (l <= -1e299) inside = 0; else ln_t += l;
@@ -771,8 +852,7 @@ MPC_HD int ctrl_linesearch(const Params &prm, const Smem &sm, Ctrl &c, int p)
     int ok = inside && (th_t == th_t) && (phi_t == phi_t);
     int acc = 0;
     if (ok && filter_acceptable(c, th_t, phi_t)) {
-        const int sw = (gd < 0.0) && (alpha * pow(-gd, NMPC_S_PHI) > pow(th, NMPC_S_THETA));
-        if (th <= c.theta_min && sw) {
+        if (th <= c.theta_min && gd < 0.0 && log(alpha) > c.sw_log) {
             if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; c.armijo = 1; }
         } else {
             if (th_t <= (1.0 - NMPC_GAMMA_THETA) * th ||
@@ -791,7 +871,8 @@ MPC_HD int ctrl_linesearch(const Params &prm, const Smem &sm, Ctrl &c, int p)
 }
 
 // LSQ multiplier start: keep the least-squares multipliers unless they are huge (W&B Sec. 3.6).
-MPC_HD void ctrl_lsq_finish(const Params &prm, const Smem &sm, Ctrl &c, int p)
+template <class SM>
+MPC_HD void ctrl_lsq_finish(const Params &prm, const SM &sm, Ctrl &c, int p)
 {
     const int N = prm.N;
     adjoint_sweep(prm, sm, p);
@@ -806,7 +887,8 @@ MPC_HD void ctrl_lsq_finish(const Params &prm, const Smem &sm, Ctrl &c, int p)
 }
 
 // Control-thread part of accepting a step: lambda_0 and the iteration counter.
-MPC_HD void ctrl_accept(const Smem &sm, Ctrl &c, int p)
+template <class SM>
+MPC_HD void ctrl_accept(const SM &sm, Ctrl &c, int p)
 {
     const double alpha = sm.P(PS_ALPHA, p);
     for (int i = 0; i < 6; i++) {

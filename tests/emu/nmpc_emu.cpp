@@ -23,6 +23,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
     prm.w_cte = prm14[4]; prm.w_etheta = prm14[5]; prm.w_vel = prm14[6]; prm.w_angvel = prm14[7];
     prm.w_accel = prm14[8]; prm.max_angvel = prm14[9]; prm.max_throttle = prm14[10];
     prm.tol = tol; prm.max_iter = max_iter;
+    prm.grp = 2;   // same grouping of partial sums as the kernel's stage threads (SPT = 2)
 
     std::vector<double> st((size_t)N * NSLOTS * PB), ps((size_t)NPS * PB);
     std::vector<int> pi((size_t)NPI * PB);
@@ -50,7 +51,11 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             for (int p = 0; p < np; p++) {
                 const int md = sm.I(PI_MODE, p);
                 if (md == MODE_RESID || md == MODE_ACCEPT)
-                    for (int k = 0; k < N; k++) stage_residuals(prm, sm, regs[(size_t)k * PB + p], k, p);
+                    for (int k0 = 0; k0 < N; k0 += prm.grp) {
+                        ResidPart acc; part_reset(acc);
+                        for (int k = k0; k < k0 + prm.grp && k < N; k++) stage_residuals(prm, sm, regs[(size_t)k * PB + p], k, p, acc);
+                        part_store(sm, k0, p, acc);
+                    }
             }
             int any_run = 0;
             for (int p = 0; p < np; p++) {
@@ -89,7 +94,11 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_STEP) {
                     HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), sm.I(PI_LSQ, p));
-                    for (int k = 0; k < N; k++) stage_step(prm, sm, regs[(size_t)k * PB + p], k, p, hd, sm.I(PI_LSQ, p));
+                    for (int k0 = 0; k0 < N; k0 += prm.grp) {
+                        StepPart acc; part_reset(acc);
+                        for (int k = k0; k < k0 + prm.grp && k < N; k++) stage_step(prm, sm, regs[(size_t)k * PB + p], k, p, hd, sm.I(PI_LSQ, p), acc);
+                        part_store(sm, k0, p, acc);
+                    }
                 }
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_STEP) {
@@ -100,7 +109,11 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             for (;;) {
                 for (int p = 0; p < np; p++)
                     if (sm.I(PI_MODE, p) == MODE_TRIAL)
-                        for (int k = 0; k < N; k++) stage_trial(prm, sm, regs[(size_t)k * PB + p], k, p);
+                        for (int k0 = 0; k0 < N; k0 += prm.grp) {
+                            TrialPart acc; part_reset(acc);
+                            for (int k = k0; k < k0 + prm.grp && k < N; k++) stage_trial(prm, sm, regs[(size_t)k * PB + p], k, p, acc);
+                            part_store(sm, k0, p, acc);
+                        }
                 int any = 0;
                 for (int p = 0; p < np; p++) {
                     if (sm.I(PI_MODE, p) != MODE_TRIAL) continue;

@@ -1,0 +1,101 @@
+// bench/mpc_bench.cpp -- ROS-free C++ harness that links the solver core directly.
+//
+//   mpc_bench latency [calls]      BASELINE config 1: repeated MPC::Solve through the adapter class
+//                                  (batch of one, host buffers, H2D/D2H included); p50/p99 latency
+//   mpc_bench batch [B] [reps]     config 2: one handle, B problems per call through the C ABI
+// Prints one JSON object per run.
+#include "mpc_planner.h"
+#include "mpc_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+int mpcgen_num_waypoints(double path_length);
+void mpcgen_problems(uint64_t seed, int batch, double path_length, double *wx, double *wy, double *pose, double *vel,
+                     int *kind_out);
+}
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int run_latency(int calls)
+{
+    MPC mpc;
+    std::map<std::string, double> p;   // mpc_params.yaml values through the LoadParams keys
+    p["DT"] = 0.1; p["STEPS"] = 20; p["REF_CTE"] = 0; p["REF_ETHETA"] = 0; p["REF_V"] = 0.5; p["W_CTE"] = 100;
+    p["W_EPSI"] = 0; p["W_V"] = 1000; p["W_ANGVEL"] = 100; p["W_A"] = 50; p["W_DANGVEL"] = 0; p["W_DA"] = 0;
+    p["ANGVEL"] = 1.5; p["MAXTHR"] = 1.0; p["BOUND"] = 1e3;
+    mpc.LoadParams(p);
+    // problem #0 of seed 20261019 on the infinity track
+    const int M = mpcgen_num_waypoints(5.0);
+    std::vector<double> wx(M), wy(M), pose(3), vel(3);
+    mpcgen_problems(20261019ULL, 1, 5.0, wx.data(), wy.data(), pose.data(), vel.data(), nullptr);
+    mpc_b200_params prm; mpc_b200_params_yaml_default(&prm); prm.delay_mode = 0;
+    mpc_b200_handle *h = nullptr;
+    if (mpc_b200_create(&h, &prm, 1, 0) != MPC_B200_OK) { fprintf(stderr, "no CUDA device\n"); return 2; }
+    double co[4], st6[6];
+    mpc_b200_prestep_batch(h, 1, M, wx.data(), wy.data(), pose.data(), vel.data(), co, st6, nullptr);
+    mpc_b200_destroy(h);
+    Eigen::VectorXd state(6), coeffs(4);
+    for (int i = 0; i < 6; i++) state[i] = st6[i];
+    for (int i = 0; i < 4; i++) coeffs[i] = co[i];
+    for (int i = 0; i < 50; i++) mpc.Solve(state, coeffs);
+    std::vector<double> t(calls);
+    std::vector<double> r;
+    for (int i = 0; i < calls; i++) {
+        const double t0 = now_s();
+        r = mpc.Solve(state, coeffs);
+        t[i] = now_s() - t0;
+    }
+    std::sort(t.begin(), t.end());
+    double mean = 0; for (double x : t) mean += x; mean /= calls;
+    printf("{\"mode\": \"latency\", \"calls\": %d, \"p50_us\": %.2f, \"p99_us\": %.2f, \"mean_us\": %.2f, \"max_us\": %.2f, "
+           "\"w0\": %.12g, \"a0\": %.12g, \"status\": %d, \"iters\": %d, \"kkt\": %.3e}\n",
+           calls, 1e6 * t[calls / 2], 1e6 * t[(size_t)(0.99 * calls)], 1e6 * mean, 1e6 * t[calls - 1], r[0], r[1],
+           mpc.last_status(), mpc.last_iterations(), mpc.last_kkt_error());
+    return 0;
+}
+
+static int run_batch(int B, int reps)
+{
+    mpc_b200_params prm; mpc_b200_params_yaml_default(&prm); prm.delay_mode = 0;
+    mpc_b200_handle *h = nullptr;
+    if (mpc_b200_create(&h, &prm, B, 0) != MPC_B200_OK) { fprintf(stderr, "no CUDA device\n"); return 2; }
+    const int M = mpcgen_num_waypoints(5.0), N = prm.mpc_steps;
+    std::vector<double> wx((size_t)M * B), wy((size_t)M * B), pose(3 * (size_t)B), vel(3 * (size_t)B);
+    mpcgen_problems(20261018ULL + 2, B, 5.0, wx.data(), wy.data(), pose.data(), vel.data(), nullptr);
+    std::vector<double> co(4 * (size_t)B), st(6 * (size_t)B), u0(2 * (size_t)B), pred(3 * (size_t)N * B), obj(B), kkt(B);
+    std::vector<int32_t> status(B), iters(B);
+    double best = 1e30, kbest = 1e30;
+    for (int r = 0; r < reps + 2; r++) {
+        const double t0 = now_s();
+        mpc_b200_prestep_batch(h, B, M, wx.data(), wy.data(), pose.data(), vel.data(), co.data(), st.data(), nullptr);
+        int rc = mpc_b200_solve_batch(h, B, st.data(), co.data(), nullptr, nullptr, u0.data(), pred.data(), obj.data(),
+                                      status.data(), iters.data(), kkt.data(), nullptr, nullptr);
+        const double t1 = now_s();
+        if (rc != MPC_B200_OK) { fprintf(stderr, "solve failed: %s\n", mpc_b200_strerror(rc)); return 3; }
+        if (r >= 2) { best = std::min(best, t1 - t0); kbest = std::min(kbest, mpc_b200_last_kernel_seconds(h)); }
+    }
+    long conv = 0, its = 0; int itmax = 0;
+    for (int i = 0; i < B; i++) { conv += status[i] == 1 && kkt[i] <= 1e-8; its += iters[i]; itmax = std::max(itmax, (int)iters[i]); }
+    printf("{\"mode\": \"batch\", \"batch\": %d, \"e2e_ms\": %.4f, \"kernel_ms\": %.4f, \"converged\": %ld, "
+           "\"solves_per_s_e2e\": %.1f, \"mean_iters\": %.3f, \"max_iters\": %d}\n",
+           B, 1e3 * best, 1e3 * kbest, conv, conv / best, (double)its / B, itmax);
+    mpc_b200_destroy(h);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc >= 2 && !strcmp(argv[1], "latency")) return run_latency(argc >= 3 ? atoi(argv[2]) : 10000);
+    if (argc >= 2 && !strcmp(argv[1], "batch")) return run_batch(argc >= 3 ? atoi(argv[2]) : 4096, argc >= 4 ? atoi(argv[3]) : 20);
+    fprintf(stderr, "usage: mpc_bench latency [calls] | batch [B] [reps]\n");
+    return 1;
+}

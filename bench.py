@@ -193,17 +193,24 @@ def run_ours(a):
     out_bytes = (2 + 3 * N + 2) * B * 8 + 2 * B * 4
     set_bytes = in_bytes + out_bytes + 10 * B * 8
     flush = torch.empty(256 * 1024 * 1024 // 8, **f64)
-    stream = torch.cuda.current_stream().cuda_stream
+    # Steps are independent batches: they are issued round-robin on S streams so that the tail of one
+    # batch (a few problems need 10-25x the median iteration count) overlaps the next batches.
+    S = max(1, a.streams)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    if a.max_ctas > 0:
+        solver.set_option("max_ctas", a.max_ctas)
 
     def step_dev(j, ev=None):
+        st = streams[j % S]
         j %= R
-        solver.prestep_raw(B, M, d_wx[j], d_wy[j], d_pose[j], d_vel[j], d_coef[j], d_state[j], stream=stream)
-        if ev is not None:
-            ev[0].record()
-        solver.solve_raw(B, d_state[j], d_coef[j], d_u0[j], d_pred[j], obj=d_obj[j], status=d_stat[j], iters=d_it[j],
-                         kkt=d_kkt[j], stream=stream)
-        if ev is not None:
-            ev[1].record()
+        with torch.cuda.stream(st):
+            solver.prestep_raw(B, M, d_wx[j], d_wy[j], d_pose[j], d_vel[j], d_coef[j], d_state[j], stream=st.cuda_stream)
+            if ev is not None:
+                ev[0].record(st)
+            solver.solve_raw(B, d_state[j], d_coef[j], d_u0[j], d_pred[j], obj=d_obj[j], status=d_stat[j],
+                             iters=d_it[j], kkt=d_kkt[j], stream=st.cuda_stream)
+            if ev is not None:
+                ev[1].record(st)
 
     def barrier():
         torch.cuda.synchronize()
@@ -222,10 +229,15 @@ def run_ours(a):
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     n0 = solver.launch_count
-    e0.record()
+    main = torch.cuda.current_stream()
+    e0.record(main)
+    for st in streams:
+        st.wait_event(e0)
     for j in range(a.steps):
         step_dev(a.warmup + j, evs[j])
-    e1.record()
+    for st in streams:
+        main.wait_stream(st)
+    e1.record(main)
     barrier()
     launches = solver.launch_count - n0
     clocks = sampler.stop() if rank == 0 else None
@@ -252,50 +264,88 @@ def run_ours(a):
     value = conv_total / (ms_total * 1e-3)
 
     # ---- roofline of the dominant kernel (the solve kernel), this rank
+    # With S > 1 launches overlap on the device: the event-to-event time of one launch then includes
+    # waiting for SMs held by its neighbours, so the launch duration that matters for the roofline is the
+    # device time per launch of the timed region (= region / launches; the pre-step kernel is < 1 % of it).
+    # A launch timed ALONE (one stream, synchronised) is reported next to it.
     flops_per_launch = FLOP_PER_ITER_N20 * iter_steps / a.steps
-    achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12
+    eff_ms = ms_total / a.steps
+    achieved = flops_per_launch / (eff_ms * 1e-3) / 1e12
+    iso = []
+    for j in range(5):
+        x = torch.cuda.Event(enable_timing=True); y = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        step_dev(j * S, (x, y))
+        torch.cuda.synchronize()
+        iso.append(x.elapsed_time(y))
+    iso_ms = float(np.median(iso))
     roofline = dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak,
-                    traffic=None, kernel="nmpc_solve_kernel", kernel_ms=kern_ms,
-                    flops_per_launch=flops_per_launch,
+                    traffic=None, kernel="nmpc_solve_kernel", kernel_ms=eff_ms, kernel_ms_event_avg=kern_ms,
+                    kernel_ms_isolated=iso_ms, achieved_isolated=flops_per_launch / (iso_ms * 1e-3) / 1e12,
+                    streams=S, flops_per_launch=flops_per_launch,
                     peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak; "
                                 "MEASURED_PEAKS.json has no FP64 entry")
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  T host threads, each with
+    # its own handle (a handle is not re-entrant), stream and pinned buffers, issue synchronous calls --
+    # the way a server feeding the solver from several request queues would.
     def pinned(shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype).pin_memory()
-    Rh = min(R, 8)
-    h_wx = [pinned((M, B)) for _ in range(Rh)]; h_wy = [pinned((M, B)) for _ in range(Rh)]
-    h_pose = [pinned((3, B)) for _ in range(Rh)]; h_vel = [pinned((3, B)) for _ in range(Rh)]
-    for j in range(Rh):
-        h_wx[j].copy_(d_wx[j]); h_wy[j].copy_(d_wy[j]); h_pose[j].copy_(d_pose[j]); h_vel[j].copy_(d_vel[j])
-    h_coef = pinned((4, B)); h_state = pinned((6, B)); h_u0 = pinned((2, B)); h_pred = pinned((3 * N, B))
-    h_obj = pinned(B); h_kkt = pinned(B); h_stat = pinned(B, torch.int32); h_it = pinned(B, torch.int32)
+    T = max(1, a.e2e_threads)
+    Rh = 4
 
-    def step_host(j):
-        j %= Rh
-        # the pre-step result stays on the device; only the raw inputs go up and the solve outputs come down
-        solver.prestep_raw(B, M, h_wx[j].numpy(), h_wy[j].numpy(), h_pose[j].numpy(), h_vel[j].numpy(),
-                           h_coef.numpy(), h_state.numpy())
-        solver.solve_raw(B, h_state.numpy(), h_coef.numpy(), h_u0.numpy(), h_pred.numpy(), obj=h_obj.numpy(),
-                         status=h_stat.numpy(), iters=h_it.numpy(), kkt=h_kkt.numpy())
-        return int(((h_stat.numpy() == 1) & (h_kkt.numpy() <= 1e-8)).sum())
+    class Worker:
+        def __init__(self, t):
+            self.solver = capi.Solver(prm, B, local)
+            self.wx = [pinned((M, B)) for _ in range(Rh)]; self.wy = [pinned((M, B)) for _ in range(Rh)]
+            self.pose = [pinned((3, B)) for _ in range(Rh)]; self.vel = [pinned((3, B)) for _ in range(Rh)]
+            for j in range(Rh):
+                q = (t * Rh + j) % R
+                self.wx[j].copy_(d_wx[q]); self.wy[j].copy_(d_wy[q]); self.pose[j].copy_(d_pose[q]); self.vel[j].copy_(d_vel[q])
+            self.coef = pinned((4, B)); self.state = pinned((6, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
+            self.obj = pinned(B); self.kkt = pinned(B); self.stat = pinned(B, torch.int32); self.it = pinned(B, torch.int32)
+            self.conv = 0
 
-    e2e_steps = max(3, min(a.steps, a.e2e_steps))
-    for j in range(3):
-        step_host(j)
+        def step(self, j):
+            j %= Rh
+            s = self.solver
+            s.prestep_raw(B, M, self.wx[j].numpy(), self.wy[j].numpy(), self.pose[j].numpy(), self.vel[j].numpy(),
+                          self.coef.numpy(), self.state.numpy())
+            s.solve_raw(B, self.state.numpy(), self.coef.numpy(), self.u0.numpy(), self.pred.numpy(), obj=self.obj.numpy(),
+                        status=self.stat.numpy(), iters=self.it.numpy(), kkt=self.kkt.numpy())
+            return int(((self.stat.numpy() == 1) & (self.kkt.numpy() <= 1e-8)).sum())
+
+        def run(self, n):
+            self.conv = 0
+            for j in range(n):
+                self.conv += self.step(j)
+
+    workers = [Worker(t) for t in range(T)]
+    per_thread = max(2, a.e2e_steps // T)
+    for w in workers:
+        w.step(0)
     barrier()
-    t0 = time.perf_counter(); conv_h = 0
-    for j in range(e2e_steps):
-        conv_h += step_host(j)
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=w.run, args=(per_thread,)) for w in workers]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    conv_h = sum(w.conv for w in workers)
+    e2e_steps = per_thread * T
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev); ce = torch.tensor([float(conv_h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce, op=dist.ReduceOp.SUM)
     h2d = (2 * M + 6) * B * 8 + 10 * B * 8          # prestep inputs + (state, coeffs) re-sent to the solve call
     d2h = 10 * B * 8 + (2 + 3 * N + 2) * B * 8 + 2 * B * 4
     e2e = dict(value=float(ce.item()) / float(te.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-               steps=e2e_steps, note="synchronous C-ABI calls with host buffers, one handle, one stream")
+               steps=e2e_steps, threads=T,
+               note="synchronous C-ABI calls with host buffers (pinned staging, H2D and D2H inside the timed region) "
+                    "from %d host threads, one handle + stream each; host wall clock" % T)
+    for w in workers:
+        w.solver.close()
 
     if rank == 0:
         cpu = None
@@ -305,7 +355,8 @@ def run_ours(a):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_total / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic",
-                    config=dict(workload=WORKLOAD, batch_per_gpu=B, mpc_steps=N, max_iter=a.max_iter,
+                    config=dict(workload=WORKLOAD, batch_per_gpu=B, mpc_steps=N, max_iter=a.max_iter, streams=S,
+                                max_ctas=a.max_ctas,
                                 l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one "
                                    "L2 flush" % (R, R * set_bytes / 1e6),
                                 converged_fraction=conv_total / (B * a.steps * world), mean_iters_converged=it_mean,
@@ -326,7 +377,10 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--sets", type=int, default=48)
     ap.add_argument("--max-iter", type=int, default=200)
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--max-ctas", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=128)
+    ap.add_argument("--e2e-threads", type=int, default=8)
     ap.add_argument("--ref-per-core", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -105,6 +105,10 @@ void mpc_b200_destroy(mpc_b200_handle *h);
  * Tracking::deceleration, driving_state.cpp:121-141).  Cheap: no rebuild. */
 int mpc_b200_set_params(mpc_b200_handle *h, const mpc_b200_params *p);
 int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p);
+/* Launch tuning, no reference counterpart.  "max_ctas": cap on the persistent grid (0 = one CTA per SM;
+ * smaller values leave SMs to batches in flight on other streams and make each lane work through
+ * several problems); "problems_per_cta": 0 = auto (up to 32).  Unknown name: MPC_B200_ERR_INVALID. */
+int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value);
 
 /* Size in doubles of one problem's warm-start record: primal (8N-2, the reference's variable
  * layout, mpc_planner.cpp:232-239) + equality multipliers (6N) + control-bound multipliers

@@ -35,7 +35,7 @@ class Params(C.Structure):
 EXPORTS = [
     "mpc_b200_params_default", "mpc_b200_params_yaml_default", "mpc_b200_params_from_yaml",
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
-    "mpc_b200_get_params", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
+    "mpc_b200_get_params", "mpc_b200_set_option", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
     "mpc_b200_prestep_batch",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
@@ -65,6 +65,8 @@ def lib():
     L.mpc_b200_set_params.restype = C.c_int
     L.mpc_b200_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
     L.mpc_b200_get_params.restype = C.c_int
+    L.mpc_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.mpc_b200_set_option.restype = C.c_int
     L.mpc_b200_warm_size.argtypes = [C.c_int32]
     L.mpc_b200_warm_size.restype = C.c_int32
     L.mpc_b200_solve_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 12
@@ -169,6 +171,11 @@ class Solver:
         if rc != 0:
             raise MpcError(rc)
         self.N = params.mpc_steps
+
+    def set_option(self, name, value):
+        rc = lib().mpc_b200_set_option(self._h, name.encode(), float(value))
+        if rc != 0:
+            raise MpcError(rc, name)
 
     def solve_raw(self, batch, state, coeffs, u0, pred, ref_vel=None, warm_in=None, obj=None, status=None,
                   iters=None, kkt=None, warm_out=None, stream=None):

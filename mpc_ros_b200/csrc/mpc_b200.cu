@@ -13,6 +13,11 @@
 using nmpc::SolveArgs;
 
 #define MAX_WAYPOINTS 64
+#define QUEUE_RING 1024
+// stages per stage thread: 1 control warp + 7 stage warps = 256 threads, so that the kernel may use
+// 255 registers per thread (the serial Riccati sweep wants ~110 live doubles)
+#define SPT 3
+#define STAGE_THREADS 224
 
 // ================================================================ K1: transform + polyfit
 // Reference: Tracking::findBestPath, mpc_ros/src/driving_state.cpp:196-235, polyfit :283-300
@@ -156,6 +161,9 @@ struct mpc_b200_handle {
     double last_kernel_s;
     long long launches;
     long long *d_prof;
+    int *d_queue;          // ring of work-queue heads, one per in-flight launch
+    int max_ctas;          // option: cap on the persistent grid (0 = one CTA per SM)
+    int opt_pb;            // option: problems per CTA (0 = auto)
     std::string last_err;
 };
 
@@ -182,6 +190,7 @@ static void free_scratch(mpc_b200_handle *h)
     cudaFree(h->d_wx); cudaFree(h->d_wy); cudaFree(h->d_pose); cudaFree(h->d_cte); cudaFree(h->d_vel);
     cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
     if (h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
+    if (h->d_queue) { cudaFree(h->d_queue); h->d_queue = NULL; }
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL;
     h->h_in = h->h_out = NULL;
@@ -205,6 +214,7 @@ static int alloc_scratch(mpc_b200_handle *h)
     CK(cudaMalloc(&h->d_pose, sizeof(double) * 3 * B));
     CK(cudaMalloc(&h->d_cte, sizeof(double) * 2 * B));
     CK(cudaMalloc(&h->d_vel, sizeof(double) * 3 * B));
+    CK(cudaMalloc(&h->d_queue, sizeof(int) * QUEUE_RING));
     h->d_warm_out = NULL;
     h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
     h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 1 + 6) * B;
@@ -216,7 +226,7 @@ static int alloc_scratch(mpc_b200_handle *h)
 static int check_params(const mpc_b200_params *p)
 {
     if (!p) return MPC_B200_ERR_INVALID;
-    if (p->mpc_steps < 2 || p->mpc_steps > 640) return MPC_B200_ERR_INVALID;
+    if (p->mpc_steps < 2 || p->mpc_steps > 600) return MPC_B200_ERR_INVALID;
     if (!(p->dt > 0.0) || !(p->max_angvel > 0.0) || !(p->max_throttle > 0.0)) return MPC_B200_ERR_INVALID;
     // rate penalties couple u_k and u_{k+1} (mpc_planner.cpp:144-147): needs the augmented-state
     // Riccati variant; not on the GPU path yet.
@@ -268,7 +278,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
-    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL;
+    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -278,8 +288,8 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     h->num_sms = sms; h->smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
     if (rc != MPC_B200_OK) { free_scratch(h); delete h; return rc; }
@@ -322,6 +332,15 @@ int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p)
     return MPC_B200_OK;
 }
 
+int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value)
+{
+    if (!h || !name) return MPC_B200_ERR_INVALID;
+    if (!strcmp(name, "max_ctas")) h->max_ctas = value > 0 ? (int)value : 0;
+    else if (!strcmp(name, "problems_per_cta")) h->opt_pb = value > 0 ? (int)value : 0;
+    else return MPC_B200_ERR_INVALID;
+    return MPC_B200_OK;
+}
+
 double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h) { return h ? h->last_kernel_s : 0.0; }
 int64_t mpc_b200_launch_count(const mpc_b200_handle *h) { return h ? h->launches : 0; }
 
@@ -329,10 +348,11 @@ int64_t mpc_b200_launch_count(const mpc_b200_handle *h) { return h ? h->launches
 // batch over all SMs (the CTA's latency does not depend on how many lanes are active).
 static int choose_pb(const mpc_b200_handle *h, int N, int batch)
 {
-    const int NG = (N + 1) / 2;
+    const int NG = (N + SPT - 1) / SPT;
     int pb = 32;
-    if (pb > 320 / NG) pb = 320 / NG;
+    if (pb > STAGE_THREADS / NG) pb = STAGE_THREADS / NG;
     while (pb > 1 && nmpc::smem_bytes(N, pb) > h->smem_optin) pb--;
+    if (h->opt_pb > 0) return h->opt_pb < pb ? h->opt_pb : pb;
     const int spread = (batch + h->num_sms - 1) / h->num_sms;
     if (spread < pb) pb = spread < 1 ? 1 : spread;
     return pb;
@@ -367,7 +387,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.prm.w_accel = P.w_accel; a.prm.max_angvel = P.max_angvel; a.prm.max_throttle = P.max_throttle;
     a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
     a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 200;
-    a.prm.grp = 2;   // = SPT of the kernel instantiation
+    a.prm.grp = SPT;
     a.batch = batch;
     a.PB = choose_pb(h, N, batch);
     a.prof = h->d_prof;
@@ -393,14 +413,19 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         a.kkt = h->d_kkt; a.warm_out = NULL;
     }
 
-    const int NG = (N + 1) / 2;
+    const int NG = (N + SPT - 1) / SPT;
     const int stage_threads = ((NG * a.PB + 31) / 32) * 32;
     const int threads = 32 + stage_threads;
-    const int grid = (batch + a.PB - 1) / a.PB;
+    // persistent grid: at most one CTA per SM (or the max_ctas option); lanes refill from the queue
+    int grid = (batch + a.PB - 1) / a.PB;
+    const int cap = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
+    if (grid > cap) grid = cap;
     const size_t smem = nmpc::smem_bytes(N, a.PB);
+    a.queue = h->d_queue + (h->launches % QUEUE_RING);
+    CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     CK(cudaEventRecord(h->ev0, st));
-    if (a.PB == 32) nmpc::nmpc_solve_kernel<2, 32><<<grid, threads, smem, st>>>(a);
-    else nmpc::nmpc_solve_kernel<2, 0><<<grid, threads, smem, st>>>(a);
+    if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32><<<grid, threads, smem, st>>>(a);
+    else nmpc::nmpc_solve_kernel<SPT, 0><<<grid, threads, smem, st>>>(a);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++;

@@ -50,6 +50,8 @@ enum PISlot {
     PI_MODE = 0,   // what the stage threads do next (see Mode)
     PI_STATUS,     // 0 while running, else final status
     PI_LSQ,        // 1 during the first cycle: least-squares multiplier start (W&B eq. (36))
+    PI_PROB,       // index of the problem this lane is working on
+    PI_NEXT,       // refill: index of the problem the lane takes over next, or -1
     NPI
 };
 
@@ -60,7 +62,8 @@ enum Mode {
     MODE_COEF,          // write Newton-system coefficients (stage_coeffs), then the Riccati sweeps
     MODE_STEP,          // sweeps succeeded: stage_step, then ctrl_step
     MODE_TRIAL,         // line search: stage_trial at PS_ALPHA, then ctrl_linesearch
-    MODE_ACCEPT         // stage_accept; doubles as MODE_RESID for the next iteration
+    MODE_ACCEPT,        // stage_accept; doubles as MODE_RESID for the next iteration
+    MODE_DONE           // problem terminated: results are flushed, then the lane is refilled from the queue
 };
 
 struct Params {

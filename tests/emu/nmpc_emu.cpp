@@ -23,7 +23,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
     prm.w_cte = prm14[4]; prm.w_etheta = prm14[5]; prm.w_vel = prm14[6]; prm.w_angvel = prm14[7];
     prm.w_accel = prm14[8]; prm.max_angvel = prm14[9]; prm.max_throttle = prm14[10];
     prm.tol = tol; prm.max_iter = max_iter;
-    prm.grp = 2;   // same grouping of partial sums as the kernel's stage threads (SPT = 2)
+    prm.grp = 3;   // same grouping of partial sums as the kernel's stage threads (SPT = 3)
 
     std::vector<double> st((size_t)N * NSLOTS * PB), ps((size_t)NPS * PB);
     std::vector<int> pi((size_t)NPI * PB);

@@ -1,0 +1,54 @@
+"""bench/gpu_sat.py -- saturation experiment: many async solve launches over S streams, lean host loop."""
+import ctypes as C, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from mpc_ros_b200 import capi
+from bench import gen_py
+
+def main():
+    B = int(sys.argv[1]); S = int(sys.argv[2]); K = int(sys.argv[3]); maxc = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    L = capi.lib(); dev = torch.device("cuda:0")
+    prm = capi.yaml_default_params(); prm.delay_mode = 0
+    sv = capi.Solver(prm, B, 0)
+    if hasattr(L, 'mpc_b200_debug_profile'): L.mpc_b200_debug_profile(sv._h, None)
+    if maxc: sv.set_option("max_ctas", maxc)
+    R = 8
+    g = gen_py.problems(20261020, B * R)
+    M = g["M"]
+    def split(x): return [torch.from_numpy(np.ascontiguousarray(x[:, j*B:(j+1)*B])).to(dev) for j in range(R)]
+    wx, wy, pose, vel = split(g["wx"]), split(g["wy"]), split(g["pose"]), split(g["vel"])
+    f64 = dict(dtype=torch.float64, device=dev)
+    coef = [torch.zeros((4, B), **f64) for _ in range(R)]; state = [torch.zeros((6, B), **f64) for _ in range(R)]
+    u0 = [torch.zeros((2, B), **f64) for _ in range(R)]; pred = [torch.zeros((60, B), **f64) for _ in range(R)]
+    stat = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(R)]
+    streams = [torch.cuda.Stream() for _ in range(S)]
+    for j in range(R):
+        sv.prestep_raw(B, M, wx[j], wy[j], pose[j], vel[j], coef[j], state[j])
+    torch.cuda.synchronize()
+    args = []
+    for j in range(R):
+        args.append((sv._h, B, state[j].data_ptr(), coef[j].data_ptr(), None, None, u0[j].data_ptr(), pred[j].data_ptr(),
+                     None, stat[j].data_ptr(), None, None, None))
+    sp = [s.cuda_stream for s in streams]
+    f = L.mpc_b200_solve_batch
+    for j in range(S):
+        f(*args[j % R], sp[j % S])
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in streams: s.wait_event(e0)
+    t0 = time.perf_counter()
+    for j in range(K):
+        f(*args[j % R], sp[j % S])
+    t1 = time.perf_counter()
+    for s in streams: torch.cuda.current_stream().wait_stream(s)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if hasattr(L, "mpc_b200_debug_profile"):
+        buf = (C.c_longlong * 1024)()
+        if L.mpc_b200_debug_profile(sv._h, buf) and buf[1000] > 0:
+            print("   avg global cycle: %.0f SM cycles (%d cycles total over all CTAs of all launches)" % (buf[1001] / buf[1000], buf[1000]))
+    print("B %d S %d K %d maxctas %d: host issue %.1f us/launch, device %.3f ms/launch, %.2f M solves/s" %
+          (B, S, K, maxc, (t1 - t0) / K * 1e6, ms / K, B * K / ms / 1e3))
+main()

@@ -290,6 +290,10 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->num_sms = sms; h->smem_optin = (size_t)optin;
     e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
     if (rc != MPC_B200_OK) { free_scratch(h); delete h; return rc; }
@@ -351,10 +355,16 @@ static int choose_pb(const mpc_b200_handle *h, int N, int batch)
     const int NG = (N + SPT - 1) / SPT;
     int pb = 32;
     if (pb > STAGE_THREADS / NG) pb = STAGE_THREADS / NG;
-    while (pb > 1 && nmpc::smem_bytes(N, pb) > h->smem_optin) pb--;
+    while (pb > 1 && nmpc::smem_bytes(N, NG, pb) > h->smem_optin) pb--;
     if (h->opt_pb > 0) return h->opt_pb < pb ? h->opt_pb : pb;
+    // a small batch is spread over all SMs; snap to the lane counts that have a compiled specialisation
     const int spread = (batch + h->num_sms - 1) / h->num_sms;
-    if (spread < pb) pb = spread < 1 ? 1 : spread;
+    if (spread < pb) {
+        int want = spread < 1 ? 1 : spread;
+        if (want > 16) want = 32; else if (want > 8) want = 16; else if (want > 4) want = 8;
+        else if (want > 1) want = 4;
+        if (want < pb) pb = want;
+    }
     return pb;
 }
 
@@ -420,12 +430,18 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     int grid = (batch + a.PB - 1) / a.PB;
     const int cap = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
     if (grid > cap) grid = cap;
-    const size_t smem = nmpc::smem_bytes(N, a.PB);
+    const size_t smem = nmpc::smem_bytes(N, NG, a.PB);
     a.queue = h->d_queue + (h->launches % QUEUE_RING);
     CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     CK(cudaEventRecord(h->ev0, st));
-    if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32><<<grid, threads, smem, st>>>(a);
-    else nmpc::nmpc_solve_kernel<SPT, 0><<<grid, threads, smem, st>>>(a);
+    switch (a.PB) {
+        case 32: nmpc::nmpc_solve_kernel<SPT, 32><<<grid, threads, smem, st>>>(a); break;
+        case 16: nmpc::nmpc_solve_kernel<SPT, 16><<<grid, threads, smem, st>>>(a); break;
+        case 8: nmpc::nmpc_solve_kernel<SPT, 8><<<grid, threads, smem, st>>>(a); break;
+        case 4: nmpc::nmpc_solve_kernel<SPT, 4><<<grid, threads, smem, st>>>(a); break;
+        case 1: nmpc::nmpc_solve_kernel<SPT, 1><<<grid, threads, smem, st>>>(a); break;
+        default: nmpc::nmpc_solve_kernel<SPT, 0><<<grid, threads, smem, st>>>(a); break;
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++;
@@ -595,11 +611,11 @@ int mpc_b200_debug_profile(mpc_b200_handle *h, long long *out12)
 #ifdef NMPC_PROFILE
     if (!h) return 0;
     if (!h->d_prof) {
-        if (cudaMalloc(&h->d_prof, sizeof(long long) * 12) != cudaSuccess) { cudaGetLastError(); return 0; }
-        cudaMemset(h->d_prof, 0, sizeof(long long) * 12);
+        if (cudaMalloc(&h->d_prof, sizeof(long long) * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cudaMemset(h->d_prof, 0, sizeof(long long) * 1024);
         return 1;
     }
-    if (out12) cudaMemcpy(out12, h->d_prof, sizeof(long long) * 12, cudaMemcpyDeviceToHost);
+    if (out12) cudaMemcpy(out12, h->d_prof, sizeof(long long) * 1024, cudaMemcpyDeviceToHost);
     return 1;
 #else
     (void)h; (void)out12;

@@ -5,12 +5,17 @@
 // lane p -- one thread per problem, 32 different problems per warp instruction (no idle lanes, no
 // shuffles in the recursions).  The other warps are stage threads: thread (g, p) owns stages
 // g*SPT .. g*SPT+SPT-1 of lane p's problem and does everything that is parallel over the horizon
-// (sin/cos, model derivatives, residual norms, line-search trial evaluation, step application).
-// All exchange goes through shared memory [stage][slot][problem]; phases are separated by CTA
-// barriers and both roles execute the same barrier sequence (B0..B9, V1, V2, R1, R2 below).
-// When a lane's problem terminates its results are written out and the lane pops the next problem
-// from the queue, so lanes never wait for the slowest problem of a batch (iteration counts range
-// from 5 to the cap).  Lanes are independent: each is at its own interior-point iteration.
+// (sin/cos, model derivatives, residual norms, trial-point evaluation, step application).
+// All exchange goes through shared memory [stage][slot][lane].
+//
+// One global cycle = the fixed phase sequence
+//   P3a apply / flush / init | P3b coefficients | P4 sweeps | P5 step work | P6 multipliers, step sizes |
+//   P1 evaluate | P2 decide
+// separated by CTA barriers; each lane is a state machine (nmpc::Mode) and takes part in the phases its
+// state asks for.  A lane that needs another factorisation (inertia correction) or a shorter trial step
+// simply repeats on the next cycle; it never stalls the other lanes.  When a lane's problem terminates,
+// its results are written out and the lane pops the next problem from the queue, so lanes never wait
+// for the slowest problem of a batch (iteration counts range from 5 to the cap).
 //
 // Replaces, per problem: CppAD::ipopt::solve + Ipopt (mpc_ros/src/mpc_planner.cpp:373-375).
 #pragma once
@@ -40,10 +45,15 @@ struct SolveArgs {
 #define PROF_DECL long long prof_t = clock64(), prof_acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}
 #define PROF_MARK(i) do { long long t_ = clock64(); prof_acc[i] += t_ - prof_t; prof_t = t_; } while (0)
 #define PROF_FLUSH() do { if (a.prof && blockIdx.x == 0 && tid == 0) for (int q_ = 0; q_ < 12; q_++) a.prof[q_] = prof_acc[q_]; } while (0)
+// raw timestamp trace of the first cycles: control thread 0 -> prof[16 + 16*cyc + i], stage thread 32 -> prof[512 + 16*cyc + i]
+#define TRACE_C(i) do { if (a.prof && blockIdx.x == 0 && tid == 0 && trace_cyc < 24) a.prof[16 + 16 * trace_cyc + (i)] = clock64(); } while (0)
+#define TRACE_S(i) do { if (a.prof && blockIdx.x == 0 && tid == 32 && trace_cyc < 24) a.prof[512 + 16 * trace_cyc + (i)] = clock64(); } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(i)
 #define PROF_FLUSH()
+#define TRACE_C(i)
+#define TRACE_S(i)
 #endif
 
 template <int SPT, int CPB>
@@ -52,11 +62,10 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;
     const int N = prm.N, PB = (CPB > 0) ? CPB : a.PB, batch = a.batch;
+    const int NG = (N + SPT - 1) / SPT;
     SmemT<CPB> sm;
-    sm.st = smem_raw;
-    sm.ps = smem_raw + (size_t)N * NSLOTS * PB;
-    sm.pi = reinterpret_cast<int *>(sm.ps + (size_t)NPS * PB);
     sm.PB = PB;
+    sm.carve(smem_raw, N, NG);
 
     const int tid = threadIdx.x;
 
@@ -66,123 +75,148 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
         const bool lane = p < PB;
         Ctrl c;
         c.status = 0; c.iter = 0; c.E0 = 0.0; c.obj = 0.0;
-        // initial problems: one queue pop for the whole CTA
-        int base = 0;
-        if (p == 0) base = atomicAdd(a.queue, PB);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane) {
-            const int idx = base + p;
-            sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_STATUS, p) = 0; sm.I(PI_LSQ, p) = 0;
-            sm.I(PI_PROB, p) = idx; sm.I(PI_NEXT, p) = (idx < batch) ? idx : -1;
-        }
-        __syncthreads();  // R1 (initial)
-        if (lane && sm.I(PI_NEXT, p) >= 0) {
-            const int idx = sm.I(PI_NEXT, p);
-            double s6[6];
-            for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + idx];
-            const double rv = a.ref_vel ? a.ref_vel[idx] : prm.ref_vel;
-            ctrl_init(prm, sm, c, p, s6, rv);
-        }
-        __syncthreads();  // R2 (initial) == B0
+        if (lane) { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_FLAGS, p) = 0; sm.I(PI_PROB, p) = -1; sm.I(PI_NEXT, p) = -1; }
+        bool fin = lane;          // every lane starts by popping a problem
         PROF_DECL;
+#ifdef NMPC_PROFILE
+        const long long prof_t0 = clock64();
+#endif
+        int trace_cyc = -1; (void)trace_cyc;
         for (;;) {
-            __syncthreads();  // B1: residual partials written
-            PROF_MARK(0);
-            int done = 0;
-            if (lane) {
-                const int md = sm.I(PI_MODE, p);
-                if (md == MODE_RESID || md == MODE_ACCEPT) {
-                    if (sm.I(PI_LSQ, p) || ctrl_check(prm, sm, c, p)) { sm.I(PI_MODE, p) = MODE_COEF; sm.P(PS_DW, p) = 0.0; }
-                    else { sm.I(PI_MODE, p) = MODE_DONE; sm.I(PI_STATUS, p) = c.status; done = 1; }
-                } else if (md == MODE_DONE) {
-                    done = 1;   // failed in the previous cycle's sweep / line search
+            trace_cyc++;
+            TRACE_C(0);
+            // ---- refill the lanes that finished (fin) from the queue
+            {
+                const unsigned m = __ballot_sync(0xffffffffu, fin);
+                int nb = 0;
+                if (p == 0 && m) nb = atomicAdd(a.queue, __popc(m));
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (fin) {
+                    int nidx = nb + __popc(m & ((1u << p) - 1u));
+                    if (nidx >= batch) nidx = -1;
+                    sm.I(PI_NEXT, p) = nidx;
+                    if (nidx >= 0) {
+                        double s6[6];
+                        for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + nidx];
+                        const double rv = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
+                        ctrl_init(prm, sm, c, p, s6, rv);
+                        sm.I(PI_MODE, p) = MODE_NEWTON;
+                        sm.I(PI_FLAGS, p) |= FL_LSQ;
+                    } else {
+                        sm.I(PI_MODE, p) = MODE_IDLE;
+                    }
                 }
+                fin = false;
             }
             PROF_MARK(1);
-            if (__syncthreads_or(done)) {  // V1: some lane finished -> flush results, refill
-                // (a lane can also be DONE because a sweep / line search failed in the previous cycle)
-                const bool fin = lane && sm.I(PI_MODE, p) == MODE_DONE;
-                if (fin) {
+            int active = 0;
+            if (lane) active = (sm.I(PI_MODE, p) != MODE_IDLE) || (sm.I(PI_FLAGS, p) & FL_FLUSH);
+            if (!__syncthreads_or(active)) break;   // B2 (vote)
+            TRACE_C(1);
+            // ---- P3a: stage threads apply / flush / init
+            __syncthreads();  // B3
+            TRACE_C(2);
+            if (lane) {   // apply / flush / init are done
+                sm.I(PI_FLAGS, p) &= ~(FL_APPLY | FL_FLUSH);
+                if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
+            }
+            // ---- P3b: stage threads write coefficients
+            __syncthreads();  // B4
+            TRACE_C(3);
+            PROF_MARK(2);
+            // ---- P4: Riccati sweeps
+            if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
+                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                const double dw = sm.P(PS_DW, p);
+                const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
+                const int okb = riccati_backward(prm, sm, p, hd);
+                PROF_MARK(3);
+                if (okb || lsq) {
+                    riccati_forward(prm, sm, p);
+                    if (dw > 0.0) c.dw_last = dw;
+                    sm.I(PI_MODE, p) = MODE_STEP;
+                } else {
+                    const double nd = next_dw(c, dw);
+                    if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_MODE, p) = MODE_FAIL; }
+                    else sm.P(PS_DW, p) = nd;       // stays MODE_NEWTON: coefficients are rewritten next cycle
+                }
+            }
+            PROF_MARK(4);
+            TRACE_C(4);
+            __syncthreads();  // B5
+            TRACE_C(5);
+            // ---- P5: stage threads, step-dependent work
+            __syncthreads();  // B6
+            TRACE_C(6);
+            PROF_MARK(5);
+            // ---- P6: multipliers, step sizes
+            if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
+                if (sm.I(PI_FLAGS, p) & FL_LSQ) {
+                    const int keep = ctrl_lsq_finish(prm, sm, p);
+                    sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
+                } else {
+                    ctrl_step(prm, sm, c, p, NG);
+                    sm.I(PI_FLAGS, p) = FL_LS;
+                }
+                sm.I(PI_MODE, p) = MODE_EVAL;
+            }
+            PROF_MARK(6);
+            TRACE_C(7);
+            __syncthreads();  // B7
+            TRACE_C(8);
+            // ---- P1: stage threads evaluate
+            __syncthreads();  // B1
+            TRACE_C(9);
+            PROF_MARK(7);
+            // ---- P2: decide
+            if (lane) {
+                const int md = sm.I(PI_MODE, p);
+                int term = 0;
+                if (md == MODE_EVAL) {
+                    const int fl = sm.I(PI_FLAGS, p);
+                    const int r = ctrl_decide(prm, sm, c, p, fl, NG);
+                    if (r == 0) {
+                        sm.I(PI_FLAGS, p) = FL_LS;
+                    } else {
+                        int nf = 0;
+                        if (fl & FL_LS) {
+                            nf = FL_APPLY;
+                            sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
+                            sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
+                            ctrl_apply(sm, p);
+                        }
+                        if (r == 1) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.P(PS_DW, p) = 0.0; sm.I(PI_FLAGS, p) = nf; }
+                        else { term = 1; sm.I(PI_FLAGS, p) = nf | FL_FLUSH; }
+                    }
+                } else if (md == MODE_FAIL) {
+                    term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
+                }
+                if (term) {
                     const size_t i = (size_t)sm.I(PI_PROB, p);
                     if (a.obj) a.obj[i] = c.obj;
                     if (a.status) a.status[i] = c.status;
                     if (a.iters) a.iters[i] = c.iter;
                     if (a.kkt) a.kkt[i] = c.E0;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, fin);
-                int nb = 0;
-                if (p == 0 && m) nb = atomicAdd(a.queue, __popc(m));
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-                int nidx = -1;
-                if (fin) { nidx = nb + __popc(m & ((1u << p) - 1u)); if (nidx >= batch) nidx = -1; }
-                if (lane) sm.I(PI_NEXT, p) = nidx;
-                __syncthreads();  // R1: results flushed by the stage threads, next problems known
-                if (fin) {
-                    if (nidx >= 0) {
-                        sm.I(PI_PROB, p) = nidx;
-                        double s6[6];
-                        for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + nidx];
-                        const double rv = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
-                        ctrl_init(prm, sm, c, p, s6, rv);
-                    } else {
-                        sm.I(PI_MODE, p) = MODE_IDLE;
+                    sm.P(PS_AP_SF, p) = sm.P(PS_SF, p);
+                    if (a.warm_out) {
+                        const size_t offl = (size_t)(8 * N - 2);
+                        for (int cc = 0; cc < 6; cc++)
+                            a.warm_out[(offl + (size_t)cc * N) * batch + i] = sm.P(PS_L0X + cc, p) / sm.P(PS_SF, p);
                     }
+                    sm.I(PI_MODE, p) = MODE_IDLE;
+                    fin = true;
                 }
-                __syncthreads();  // R2: new problems initialised
             }
-            int running = 0;
-            if (lane) running = sm.I(PI_MODE, p) != MODE_IDLE;
-            if (!__syncthreads_or(running)) break;  // V2
-            for (;;) {
-                __syncthreads();  // B3: coefficients written
-                PROF_MARK(2);
-                int retry = 0;
-                if (lane && sm.I(PI_MODE, p) == MODE_COEF) {
-                    const int lsq = sm.I(PI_LSQ, p);
-                    const double dw = sm.P(PS_DW, p);
-                    const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
-                    const int okb = riccati_backward(prm, sm, p, hd);
-                    PROF_MARK(3);
-                    if (okb || lsq) {
-                        riccati_forward(prm, sm, p);
-                        if (dw > 0.0) c.dw_last = dw;
-                        sm.I(PI_MODE, p) = MODE_STEP;
-                    } else {
-                        const double nd = next_dw(c, dw);
-                        if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_STATUS, p) = 10; sm.I(PI_MODE, p) = MODE_DONE; }
-                        else { sm.P(PS_DW, p) = nd; retry = 1; }
-                    }
-                }
-                PROF_MARK(4);
-                if (!__syncthreads_or(retry)) break;  // B4
-            }
-            __syncthreads();  // B5: step partials written
-            PROF_MARK(5);
-            if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
-                if (sm.I(PI_LSQ, p)) { ctrl_lsq_finish(prm, sm, c, p); sm.I(PI_MODE, p) = MODE_ACCEPT; }
-                else { ctrl_step(prm, sm, c, p); sm.I(PI_MODE, p) = MODE_TRIAL; }
-            }
-            PROF_MARK(6);
-            __syncthreads();  // B6
-            for (;;) {
-                __syncthreads();  // B7: trial partials written
-                PROF_MARK(7);
-                int again = 0;
-                if (lane && sm.I(PI_MODE, p) == MODE_TRIAL) {
-                    const int r = ctrl_linesearch(prm, sm, c, p);
-                    if (r == 1) sm.I(PI_MODE, p) = MODE_ACCEPT;
-                    else if (r < 0) { c.status = 9; sm.I(PI_STATUS, p) = 9; sm.I(PI_MODE, p) = MODE_DONE; }
-                    else again = 1;
-                }
-                PROF_MARK(8);
-                if (!__syncthreads_or(again)) break;  // B8
-            }
-            if (lane && sm.I(PI_MODE, p) == MODE_ACCEPT && !sm.I(PI_LSQ, p)) ctrl_accept(sm, c, p);
-            __syncthreads();  // B9: step applied
-            PROF_MARK(9);
-            if (lane) sm.I(PI_LSQ, p) = 0;
+            PROF_MARK(8);
+            TRACE_C(10);
         }
         PROF_FLUSH();
+#ifdef NMPC_PROFILE
+        if (a.prof && tid == 0) {   // all CTAs: number of global cycles and their total duration
+            atomicAdd((unsigned long long *)&a.prof[1000], (unsigned long long)(trace_cyc));
+            atomicAdd((unsigned long long *)&a.prof[1001], (unsigned long long)(clock64() - prof_t0));
+        }
+#endif
     } else {
         // ------------------------------------------------------------ stage threads
         const int t = tid - 32;
@@ -191,33 +225,22 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
         const int k0 = g * SPT;
         const bool mine = k0 < N;
         StageRegs r[SPT];
-        __syncthreads();  // R1 (initial)
-        if (mine && sm.I(PI_NEXT, p) >= 0) {
-            const int idx = sm.I(PI_NEXT, p);
-            double s6[6], c4[4];
-            for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + idx];
-            for (int i = 0; i < 4; i++) c4[i] = a.coeffs[(size_t)i * batch + idx];
-#pragma unroll
-            for (int j = 0; j < SPT; j++)
-                if (k0 + j < N) stage_init(prm, sm, r[j], k0 + j, p, s6, c4);
-        }
-        __syncthreads();  // R2 (initial) == B0
+        int trace_cyc = -1; (void)trace_cyc;
         for (;;) {
+            trace_cyc++;
+            TRACE_S(0);
+            if (!__syncthreads_or(0)) break;   // B2 (vote)
+            TRACE_S(1);
+            // ---- P3a: apply the accepted step, flush a finished problem, start the next one
             if (mine) {
-                const int md = sm.I(PI_MODE, p);
-                if (md == MODE_RESID || md == MODE_ACCEPT) {
-                    ResidPart acc;
-                    part_reset(acc);
+                const int fl = sm.I(PI_FLAGS, p);
+                if (fl & FL_APPLY) {
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_residuals(prm, sm, r[j], k0 + j, p, acc);
-                    part_store(sm, k0, p, acc);
+                        if (k0 + j < N) stage_apply(prm, sm, r[j], k0 + j, p);
                 }
-            }
-            __syncthreads();  // B1
-            if (__syncthreads_or(0)) {  // V1
-                // ---- flush the finished problem: the last iterate whatever the status (mpc_planner.cpp:378-401)
-                if (mine && sm.I(PI_MODE, p) == MODE_DONE) {
+                if (fl & FL_FLUSH) {
+                    // the last iterate whatever the status (mpc_planner.cpp:378-401)
                     const size_t i = (size_t)sm.I(PI_PROB, p);
 #pragma unroll
                     for (int j = 0; j < SPT; j++) {
@@ -231,30 +254,26 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                             // primal in the reference's variable layout (mpc_planner.cpp:232-239), then equality
                             // multipliers (row layout of :153-158, unscaled), then zL, zU of w and a.
                             double *wo = a.warm_out;
-                            const double sf = sm.P(PS_SF, p);
+                            const double isf = 1.0 / sm.P(PS_AP_SF, p);
                             for (int cc = 0; cc < 6; cc++) wo[((size_t)cc * N + k) * batch + i] = sm.at(k, S_X + cc, p);
                             const size_t offl = (size_t)(8 * N - 2);
                             if (k < N - 1) {
                                 wo[((size_t)6 * N + k) * batch + i] = r[j].uw;
                                 wo[((size_t)7 * N - 1 + k) * batch + i] = r[j].ua;
                                 for (int cc = 0; cc < 6; cc++)
-                                    wo[(offl + (size_t)cc * N + k + 1) * batch + i] = sm.at(k, L_X + cc, p) / sf;
+                                    wo[(offl + (size_t)cc * N + k + 1) * batch + i] = sm.at(k, L_X + cc, p) * isf;
                                 const size_t offz = offl + (size_t)6 * N;
                                 const int nu = N - 1;
-                                wo[(offz + k) * batch + i] = r[j].zlw / sf;
-                                wo[(offz + nu + k) * batch + i] = r[j].zla / sf;
-                                wo[(offz + 2 * nu + k) * batch + i] = r[j].zuw / sf;
-                                wo[(offz + 3 * nu + k) * batch + i] = r[j].zua / sf;
+                                wo[(offz + k) * batch + i] = r[j].zlw * isf;
+                                wo[(offz + nu + k) * batch + i] = r[j].zla * isf;
+                                wo[(offz + 2 * nu + k) * batch + i] = r[j].zuw * isf;
+                                wo[(offz + 3 * nu + k) * batch + i] = r[j].zua * isf;
                             }
-                            if (k == 0)
-                                for (int cc = 0; cc < 6; cc++)
-                                    wo[(offl + (size_t)cc * N) * batch + i] = sm.P(PS_L0X + cc, p) / sf;
                         }
                     }
                 }
-                __syncthreads();  // R1
-                if (mine && sm.I(PI_NEXT, p) >= 0) {
-                    const int idx = sm.I(PI_NEXT, p);
+                const int idx = sm.I(PI_NEXT, p);
+                if (idx >= 0) {
                     double s6[6], c4[4];
                     for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + idx];
                     for (int i = 0; i < 4; i++) c4[i] = a.coeffs[(size_t)i * batch + idx];
@@ -262,51 +281,54 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     for (int j = 0; j < SPT; j++)
                         if (k0 + j < N) stage_init(prm, sm, r[j], k0 + j, p, s6, c4);
                 }
-                __syncthreads();  // R2
             }
-            if (!__syncthreads_or(0)) break;  // V2
-            for (;;) {
-                if (mine && sm.I(PI_MODE, p) == MODE_COEF) {
-                    const int lsq = sm.I(PI_LSQ, p);
+            TRACE_S(2);
+            __syncthreads();  // B3
+            TRACE_S(3);
+            // ---- P3b: Newton-system coefficients
+            if (mine) {
+                if (sm.I(PI_MODE, p) == MODE_NEWTON) {
+                    const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
                         if (k0 + j < N) stage_coeffs(prm, sm, r[j], k0 + j, p, lsq);
                 }
-                __syncthreads();  // B3
-                if (!__syncthreads_or(0)) break;  // B4
             }
+            TRACE_S(4);
+            __syncthreads();  // B4
+            // ---- P4: control
+            __syncthreads();  // B5
+            TRACE_S(5);
+            // ---- P5: step-dependent work
             if (mine && sm.I(PI_MODE, p) == MODE_STEP) {
-                const int lsq = sm.I(PI_LSQ, p);
+                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
                 StepPart acc;
                 part_reset(acc);
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
                     if (k0 + j < N) stage_step(prm, sm, r[j], k0 + j, p, hd, lsq, acc);
-                part_store(sm, k0, p, acc);
+                part_store(sm, g, p, acc);
             }
-            __syncthreads();  // B5
+            TRACE_S(6);
             __syncthreads();  // B6
-            for (;;) {
-                if (mine && sm.I(PI_MODE, p) == MODE_TRIAL) {
-                    TrialPart acc;
-                    part_reset(acc);
-#pragma unroll
-                    for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_trial(prm, sm, r[j], k0 + j, p, acc);
-                    part_store(sm, k0, p, acc);
-                }
-                __syncthreads();  // B7
-                if (!__syncthreads_or(0)) break;  // B8
-            }
-            if (mine && sm.I(PI_MODE, p) == MODE_ACCEPT) {
-                const int lsq = sm.I(PI_LSQ, p);
-                // stage k reads ds_k from stage k-1's D slots and writes only its own S/L slots
+            // ---- P6: control
+            __syncthreads();  // B7
+            TRACE_S(7);
+            // ---- P1: evaluate
+            if (mine && sm.I(PI_MODE, p) == MODE_EVAL) {
+                const int fl = sm.I(PI_FLAGS, p);
+                EvalPart acc;
+                part_reset(acc);
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_accept(prm, sm, r[j], k0 + j, p, lsq);
+                    if (k0 + j < N) stage_eval(prm, sm, r[j], k0 + j, p, fl, acc);
+                part_store(sm, g, p, acc);
             }
-            __syncthreads();  // B9
+            TRACE_S(8);
+            __syncthreads();  // B1
+            TRACE_S(9);
+            // ---- P2: control
         }
     }
 }

@@ -4,19 +4,22 @@
 // What it replaces in the reference (OkDoky/mpc_ros):
 //   * FG_eval's CppAD-taped cost / dynamics and taped Jacobian / Hessian
 //     (mpc_ros/src/mpc_planner.cpp:102-217, cppad/ipopt/solve_callback.hpp:625-1020)
-//     -> closed-form stage derivatives (stage_eval / stage_coeffs below);
+//     -> closed-form stage derivatives (stage_eval / stage_apply_coeffs below);
 //   * Ipopt's primal-dual interior-point loop (call site cppad/ipopt/solve.hpp:586)
 //     -> the same published algorithm (Waechter & Biegler 2006, Ipopt 3.12 defaults: monotone
 //     barrier, filter line search, inertia-correcting regularisation) with the stage-wise
 //     block-tridiagonal KKT system solved by a sparsity-exploiting Riccati recursion.
 //
-// Execution model (see nmpc_kernel.cu): a CTA owns PB problems.  "Stage threads" own one
-// (problem, stage) pair each in the stage-parallel phases; one "control thread" per problem
-// (lane == problem in warp 0) runs the per-problem logic and the serial Riccati sweeps.  All
-// cross-thread data goes through the CTA's shared-memory block, indexed
-// [stage][slot][problem] so that a warp touches 32 consecutive doubles.  Phases are separated
-// by CTA barriers, which is also what lets tests/emu run the identical phase functions
-// sequentially on the host as a logic check (test-only; the product has no CPU path).
+// Execution model (see nmpc_kernel.cuh): a CTA has PB problem lanes.  "Stage threads" own a few
+// (lane, stage) pairs each in the stage-parallel phases; one "control thread" per lane (lane ==
+// thread of warp 0) runs the per-problem logic and the serial Riccati sweeps.  All cross-thread data
+// goes through the CTA's shared memory, indexed [stage][slot][lane] so that a warp touches 32
+// consecutive doubles.  Every lane is a small state machine (enum Mode); one global cycle runs the six
+// phases P1..P6 once and each lane does the work its state asks for, so a lane that needs an extra
+// factorisation (inertia correction) or a shorter trial step repeats on the next cycle without stalling
+// the other lanes.  Phases are separated by CTA barriers, which is also what lets tests/emu run the
+// identical phase functions sequentially on the host as a logic check (test-only; the product has no
+// CPU path).
 #pragma once
 
 #include <math.h>
@@ -38,32 +41,43 @@ enum Slot {
     W_0, W_1, W_2, W_3, W_4, W_5, W_6, W_7, W_8, W_9, W_10, W_11,  // work slots (see phases)
     NSLOTS
 };
+// partial sums, one set per group of stages: [group][NPART][lane]
+enum PartSlot { PT_0 = 0, PT_1, PT_2, PT_3, PT_4, PT_5, PT_6, PT_7, PT_8, NPART };
 
-// per-problem scalars shared between the control thread and the stage threads
+// per-lane scalars shared between the control thread and the stage threads
 enum PSlot {
-    PS_MU = 0, PS_TAU, PS_SF, PS_REFV, PS_ALPHA, PS_ALPHA_Z, PS_DW,
+    PS_MU = 0,     // barrier parameter of the Newton system being built / solved
+    PS_MU_STEP,    // barrier parameter the pending step was computed with (for the z update, W&B eq. (16))
+    PS_TAU, PS_SF, PS_REFV, PS_ALPHA, PS_ALPHA_Z, PS_DW,
     PS_L0X, PS_L0Y, PS_L0T, PS_L0V, PS_L0C, PS_L0E,       // lambda_0 (initial-condition rows)
     PS_N0X, PS_N0Y, PS_N0T, PS_N0V, PS_N0C, PS_N0E,       // its Newton target lambda_0^+
+    PS_AP_ALPHA, PS_AP_AZ, PS_AP_MU, PS_AP_SF,            // the step to apply in P3 (copied in P2: the lane may
+                                                          // already have been re-initialised for its next problem)
     NPS
 };
 enum PISlot {
-    PI_MODE = 0,   // what the stage threads do next (see Mode)
-    PI_STATUS,     // 0 while running, else final status
-    PI_LSQ,        // 1 during the first cycle: least-squares multiplier start (W&B eq. (36))
-    PI_PROB,       // index of the problem this lane is working on
-    PI_NEXT,       // refill: index of the problem the lane takes over next, or -1
+    PI_MODE = 0,   // lane state (enum Mode)
+    PI_FLAGS,      // enum Flag bits
+    PI_PROB,       // index of the problem in this lane
+    PI_NEXT,       // refill: index of the problem the lane takes over in P3, or -1
     NPI
 };
 
-// Per-problem phase, written by the control thread, read by the stage threads.
+// Lane state, written by the control thread, read by the stage threads.
 enum Mode {
-    MODE_IDLE = 0,      // problem finished / lane unused
-    MODE_RESID,         // evaluate residuals at the iterate (stage_residuals), then ctrl_check
-    MODE_COEF,          // write Newton-system coefficients (stage_coeffs), then the Riccati sweeps
-    MODE_STEP,          // sweeps succeeded: stage_step, then ctrl_step
-    MODE_TRIAL,         // line search: stage_trial at PS_ALPHA, then ctrl_linesearch
-    MODE_ACCEPT,        // stage_accept; doubles as MODE_RESID for the next iteration
-    MODE_DONE           // problem terminated: results are flushed, then the lane is refilled from the queue
+    MODE_IDLE = 0,   // no problem in this lane
+    MODE_EVAL,       // P1: evaluate the point iterate + alpha * step (alpha may be 0); P2: decide
+    MODE_NEWTON,     // P3: (apply the accepted step and) write the Newton-system coefficients; P4: sweeps
+    MODE_STEP,       // P5: step-dependent stage work; P6: multipliers + step-size limits
+    MODE_FAIL        // the Newton system could not be regularised: flushed at the next P2
+};
+enum Flag {
+    FL_LSQ = 1,      // the system being solved is the least-squares multiplier start (W&B eq. (36))
+    FL_APPLY = 2,    // P3 must first apply the step accepted in P2
+    FL_ADOPT = 4,    // P1 must first adopt the least-squares multipliers (or zero them)
+    FL_LS = 8,       // the point evaluated in P1 is a line-search trial (else it is accepted as is)
+    FL_FLUSH = 16,   // P3 must write this lane's finished problem out
+    FL_KEEP = 32     // with FL_ADOPT: keep the least-squares multipliers (else reset to zero)
 };
 
 struct Params {
@@ -76,30 +90,44 @@ struct Params {
     int grp;      // stages per stage thread: partial sums are pre-reduced over groups of grp stages
 };
 
-// View of the CTA's shared-memory block.  CPB > 0 fixes the problems-per-CTA at compile time so
-// that every access is base + lane*8 + immediate (no index arithmetic in the sweeps).
+#define NMPC_MAX_FILTER 8
+
+// View of the CTA's shared-memory block.  CPB > 0 fixes the lanes-per-CTA at compile time so that
+// every access is base + lane*8 + immediate (no index arithmetic in the sweeps).
 template <int CPB>
 struct SmemT {
     double *st;   // [N][NSLOTS][PB]
+    double *pt;   // [NG][NPART][PB]
     double *ps;   // [NPS][PB]
+    double *fl;   // [2*NMPC_MAX_FILTER][PB]  filter entries (theta, phi)
     int *pi;      // [NPI][PB]
     int PB;
     MPC_HD int pb() const { return CPB > 0 ? CPB : PB; }
     MPC_HD double &at(int k, int slot, int p) const { return st[(k * NSLOTS + slot) * pb() + p]; }
+    MPC_HD double &part(int g, int slot, int p) const { return pt[(g * NPART + slot) * pb() + p]; }
     MPC_HD double &P(int slot, int p) const { return ps[slot * pb() + p]; }
+    MPC_HD double &F(int slot, int p) const { return fl[slot * pb() + p]; }
     MPC_HD int &I(int slot, int p) const { return pi[slot * pb() + p]; }
+    MPC_HD void carve(double *base, int N, int NG)
+    {
+        st = base;
+        pt = st + (size_t)N * NSLOTS * pb();
+        ps = pt + (size_t)NG * NPART * pb();
+        fl = ps + (size_t)NPS * pb();
+        pi = reinterpret_cast<int *>(fl + (size_t)2 * NMPC_MAX_FILTER * pb());
+    }
 };
 typedef SmemT<0> Smem;
 
-MPC_HD size_t smem_bytes(int N, int PB)
+MPC_HD size_t smem_bytes(int N, int NG, int PB)
 {
-    return sizeof(double) * ((size_t)N * NSLOTS * PB + (size_t)NPS * PB) + sizeof(int) * (size_t)NPI * PB;
+    return sizeof(double) * ((size_t)N * NSLOTS + (size_t)NG * NPART + NPS + 2 * NMPC_MAX_FILTER) * PB +
+           sizeof(int) * (size_t)NPI * PB;
 }
 
 // Ipopt 3.12 default constants (Waechter & Biegler 2006)
 #define NMPC_KAPPA_EPS 10.0
 #define NMPC_KAPPA_MU 0.2
-#define NMPC_THETA_MU 1.5
 #define NMPC_TAU_MIN 0.99
 #define NMPC_S_MAX 100.0
 #define NMPC_GAMMA_THETA 1e-5
@@ -119,18 +147,18 @@ MPC_HD size_t smem_bytes(int N, int PB)
 #define NMPC_KW_PLUS 8.0
 #define NMPC_KW_PLUS_BAR 100.0
 #define NMPC_EPS_MACH 2.220446049250313e-16
-#define NMPC_MAX_FILTER 12
 
-// ---------------------------------------------------------------- per-(problem, stage) registers
+// ---------------------------------------------------------------- per-(lane, stage) registers
 struct StageRegs {
     double uw, ua;              // controls of this stage (k <= N-2)
     double zlw, zuw, zla, zua;  // bound multipliers of the controls (scaled problem)
-    double sn, cs, se, ce;      // sin/cos(theta_k), sin/cos(etheta_k) at the current iterate
-    double tsn, tcs, tse, tce;  // the same at the last trial point
-    double qv, qc, qe;          // objective gradient wrt (v, cte, etheta) at the current iterate
+    double sn, cs, se, ce;      // sin/cos(theta_k), sin/cos(etheta_k) at the iterate
+    double tsn, tcs, tse, tce;  // the same at the last evaluated point
+    double qv, qc, qe;          // objective gradient wrt (v, cte, etheta) at the iterate
     double hxx, htt, htv, hee, hev;  // Lagrangian-Hessian entries of this stage
     double duw, dua;            // Newton step of the controls
     double c0, c1, c2, c3;      // path polynomial coefficients
+    double ilw, iuw, ila, iua;  // reciprocals of the four bound slacks at the iterate
 };
 
 MPC_HD double fmax2(double a, double b) { return a > b ? a : b; }
@@ -161,39 +189,41 @@ MPC_HD double fast_rcp(double x)
 #endif
 }
 
-// Partial sums a stage thread accumulates over its group of stages before one shared-memory write.
-struct ResidPart { double prinf, pr1, duinf, vmax, vmin, l1, z1, f, lnsum; };
-struct StepPart { double amax, az, gd; };
-struct TrialPart { double pr1, f, lnsum; int inside; };
-MPC_HD void part_reset(ResidPart &a) { a.prinf = 0; a.pr1 = 0; a.duinf = 0; a.vmax = -1e300; a.vmin = 1e300; a.l1 = 0; a.z1 = 0; a.f = 0; a.lnsum = 0; }
-MPC_HD void part_reset(StepPart &a) { a.amax = 1.0; a.az = 1.0; a.gd = 0.0; }
-MPC_HD void part_reset(TrialPart &a) { a.pr1 = 0; a.f = 0; a.lnsum = 0; a.inside = 1; }
-template <class SM> MPC_HD void part_store(const SM &sm, int k0, int p, const ResidPart &a)
-{
-    sm.at(k0, W_0, p) = a.prinf; sm.at(k0, W_1, p) = a.pr1; sm.at(k0, W_2, p) = a.duinf;
-    sm.at(k0, W_3, p) = a.vmax; sm.at(k0, W_4, p) = a.vmin; sm.at(k0, W_5, p) = a.l1;
-    sm.at(k0, W_6, p) = a.z1; sm.at(k0, W_7, p) = a.f; sm.at(k0, W_8, p) = a.lnsum;
-}
-template <class SM> MPC_HD void part_store(const SM &sm, int k0, int p, const StepPart &a)
-{
-    sm.at(k0, W_6, p) = a.amax; sm.at(k0, W_7, p) = a.az; sm.at(k0, W_8, p) = a.gd;
-}
-template <class SM> MPC_HD void part_store(const SM &sm, int k0, int p, const TrialPart &a)
-{
-    sm.at(k0, W_0, p) = a.pr1; sm.at(k0, W_1, p) = a.f; sm.at(k0, W_2, p) = a.inside ? a.lnsum : -1e300;
-}
-
 // relaxed control bounds (Ipopt bound_relax_factor, W&B Sec. 3.5)
 MPC_HD double relaxed(double b) { return b + NMPC_BOUND_RELAX * fmax2(1.0, b); }
+// keep a bound multiplier within kappa_Sigma of mu / slack (W&B eq. (16))
+MPC_HD double zclamp(double z, double mu, double islack)
+{
+    const double c = mu * islack;
+    return fmax2(fmin2(z, NMPC_KAPPA_SIGMA * c), (1.0 / NMPC_KAPPA_SIGMA) * c);
+}
 
-// ---------------------------------------------------------------- init
-// Reference cold start (mpc_planner.cpp:288-300): zeros except stage 0 = state.
+// Partial sums of one group of stages at an evaluated point.
+struct EvalPart { double prinf, pr1, duinf, vmax, vmin, l1, z1, f, lnsum; int inside; };
+struct StepPart { double rmax, rzmax, gd; };
+MPC_HD void part_reset(EvalPart &a) { a.prinf = 0; a.pr1 = 0; a.duinf = 0; a.vmax = -1e300; a.vmin = 1e300; a.l1 = 0; a.z1 = 0; a.f = 0; a.lnsum = 0; a.inside = 1; }
+MPC_HD void part_reset(StepPart &a) { a.rmax = 0.0; a.rzmax = 0.0; a.gd = 0.0; }
+template <class SM> MPC_HD void part_store(const SM &sm, int g, int p, const EvalPart &a)
+{
+    sm.part(g, PT_0, p) = a.prinf; sm.part(g, PT_1, p) = a.pr1; sm.part(g, PT_2, p) = a.duinf;
+    sm.part(g, PT_3, p) = a.vmax; sm.part(g, PT_4, p) = a.vmin; sm.part(g, PT_5, p) = a.l1;
+    sm.part(g, PT_6, p) = a.z1; sm.part(g, PT_7, p) = a.f; sm.part(g, PT_8, p) = a.inside ? a.lnsum : -1e300;
+}
+template <class SM> MPC_HD void part_store(const SM &sm, int g, int p, const StepPart &a)
+{
+    sm.part(g, PT_0, p) = a.rmax; sm.part(g, PT_1, p) = a.rzmax; sm.part(g, PT_2, p) = a.gd;
+}
+
+// ---------------------------------------------------------------- init (new problem in a lane)
+// Reference cold start (mpc_planner.cpp:288-300): zeros except stage 0 = state; z = 1; lambda = 0.
 template <class SM>
 MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int p,
                        const double *state6, const double *coef4)
 {
     for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
     for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = 0.0;
+    for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
+    for (int c = 0; c < 12; c++) sm.at(k, W_0 + c, p) = 0.0;
     r.uw = 0.0; r.ua = 0.0;
     r.zlw = r.zuw = r.zla = r.zua = 1.0;      // bound_mult_init_val
     r.c0 = coef4[0]; r.c1 = coef4[1]; r.c2 = coef4[2]; r.c3 = coef4[3];
@@ -203,107 +233,206 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
     r.qv = r.qc = r.qe = 0.0;
     r.tsn = r.sn; r.tcs = r.cs; r.tse = r.se; r.tce = r.ce;
-    (void)prm;
+    r.ilw = r.iuw = 1.0 / relaxed(prm.max_angvel); r.ila = r.iua = 1.0 / relaxed(prm.max_throttle);
 }
 
-// ---------------------------------------------------------------- phase A1: residuals at the iterate
-// Accumulates the stage's partial sums into `acc` (stored by part_store into W_0..W_8 of the group's
-// first stage): max|c|, sum|c|, max|dual residual|, max / min complementarity product, sum|lambda|,
-// sum|z|, scaled objective part, sum of the logs of the bound slacks.
-// Also leaves d_k = -c_{k+1} in the D slots and the objective gradient in r.q*.
+// trial bound multipliers  z + alpha_z dz, clamped (W&B eq. (16)); dz from W&B eq. (12)
+MPC_HD void trial_z(const Params &prm, const StageRegs &r, double az, double mu, double uw, double ua,
+                    double &zlw, double &zuw, double &zla, double &zua)
+{
+    const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+    if (az != 0.0) {
+        zlw = r.zlw + az * (mu * r.ilw - r.zlw - r.zlw * r.ilw * r.duw);
+        zuw = r.zuw + az * (mu * r.iuw - r.zuw + r.zuw * r.iuw * r.duw);
+        zla = r.zla + az * (mu * r.ila - r.zla - r.zla * r.ila * r.dua);
+        zua = r.zua + az * (mu * r.iua - r.zua + r.zua * r.iua * r.dua);
+        zlw = zclamp(zlw, mu, fast_rcp(uw + Uw)); zuw = zclamp(zuw, mu, fast_rcp(Uw - uw));
+        zla = zclamp(zla, mu, fast_rcp(ua + Ua)); zua = zclamp(zua, mu, fast_rcp(Ua - ua));
+    } else {
+        zlw = r.zlw; zuw = r.zuw; zla = r.zla; zua = r.zua;
+    }
+}
+
+// ---------------------------------------------------------------- P1: evaluate  iterate + alpha * step
+// Everything the control thread needs to (a) run the filter line search on this point and (b), if it
+// becomes the iterate, test convergence and update mu: sum|c|, max|c|, scaled objective, log-barrier
+// sum, max|dual residual| and the extreme complementarity products with the trial multipliers
+// lambda + alpha (lambda^+ - lambda), z + alpha_z dz, plus the multiplier norms.
 template <class SM>
-MPC_HD void stage_residuals(const Params &prm, const SM &sm, StageRegs &r, int k, int p, ResidPart &acc)
+MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int flags, EvalPart &acc)
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
-    const double x = sm.at(k, S_X, p), y = sm.at(k, S_Y, p), th = sm.at(k, S_T, p);
-    const double v = sm.at(k, S_V, p), ct = sm.at(k, S_C, p), e = sm.at(k, S_E, p);
-    (void)th;
-    // objective part of this stage (mpc_planner.cpp:122-140)
+    if (flags & FL_ADOPT) {
+        // adopt the least-squares multipliers left in W_6..W_11 by the adjoint sweep (or zero them)
+        const bool keep = (flags & FL_KEEP) != 0;
+        if (k < N - 1)
+            for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = keep ? sm.at(k, W_6 + c, p) : 0.0;
+    }
+    const bool ls = (flags & FL_LS) != 0;
+    const double alpha = ls ? sm.P(PS_ALPHA, p) : 0.0;
+    const double az = ls ? sm.P(PS_ALPHA_Z, p) : 0.0;
+    const double mu = sm.P(PS_MU_STEP, p);
+    double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
+    if (k > 0 && ls) {
+        dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
+        dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
+    }
+    const double x = sm.at(k, S_X, p) + alpha * dsx, y = sm.at(k, S_Y, p) + alpha * dsy;
+    const double th = sm.at(k, S_T, p) + alpha * dst, v = sm.at(k, S_V, p) + alpha * dsv;
+    const double ct = sm.at(k, S_C, p) + alpha * dsc, e = sm.at(k, S_E, p) + alpha * dse;
+    sincos_d(th, &r.tsn, &r.tcs);
+    sincos_d(e, &r.tse, &r.tce);
+    // objective part of this stage (mpc_planner.cpp:122-140) and its gradient
     const double ec = ct - prm.ref_cte, ee = e - prm.ref_etheta, ev = v - refv;
     double f = prm.w_cte * ec * ec + prm.w_etheta * ee * ee + prm.w_vel * ev * ev;
-    r.qv = 2.0 * sf * prm.w_vel * ev;
-    r.qc = 2.0 * sf * prm.w_cte * ec;
-    r.qe = 2.0 * sf * prm.w_etheta * ee;
-    double prinf = 0.0, pr1 = 0.0, duinf = 0.0, vmax = -1e300, vmin = 1e300, l1 = 0.0, z1 = 0.0, lnsum = 0.0;
-    // lambda_k (multiplier of the constraint that defines s_k) lives in stage k-1's L slots
-    double lkx, lky, lkt, lkv, lkc, lke;
+    const double qv = 2.0 * sf * prm.w_vel * ev, qc = 2.0 * sf * prm.w_cte * ec, qe = 2.0 * sf * prm.w_etheta * ee;
+    // lambda_k (multiplier of the rows that define s_k) lives with stage k-1 (lambda_0: per-lane scalars)
+    double lkx, lky, lkt, lkv, lkc, lke, l1 = 0.0;
     if (k == 0) {
-        lkx = sm.P(PS_L0X, p); lky = sm.P(PS_L0Y, p); lkt = sm.P(PS_L0T, p);
-        lkv = sm.P(PS_L0V, p); lkc = sm.P(PS_L0C, p); lke = sm.P(PS_L0E, p);
+        if (flags & FL_ADOPT) {
+            const bool keep = (flags & FL_KEEP) != 0;
+            lkx = keep ? sm.P(PS_N0X, p) : 0.0; lky = keep ? sm.P(PS_N0Y, p) : 0.0; lkt = keep ? sm.P(PS_N0T, p) : 0.0;
+            lkv = keep ? sm.P(PS_N0V, p) : 0.0; lkc = keep ? sm.P(PS_N0C, p) : 0.0; lke = keep ? sm.P(PS_N0E, p) : 0.0;
+        } else {
+            lkx = sm.P(PS_L0X, p); lky = sm.P(PS_L0Y, p); lkt = sm.P(PS_L0T, p);
+            lkv = sm.P(PS_L0V, p); lkc = sm.P(PS_L0C, p); lke = sm.P(PS_L0E, p);
+            if (ls) {
+                lkx += alpha * (sm.P(PS_N0X, p) - lkx); lky += alpha * (sm.P(PS_N0Y, p) - lky);
+                lkt += alpha * (sm.P(PS_N0T, p) - lkt); lkv += alpha * (sm.P(PS_N0V, p) - lkv);
+                lkc += alpha * (sm.P(PS_N0C, p) - lkc); lke += alpha * (sm.P(PS_N0E, p) - lke);
+            }
+        }
         l1 += fabs(lkx) + fabs(lky) + fabs(lkt) + fabs(lkv) + fabs(lkc) + fabs(lke);
     } else {
-        lkx = sm.at(k - 1, L_X, p); lky = sm.at(k - 1, L_Y, p); lkt = sm.at(k - 1, L_T, p);
-        lkv = sm.at(k - 1, L_V, p); lkc = sm.at(k - 1, L_C, p); lke = sm.at(k - 1, L_E, p);
+        if (flags & FL_ADOPT) {
+            const bool keep = (flags & FL_KEEP) != 0;
+            lkx = keep ? sm.at(k - 1, W_6, p) : 0.0; lky = keep ? sm.at(k - 1, W_7, p) : 0.0;
+            lkt = keep ? sm.at(k - 1, W_8, p) : 0.0; lkv = keep ? sm.at(k - 1, W_9, p) : 0.0;
+            lkc = keep ? sm.at(k - 1, W_10, p) : 0.0; lke = keep ? sm.at(k - 1, W_11, p) : 0.0;
+        } else {
+            lkx = sm.at(k - 1, L_X, p); lky = sm.at(k - 1, L_Y, p); lkt = sm.at(k - 1, L_T, p);
+            lkv = sm.at(k - 1, L_V, p); lkc = sm.at(k - 1, L_C, p); lke = sm.at(k - 1, L_E, p);
+            if (ls) {
+                lkx += alpha * (sm.at(k - 1, W_6, p) - lkx); lky += alpha * (sm.at(k - 1, W_7, p) - lky);
+                lkt += alpha * (sm.at(k - 1, W_8, p) - lkt); lkv += alpha * (sm.at(k - 1, W_9, p) - lkv);
+                lkc += alpha * (sm.at(k - 1, W_10, p) - lkc); lke += alpha * (sm.at(k - 1, W_11, p) - lke);
+            }
+        }
     }
+    double prinf = 0.0, pr1 = 0.0, duinf, vmax = -1e300, vmin = 1e300, z1 = 0.0, lnsum = 0.0;
     if (k < N - 1) {
-        f += prm.w_angvel * r.uw * r.uw + prm.w_accel * r.ua * r.ua;
+        const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
+        f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
         const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
         const double dpoly = r.c1 + x * (2.0 * r.c2 + 3.0 * r.c3 * x);
+        double nx = sm.at(k + 1, S_X, p), ny = sm.at(k + 1, S_Y, p), nt = sm.at(k + 1, S_T, p);
+        double nv = sm.at(k + 1, S_V, p), nc = sm.at(k + 1, S_C, p), ne = sm.at(k + 1, S_E, p);
+        if (ls) {
+            nx += alpha * sm.at(k, D_X, p); ny += alpha * sm.at(k, D_Y, p); nt += alpha * sm.at(k, D_T, p);
+            nv += alpha * sm.at(k, D_V, p); nc += alpha * sm.at(k, D_C, p); ne += alpha * sm.at(k, D_E, p);
+        }
         // defect of the dynamics interval k -> k+1 (mpc_planner.cpp:208-215)
-        const double cx = sm.at(k + 1, S_X, p) - (x + v * r.cs * dt);
-        const double cy = sm.at(k + 1, S_Y, p) - (y + v * r.sn * dt);
-        const double cth = sm.at(k + 1, S_T, p) - (th + r.uw * dt);
-        const double cv = sm.at(k + 1, S_V, p) - (v + r.ua * dt);
-        const double cc = sm.at(k + 1, S_C, p) - ((poly - y) + v * r.se * dt);
-        const double ce_ = sm.at(k + 1, S_E, p) - (e + r.uw * dt);
-        sm.at(k, D_X, p) = -cx; sm.at(k, D_Y, p) = -cy; sm.at(k, D_T, p) = -cth;
-        sm.at(k, D_V, p) = -cv; sm.at(k, D_C, p) = -cc; sm.at(k, D_E, p) = -ce_;
+        const double cx = nx - (x + v * r.tcs * dt);
+        const double cy = ny - (y + v * r.tsn * dt);
+        const double cth = nt - (th + uw * dt);
+        const double cv = nv - (v + ua * dt);
+        const double cc = nc - ((poly - y) + v * r.tse * dt);
+        const double ce_ = ne - (e + uw * dt);
         prinf = fmax2(fmax2(fmax2(fabs(cx), fabs(cy)), fmax2(fabs(cth), fabs(cv))), fmax2(fabs(cc), fabs(ce_)));
         pr1 = fabs(cx) + fabs(cy) + fabs(cth) + fabs(cv) + fabs(cc) + fabs(ce_);
+        // trial lambda_{k+1}
+        double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mt = sm.at(k, L_T, p);
+        double mv = sm.at(k, L_V, p), mc = sm.at(k, L_C, p), me = sm.at(k, L_E, p);
+        if (ls) {
+            mx += alpha * (sm.at(k, W_6, p) - mx); my += alpha * (sm.at(k, W_7, p) - my);
+            mt += alpha * (sm.at(k, W_8, p) - mt); mv += alpha * (sm.at(k, W_9, p) - mv);
+            mc += alpha * (sm.at(k, W_10, p) - mc); me += alpha * (sm.at(k, W_11, p) - me);
+        }
         // stationarity wrt s_k:  grad f + lambda_k - A_k^T lambda_{k+1}
-        const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mt = sm.at(k, L_T, p);
-        const double mv = sm.at(k, L_V, p), mc = sm.at(k, L_C, p), me = sm.at(k, L_E, p);
-        const double a13 = -v * r.sn * dt, a14 = r.cs * dt, a23 = v * r.cs * dt, a24 = r.sn * dt;
-        const double a51 = dpoly, a54 = r.se * dt, a56 = v * r.ce * dt;
+        const double a13 = -v * r.tsn * dt, a14 = r.tcs * dt, a23 = v * r.tcs * dt, a24 = r.tsn * dt;
+        const double a51 = dpoly, a54 = r.tse * dt, a56 = v * r.tce * dt;
         const double rx = lkx - (mx + a51 * mc);
         const double ry = lky - (my - mc);
         const double rt = lkt - (a13 * mx + a23 * my + mt);
-        const double rv = r.qv + lkv - (a14 * mx + a24 * my + mv + a54 * mc);
-        const double rc = r.qc + lkc;
-        const double re = r.qe + lke - (a56 * mc + me);
+        const double rv = qv + lkv - (a14 * mx + a24 * my + mv + a54 * mc);
+        const double rc = qc + lkc;
+        const double re = qe + lke - (a56 * mc + me);
         // stationarity wrt u_k:  grad f - B^T lambda_{k+1} - zL + zU
-        const double rw = 2.0 * sf * prm.w_angvel * r.uw - dt * (mt + me) - r.zlw + r.zuw;
-        const double ra = 2.0 * sf * prm.w_accel * r.ua - dt * mv - r.zla + r.zua;
+        double zlw, zuw, zla, zua;
+        trial_z(prm, r, az, mu, uw, ua, zlw, zuw, zla, zua);
+        const double rw = 2.0 * sf * prm.w_angvel * uw - dt * (mt + me) - zlw + zuw;
+        const double ra = 2.0 * sf * prm.w_accel * ua - dt * mv - zla + zua;
         duinf = fmax2(fmax2(fmax2(fabs(rx), fabs(ry)), fmax2(fabs(rt), fabs(rv))),
                       fmax2(fmax2(fabs(rc), fabs(re)), fmax2(fabs(rw), fabs(ra))));
         l1 += fabs(mx) + fabs(my) + fabs(mt) + fabs(mv) + fabs(mc) + fabs(me);
-        z1 = r.zlw + r.zuw + r.zla + r.zua;
+        z1 = zlw + zuw + zla + zua;
         const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
-        const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
-        const double p1 = slw * r.zlw, p2 = suw * r.zuw, p3 = sla * r.zla, p4 = sua * r.zua;
+        const double slw = uw + Uw, suw = Uw - uw, sla = ua + Ua, sua = Ua - ua;
+        const double p1 = slw * zlw, p2 = suw * zuw, p3 = sla * zla, p4 = sua * zua;
         vmax = fmax2(fmax2(p1, p2), fmax2(p3, p4));
         vmin = fmin2(fmin2(p1, p2), fmin2(p3, p4));
-        lnsum = log((slw * suw) * (sla * sua));
+        if (slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0) lnsum = log((slw * suw) * (sla * sua));
+        else acc.inside = 0;
     } else {
         // last stage: no dynamics, no control
-        const double rx = lkx, ry = lky, rt = lkt, rv = r.qv + lkv, rc = r.qc + lkc, re = r.qe + lke;
-        duinf = fmax2(fmax2(fmax2(fabs(rx), fabs(ry)), fmax2(fabs(rt), fabs(rv))), fmax2(fabs(rc), fabs(re)));
+        const double rv = qv + lkv, rc = qc + lkc, re = qe + lke;
+        duinf = fmax2(fmax2(fmax2(fabs(lkx), fabs(lky)), fmax2(fabs(lkt), fabs(rv))), fmax2(fabs(rc), fabs(re)));
     }
     acc.prinf = fmax2(acc.prinf, prinf); acc.pr1 += pr1; acc.duinf = fmax2(acc.duinf, duinf);
     acc.vmax = fmax2(acc.vmax, vmax); acc.vmin = fmin2(acc.vmin, vmin); acc.l1 += l1;
     acc.z1 += z1; acc.f += sf * f; acc.lnsum += lnsum;
 }
 
-// ---------------------------------------------------------------- phase A2: Newton-system coefficients
-// Writes A_k and the work slots  W_0 qv, W_1 qc, W_2 qe, W_3 qw, W_4 qa, W_5 hxx, W_6 htt,
-// W_7 htv, W_8 hee, W_9 hev, W_10 rw, W_11 ra  for the Riccati sweep.
-// lsq != 0: the least-squares multiplier system (identity Hessian, zero defect).
+// ---------------------------------------------------------------- P3: apply the accepted step, write coefficients
+// With FL_APPLY: s += alpha ds, lambda += alpha (lambda^+ - lambda), u, z updated (W&B A-6); the sin/cos of
+// the point evaluated in P1 become the iterate's.  Then writes A_k, d_k and the work slots
+//   W_0 qv, W_1 qc, W_2 qe, W_3 qw, W_4 qa, W_5 hxx, W_6 htt, W_7 htv, W_8 hee, W_9 hev, W_10 rw, W_11 ra
+// for the Riccati sweep.  FL_LSQ: the least-squares multiplier system (identity Hessian, zero defect).
+// Must be called for ALL stages of a lane before any stage's coefficients are written when FL_APPLY is
+// set (stage k reads stage k-1's D slots and stage k+1's S slots): the caller runs apply for its whole
+// group first (apply==1), synchronises the CTA, then calls again with apply==0.
+template <class SM>
+MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, int p)
+{
+    const int N = prm.N;
+    const double alpha = sm.P(PS_AP_ALPHA, p), az = sm.P(PS_AP_AZ, p), mu = sm.P(PS_AP_MU, p);
+    if (k > 0)
+        for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) += alpha * sm.at(k - 1, D_X + c, p);
+    if (k < N - 1) {
+        for (int c = 0; c < 6; c++) {
+            const double l = sm.at(k, L_X + c, p);
+            sm.at(k, L_X + c, p) = l + alpha * (sm.at(k, W_6 + c, p) - l);
+        }
+        const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
+        double zlw, zuw, zla, zua;
+        trial_z(prm, r, az, mu, uw, ua, zlw, zuw, zla, zua);
+        r.uw = uw; r.ua = ua; r.zlw = zlw; r.zuw = zuw; r.zla = zla; r.zua = zua;
+    }
+    r.sn = r.tsn; r.cs = r.tcs; r.se = r.tse; r.ce = r.tce;
+}
+
 template <class SM>
 MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq)
 {
     const int N = prm.N;
-    const double sf = sm.P(PS_SF, p), mu = sm.P(PS_MU, p), dt = prm.dt;
-    const double x = sm.at(k, S_X, p), v = sm.at(k, S_V, p);
+    const double sf = sm.P(PS_SF, p), mu = sm.P(PS_MU, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
+    const double x = sm.at(k, S_X, p), y = sm.at(k, S_Y, p), th = sm.at(k, S_T, p);
+    const double v = sm.at(k, S_V, p), ct = sm.at(k, S_C, p), e = sm.at(k, S_E, p);
+    r.qv = 2.0 * sf * prm.w_vel * (v - refv);
+    r.qc = 2.0 * sf * prm.w_cte * (ct - prm.ref_cte);
+    r.qe = 2.0 * sf * prm.w_etheta * (e - prm.ref_etheta);
     if (k < N - 1) {
+        const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
         const double dpoly = r.c1 + x * (2.0 * r.c2 + 3.0 * r.c3 * x);
         const double ddpoly = 2.0 * r.c2 + 6.0 * r.c3 * x;
         sm.at(k, A_13, p) = -v * r.sn * dt; sm.at(k, A_14, p) = r.cs * dt;
         sm.at(k, A_23, p) = v * r.cs * dt;  sm.at(k, A_24, p) = r.sn * dt;
         sm.at(k, A_51, p) = dpoly; sm.at(k, A_54, p) = r.se * dt; sm.at(k, A_56, p) = v * r.ce * dt;
         const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
-        const double ilw = 1.0 / (r.uw + Uw), iuw = 1.0 / (Uw - r.uw);
-        const double ila = 1.0 / (r.ua + Ua), iua = 1.0 / (Ua - r.ua);
+        const double ilw = fast_rcp(r.uw + Uw), iuw = fast_rcp(Uw - r.uw);
+        const double ila = fast_rcp(r.ua + Ua), iua = fast_rcp(Ua - r.ua);
+        r.ilw = ilw; r.iuw = iuw; r.ila = ila; r.iua = iua;
         const double gw = 2.0 * sf * prm.w_angvel * r.uw, ga = 2.0 * sf * prm.w_accel * r.ua;
         if (lsq) {
             r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
@@ -312,6 +441,13 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             sm.at(k, W_10, p) = 1.0; sm.at(k, W_11, p) = 1.0;
             for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
         } else {
+            // d_k = -(s_{k+1} - phi(s_k, u_k))  (mpc_planner.cpp:208-215)
+            sm.at(k, D_X, p) = (x + v * r.cs * dt) - sm.at(k + 1, S_X, p);
+            sm.at(k, D_Y, p) = (y + v * r.sn * dt) - sm.at(k + 1, S_Y, p);
+            sm.at(k, D_T, p) = (th + r.uw * dt) - sm.at(k + 1, S_T, p);
+            sm.at(k, D_V, p) = (v + r.ua * dt) - sm.at(k + 1, S_V, p);
+            sm.at(k, D_C, p) = ((poly - y) + v * r.se * dt) - sm.at(k + 1, S_C, p);
+            sm.at(k, D_E, p) = (e + r.uw * dt) - sm.at(k + 1, S_E, p);
             const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mc = sm.at(k, L_C, p);
             // second derivatives of the constraint rows weighted by lambda_{k+1}
             r.hxx = -mc * ddpoly;
@@ -331,7 +467,7 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
 }
 
 // ---------------------------------------------------------------- Riccati sweeps (control thread)
-// Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}.
+// Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}, u.
 struct HessDiag { double dx, dy, dt_, dv, dc, de, du; };
 
 // Coefficients of one stage as the backward sweep consumes them.
@@ -506,42 +642,35 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p)
     }
 }
 
-// ---------------------------------------------------------------- phase C: step-dependent stage work
+// ---------------------------------------------------------------- P5: step-dependent stage work
 // Reads ds_k, du_k; writes g_k = q_s + Q_k ds_k into W_0..W_5 and accumulates the partials
-// (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`
-// (stored by part_store into W_6..W_8 of the group's first stage AFTER all of the group's g_k).
+// (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`.
 template <class SM>
 MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq,
                        StepPart &acc)
 {
     const int N = prm.N;
-    const double mu = sm.P(PS_MU, p), tau = sm.P(PS_TAU, p), sf = sm.P(PS_SF, p);
+    const double mu = sm.P(PS_MU, p), sf = sm.P(PS_SF, p);
     double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
     if (k > 0) {
         dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
         dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
     }
-    double amax = 1.0, az = 1.0, gd = r.qv * dsv + r.qc * dsc + r.qe * dse;
+    // fraction to the boundary (W&B eq. (15)) as the largest step / slack ratio: alpha_max = min(1, tau / ratio)
+    double rmax = 0.0, rzmax = 0.0, gd = r.qv * dsv + r.qc * dsc + r.qe * dse;
     if (k < N - 1) {
         r.duw = sm.at(k, W_10, p); r.dua = sm.at(k, W_11, p);
         if (!lsq) {
-            const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
-            const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
-            // fraction to the boundary (W&B eq. (15))
-            if (r.duw < 0.0) amax = fmin2(amax, -tau * slw / r.duw);
-            if (r.duw > 0.0) amax = fmin2(amax, tau * suw / r.duw);
-            if (r.dua < 0.0) amax = fmin2(amax, -tau * sla / r.dua);
-            if (r.dua > 0.0) amax = fmin2(amax, tau * sua / r.dua);
-            const double dzlw = mu / slw - r.zlw - r.zlw / slw * r.duw;
-            const double dzuw = mu / suw - r.zuw + r.zuw / suw * r.duw;
-            const double dzla = mu / sla - r.zla - r.zla / sla * r.dua;
-            const double dzua = mu / sua - r.zua + r.zua / sua * r.dua;
-            if (dzlw < 0.0) az = fmin2(az, -tau * r.zlw / dzlw);
-            if (dzuw < 0.0) az = fmin2(az, -tau * r.zuw / dzuw);
-            if (dzla < 0.0) az = fmin2(az, -tau * r.zla / dzla);
-            if (dzua < 0.0) az = fmin2(az, -tau * r.zua / dzua);
-            const double gw = 2.0 * sf * prm.w_angvel * r.uw - mu / slw + mu / suw;
-            const double ga = 2.0 * sf * prm.w_accel * r.ua - mu / sla + mu / sua;
+            rmax = fmax2(fmax2(-r.duw * r.ilw, r.duw * r.iuw), fmax2(-r.dua * r.ila, r.dua * r.iua));
+            const double mlw = mu * r.ilw, muw = mu * r.iuw, mla = mu * r.ila, mua = mu * r.iua;
+            const double dzlw = mlw - r.zlw - r.zlw * r.ilw * r.duw;
+            const double dzuw = muw - r.zuw + r.zuw * r.iuw * r.duw;
+            const double dzla = mla - r.zla - r.zla * r.ila * r.dua;
+            const double dzua = mua - r.zua + r.zua * r.iua * r.dua;
+            rzmax = fmax2(fmax2(-dzlw * fast_rcp(r.zlw), -dzuw * fast_rcp(r.zuw)),
+                          fmax2(-dzla * fast_rcp(r.zla), -dzua * fast_rcp(r.zua)));
+            const double gw = 2.0 * sf * prm.w_angvel * r.uw - mlw + muw;
+            const double ga = 2.0 * sf * prm.w_accel * r.ua - mla + mua;
             gd += gw * r.duw + ga * r.dua;
         }
     }
@@ -552,7 +681,7 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
     sm.at(k, W_3, p) = r.qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
     sm.at(k, W_4, p) = r.qc + hd.dc * dsc;
     sm.at(k, W_5, p) = r.qe + r.hev * dsv + (hd.de + r.hee) * dse;
-    acc.amax = fmin2(acc.amax, amax); acc.az = fmin2(acc.az, az); acc.gd += gd;
+    acc.rmax = fmax2(acc.rmax, rmax); acc.rzmax = fmax2(acc.rzmax, rzmax); acc.gd += gd;
 }
 
 // Adjoint sweep (control thread): lambda_k^+ = A_k^T lambda_{k+1}^+ - g_k, k = N-1 .. 0.
@@ -581,111 +710,19 @@ MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
     sm.P(PS_N0V, p) = lv; sm.P(PS_N0C, p) = lc; sm.P(PS_N0E, p) = le;
 }
 
-// ---------------------------------------------------------------- phase E1: trial point
-// Evaluates the trial iterate s + alpha ds, u + alpha du; accumulates sum|c|, the scaled objective
-// part and the sum of the logs of the bound slacks (flag `inside` cleared if a bound is crossed).
-template <class SM>
-MPC_HD void stage_trial(const Params &prm, const SM &sm, StageRegs &r, int k, int p, TrialPart &acc)
-{
-    const int N = prm.N;
-    const double alpha = sm.P(PS_ALPHA, p), sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
-    double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
-    if (k > 0) {
-        dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
-        dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
-    }
-    const double x = sm.at(k, S_X, p) + alpha * dsx, y = sm.at(k, S_Y, p) + alpha * dsy;
-    const double th = sm.at(k, S_T, p) + alpha * dst, v = sm.at(k, S_V, p) + alpha * dsv;
-    const double ct = sm.at(k, S_C, p) + alpha * dsc, e = sm.at(k, S_E, p) + alpha * dse;
-    sincos_d(th, &r.tsn, &r.tcs);
-    sincos_d(e, &r.tse, &r.tce);
-    const double ec = ct - prm.ref_cte, ee = e - prm.ref_etheta, ev = v - refv;
-    double f = prm.w_cte * ec * ec + prm.w_etheta * ee * ee + prm.w_vel * ev * ev;
-    double pr1 = 0.0, lnsum = 0.0;
-    if (k < N - 1) {
-        const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
-        f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
-        const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
-        const double nx = sm.at(k + 1, S_X, p) + alpha * sm.at(k, D_X, p);
-        const double ny = sm.at(k + 1, S_Y, p) + alpha * sm.at(k, D_Y, p);
-        const double nt = sm.at(k + 1, S_T, p) + alpha * sm.at(k, D_T, p);
-        const double nv = sm.at(k + 1, S_V, p) + alpha * sm.at(k, D_V, p);
-        const double nc = sm.at(k + 1, S_C, p) + alpha * sm.at(k, D_C, p);
-        const double ne = sm.at(k + 1, S_E, p) + alpha * sm.at(k, D_E, p);
-        const double cx = nx - (x + v * r.tcs * dt);
-        const double cy = ny - (y + v * r.tsn * dt);
-        const double cth = nt - (th + uw * dt);
-        const double cv = nv - (v + ua * dt);
-        const double cc = nc - ((poly - y) + v * r.tse * dt);
-        const double ce_ = ne - (e + uw * dt);
-        pr1 = fabs(cx) + fabs(cy) + fabs(cth) + fabs(cv) + fabs(cc) + fabs(ce_);
-        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
-        const double slw = uw + Uw, suw = Uw - uw, sla = ua + Ua, sua = Ua - ua;
-        if (slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0)
-            lnsum = log((slw * suw) * (sla * sua));
-        else
-            acc.inside = 0;
-    }
-    acc.pr1 += pr1; acc.f += sf * f; acc.lnsum += lnsum;
-}
-
-// ---------------------------------------------------------------- phase F: accept the step
-template <class SM>
-MPC_HD void stage_accept(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq)
-{
-    const int N = prm.N;
-    if (lsq) {
-        // adopt the least-squares multipliers (or zero if too large; decided by the control thread
-        // through PS_ALPHA = 1 / 0)
-        const double keep = sm.P(PS_ALPHA, p);
-        if (k < N - 1)
-            for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = (keep != 0.0) ? sm.at(k, W_6 + c, p) : 0.0;
-        return;
-    }
-    const double alpha = sm.P(PS_ALPHA, p), az = sm.P(PS_ALPHA_Z, p), mu = sm.P(PS_MU, p);
-    if (k > 0)
-        for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) += alpha * sm.at(k - 1, D_X + c, p);
-    if (k < N - 1) {
-        for (int c = 0; c < 6; c++) {
-            const double l = sm.at(k, L_X + c, p);
-            sm.at(k, L_X + c, p) = l + alpha * (sm.at(k, W_6 + c, p) - l);
-        }
-        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
-        {
-            const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
-            r.zlw += az * (mu / slw - r.zlw - r.zlw / slw * r.duw);
-            r.zuw += az * (mu / suw - r.zuw + r.zuw / suw * r.duw);
-            r.zla += az * (mu / sla - r.zla - r.zla / sla * r.dua);
-            r.zua += az * (mu / sua - r.zua + r.zua / sua * r.dua);
-        }
-        r.uw += alpha * r.duw; r.ua += alpha * r.dua;
-        {
-            // keep the multipliers within kappa_Sigma of mu / slack (W&B eq. (16))
-            const double slw = r.uw + Uw, suw = Uw - r.uw, sla = r.ua + Ua, sua = Ua - r.ua;
-            r.zlw = fmax2(fmin2(r.zlw, NMPC_KAPPA_SIGMA * mu / slw), mu / (NMPC_KAPPA_SIGMA * slw));
-            r.zuw = fmax2(fmin2(r.zuw, NMPC_KAPPA_SIGMA * mu / suw), mu / (NMPC_KAPPA_SIGMA * suw));
-            r.zla = fmax2(fmin2(r.zla, NMPC_KAPPA_SIGMA * mu / sla), mu / (NMPC_KAPPA_SIGMA * sla));
-            r.zua = fmax2(fmin2(r.zua, NMPC_KAPPA_SIGMA * mu / sua), mu / (NMPC_KAPPA_SIGMA * sua));
-        }
-    }
-    r.sn = r.tsn; r.cs = r.tcs; r.se = r.tse; r.ce = r.tce;
-}
-
 // ---------------------------------------------------------------- control thread state + logic
+// Scalars only (lives in registers); the filter entries are in shared memory (sm.F).
 struct Ctrl {
     int iter;
     int status;
     int n_accept;          // consecutive "acceptable" iterations
     int nfilt;
-    int armijo;            // the pending accepted step is an Armijo (f-type) step
-    int ls_first;
-    int lsq_pending;
+    int have_theta0;
     double dw_last;
-    double theta0, theta_min, theta_max;
+    double theta_min, theta_max;
     double theta, phi, gd;          // at the current iterate, for the line search
     double alpha_min, sw_log;
     double E0, obj;
-    double fth[NMPC_MAX_FILTER], fph[NMPC_MAX_FILTER];
 };
 
 MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
@@ -713,76 +750,111 @@ MPC_HD double objective_scaling(const Params &prm, const double *state6, double 
     return g > 100.0 ? 100.0 / g : 1.0;
 }
 
+// New problem in lane p: the first cycle solves the least-squares multiplier system.
 template <class SM>
 MPC_HD void ctrl_init(const Params &prm, const SM &sm, Ctrl &c, int p, const double *state6, double refv)
 {
-    c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.armijo = 0; c.ls_first = 1; c.lsq_pending = 1;
-    c.dw_last = 0.0; c.theta0 = 0.0; c.theta_min = 0.0; c.theta_max = 0.0; c.theta = 0.0; c.phi = 0.0; c.gd = 0.0;
+    c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.have_theta0 = 0;
+    c.dw_last = 0.0; c.theta_min = 0.0; c.theta_max = 0.0; c.theta = 0.0; c.phi = 0.0; c.gd = 0.0;
     c.alpha_min = 0.0; c.sw_log = 0.0; c.E0 = 1e300; c.obj = 0.0;
     sm.P(PS_MU, p) = NMPC_MU_INIT;
+    sm.P(PS_MU_STEP, p) = NMPC_MU_INIT;
     sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - NMPC_MU_INIT);
     sm.P(PS_SF, p) = objective_scaling(prm, state6, refv);
     sm.P(PS_REFV, p) = refv;
     sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; sm.P(PS_DW, p) = 0.0;
     for (int i = 0; i < 6; i++) { sm.P(PS_L0X + i, p) = 0.0; sm.P(PS_N0X + i, p) = 0.0; }
-    sm.I(PI_MODE, p) = MODE_RESID;
-    sm.I(PI_STATUS, p) = 0;
-    sm.I(PI_LSQ, p) = 1;
 }
 
-MPC_HD int filter_acceptable(const Ctrl &c, double theta, double phi)
+template <class SM>
+MPC_HD int filter_acceptable(const SM &sm, const Ctrl &c, int p, double theta, double phi)
 {
     if (!(theta < c.theta_max)) return 0;
     for (int i = 0; i < c.nfilt; i++)
-        if (theta >= c.fth[i] && phi >= c.fph[i]) return 0;
+        if (theta >= sm.F(2 * i, p) && phi >= sm.F(2 * i + 1, p)) return 0;
     return 1;
 }
 
-MPC_HD void filter_add(Ctrl &c, double theta, double phi)
+template <class SM>
+MPC_HD void filter_add(const SM &sm, Ctrl &c, int p, double theta, double phi)
 {
     const double th = (1.0 - NMPC_GAMMA_THETA) * theta, ph = phi - NMPC_GAMMA_PHI * theta;
-    if (c.nfilt < NMPC_MAX_FILTER) { c.fth[c.nfilt] = th; c.fph[c.nfilt] = ph; c.nfilt++; }
+    int j = c.nfilt;
+    if (j < NMPC_MAX_FILTER) c.nfilt++;
     else {
         // full: overwrite the entry that dominates least (largest theta)
-        int j = 0;
-        for (int i = 1; i < NMPC_MAX_FILTER; i++) if (c.fth[i] > c.fth[j]) j = i;
-        c.fth[j] = th; c.fph[j] = ph;
+        j = 0;
+        for (int i = 1; i < NMPC_MAX_FILTER; i++) if (sm.F(2 * i, p) > sm.F(2 * j, p)) j = i;
     }
+    sm.F(2 * j, p) = th; sm.F(2 * j + 1, p) = ph;
 }
 
-// Phase B: reduce the residual partials, test convergence, update mu.  Returns 1 when the problem
-// continues with a Newton step, 0 when it has terminated (status set).
+// P2: the point evaluated in P1.  Line-search trial (FL_LS): filter test (W&B A-5); a rejected trial
+// halves alpha and is evaluated again next cycle.  An accepted point (or a plain evaluation) becomes the
+// iterate: convergence test (W&B eq. (5), (6)) and monotone barrier update (eq. (7)).
+// Returns: 0 = evaluate again (alpha halved), 1 = iterate accepted, continue with a Newton step,
+//          2 = terminated (c.status set; the step, if any, still has to be applied before flushing).
 template <class SM>
-MPC_HD int ctrl_check(const Params &prm, const SM &sm, Ctrl &c, int p)
+MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flags, int NG)
 {
     const int N = prm.N;
     double prinf = 0, pr1 = 0, duinf = 0, vmax = -1e300, vmin = 1e300, l1 = 0, z1 = 0, f = 0, lnsum = 0;
-    for (int k = 0; k < N; k += prm.grp) {
-        prinf = fmax2(prinf, sm.at(k, W_0, p)); pr1 += sm.at(k, W_1, p);
-        duinf = fmax2(duinf, sm.at(k, W_2, p));
-        vmax = fmax2(vmax, sm.at(k, W_3, p)); vmin = fmin2(vmin, sm.at(k, W_4, p));
-        l1 += sm.at(k, W_5, p); z1 += sm.at(k, W_6, p); f += sm.at(k, W_7, p); lnsum += sm.at(k, W_8, p);
+    int inside = 1;
+    for (int g = 0; g < NG; g++) {
+        prinf = fmax2(prinf, sm.part(g, PT_0, p)); pr1 += sm.part(g, PT_1, p);
+        duinf = fmax2(duinf, sm.part(g, PT_2, p));
+        vmax = fmax2(vmax, sm.part(g, PT_3, p)); vmin = fmin2(vmin, sm.part(g, PT_4, p));
+        l1 += sm.part(g, PT_5, p); z1 += sm.part(g, PT_6, p); f += sm.part(g, PT_7, p);
+        const double l = sm.part(g, PT_8, p);
+        if (l <= -1e299) inside = 0; else lnsum += l;
     }
     double mu = sm.P(PS_MU, p);
     const double sf = sm.P(PS_SF, p);
+    if (flags & FL_LS) {
+        const double alpha = sm.P(PS_ALPHA, p);
+        const double phi_t = f - mu * lnsum;
+        const double th = c.theta, phi = c.phi, gd = c.gd;
+        const int ok = inside && (pr1 == pr1) && (phi_t == phi_t);
+        int acc = 0, armijo = 0;
+        if (ok && filter_acceptable(sm, c, p, pr1, phi_t)) {
+            if (th <= c.theta_min && gd < 0.0 && log(alpha) > c.sw_log) {
+                if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; armijo = 1; }
+            } else {
+                if (pr1 <= (1.0 - NMPC_GAMMA_THETA) * th ||
+                    phi_t - 10.0 * NMPC_EPS_MACH * fabs(phi) <= phi - NMPC_GAMMA_PHI * th) acc = 1;
+            }
+        }
+        if (!acc) {
+            const double a2 = 0.5 * alpha;
+            if (a2 < c.alpha_min) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; return 2; }
+            sm.P(PS_ALPHA, p) = a2;
+            return 0;
+        }
+        if (!armijo) filter_add(sm, c, p, th, phi);
+        c.iter++;
+    }
+    // ---- the evaluated point is now the iterate
     const int m = 6 * N, nb = 4 * (N - 1);
-    const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) / NMPC_S_MAX;
-    const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) / NMPC_S_MAX;
+    const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) * (1.0 / NMPC_S_MAX);
+    const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) * (1.0 / NMPC_S_MAX);
+    const double isd = 1.0 / s_d, isc = 1.0 / s_c, isf = 1.0 / sf;
     const double compl0 = fmax2(fabs(vmax), fabs(vmin));
-    const double E0 = fmax2(fmax2(duinf / s_d, prinf), compl0 / s_c);
-    c.E0 = E0; c.obj = f / sf;
-    if (!(E0 == E0) || !(f == f)) { c.status = 11; return 0; }
-    if (E0 <= prm.tol && duinf / sf <= 1.0 && prinf <= 1e-4 && compl0 / sf <= 1e-4) { c.status = 1; return 0; }
-    if (E0 <= 1e-6 && prinf <= 1e-2 && compl0 / sf <= 1e-2) c.n_accept++; else c.n_accept = 0;
-    if (c.n_accept >= 15) { c.status = 4; return 0; }
-    if (c.iter >= prm.max_iter) { c.status = 2; return 0; }
+    const double du_s = duinf * isd;
+    const double E0 = fmax2(fmax2(du_s, prinf), compl0 * isc);
+    c.E0 = E0; c.obj = f * isf;
+    if (!(E0 == E0) || !(f == f)) { c.status = 11; return 2; }
+    if (E0 <= prm.tol && duinf * isf <= 1.0 && prinf <= 1e-4 && compl0 * isf <= 1e-4) { c.status = 1; return 2; }
+    if (E0 <= 1e-6 && prinf <= 1e-2 && compl0 * isf <= 1e-2) c.n_accept++; else c.n_accept = 0;
+    if (c.n_accept >= 15) { c.status = 4; return 2; }
+    if (c.iter >= prm.max_iter) { c.status = 2; return 2; }
     // monotone barrier update (W&B eq. (7)); repeated while the barrier problem is already solved
     int changed = 0;
+    const double base_err = fmax2(du_s, prinf);
+    const double floor_ = fmin2(prm.tol, 1e-4) * (1.0 / (NMPC_KAPPA_EPS + 1.0));
     for (;;) {
         const double cmu = fmax2(fabs(vmax - mu), fabs(vmin - mu));
-        const double Emu = fmax2(fmax2(duinf / s_d, prinf), cmu / s_c);
+        const double Emu = fmax2(base_err, cmu * isc);
         if (!(Emu <= NMPC_KAPPA_EPS * mu)) break;
-        const double floor_ = fmin2(prm.tol, 1e-4) / (NMPC_KAPPA_EPS + 1.0);
         const double mun = fmax2(floor_, fmin2(NMPC_KAPPA_MU * mu, mu * sqrt(mu)));   // theta_mu = 1.5
         if (!(mun < mu)) break;
         mu = mun; changed = 1;
@@ -794,8 +866,8 @@ MPC_HD int ctrl_check(const Params &prm, const SM &sm, Ctrl &c, int p)
     }
     c.theta = pr1;
     c.phi = f - mu * lnsum;
-    if (c.iter == 0 && c.theta_max == 0.0) {
-        c.theta0 = pr1;
+    if (!c.have_theta0) {
+        c.have_theta0 = 1;
         c.theta_max = 1e4 * fmax2(1.0, pr1);
         c.theta_min = 1e-4 * fmax2(1.0, pr1);
     }
@@ -809,16 +881,18 @@ MPC_HD double next_dw(const Ctrl &c, double dw)
     return (c.dw_last == 0.0) ? NMPC_KW_PLUS_BAR * dw : NMPC_KW_PLUS * dw;
 }
 
-// Phase D: after the step is known.  Reduces the step partials, runs the adjoint sweep, sets
-// up the line search.  Leaves PS_ALPHA (first trial) and PS_ALPHA_Z.
+// P6: after the step is known.  Reduces the step partials, runs the adjoint sweep, sets up the line
+// search.  Leaves PS_ALPHA (first trial), PS_ALPHA_Z and PS_MU_STEP.
 template <class SM>
-MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p)
+MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
 {
-    const int N = prm.N;
-    double amax = 1.0, az = 1.0, gd = 0.0;
-    for (int k = 0; k < N; k += prm.grp) {
-        amax = fmin2(amax, sm.at(k, W_6, p)); az = fmin2(az, sm.at(k, W_7, p)); gd += sm.at(k, W_8, p);
+    double rmax = 0.0, rzmax = 0.0, gd = 0.0;
+    for (int g = 0; g < NG; g++) {
+        rmax = fmax2(rmax, sm.part(g, PT_0, p)); rzmax = fmax2(rzmax, sm.part(g, PT_1, p)); gd += sm.part(g, PT_2, p);
     }
+    const double tau = sm.P(PS_TAU, p);
+    const double amax = (rmax > tau) ? tau / rmax : 1.0;      // fraction to the boundary, W&B eq. (15)
+    const double az = (rzmax > tau) ? tau / rzmax : 1.0;
     adjoint_sweep(prm, sm, p);
     c.gd = gd;
     const double th = c.theta;
@@ -831,51 +905,15 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p)
         c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd));
     else
         c.alpha_min = NMPC_GAMMA_ALPHA * NMPC_GAMMA_THETA;
-    c.ls_first = 1;
     sm.P(PS_ALPHA, p) = amax;
     sm.P(PS_ALPHA_Z, p) = az;
+    sm.P(PS_MU_STEP, p) = sm.P(PS_MU, p);
 }
 
-// Phase E2: filter line-search decision for the trial just evaluated (W&B A-5).
-// Returns 1 accepted, 0 backtrack (PS_ALPHA halved), -1 failed (alpha < alpha_min).
+// P6 of the first cycle: keep the least-squares multipliers unless they are huge (W&B Sec. 3.6).
+// Returns the FL_KEEP flag (or 0).
 template <class SM>
-MPC_HD int ctrl_linesearch(const Params &prm, const SM &sm, Ctrl &c, int p)
-{
-    const int N = prm.N;
-    double th_t = 0.0, f_t = 0.0, ln_t = 0.0;
-    int inside = 1;
-    for (int k = 0; k < N; k += prm.grp) {
-        th_t += sm.at(k, W_0, p); f_t += sm.at(k, W_1, p);
-        const double l = sm.at(k, W_2, p);
-        if (l <= -1e299) inside = 0; else ln_t += l;
-    }
-    const double mu = sm.P(PS_MU, p), alpha = sm.P(PS_ALPHA, p);
-    const double phi_t = f_t - mu * ln_t;
-    const double th = c.theta, phi = c.phi, gd = c.gd;
-    int ok = inside && (th_t == th_t) && (phi_t == phi_t);
-    int acc = 0;
-    if (ok && filter_acceptable(c, th_t, phi_t)) {
-        if (th <= c.theta_min && gd < 0.0 && log(alpha) > c.sw_log) {
-            if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; c.armijo = 1; }
-        } else {
-            if (th_t <= (1.0 - NMPC_GAMMA_THETA) * th ||
-                phi_t - 10.0 * NMPC_EPS_MACH * fabs(phi) <= phi - NMPC_GAMMA_PHI * th) { acc = 1; c.armijo = 0; }
-        }
-    }
-    if (acc) {
-        if (!c.armijo) filter_add(c, th, phi);
-        return 1;
-    }
-    c.ls_first = 0;
-    const double a2 = 0.5 * alpha;
-    if (a2 < c.alpha_min) return -1;
-    sm.P(PS_ALPHA, p) = a2;
-    return 0;
-}
-
-// LSQ multiplier start: keep the least-squares multipliers unless they are huge (W&B Sec. 3.6).
-template <class SM>
-MPC_HD void ctrl_lsq_finish(const Params &prm, const SM &sm, Ctrl &c, int p)
+MPC_HD int ctrl_lsq_finish(const Params &prm, const SM &sm, int p)
 {
     const int N = prm.N;
     adjoint_sweep(prm, sm, p);
@@ -883,22 +921,20 @@ MPC_HD void ctrl_lsq_finish(const Params &prm, const SM &sm, Ctrl &c, int p)
     for (int k = 0; k < N - 1; k++)
         for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.at(k, W_6 + i, p)));
     for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.P(PS_N0X + i, p)));
-    const double keep = (lmax <= NMPC_LAM_MAX) ? 1.0 : 0.0;   // NaN compares false -> 0
-    sm.P(PS_ALPHA, p) = keep;
-    for (int i = 0; i < 6; i++) sm.P(PS_L0X + i, p) = (keep != 0.0) ? sm.P(PS_N0X + i, p) : 0.0;
-    c.lsq_pending = 0;
+    const int keep = (lmax <= NMPC_LAM_MAX) ? 1 : 0;   // NaN compares false -> 0
+    for (int i = 0; i < 6; i++) sm.P(PS_L0X + i, p) = keep ? sm.P(PS_N0X + i, p) : 0.0;
+    return keep ? FL_KEEP : 0;
 }
 
-// Control-thread part of accepting a step: lambda_0 and the iteration counter.
+// Control-thread part of applying an accepted step: lambda_0.
 template <class SM>
-MPC_HD void ctrl_accept(const SM &sm, Ctrl &c, int p)
+MPC_HD void ctrl_apply(const SM &sm, int p)
 {
     const double alpha = sm.P(PS_ALPHA, p);
     for (int i = 0; i < 6; i++) {
         const double l = sm.P(PS_L0X + i, p);
         sm.P(PS_L0X + i, p) = l + alpha * (sm.P(PS_N0X + i, p) - l);
     }
-    c.iter++;
 }
 
 }  // namespace nmpc

@@ -1,11 +1,13 @@
 // tests/emu/nmpc_emu.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 //
 // Runs the solver's phase functions (mpc_ros_b200/csrc/nmpc_phases.cuh, the code the CUDA
-// kernel executes) sequentially on the host, one emulated CTA of PB problems at a time, with
-// the kernel's barrier structure turned into plain loops.  It exists so that the solver LOGIC
-// can be checked against the oracle in the CPU-only test tier (this container has no GPU).
-// It is built only by tests/ (tests/emu/Makefile) into tests/emu/libnmpc_emu.so, is never
-// linked into libmpc_b200.so, and nothing in the product path can reach it.
+// kernel executes) sequentially on the host, one emulated CTA of PB lanes at a time, with the
+// kernel's cycle / barrier structure (nmpc_kernel.cuh) turned into plain loops -- including the
+// per-lane state machine.  (The kernel's work queue is not emulated: lanes get their problems
+// statically; results do not depend on the lane, which the tests check.)  It exists so that the
+// solver LOGIC can be checked against the oracle in the CPU-only test tier (this container has no
+// GPU).  It is built only by tests/ into tests/emu/libnmpc_emu.so, is never linked into
+// libmpc_b200.so, and nothing in the product path can reach it.
 #include "../../mpc_ros_b200/csrc/nmpc_phases.cuh"
 #include <vector>
 #include <cstring>
@@ -23,135 +25,158 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
     prm.w_cte = prm14[4]; prm.w_etheta = prm14[5]; prm.w_vel = prm14[6]; prm.w_angvel = prm14[7];
     prm.w_accel = prm14[8]; prm.max_angvel = prm14[9]; prm.max_throttle = prm14[10];
     prm.tol = tol; prm.max_iter = max_iter;
-    prm.grp = 3;   // same grouping of partial sums as the kernel's stage threads (SPT = 3)
+    const int SPT = 3;   // same grouping of partial sums as the kernel's stage threads
+    prm.grp = SPT;
+    const int NG = (N + SPT - 1) / SPT;
 
-    std::vector<double> st((size_t)N * NSLOTS * PB), ps((size_t)NPS * PB);
-    std::vector<int> pi((size_t)NPI * PB);
-    Smem sm; sm.st = st.data(); sm.ps = ps.data(); sm.pi = pi.data(); sm.PB = PB;
+    std::vector<double> mem(smem_bytes(N, NG, PB) / sizeof(double) + 8);
+    Smem sm; sm.PB = PB; sm.carve(mem.data(), N, NG);
     std::vector<StageRegs> regs((size_t)N * PB);
     std::vector<Ctrl> ctrl(PB);
     std::vector<int> nreg(PB);
+#define REG(k, p) regs[(size_t)(k) * PB + (p)]
 
     for (int base = 0; base < batch; base += PB) {
         const int np = (batch - base < PB) ? batch - base : PB;
-        std::fill(st.begin(), st.end(), 0.0);
-        for (int p = 0; p < PB; p++) sm.I(PI_MODE, p) = MODE_IDLE;
-        // ---- init
+        std::fill(mem.begin(), mem.end(), 0.0);
+        for (int p = 0; p < PB; p++) { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_FLAGS, p) = 0; sm.I(PI_PROB, p) = -1; sm.I(PI_NEXT, p) = -1; }
+        // ---- "refill": every lane starts its problem
         for (int p = 0; p < np; p++) {
-            double s6[6], c4[4];
+            double s6[6];
             for (int c = 0; c < 6; c++) s6[c] = state[(size_t)c * batch + base + p];
-            for (int c = 0; c < 4; c++) c4[c] = coeffs[(size_t)c * batch + base + p];
             const double rv = ref_vel ? ref_vel[base + p] : prm.ref_vel;
-            for (int k = 0; k < N; k++) stage_init(prm, sm, regs[(size_t)k * PB + p], k, p, s6, c4);
             ctrl_init(prm, sm, ctrl[p], p, s6, rv);
+            sm.I(PI_NEXT, p) = base + p;
+            sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_LSQ;
             nreg[p] = 0;
         }
-        // ---- cycles (same phase / barrier structure as nmpc_solve_kernel)
         for (;;) {
+            int active = 0;
+            for (int p = 0; p < np; p++) active |= (sm.I(PI_MODE, p) != MODE_IDLE) || (sm.I(PI_FLAGS, p) & FL_FLUSH);
+            if (!active) break;
+            // ---- P3a
             for (int p = 0; p < np; p++) {
-                const int md = sm.I(PI_MODE, p);
-                if (md == MODE_RESID || md == MODE_ACCEPT)
-                    for (int k0 = 0; k0 < N; k0 += prm.grp) {
-                        ResidPart acc; part_reset(acc);
-                        for (int k = k0; k < k0 + prm.grp && k < N; k++) stage_residuals(prm, sm, regs[(size_t)k * PB + p], k, p, acc);
-                        part_store(sm, k0, p, acc);
+                const int fl = sm.I(PI_FLAGS, p);
+                if (fl & FL_APPLY) for (int k = 0; k < N; k++) stage_apply(prm, sm, REG(k, p), k, p);
+                if (fl & FL_FLUSH) {
+                    const size_t i = (size_t)sm.I(PI_PROB, p);
+                    u0[i] = REG(0, p).uw; u0[(size_t)batch + i] = REG(0, p).ua;
+                    for (int k = 0; k < N; k++) {
+                        pred[((size_t)0 * N + k) * batch + i] = sm.at(k, S_X, p);
+                        pred[((size_t)1 * N + k) * batch + i] = sm.at(k, S_Y, p);
+                        pred[((size_t)2 * N + k) * batch + i] = sm.at(k, S_T, p);
                     }
+                    if (lam_out) {
+                        const double sf = sm.P(PS_AP_SF, p);
+                        for (int c = 0; c < 6; c++)
+                            for (int k = 0; k < N - 1; k++)
+                                lam_out[((size_t)c * N + k + 1) * batch + i] = sm.at(k, L_X + c, p) / sf;
+                    }
+                }
+                const int idx = sm.I(PI_NEXT, p);
+                if (idx >= 0) {
+                    double s6[6], c4[4];
+                    for (int c = 0; c < 6; c++) s6[c] = state[(size_t)c * batch + idx];
+                    for (int c = 0; c < 4; c++) c4[c] = coeffs[(size_t)c * batch + idx];
+                    for (int k = 0; k < N; k++) stage_init(prm, sm, REG(k, p), k, p, s6, c4);
+                }
             }
-            int any_run = 0;
             for (int p = 0; p < np; p++) {
+                sm.I(PI_FLAGS, p) &= ~(FL_APPLY | FL_FLUSH);
+                if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
+            }
+            // ---- P3b
+            for (int p = 0; p < np; p++)
+                if (sm.I(PI_MODE, p) == MODE_NEWTON)
+                    for (int k = 0; k < N; k++) stage_coeffs(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ);
+            // ---- P4
+            for (int p = 0; p < np; p++) {
+                if (sm.I(PI_MODE, p) != MODE_NEWTON) continue;
+                Ctrl &c = ctrl[p];
+                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                const double dw = sm.P(PS_DW, p);
+                const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
+                if (riccati_backward(prm, sm, p, hd) || lsq) {
+                    riccati_forward(prm, sm, p);
+                    if (dw > 0.0) c.dw_last = dw;
+                    sm.I(PI_MODE, p) = MODE_STEP;
+                } else {
+                    const double nd = next_dw(c, dw);
+                    nreg[p]++;
+                    if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_MODE, p) = MODE_FAIL; }
+                    else sm.P(PS_DW, p) = nd;
+                }
+            }
+            // ---- P5
+            for (int p = 0; p < np; p++) {
+                if (sm.I(PI_MODE, p) != MODE_STEP) continue;
+                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
+                for (int g = 0; g < NG; g++) {
+                    StepPart acc; part_reset(acc);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step(prm, sm, REG(k, p), k, p, hd, lsq, acc);
+                    part_store(sm, g, p, acc);
+                }
+            }
+            // ---- P6
+            for (int p = 0; p < np; p++) {
+                if (sm.I(PI_MODE, p) != MODE_STEP) continue;
+                if (sm.I(PI_FLAGS, p) & FL_LSQ) {
+                    const int keep = ctrl_lsq_finish(prm, sm, p);
+                    sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
+                } else {
+                    ctrl_step(prm, sm, ctrl[p], p, NG);
+                    sm.I(PI_FLAGS, p) = FL_LS;
+                }
+                sm.I(PI_MODE, p) = MODE_EVAL;
+            }
+            // ---- P1
+            for (int p = 0; p < np; p++) {
+                if (sm.I(PI_MODE, p) != MODE_EVAL) continue;
+                const int fl = sm.I(PI_FLAGS, p);
+                // all stages read their neighbours' slots before FL_ADOPT overwrites the L slots of a stage:
+                // stage k writes only its own L slots and reads lambda^+ of stage k-1 from W, as in the kernel
+                for (int g = 0; g < NG; g++) {
+                    EvalPart acc; part_reset(acc);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval(prm, sm, REG(k, p), k, p, fl, acc);
+                    part_store(sm, g, p, acc);
+                }
+            }
+            // ---- P2
+            for (int p = 0; p < np; p++) {
+                Ctrl &c = ctrl[p];
                 const int md = sm.I(PI_MODE, p);
-                if (md == MODE_RESID || md == MODE_ACCEPT) {
-                    if (sm.I(PI_LSQ, p) || ctrl_check(prm, sm, ctrl[p], p)) { sm.I(PI_MODE, p) = MODE_COEF; sm.P(PS_DW, p) = 0.0; }
-                    else { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_STATUS, p) = ctrl[p].status; }
-                }
-                any_run |= sm.I(PI_MODE, p) != MODE_IDLE;
-            }
-            if (!any_run) break;
-            // Newton system, with inertia-correction retries
-            for (;;) {
-                for (int p = 0; p < np; p++)
-                    if (sm.I(PI_MODE, p) == MODE_COEF)
-                        for (int k = 0; k < N; k++) stage_coeffs(prm, sm, regs[(size_t)k * PB + p], k, p, sm.I(PI_LSQ, p));
-                int any = 0;
-                for (int p = 0; p < np; p++) {
-                    if (sm.I(PI_MODE, p) != MODE_COEF) continue;
-                    Ctrl &c = ctrl[p];
-                    const double dw = sm.P(PS_DW, p);
-                    HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, sm.I(PI_LSQ, p));
-                    if (riccati_backward(prm, sm, p, hd) || sm.I(PI_LSQ, p)) {
-                        riccati_forward(prm, sm, p);
-                        if (dw > 0.0) c.dw_last = dw;
-                        sm.I(PI_MODE, p) = MODE_STEP;
-                    } else {
-                        const double nd = next_dw(c, dw);
-                        nreg[p]++;
-                        if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_STATUS, p) = 10; sm.I(PI_MODE, p) = MODE_IDLE; }
-                        else { sm.P(PS_DW, p) = nd; any = 1; }
-                    }
-                }
-                if (!any) break;
-            }
-            for (int p = 0; p < np; p++)
-                if (sm.I(PI_MODE, p) == MODE_STEP) {
-                    HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), sm.I(PI_LSQ, p));
-                    for (int k0 = 0; k0 < N; k0 += prm.grp) {
-                        StepPart acc; part_reset(acc);
-                        for (int k = k0; k < k0 + prm.grp && k < N; k++) stage_step(prm, sm, regs[(size_t)k * PB + p], k, p, hd, sm.I(PI_LSQ, p), acc);
-                        part_store(sm, k0, p, acc);
-                    }
-                }
-            for (int p = 0; p < np; p++)
-                if (sm.I(PI_MODE, p) == MODE_STEP) {
-                    if (sm.I(PI_LSQ, p)) { ctrl_lsq_finish(prm, sm, ctrl[p], p); sm.I(PI_MODE, p) = MODE_ACCEPT; }
-                    else { ctrl_step(prm, sm, ctrl[p], p); sm.I(PI_MODE, p) = MODE_TRIAL; }
-                }
-            // line search
-            for (;;) {
-                for (int p = 0; p < np; p++)
-                    if (sm.I(PI_MODE, p) == MODE_TRIAL)
-                        for (int k0 = 0; k0 < N; k0 += prm.grp) {
-                            TrialPart acc; part_reset(acc);
-                            for (int k = k0; k < k0 + prm.grp && k < N; k++) stage_trial(prm, sm, regs[(size_t)k * PB + p], k, p, acc);
-                            part_store(sm, k0, p, acc);
+                int term = 0;
+                if (md == MODE_EVAL) {
+                    const int fl = sm.I(PI_FLAGS, p);
+                    const int r = ctrl_decide(prm, sm, c, p, fl, NG);
+                    if (r == 0) sm.I(PI_FLAGS, p) = FL_LS;
+                    else {
+                        int nf = 0;
+                        if (fl & FL_LS) {
+                            nf = FL_APPLY;
+                            sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
+                            sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
+                            ctrl_apply(sm, p);
                         }
-                int any = 0;
-                for (int p = 0; p < np; p++) {
-                    if (sm.I(PI_MODE, p) != MODE_TRIAL) continue;
-                    const int r = ctrl_linesearch(prm, sm, ctrl[p], p);
-                    if (r == 1) sm.I(PI_MODE, p) = MODE_ACCEPT;
-                    else if (r < 0) { ctrl[p].status = 9; sm.I(PI_STATUS, p) = 9; sm.I(PI_MODE, p) = MODE_IDLE; }
-                    else any = 1;
+                        if (r == 1) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.P(PS_DW, p) = 0.0; sm.I(PI_FLAGS, p) = nf; }
+                        else { term = 1; sm.I(PI_FLAGS, p) = nf | FL_FLUSH; }
+                    }
+                } else if (md == MODE_FAIL) {
+                    term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
                 }
-                if (!any) break;
-            }
-            for (int p = 0; p < np; p++)
-                if (sm.I(PI_MODE, p) == MODE_ACCEPT) {
-                    for (int k = 0; k < N; k++) stage_accept(prm, sm, regs[(size_t)k * PB + p], k, p, sm.I(PI_LSQ, p));
-                    if (!sm.I(PI_LSQ, p)) ctrl_accept(sm, ctrl[p], p);
-                }
-            for (int p = 0; p < np; p++) sm.I(PI_LSQ, p) = 0;
-        }
-        // ---- outputs (the reference returns the last iterate whatever the status, mpc_planner.cpp:378-401)
-        for (int p = 0; p < np; p++) {
-            const size_t i = (size_t)base + p;
-            u0[i] = regs[p].uw; u0[(size_t)batch + i] = regs[p].ua;
-            for (int k = 0; k < N; k++) {
-                pred[((size_t)0 * N + k) * batch + i] = sm.at(k, S_X, p);
-                pred[((size_t)1 * N + k) * batch + i] = sm.at(k, S_Y, p);
-                pred[((size_t)2 * N + k) * batch + i] = sm.at(k, S_T, p);
-            }
-            if (obj) obj[i] = ctrl[p].obj;
-            if (status) status[i] = ctrl[p].status;
-            if (iters) iters[i] = ctrl[p].iter;
-            if (kkt) kkt[i] = ctrl[p].E0;
-            if (n_reg) n_reg[i] = nreg[p];
-            if (lam_out) {
-                // reference row layout: component-major, row comp*N + k (mpc_planner.cpp:153-158); unscaled
-                const double sf = sm.P(PS_SF, p);
-                for (int c = 0; c < 6; c++) {
-                    lam_out[((size_t)c * N + 0) * batch + i] = sm.P(PS_L0X + c, p) / sf;
-                    for (int k = 0; k < N - 1; k++)
-                        lam_out[((size_t)c * N + k + 1) * batch + i] = sm.at(k, L_X + c, p) / sf;
+                if (term) {
+                    const size_t i = (size_t)sm.I(PI_PROB, p);
+                    if (obj) obj[i] = c.obj;
+                    if (status) status[i] = c.status;
+                    if (iters) iters[i] = c.iter;
+                    if (kkt) kkt[i] = c.E0;
+                    if (n_reg) n_reg[i] = nreg[p];
+                    sm.P(PS_AP_SF, p) = sm.P(PS_SF, p);
+                    if (lam_out)
+                        for (int cc = 0; cc < 6; cc++)
+                            lam_out[((size_t)cc * N) * batch + i] = sm.P(PS_L0X + cc, p) / sm.P(PS_SF, p);
+                    sm.I(PI_MODE, p) = MODE_IDLE;
                 }
             }
         }

@@ -1,0 +1,172 @@
+"""bench/closed_loop.py -- BASELINE config 5: closed-loop simulation, R robots x T control ticks.
+
+Per tick (the reference's control tick, SURVEY section 3A, with the ROS plumbing replaced by arrays):
+  window the reference path ahead of the robot and down-sample it (mpc_planner_ros.cpp:266-291, :365-391)
+  -> pre-step: transform + polyfit + delay-compensated state (driving_state.cpp:196-256)   [GPU, K1]
+  -> MPC::Solve, warm-started from the previous tick's shifted solution                     [GPU, K3]
+  -> speed command clamp (driving_state.cpp:263-269) -> unicycle plant step.
+The windowing and the plant are a few numpy lines on the host (SURVEY 8f-2 / 8f-1 are "next" rows).
+
+    python bench/closed_loop.py [robots] [ticks] [--cold] [--oracle-subset K]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+from bench import gen_py  # noqa: E402
+
+DS = 0.05
+
+
+class Fleet:
+    """R robots on the three synthetic tracks (robot i on track i % 3)."""
+
+    def __init__(self, R, seed=20261018 + 5, path_length=5.0):
+        self.R = R
+        self.paths = [gen_py.path(k) for k in range(3)]
+        rng = np.random.default_rng(seed)
+        self.kind = np.arange(R) % 3
+        self.idx = np.zeros(R, dtype=np.int64)
+        self.pose = np.zeros((3, R))
+        self.v = np.zeros(R); self.w = np.zeros(R); self.thr = np.zeros(R)
+        for i in range(R):
+            px, py = self.paths[self.kind[i]]
+            n = len(px)
+            j = int(rng.integers(n))
+            tx, ty = px[(j + 1) % n] - px[j], py[(j + 1) % n] - py[j]
+            tl = np.hypot(tx, ty)
+            lat = rng.uniform(-0.2, 0.2)
+            self.idx[i] = j
+            self.pose[:, i] = [px[j] - ty / tl * lat, py[j] + tx / tl * lat, np.arctan2(ty, tx) + rng.uniform(-0.3, 0.3)]
+            self.v[i] = rng.uniform(0.0, 0.4)
+        self.win = int(round(path_length / DS))
+        self.step = int(path_length / 10.0 / DS)
+        self.M = gen_py._lib().mpcgen_num_waypoints(path_length)
+
+    def window(self):
+        """Cut the plan at the nearest point ahead and down-sample (mpc_planner_ros.cpp:266-291, :365-391)."""
+        R, M = self.R, self.M
+        wx = np.zeros((M, R)); wy = np.zeros((M, R))
+        for i in range(R):
+            px, py = self.paths[self.kind[i]]
+            n = len(px)
+            cand = (self.idx[i] + np.arange(0, 60)) % n
+            d2 = (px[cand] - self.pose[0, i]) ** 2 + (py[cand] - self.pose[1, i]) ** 2
+            self.idx[i] = cand[int(np.argmin(d2))]
+            sel = list(range(0, self.win, self.step)) + [self.win - 1]
+            q = (self.idx[i] + np.array(sel)) % n
+            wx[:, i] = px[q]; wy[:, i] = py[q]
+        return wx, wy
+
+    def vel(self):
+        return np.stack([self.v, self.w, self.thr])
+
+    def actuate(self, w, thr, dt, ref_v):
+        """driving_state.cpp:263-269 then a unicycle plant."""
+        speed = self.v + thr * dt
+        speed = np.minimum(speed, ref_v)
+        self.w = w.copy(); self.thr = thr.copy()
+        self.pose[0] += speed * np.cos(self.pose[2]) * dt
+        self.pose[1] += speed * np.sin(self.pose[2]) * dt
+        self.pose[2] += w * dt
+        self.pose[2] = (self.pose[2] + np.pi) % (2 * np.pi) - np.pi
+        self.v = speed
+
+
+def run_gpu(R, T, warm=True, seed=20261018 + 5, record_solver=False):
+    import torch
+    from mpc_ros_b200 import capi
+    prm = capi.yaml_default_params()          # delay_mode true, as in mpc_params.yaml:4
+    N = prm.mpc_steps; dt = prm.dt
+    sv = capi.Solver(prm, R, 0)
+    fleet = Fleet(R, seed)
+    dev = torch.device("cuda:0")
+    ws = capi.lib().mpc_b200_warm_size(N)
+    f64 = dict(dtype=torch.float64, device=dev)
+    warm_a = torch.zeros((ws, R), **f64); warm_b = torch.zeros((ws, R), **f64)
+    d_state = torch.zeros((6, R), **f64); d_coef = torch.zeros((4, R), **f64)
+    d_u0 = torch.zeros((2, R), **f64); d_pred = torch.zeros((3 * N, R), **f64)
+    d_it = torch.zeros(R, dtype=torch.int32, device=dev); d_st = torch.zeros(R, dtype=torch.int32, device=dev)
+    trace = dict(cte=[], eth=[], iters=[], conv=[], w=[], thr=[])
+    t_solve = 0.0
+    for t in range(T):
+        wx, wy = fleet.window()
+        d_wx = torch.from_numpy(wx).to(dev); d_wy = torch.from_numpy(wy).to(dev)
+        d_pose = torch.from_numpy(np.ascontiguousarray(fleet.pose)).to(dev)
+        d_vel = torch.from_numpy(np.ascontiguousarray(fleet.vel())).to(dev)
+        # tracking errors as the reference logs them (cte = c[0], etheta before delay compensation)
+        cte_e = torch.zeros((2, R), **f64)
+        sv.polyfit_raw(R, fleet.M, d_wx, d_wy, d_pose, d_coef, cte_e)
+        sv.prestep_raw(R, fleet.M, d_wx, d_wy, d_pose, d_vel, d_coef, d_state)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        use_warm = warm and t > 0
+        sv.solve_raw(R, d_state, d_coef, d_u0, d_pred, warm_in=warm_a if use_warm else None, status=d_st, iters=d_it,
+                     warm_out=warm_b)
+        torch.cuda.synchronize()
+        t_solve += time.perf_counter() - t0
+        sv.warm_shift(R, warm_b, warm_a)
+        u0 = d_u0.cpu().numpy()
+        ce = cte_e.cpu().numpy()
+        trace["cte"].append(ce[0].copy()); trace["eth"].append(ce[1].copy())
+        trace["iters"].append(d_it.cpu().numpy().copy()); trace["conv"].append((d_st.cpu().numpy() == 1))
+        trace["w"].append(u0[0].copy()); trace["thr"].append(u0[1].copy())
+        fleet.actuate(u0[0], u0[1], dt, prm.ref_vel)
+    sv.close()
+    out = {k: np.array(v) for k, v in trace.items()}
+    out["solve_s"] = t_solve
+    return out
+
+
+def run_oracle(R, T, seed=20261018 + 5):
+    """The reference loop: cold-started CPU solve every tick (oracle restatement of MPC::Solve)."""
+    from oracle.oracle_py import Oracle, YAML_DEFAULT
+    orc = Oracle()
+    dt = YAML_DEFAULT["DT"]
+    fleet = Fleet(R, seed)
+    trace = dict(cte=[], eth=[], w=[], thr=[], iters=[])
+    for t in range(T):
+        wx, wy = fleet.window()
+        w = np.zeros(R); thr = np.zeros(R); cte = np.zeros(R); eth = np.zeros(R); its = np.zeros(R)
+        for i in range(R):
+            c, ct, e = orc.prestep(wx[:, i], wy[:, i], *fleet.pose[:, i])
+            v, pw, pt = fleet.v[i], fleet.w[i], fleet.thr[i]
+            st = np.array([v * dt, 0.0, pw * dt, v + pt * dt, ct + v * np.sin(e) * dt, e - pw * dt])   # delay mode
+            r = orc.solve(YAML_DEFAULT, st, c)
+            w[i], thr[i] = r["u0"]; cte[i] = ct; eth[i] = e; its[i] = r["iters"]
+        trace["cte"].append(cte); trace["eth"].append(eth); trace["w"].append(w.copy()); trace["thr"].append(thr.copy())
+        trace["iters"].append(its)
+        fleet.actuate(w, thr, dt, YAML_DEFAULT["REF_V"])
+    return {k: np.array(v) for k, v in trace.items()}
+
+
+def main():
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    T = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+    cold = "--cold" in sys.argv
+    K = 0
+    if "--oracle-subset" in sys.argv:
+        K = int(sys.argv[sys.argv.index("--oracle-subset") + 1])
+    g = run_gpu(R, T, warm=not cold)
+    res = dict(robots=R, ticks=T, warm=not cold, solve_s=g["solve_s"], solves_per_s=R * T / g["solve_s"],
+               mean_abs_cte=float(np.abs(g["cte"]).mean()), max_abs_cte=float(np.abs(g["cte"]).max()),
+               mean_abs_etheta=float(np.abs(g["eth"]).mean()), mean_iters=float(g["iters"].mean()),
+               converged_fraction=float(g["conv"].mean()),
+               mean_abs_cte_last100=float(np.abs(g["cte"][-100:]).mean()))
+    if K > 0:
+        o = run_oracle(K, T)
+        gk = run_gpu(K, T, warm=not cold)
+        res["oracle_subset"] = dict(robots=K, mean_abs_cte_oracle=float(np.abs(o["cte"]).mean()),
+                                    mean_abs_cte_gpu=float(np.abs(gk["cte"]).mean()),
+                                    max_trace_gap_cte=float(np.abs(np.abs(o["cte"]).mean(1) - np.abs(gk["cte"]).mean(1)).max()),
+                                    mean_iters_oracle=float(o["iters"].mean()), mean_iters_gpu=float(gk["iters"].mean()))
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,8 @@ typedef struct mpc_b200_params {
     double waypoints_dist;  /* waypoints_dist */
     double goal_radius;     /* goal_radius */
     double controller_freq; /* controller_freq */
+    /* warm start (no reference counterpart): barrier parameter a warm-started solve begins with */
+    double warm_mu_init;    /* default 1e-3 */
 } mpc_b200_params;
 
 /* Defaults = the constructor defaults of MPC::MPC (mpc_planner.cpp:223-241) and
@@ -121,14 +123,16 @@ int32_t mpc_b200_warm_size(int32_t mpc_steps);
  *   coeffs   4 x batch   cubic reference-path coefficients    (:186-190; driving_state.cpp:210)
  *   ref_vel  batch       optional per-problem REF_V override (NULL = params.ref_vel); the reference
  *                        rewrites REF_V per tick (driving_state.cpp:127-139)
- *   warm_in  warm_size x batch, optional (NULL = the reference's cold start, :288-300)
+ *   warm_in  warm_size x batch, optional, DEVICE memory (NULL = the reference's cold start, :288-300):
+ *            controls, equality and bound multipliers are taken from it, the states are re-derived
+ *            by a roll-out of the model from `state`
  *   u0       2 x batch   {w_0, throttle_0} = MPC::Solve's return value (:398-401)
  *   pred     3N x batch  mpc_x, mpc_y, mpc_theta (:388-396)
  *   obj      batch       objective value (solution.obj_value, :381), optional
  *   status   batch       per-problem status (:378), optional
  *   iters    batch       interior-point iterations, optional
  *   kkt_res  batch       final scaled optimality error E_0 (Ipopt's `tol` measure), optional
- *   warm_out warm_size x batch, optional
+ *   warm_out warm_size x batch, optional, DEVICE memory
  *   stream   cudaStream_t, or NULL for the handle's own stream.  The call returns after the
  *            results are in the caller's buffers (synchronous, like MPC::Solve) unless every
  *            buffer is device memory AND a stream is given, in which case it only enqueues.
@@ -138,6 +142,10 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
                          const double *warm_in,
                          double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
                          double *kkt_res, double *warm_out, void *stream);
+
+/* Next tick's warm start from this tick's solution (device buffers): every block of the record moves
+ * one stage forward, the last entry is repeated. */
+int mpc_b200_warm_shift(mpc_b200_handle *h, int32_t batch, const double *warm_prev, double *warm_next, void *stream);
 
 /*
  * Batched waypoint transform + cubic polyfit + (cte, etheta): the reference pre-step

@@ -28,6 +28,7 @@ class Params(C.Structure):
         ("tol", C.c_double), ("max_iter", C.c_int32),
         ("delay_mode", C.c_int32), ("max_speed", C.c_double), ("path_length", C.c_double),
         ("waypoints_dist", C.c_double), ("goal_radius", C.c_double), ("controller_freq", C.c_double),
+        ("warm_mu_init", C.c_double),
     ]
 
 
@@ -36,7 +37,7 @@ EXPORTS = [
     "mpc_b200_params_default", "mpc_b200_params_yaml_default", "mpc_b200_params_from_yaml",
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
     "mpc_b200_get_params", "mpc_b200_set_option", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
-    "mpc_b200_prestep_batch",
+    "mpc_b200_prestep_batch", "mpc_b200_warm_shift",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
 ]
@@ -75,6 +76,8 @@ def lib():
     L.mpc_b200_polyfit_batch.restype = C.c_int
     L.mpc_b200_prestep_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.mpc_b200_prestep_batch.restype = C.c_int
+    L.mpc_b200_warm_shift.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mpc_b200_warm_shift.restype = C.c_int
     L.mpc_b200_last_kernel_seconds.argtypes = [C.c_void_p]
     L.mpc_b200_last_kernel_seconds.restype = C.c_double
     L.mpc_b200_launch_count.argtypes = [C.c_void_p]
@@ -215,6 +218,11 @@ class Solver:
                                           _addr(cte_etheta), stream)
         if rc != 0:
             raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def warm_shift(self, batch, prev, nxt, stream=None):
+        rc = lib().mpc_b200_warm_shift(self._h, batch, _addr(prev), _addr(nxt), stream)
+        if rc != 0:
+            raise MpcError(rc)
 
     def prestep_raw(self, batch, M, wx, wy, pose, vel, coeffs, state, stream=None):
         rc = lib().mpc_b200_prestep_batch(self._h, batch, M, _addr(wx), _addr(wy), _addr(pose), _addr(vel),

@@ -115,6 +115,25 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
     }
 }
 
+// ================================================================ warm-start shift
+// Next tick's warm start from this tick's solution: every block of the record (6 state components,
+// 2 controls, 6 multiplier components, 4 bound multipliers) moves one stage forward, the last entry is
+// repeated.  (The solver re-derives the states by a roll-out; they are shifted only for completeness.)
+__global__ void warm_shift_kernel(int batch, int N, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    size_t off = 0;
+    for (int blk = 0; blk < 18; blk++) {
+        const int len = (blk < 6) ? N : (blk < 8) ? N - 1 : (blk < 14) ? N : N - 1;
+        for (int j = 0; j < len; j++) {
+            const int src = (j + 1 < len) ? j + 1 : len - 1;
+            out[(off + j) * (size_t)batch + i] = in[(off + src) * (size_t)batch + i];
+        }
+        off += len;
+    }
+}
+
 // ================================================================ FP64 probes
 // mode 0: throughput -- 8 independent DFMA chains per thread, every SM busy
 // mode 1..: single-warp issue/latency probes (see mpc_b200_debug_fp64_probe)
@@ -288,12 +307,12 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     h->num_sms = sms; h->smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc::nmpc_solve_kernel<SPT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+#define SET_SMEM(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 16, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 8, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 4, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 1, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, true>));
+#undef SET_SMEM
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
     if (rc != MPC_B200_OK) { free_scratch(h); delete h; return rc; }
@@ -375,7 +394,6 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
                          double *kkt_res, double *warm_out, void *stream_v)
 {
     if (!h || batch < 0 || batch > h->max_batch || !state || !coeffs || !u0 || !pred) return MPC_B200_ERR_INVALID;
-    if (warm_in) return MPC_B200_ERR_UNSUPPORTED;   // warm start lands with the closed-loop row
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
     const mpc_b200_params &P = h->params;
@@ -386,10 +404,13 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     const bool dev_in = is_device_ptr(state);
     const bool dev_out = is_device_ptr(u0);
     if (is_device_ptr(coeffs) != dev_in || (ref_vel && is_device_ptr(ref_vel) != dev_in)) return MPC_B200_ERR_INVALID;
+    // warm-start records are large and meant to stay on the device between ticks
+    if (warm_in && !is_device_ptr(warm_in)) return MPC_B200_ERR_UNSUPPORTED;
     if (is_device_ptr(pred) != dev_out || (obj && is_device_ptr(obj) != dev_out) ||
         (status && is_device_ptr(status) != dev_out) || (iters && is_device_ptr(iters) != dev_out) ||
-        (kkt_res && is_device_ptr(kkt_res) != dev_out) || (warm_out && is_device_ptr(warm_out) != dev_out))
+        (kkt_res && is_device_ptr(kkt_res) != dev_out))
         return MPC_B200_ERR_INVALID;
+    if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
 
     SolveArgs a;
     a.prm.N = N; a.prm.dt = P.dt; a.prm.ref_cte = P.ref_cte; a.prm.ref_etheta = P.ref_etheta; a.prm.ref_vel = P.ref_vel;
@@ -398,6 +419,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
     a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 200;
     a.prm.grp = SPT;
+    a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
     a.batch = batch;
     a.PB = choose_pb(h, N, batch);
     a.prof = h->d_prof;
@@ -405,6 +427,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     if (dev_in) {
         a.state = state; a.coeffs = coeffs; a.ref_vel = ref_vel;
     } else {
+        if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
         double *hi = h->h_in;
         memcpy(hi, state, sizeof(double) * 6 * B);
         memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B);
@@ -415,12 +438,12 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, hi + 10 * B, sizeof(double) * B, cudaMemcpyHostToDevice, st));
         a.state = h->d_state; a.coeffs = h->d_coeffs; a.ref_vel = ref_vel ? h->d_refv : NULL;
     }
-    if (warm_out && !dev_out) return MPC_B200_ERR_UNSUPPORTED;  // host warm_out staging not wired yet
+    a.warm_in = warm_in;
     if (dev_out) {
         a.u0 = u0; a.pred = pred; a.obj = obj; a.status = status; a.iters = iters; a.kkt = kkt_res; a.warm_out = warm_out;
     } else {
         a.u0 = h->d_u0; a.pred = h->d_pred; a.obj = h->d_obj; a.status = h->d_status; a.iters = h->d_iters;
-        a.kkt = h->d_kkt; a.warm_out = NULL;
+        a.kkt = h->d_kkt; a.warm_out = warm_out;
     }
 
     const int NG = (N + SPT - 1) / SPT;
@@ -434,13 +457,16 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.queue = h->d_queue + (h->launches % QUEUE_RING);
     CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     CK(cudaEventRecord(h->ev0, st));
-    switch (a.PB) {
-        case 32: nmpc::nmpc_solve_kernel<SPT, 32><<<grid, threads, smem, st>>>(a); break;
-        case 16: nmpc::nmpc_solve_kernel<SPT, 16><<<grid, threads, smem, st>>>(a); break;
-        case 8: nmpc::nmpc_solve_kernel<SPT, 8><<<grid, threads, smem, st>>>(a); break;
-        case 4: nmpc::nmpc_solve_kernel<SPT, 4><<<grid, threads, smem, st>>>(a); break;
-        case 1: nmpc::nmpc_solve_kernel<SPT, 1><<<grid, threads, smem, st>>>(a); break;
-        default: nmpc::nmpc_solve_kernel<SPT, 0><<<grid, threads, smem, st>>>(a); break;
+    if (a.warm_in) {
+        if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32, true><<<grid, threads, smem, st>>>(a);
+        else nmpc::nmpc_solve_kernel<SPT, 0, true><<<grid, threads, smem, st>>>(a);
+    } else switch (a.PB) {
+        case 32: nmpc::nmpc_solve_kernel<SPT, 32, false><<<grid, threads, smem, st>>>(a); break;
+        case 16: nmpc::nmpc_solve_kernel<SPT, 16, false><<<grid, threads, smem, st>>>(a); break;
+        case 8: nmpc::nmpc_solve_kernel<SPT, 8, false><<<grid, threads, smem, st>>>(a); break;
+        case 4: nmpc::nmpc_solve_kernel<SPT, 4, false><<<grid, threads, smem, st>>>(a); break;
+        case 1: nmpc::nmpc_solve_kernel<SPT, 1, false><<<grid, threads, smem, st>>>(a); break;
+        default: nmpc::nmpc_solve_kernel<SPT, 0, false><<<grid, threads, smem, st>>>(a); break;
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
@@ -570,6 +596,20 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
     }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_warm_shift(mpc_b200_handle *h, int32_t batch, const double *warm_prev, double *warm_next, void *stream_v)
+{
+    if (!h || batch < 0 || !warm_prev || !warm_next || warm_prev == warm_next) return MPC_B200_ERR_INVALID;
+    if (!is_device_ptr(warm_prev) || !is_device_ptr(warm_next)) return MPC_B200_ERR_UNSUPPORTED;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    warm_shift_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, h->params.mpc_steps, warm_prev, warm_next);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (!stream_v) CK(cudaStreamSynchronize(st));
     return MPC_B200_OK;
 }
 

@@ -37,6 +37,7 @@ struct SolveArgs {
     int *iters;             // batch or NULL
     double *kkt;            // batch or NULL
     double *warm_out;       // warm_size x batch or NULL
+    const double *warm_in;  // warm_size x batch or NULL (cold start)
     int *queue;             // work-queue head (zeroed by the host before the launch)
     long long *prof;        // NMPC_PROFILE builds only: per-phase cycle counters of CTA 0
 };
@@ -56,7 +57,7 @@ struct SolveArgs {
 #define TRACE_S(i)
 #endif
 
-template <int SPT, int CPB>
+template <int SPT, int CPB, bool WARM>
 __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
@@ -100,8 +101,18 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                         for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + nidx];
                         const double rv = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
                         ctrl_init(prm, sm, c, p, s6, rv);
-                        sm.I(PI_MODE, p) = MODE_NEWTON;
-                        sm.I(PI_FLAGS, p) |= FL_LSQ;
+                        if (WARM) {
+                            sm.P(PS_MU, p) = prm.warm_mu; sm.P(PS_MU_STEP, p) = prm.warm_mu;
+                            sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - prm.warm_mu);
+                            const size_t offl = (size_t)(8 * N - 2);
+                            for (int i = 0; i < 6; i++)
+                                sm.P(PS_L0X + i, p) = sm.P(PS_SF, p) * a.warm_in[(offl + (size_t)i * N) * batch + nidx];
+                            sm.I(PI_MODE, p) = MODE_ROLLOUT;
+                            sm.I(PI_FLAGS, p) |= FL_WARM;
+                        } else {
+                            sm.I(PI_MODE, p) = MODE_NEWTON;
+                            sm.I(PI_FLAGS, p) |= FL_LSQ;
+                        }
                     } else {
                         sm.I(PI_MODE, p) = MODE_IDLE;
                     }
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
             __syncthreads();  // B3
             TRACE_C(2);
             if (lane) {   // apply / flush / init are done
-                sm.I(PI_FLAGS, p) &= ~(FL_APPLY | FL_FLUSH);
+                sm.I(PI_FLAGS, p) &= ~(FL_APPLY | FL_FLUSH | FL_WARM);
                 if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
             }
             // ---- P3b: stage threads write coefficients
@@ -140,6 +151,14 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_MODE, p) = MODE_FAIL; }
                     else sm.P(PS_DW, p) = nd;       // stays MODE_NEWTON: coefficients are rewritten next cycle
                 }
+            }
+            if (WARM && lane && sm.I(PI_MODE, p) == MODE_ROLLOUT) {
+                const size_t i = (size_t)sm.I(PI_PROB, p);
+                double c4[4];
+                for (int q = 0; q < 4; q++) c4[q] = a.coeffs[(size_t)q * batch + i];
+                ctrl_rollout(prm, sm, p, c4);
+                sm.I(PI_MODE, p) = MODE_EVAL;       // plain evaluation of the start point in P1
+                sm.I(PI_FLAGS, p) = 0;
             }
             PROF_MARK(4);
             TRACE_C(4);
@@ -179,12 +198,16 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                         sm.I(PI_FLAGS, p) = FL_LS;
                     } else {
                         int nf = 0;
+                        // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
+                        // a step of length 0 -- it still adopts the sin/cos computed at the evaluated point)
+                        nf = FL_APPLY;
                         if (fl & FL_LS) {
-                            nf = FL_APPLY;
                             sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
-                            sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
                             ctrl_apply(sm, p);
+                        } else {
+                            sm.P(PS_AP_ALPHA, p) = 0.0; sm.P(PS_AP_AZ, p) = 0.0;
                         }
+                        sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
                         if (r == 1) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.P(PS_DW, p) = 0.0; sm.I(PI_FLAGS, p) = nf; }
                         else { term = 1; sm.I(PI_FLAGS, p) = nf | FL_FLUSH; }
                     }
@@ -277,9 +300,15 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     double s6[6], c4[4];
                     for (int i = 0; i < 6; i++) s6[i] = a.state[(size_t)i * batch + idx];
                     for (int i = 0; i < 4; i++) c4[i] = a.coeffs[(size_t)i * batch + idx];
+                    if (WARM && (fl & FL_WARM)) {
 #pragma unroll
-                    for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_init(prm, sm, r[j], k0 + j, p, s6, c4);
+                        for (int j = 0; j < SPT; j++)
+                            if (k0 + j < N) stage_init_warm(prm, sm, r[j], k0 + j, p, s6, c4, a.warm_in, (size_t)batch, (size_t)idx);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < SPT; j++)
+                            if (k0 + j < N) stage_init(prm, sm, r[j], k0 + j, p, s6, c4);
+                    }
                 }
             }
             TRACE_S(2);

@@ -69,7 +69,8 @@ enum Mode {
     MODE_EVAL,       // P1: evaluate the point iterate + alpha * step (alpha may be 0); P2: decide
     MODE_NEWTON,     // P3: (apply the accepted step and) write the Newton-system coefficients; P4: sweeps
     MODE_STEP,       // P5: step-dependent stage work; P6: multipliers + step-size limits
-    MODE_FAIL        // the Newton system could not be regularised: flushed at the next P2
+    MODE_FAIL,       // the Newton system could not be regularised: flushed at the next P2
+    MODE_ROLLOUT     // warm start: P4 rolls the model out from the given state with the warm controls
 };
 enum Flag {
     FL_LSQ = 1,      // the system being solved is the least-squares multiplier start (W&B eq. (36))
@@ -77,7 +78,8 @@ enum Flag {
     FL_ADOPT = 4,    // P1 must first adopt the least-squares multipliers (or zero them)
     FL_LS = 8,       // the point evaluated in P1 is a line-search trial (else it is accepted as is)
     FL_FLUSH = 16,   // P3 must write this lane's finished problem out
-    FL_KEEP = 32     // with FL_ADOPT: keep the least-squares multipliers (else reset to zero)
+    FL_KEEP = 32,    // with FL_ADOPT: keep the least-squares multipliers (else reset to zero)
+    FL_WARM = 64     // P3a initialises the lane from a warm-start record instead of the cold start
 };
 
 struct Params {
@@ -88,6 +90,7 @@ struct Params {
     double tol;
     int max_iter;
     int grp;      // stages per stage thread: partial sums are pre-reduced over groups of grp stages
+    double warm_mu;   // initial barrier parameter of a warm-started problem
 };
 
 #define NMPC_MAX_FILTER 8
@@ -234,6 +237,59 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     r.qv = r.qc = r.qe = 0.0;
     r.tsn = r.sn; r.tcs = r.cs; r.tse = r.se; r.tce = r.ce;
     r.ilw = r.iuw = 1.0 / relaxed(prm.max_angvel); r.ila = r.iua = 1.0 / relaxed(prm.max_throttle);
+}
+
+// Warm start (new capability; the reference cold-starts every call, solve_callback.hpp:595-597).
+// Record layout (mpc_b200_warm_size doubles per problem, SoA over the batch): primal in the reference's
+// variable layout (mpc_planner.cpp:232-239), equality multipliers in its row layout (:153-158), then
+// zL_w, zL_a, zU_w, zU_a.  Controls and multipliers are taken from the record (controls pushed into the
+// interior of their bounds); the states are NOT taken from it: the control thread rolls the model out
+// from the given state (ctrl_rollout), so the start point satisfies the dynamics exactly.
+template <class SM>
+MPC_HD void stage_init_warm(const Params &prm, const SM &sm, StageRegs &r, int k, int p,
+                            const double *state6, const double *coef4, const double *warm, size_t stride, size_t idx)
+{
+    const int N = prm.N;
+    stage_init(prm, sm, r, k, p, state6, coef4);
+    if (k < N - 1) {
+        const double sf = sm.P(PS_SF, p), mu = prm.warm_mu;
+        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+        double uw = warm[((size_t)6 * N + k) * stride + idx], ua = warm[((size_t)7 * N - 1 + k) * stride + idx];
+        const double pw = 1e-3 * Uw, pa = 1e-3 * Ua;       // warm_start_bound_push
+        uw = fmax2(fmin2(uw, Uw - pw), -Uw + pw); ua = fmax2(fmin2(ua, Ua - pa), -Ua + pa);
+        r.uw = uw; r.ua = ua;
+        sm.at(k, W_10, p) = uw; sm.at(k, W_11, p) = ua;    // for the roll-out
+        const size_t offl = (size_t)(8 * N - 2), offz = offl + (size_t)6 * N;
+        for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = sf * warm[(offl + (size_t)c * N + k + 1) * stride + idx];
+        const int nu = N - 1;
+        // multipliers of the control bounds: at least on the central path of the starting mu
+        r.zlw = fmax2(sf * warm[(offz + k) * stride + idx], mu / (uw + Uw));
+        r.zla = fmax2(sf * warm[(offz + nu + k) * stride + idx], mu / (ua + Ua));
+        r.zuw = fmax2(sf * warm[(offz + 2 * nu + k) * stride + idx], mu / (Uw - uw));
+        r.zua = fmax2(sf * warm[(offz + 3 * nu + k) * stride + idx], mu / (Ua - ua));
+    }
+}
+
+// Roll-out of the model from s_0 with the controls left in W_10/W_11 (control thread).
+template <class SM>
+MPC_HD void ctrl_rollout(const Params &prm, const SM &sm, int p, const double *coef4)
+{
+    const int N = prm.N;
+    const double dt = prm.dt;
+    double x = sm.at(0, S_X, p), y = sm.at(0, S_Y, p), th = sm.at(0, S_T, p), v = sm.at(0, S_V, p), e = sm.at(0, S_E, p);
+    for (int k = 0; k < N - 1; k++) {
+        const double uw = sm.at(k, W_10, p), ua = sm.at(k, W_11, p);
+        double sn, cs, se, ce;
+        sincos_d(th, &sn, &cs);
+        sincos_d(e, &se, &ce);
+        const double poly = coef4[0] + x * (coef4[1] + x * (coef4[2] + x * coef4[3]));
+        const double nc = (poly - y) + v * se * dt;
+        const double nx = x + v * cs * dt, ny = y + v * sn * dt;
+        th += uw * dt; e += uw * dt; v += ua * dt; x = nx; y = ny;
+        sm.at(k + 1, S_X, p) = x; sm.at(k + 1, S_Y, p) = y; sm.at(k + 1, S_T, p) = th;
+        sm.at(k + 1, S_V, p) = v; sm.at(k + 1, S_C, p) = nc; sm.at(k + 1, S_E, p) = e;
+        sm.at(k, W_10, p) = 0.0; sm.at(k, W_11, p) = 0.0;
+    }
 }
 
 // trial bound multipliers  z + alpha_z dz, clamped (W&B eq. (16)); dz from W&B eq. (12)

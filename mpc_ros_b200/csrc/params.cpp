@@ -29,6 +29,7 @@ void mpc_b200_params_default(mpc_b200_params *p)
     // DrivingStateContext defaults (mpc_ros/src/driving_state.cpp:24-29) / MPCPlanner.cfg:14-20
     p->delay_mode = 1; p->max_speed = 0.7; p->path_length = 5.0; p->waypoints_dist = -1.0;
     p->goal_radius = 0.5; p->controller_freq = 10.0;
+    p->warm_mu_init = 1e-3;
 }
 
 void mpc_b200_params_yaml_default(mpc_b200_params *p)

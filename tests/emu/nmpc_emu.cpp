@@ -153,12 +153,16 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                     if (r == 0) sm.I(PI_FLAGS, p) = FL_LS;
                     else {
                         int nf = 0;
+                        // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
+                        // a step of length 0 -- it still adopts the sin/cos computed at the evaluated point)
+                        nf = FL_APPLY;
                         if (fl & FL_LS) {
-                            nf = FL_APPLY;
                             sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
-                            sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
                             ctrl_apply(sm, p);
+                        } else {
+                            sm.P(PS_AP_ALPHA, p) = 0.0; sm.P(PS_AP_AZ, p) = 0.0;
                         }
+                        sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
                         if (r == 1) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.P(PS_DW, p) = 0.0; sm.I(PI_FLAGS, p) = nf; }
                         else { term = 1; sm.I(PI_FLAGS, p) = nf | FL_FLUSH; }
                     }

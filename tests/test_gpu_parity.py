@@ -220,3 +220,64 @@ def test_edge_cases():
     out = sv.solve(st, np.zeros((4, 1)))
     assert out["status"][0] != 1
     sv.close()
+
+
+def test_warm_start_reaches_the_same_solution(oracle):
+    """Warm start (new capability): re-solving from a converged record gives the same KKT point in far
+    fewer iterations; a shifted record of a neighbouring problem still converges to the oracle's answer."""
+    torch = pytest.importorskip("torch")
+    state, coeffs = mild(51, 64)
+    B = 64; N = 20
+    dev = torch.device("cuda:0")
+    sv = _solver(YAML_DEFAULT, B)
+    ws = capi.lib().mpc_b200_warm_size(N)
+    f64 = dict(dtype=torch.float64, device=dev)
+    ds = torch.from_numpy(state).to(dev); dc = torch.from_numpy(coeffs).to(dev)
+    u_cold = torch.zeros((2, B), **f64); pred = torch.zeros((3 * N, B), **f64)
+    it_cold = torch.zeros(B, dtype=torch.int32, device=dev); st = torch.zeros(B, dtype=torch.int32, device=dev)
+    wo = torch.zeros((ws, B), **f64)
+    sv.solve_raw(B, ds, dc, u_cold, pred, status=st, iters=it_cold, warm_out=wo)
+    torch.cuda.synchronize()
+    assert bool((st == 1).all())
+    # the record's primal block is the solution in the reference's variable layout
+    rec = wo.cpu().numpy()
+    np.testing.assert_allclose(rec[6 * N], u_cold.cpu().numpy()[0], atol=0)         # w_0
+    np.testing.assert_allclose(rec[7 * N - 1], u_cold.cpu().numpy()[1], atol=0)     # a_0
+    np.testing.assert_allclose(rec[:N], pred.cpu().numpy()[:N], atol=0)             # x_k
+    # (a) same problem, warm: same answer, fewer iterations
+    u_w = torch.zeros((2, B), **f64); it_w = torch.zeros(B, dtype=torch.int32, device=dev)
+    sv.solve_raw(B, ds, dc, u_w, pred, warm_in=wo, status=st, iters=it_w)
+    torch.cuda.synchronize()
+    assert bool((st == 1).all())
+    assert float((u_w - u_cold).abs().max()) <= U_TOL
+    assert float(it_w.double().mean()) <= 0.7 * float(it_cold.double().mean())
+    # (b) perturbed problem warm-started from the shifted record: still the oracle's solution
+    state2 = state.copy(); state2[3] += 0.03; state2[4] += 0.02; state2[5] -= 0.03
+    ds2 = torch.from_numpy(state2).to(dev)
+    wsft = torch.zeros((ws, B), **f64)
+    sv.warm_shift(B, wo, wsft)
+    sv.solve_raw(B, ds2, dc, u_w, pred, warm_in=wsft, status=st, iters=it_w)
+    torch.cuda.synchronize()
+    sv.close()
+    uw = u_w.cpu().numpy()
+    assert bool((st == 1).all())
+    for i in range(0, B, 4):
+        o = oracle.solve(YAML_DEFAULT, state2[:, i], coeffs[:, i])
+        assert np.abs(uw[:, i] - o["u0"]).max() <= U_TOL
+
+
+def test_closed_loop_tracks_like_the_reference_loop():
+    """BASELINE config 5 in small: warm-started GPU loop vs the cold-started oracle loop (the reference
+    cold-starts every tick), same robots, same plant."""
+    from bench import closed_loop
+    R, T = 12, 40
+    g = closed_loop.run_gpu(R, T, warm=True)
+    o = closed_loop.run_oracle(R, T)
+    assert g["conv"].mean() >= 0.99
+    # same commands tick by tick while the two loops see the same states (they do until round-off grows)
+    assert np.abs(g["w"][:5] - o["w"][:5]).max() <= 1e-4
+    assert np.abs(g["thr"][:5] - o["thr"][:5]).max() <= 1e-4
+    # and the same tracking quality over the run
+    assert abs(np.abs(g["cte"]).mean() - np.abs(o["cte"]).mean()) <= 0.01
+    assert np.abs(g["cte"][-10:]).mean() <= 0.12          # the order of the reference's own trace (assets/mpc.csv)
+    assert g["iters"][1:].mean() < o["iters"][1:].mean()  # warm start pays

@@ -197,10 +197,12 @@ def run_ours(a):
     flush = torch.empty(256 * 1024 * 1024 // 8, **f64)
     # Steps are independent batches: they are issued round-robin on S streams so that the tail of one
     # batch (a few problems need 10-25x the median iteration count) overlaps the next batches.
-    S = max(1, a.streams)
+    S = max(1, min(a.streams, a.steps))
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
-    if a.max_ctas > 0:
-        solver.set_option("max_ctas", a.max_ctas)
+    # persistent-grid size per launch: with many batches in flight each launch takes a slice of the SMs and
+    # every lane works through several problems; with few steps a launch must cover the machine by itself
+    max_ctas = a.max_ctas if a.max_ctas > 0 else max(16, min(128, -(-296 // S)))
+    solver.set_option("max_ctas", max_ctas)
 
     # pre-marshalled C-ABI argument tuples (the timed loop is launches only, ~10 us of host time each)
     pre_f = L.mpc_b200_prestep_batch; sol_f = L.mpc_b200_solve_batch
@@ -365,7 +367,7 @@ def run_ours(a):
                     ms_per_step=ms_total / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic",
                     config=dict(workload=WORKLOAD, batch_per_gpu=B, mpc_steps=N, max_iter=a.max_iter, streams=S,
-                                max_ctas=a.max_ctas,
+                                max_ctas=max_ctas,
                                 l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one "
                                    "L2 flush" % (R, R * set_bytes / 1e6),
                                 converged_fraction=conv_total / (B * a.steps * world), mean_iters_converged=it_mean,
@@ -387,7 +389,7 @@ def main():
     ap.add_argument("--sets", type=int, default=48)
     ap.add_argument("--max-iter", type=int, default=200)
     ap.add_argument("--streams", type=int, default=32)
-    ap.add_argument("--max-ctas", type=int, default=16)
+    ap.add_argument("--max-ctas", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=128)
     ap.add_argument("--e2e-threads", type=int, default=8)
     ap.add_argument("--ref-per-core", type=int, default=160)

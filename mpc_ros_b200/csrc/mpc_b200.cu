@@ -194,6 +194,16 @@ static bool is_device_ptr(const void *p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): copies can go
+// straight from / to the caller's buffer without the handle's staging area
+static bool is_pinned_host(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 static int cuda_fail(mpc_b200_handle *h, cudaError_t e, const char *what)
 {
     if (h) h->last_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -429,13 +439,14 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     } else {
         if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
         double *hi = h->h_in;
-        memcpy(hi, state, sizeof(double) * 6 * B);
-        memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B);
-        if (ref_vel) memcpy(hi + 10 * B, ref_vel, sizeof(double) * B);
+        const double *src_s = state, *src_c = coeffs, *src_r = ref_vel;
+        if (!is_pinned_host(state)) { memcpy(hi, state, sizeof(double) * 6 * B); src_s = hi; }
+        if (!is_pinned_host(coeffs)) { memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B); src_c = hi + 6 * B; }
+        if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + 10 * B, ref_vel, sizeof(double) * B); src_r = hi + 10 * B; }
         // state and coeffs scratch are separate allocations: two copies (three with ref_vel)
-        CK(cudaMemcpyAsync(h->d_state, hi, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(h->d_coeffs, hi + 6 * B, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, st));
-        if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, hi + 10 * B, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_state, src_s, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_coeffs, src_c, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, st));
+        if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, src_r, sizeof(double) * B, cudaMemcpyHostToDevice, st));
         a.state = h->d_state; a.coeffs = h->d_coeffs; a.ref_vel = ref_vel ? h->d_refv : NULL;
     }
     a.warm_in = warm_in;
@@ -476,19 +487,21 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         double *ho = h->h_out;
         double *ho_u0 = ho, *ho_pred = ho + 2 * B, *ho_obj = ho_pred + 3 * (size_t)N * B, *ho_kkt = ho_obj + B;
         int *ho_status = reinterpret_cast<int *>(ho_kkt + B), *ho_iters = ho_status + B;
-        CK(cudaMemcpyAsync(ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
-        if (obj) CK(cudaMemcpyAsync(ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        if (kkt_res) CK(cudaMemcpyAsync(ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        if (status) CK(cudaMemcpyAsync(ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-        if (iters) CK(cudaMemcpyAsync(ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        const bool pu = is_pinned_host(u0), pp = is_pinned_host(pred), po = is_pinned_host(obj), pk = is_pinned_host(kkt_res),
+                   ps = is_pinned_host(status), pi = is_pinned_host(iters);
+        CK(cudaMemcpyAsync(pu ? u0 : ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pp ? pred : ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
+        if (obj) CK(cudaMemcpyAsync(po ? obj : ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        if (kkt_res) CK(cudaMemcpyAsync(pk ? kkt_res : ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        if (status) CK(cudaMemcpyAsync(ps ? status : ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        if (iters) CK(cudaMemcpyAsync(pi ? iters : ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        memcpy(u0, ho_u0, sizeof(double) * 2 * B);
-        memcpy(pred, ho_pred, sizeof(double) * 3 * N * B);
-        if (obj) memcpy(obj, ho_obj, sizeof(double) * B);
-        if (kkt_res) memcpy(kkt_res, ho_kkt, sizeof(double) * B);
-        if (status) memcpy(status, ho_status, sizeof(int) * B);
-        if (iters) memcpy(iters, ho_iters, sizeof(int) * B);
+        if (!pu) memcpy(u0, ho_u0, sizeof(double) * 2 * B);
+        if (!pp) memcpy(pred, ho_pred, sizeof(double) * 3 * N * B);
+        if (obj && !po) memcpy(obj, ho_obj, sizeof(double) * B);
+        if (kkt_res && !pk) memcpy(kkt_res, ho_kkt, sizeof(double) * B);
+        if (status && !ps) memcpy(status, ho_status, sizeof(int) * B);
+        if (iters && !pi) memcpy(iters, ho_iters, sizeof(int) * B);
     } else if (!(dev_in && stream_v)) {
         CK(cudaStreamSynchronize(st));
     }

@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--sets", type=int, default=48)
-    ap.add_argument("--max-iter", type=int, default=200)
+    ap.add_argument("--max-iter", type=int, default=100)
     ap.add_argument("--streams", type=int, default=32)
     ap.add_argument("--max-ctas", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=128)

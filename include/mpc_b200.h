@@ -73,7 +73,7 @@ typedef struct mpc_b200_params {
     /* solver controls; the reference leaves these at Ipopt's defaults
      * (only print_level and max_cpu_time are set, mpc_planner.cpp:358,368) */
     double tol;             /* Ipopt tol, 1e-8 */
-    int32_t max_iter;       /* iteration cap per problem (Ipopt: 3000; default here 200) */
+    int32_t max_iter;       /* iteration cap per problem (Ipopt: 3000; default here 100) */
     /* non-solver keys of mpc_params.yaml:2-9, carried for the callers above MPC::Solve */
     int32_t delay_mode;     /* delay_mode */
     double max_speed;       /* max_speed */

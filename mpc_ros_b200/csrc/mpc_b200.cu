@@ -427,7 +427,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.prm.w_cte = P.w_cte; a.prm.w_etheta = P.w_etheta; a.prm.w_vel = P.w_vel; a.prm.w_angvel = P.w_angvel;
     a.prm.w_accel = P.w_accel; a.prm.max_angvel = P.max_angvel; a.prm.max_throttle = P.max_throttle;
     a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
-    a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 200;
+    a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 100;
     a.prm.grp = SPT;
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
     a.batch = batch;

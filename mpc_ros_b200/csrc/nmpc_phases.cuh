@@ -23,6 +23,7 @@
 #pragma once
 
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MPC_HD __host__ __device__ __forceinline__
@@ -53,6 +54,8 @@ enum PSlot {
     PS_N0X, PS_N0Y, PS_N0T, PS_N0V, PS_N0C, PS_N0E,       // its Newton target lambda_0^+
     PS_AP_ALPHA, PS_AP_AZ, PS_AP_MU, PS_AP_SF,            // the step to apply in P3 (copied in P2: the lane may
                                                           // already have been re-initialised for its next problem)
+    PS_NX0, PS_NX1, PS_NX2, PS_NX3, PS_NX4, PS_NX5,       // staged inputs of the lane's next problem: state (6),
+    PS_NX6, PS_NX7, PS_NX8, PS_NX9, PS_NX10,              // coeffs (4), ref_vel -- prefetched during the sweeps
     NPS
 };
 enum PISlot {
@@ -167,13 +170,84 @@ struct StageRegs {
 MPC_HD double fmax2(double a, double b) { return a > b ? a : b; }
 MPC_HD double fmin2(double a, double b) { return a < b ? a : b; }
 
+// sin and cos together, branch-free (so that the evaluations of a thread's stages interleave):
+// Cody-Waite reduction by pi/2 in three parts, then the classical minimax kernels on [-pi/4, pi/4].
+// Accurate to about 1 ulp for |a| < 1e5 (heading angles here are a few radians); beyond that the
+// reduction loses bits gradually, NaN / Inf propagate as NaN.
 MPC_HD void sincos_d(double a, double *s, double *c)
 {
+    const double TWO_OVER_PI = 6.36619772367581382433e-01;
+    const double PIO2_1 = 1.57079632673412561417e+00;   // first 33 bits of pi/2
+    const double PIO2_2 = 6.07710050630396597660e-11;   // next 33 bits
+    const double PIO2_3 = 2.02226624871116645580e-21;   // next 33 bits
+    const double PIO2_3T = 8.47842766036889956997e-32;  // tail
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: round to nearest integer
+    const double qd = (a * TWO_OVER_PI + MAGIC) - MAGIC;
+    double r = fma(-qd, PIO2_1, a);
+    r = fma(-qd, PIO2_2, r);
+    r = fma(-qd, PIO2_3, r);
+    r = fma(-qd, PIO2_3T, r);
+    const int q = (int)qd;
+    const double z = r * r;
+    // sin kernel
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double ps = S1 + z * (S2 + z * (S3 + z * (S4 + z * (S5 + z * S6))));
+    const double sr = fma(r * z, ps, r);
+    // cos kernel
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double pc = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    const double cr = fma(z, pc, fma(-0.5, z, 1.0));
+    // quadrant
+    const bool swap = (q & 1) != 0;
+    double ss = swap ? cr : sr, cc = swap ? sr : cr;
+    if (q & 2) ss = -ss;
+    if ((q + 1) & 2) cc = -cc;
+    *s = ss; *c = cc;
+}
+
+// natural logarithm of a positive normal number, branch-free (the caller has checked x > 0).
+MPC_HD double log_pos(double x)
+{
 #if defined(__CUDA_ARCH__)
-    sincos(a, s, c);
+    long long ix = __double_as_longlong(x);
 #else
-    *s = sin(a); *c = cos(a);
+    long long ix; { double t_ = x; memcpy(&ix, &t_, sizeof(ix)); }
 #endif
+    // split x = 2^k * m with m in [sqrt(1/2), sqrt(2))
+    int hx = (int)(ix >> 32);
+    hx += 0x3ff00000 - 0x3fe6a09e;
+    const int k = (hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffff) + 0x3fe6a09e;
+    const long long im = ((long long)hx << 32) | (ix & 0xffffffffLL);
+#if defined(__CUDA_ARCH__)
+    const double m = __longlong_as_double(im);
+#else
+    double m; memcpy(&m, &im, sizeof(m));
+#endif
+    const double f = m - 1.0;
+    const double hfsq = 0.5 * f * f;
+    const double sden = 2.0 + f;
+#if defined(__CUDA_ARCH__)
+    double inv; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(sden));
+    double e_ = fma(-sden, inv, 1.0); inv = fma(inv, e_, inv);
+    e_ = fma(-sden, inv, 1.0); inv = fma(inv, e_, inv);
+    e_ = fma(-sden, inv, 1.0); inv = fma(inv, e_, inv);
+#else
+    const double inv = 1.0 / sden;
+#endif
+    const double s_ = f * inv;
+    const double z = s_ * s_, w = z * z;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    const double R = t2 + t1;
+    const double dk = (double)k;
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    return dk * ln2_hi - ((hfsq - (s_ * (hfsq + R) + dk * ln2_lo)) - f);
 }
 
 // Reciprocal for the 2x2 Riccati pivot: hardware seed + Newton steps (no special-case branch; the
@@ -292,7 +366,15 @@ MPC_HD void ctrl_rollout(const Params &prm, const SM &sm, int p, const double *c
     }
 }
 
-// trial bound multipliers  z + alpha_z dz, clamped (W&B eq. (16)); dz from W&B eq. (12)
+// trial bound multipliers  z + alpha_z dz (dz from W&B eq. (12)), kept within kappa_Sigma of mu / slack
+// (W&B eq. (16)).  The safeguard almost never binds, so it is tested on the complementarity product
+// z * slack (needed anyway) and the division only happens on the rare path.
+MPC_HD double zsafe(double z, double mu, double slack)
+{
+    const double prod = z * slack;
+    if (prod > NMPC_KAPPA_SIGMA * mu || prod < (1.0 / NMPC_KAPPA_SIGMA) * mu) z = zclamp(z, mu, 1.0 / slack);
+    return z;
+}
 MPC_HD void trial_z(const Params &prm, const StageRegs &r, double az, double mu, double uw, double ua,
                     double &zlw, double &zuw, double &zla, double &zua)
 {
@@ -302,11 +384,22 @@ MPC_HD void trial_z(const Params &prm, const StageRegs &r, double az, double mu,
         zuw = r.zuw + az * (mu * r.iuw - r.zuw + r.zuw * r.iuw * r.duw);
         zla = r.zla + az * (mu * r.ila - r.zla - r.zla * r.ila * r.dua);
         zua = r.zua + az * (mu * r.iua - r.zua + r.zua * r.iua * r.dua);
-        zlw = zclamp(zlw, mu, fast_rcp(uw + Uw)); zuw = zclamp(zuw, mu, fast_rcp(Uw - uw));
-        zla = zclamp(zla, mu, fast_rcp(ua + Ua)); zua = zclamp(zua, mu, fast_rcp(Ua - ua));
+        zlw = zsafe(zlw, mu, uw + Uw); zuw = zsafe(zuw, mu, Uw - uw);
+        zla = zsafe(zla, mu, ua + Ua); zua = zsafe(zua, mu, Ua - ua);
     } else {
         zlw = r.zlw; zuw = r.zuw; zla = r.zla; zua = r.zua;
     }
+}
+
+// P1, before the evaluation, lanes with FL_ADOPT: adopt the least-squares multipliers left in W_6..W_11 by
+// the adjoint sweep (or zero them).  Kept apart from stage_eval so that the evaluations of a thread's
+// stages contain no shared-memory stores and can be interleaved by the compiler.
+template <class SM>
+MPC_HD void stage_adopt(const Params &prm, const SM &sm, int k, int p, int flags)
+{
+    const bool keep = (flags & FL_KEEP) != 0;
+    if (k < prm.N - 1)
+        for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = keep ? sm.at(k, W_6 + c, p) : 0.0;
 }
 
 // ---------------------------------------------------------------- P1: evaluate  iterate + alpha * step
@@ -319,12 +412,6 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
-    if (flags & FL_ADOPT) {
-        // adopt the least-squares multipliers left in W_6..W_11 by the adjoint sweep (or zero them)
-        const bool keep = (flags & FL_KEEP) != 0;
-        if (k < N - 1)
-            for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = keep ? sm.at(k, W_6 + c, p) : 0.0;
-    }
     const bool ls = (flags & FL_LS) != 0;
     const double alpha = ls ? sm.P(PS_ALPHA, p) : 0.0;
     const double az = ls ? sm.P(PS_ALPHA_Z, p) : 0.0;
@@ -428,8 +515,9 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         const double p1 = slw * zlw, p2 = suw * zuw, p3 = sla * zla, p4 = sua * zua;
         vmax = fmax2(fmax2(p1, p2), fmax2(p3, p4));
         vmin = fmin2(fmin2(p1, p2), fmin2(p3, p4));
-        if (slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0) lnsum = log((slw * suw) * (sla * sua));
-        else acc.inside = 0;
+        const bool in_ = slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0;
+        lnsum = in_ ? log_pos((slw * suw) * (sla * sua)) : 0.0;
+        if (!in_) acc.inside = 0;
     } else {
         // last stage: no dynamics, no control
         const double rv = qv + lkv, rc = qc + lkc, re = qe + lke;
@@ -699,11 +787,11 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p)
 }
 
 // ---------------------------------------------------------------- P5: step-dependent stage work
-// Reads ds_k, du_k; writes g_k = q_s + Q_k ds_k into W_0..W_5 and accumulates the partials
+// Reads ds_k, du_k; returns g_k = q_s + Q_k ds_k (to be stored into W_0..W_5) and accumulates the partials
 // (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`.
 template <class SM>
 MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq,
-                       StepPart &acc)
+                       StepPart &acc, double *g6)
 {
     const int N = prm.N;
     const double mu = sm.P(PS_MU, p), sf = sm.P(PS_SF, p);
@@ -731,12 +819,13 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
         }
     }
     // g_k = q_s,k + Q_k ds_k  (Q_k = diag + the five lambda-weighted entries)
-    sm.at(k, W_0, p) = (hd.dx + r.hxx) * dsx;
-    sm.at(k, W_1, p) = hd.dy * dsy;
-    sm.at(k, W_2, p) = (hd.dt_ + r.htt) * dst + r.htv * dsv;
-    sm.at(k, W_3, p) = r.qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
-    sm.at(k, W_4, p) = r.qc + hd.dc * dsc;
-    sm.at(k, W_5, p) = r.qe + r.hev * dsv + (hd.de + r.hee) * dse;
+    // (returned in g6; the caller stores W_0..W_5 after all of its stages are computed)
+    g6[0] = (hd.dx + r.hxx) * dsx;
+    g6[1] = hd.dy * dsy;
+    g6[2] = (hd.dt_ + r.htt) * dst + r.htv * dsv;
+    g6[3] = r.qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
+    g6[4] = r.qc + hd.dc * dsc;
+    g6[5] = r.qe + r.hev * dsv + (hd.de + r.hee) * dse;
     acc.rmax = fmax2(acc.rmax, rmax); acc.rzmax = fmax2(acc.rzmax, rzmax); acc.gd += gd;
 }
 

@@ -25,7 +25,7 @@ void mpc_b200_params_default(mpc_b200_params *p)
     p->w_cte = 100.0; p->w_etheta = 100.0; p->w_vel = 1.0;
     p->w_angvel = 100.0; p->w_accel = 50.0; p->w_angvel_d = 0.0; p->w_accel_d = 0.0;
     p->tol = 1e-8;
-    p->max_iter = 200;
+    p->max_iter = 100;
     // DrivingStateContext defaults (mpc_ros/src/driving_state.cpp:24-29) / MPCPlanner.cfg:14-20
     p->delay_mode = 1; p->max_speed = 0.7; p->path_length = 5.0; p->waypoints_dist = -1.0;
     p->goal_radius = 0.5; p->controller_freq = 10.0;

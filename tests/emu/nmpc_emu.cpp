@@ -114,7 +114,10 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
                 for (int g = 0; g < NG; g++) {
                     StepPart acc; part_reset(acc);
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step(prm, sm, REG(k, p), k, p, hd, lsq, acc);
+                    double gk[SPT][6];
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT]);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++)
+                        for (int q = 0; q < 6; q++) sm.at(k, W_0 + q, p) = gk[k - g * SPT][q];
                     part_store(sm, g, p, acc);
                 }
             }
@@ -136,6 +139,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 const int fl = sm.I(PI_FLAGS, p);
                 // all stages read their neighbours' slots before FL_ADOPT overwrites the L slots of a stage:
                 // stage k writes only its own L slots and reads lambda^+ of stage k-1 from W, as in the kernel
+                if (fl & FL_ADOPT) for (int k = 0; k < N; k++) stage_adopt(prm, sm, k, p, fl);
                 for (int g = 0; g < NG; g++) {
                     EvalPart acc; part_reset(acc);
                     for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval(prm, sm, REG(k, p), k, p, fl, acc);

@@ -201,7 +201,7 @@ def run_ours(a):
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     # persistent-grid size per launch: with many batches in flight each launch takes a slice of the SMs and
     # every lane works through several problems; with few steps a launch must cover the machine by itself
-    max_ctas = a.max_ctas if a.max_ctas > 0 else max(16, min(128, -(-296 // S)))
+    max_ctas = a.max_ctas if a.max_ctas > 0 else max(8, min(128, -(-256 // S)))
     solver.set_option("max_ctas", max_ctas)
 
     # pre-marshalled C-ABI argument tuples (the timed loop is launches only, ~10 us of host time each)
@@ -254,10 +254,6 @@ def run_ours(a):
     launches = solver.launch_count - n0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
 
     # converged problems and iterations actually taken in the timed steps (results are deterministic per set)
     conv_steps = 0; iter_steps = 0.0; per_set = {}
@@ -268,10 +264,8 @@ def run_ours(a):
             ok = (st == 1) & (kk <= 1e-8)
             per_set[s] = (int(ok.sum()), float(it.sum()), float(it[ok].mean()) if ok.any() else 0.0, int(it.max()))
         conv_steps += per_set[s][0]; iter_steps += per_set[s][1]
-    cnt = torch.tensor([conv_steps, iter_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    conv_total = float(cnt[0].item())
+    from mpc_ros_b200.sharding import reduce_over_ranks
+    ms_total, (conv_total, _iters_all) = reduce_over_ranks(ms_total, [conv_steps, iter_steps], device=dev)
     value = conv_total / (ms_total * 1e-3)
 
     # ---- roofline of the dominant kernel (the solve kernel), this rank
@@ -390,8 +384,8 @@ def main():
     ap.add_argument("--max-iter", type=int, default=100)
     ap.add_argument("--streams", type=int, default=32)
     ap.add_argument("--max-ctas", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=128)
-    ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=512)
+    ap.add_argument("--e2e-threads", type=int, default=16)
     ap.add_argument("--ref-per-core", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

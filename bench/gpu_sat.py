@@ -49,6 +49,8 @@ def main():
         buf = (C.c_longlong * 1024)()
         if L.mpc_b200_debug_profile(sv._h, buf) and buf[1000] > 0:
             print("   avg global cycle: %.0f SM cycles (%d cycles total over all CTAs of all launches)" % (buf[1001] / buf[1000], buf[1000]))
+            names = ["-", "refill", "P3_apply_coeffs", "P4_backward", "P4_forward(+rollout,prefetch)", "P5_step", "P6", "P1_eval", "P2_decide"]
+            print("   per-cycle breakdown (control thread 0 of every CTA): " + ", ".join("%s %.0f" % (names[i], buf[1008 + i] / buf[1000]) for i in range(1, 9)))
     print("B %d S %d K %d maxctas %d: host issue %.1f us/launch, device %.3f ms/launch, %.2f M solves/s" %
           (B, S, K, maxc, (t1 - t0) / K * 1e6, ms / K, B * K / ms / 1e3))
 main()

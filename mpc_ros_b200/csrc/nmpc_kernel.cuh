@@ -45,7 +45,7 @@ struct SolveArgs {
 #ifdef NMPC_PROFILE
 #define PROF_DECL long long prof_t = clock64(), prof_acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}
 #define PROF_MARK(i) do { long long t_ = clock64(); prof_acc[i] += t_ - prof_t; prof_t = t_; } while (0)
-#define PROF_FLUSH() do { if (a.prof && blockIdx.x == 0 && tid == 0) for (int q_ = 0; q_ < 12; q_++) a.prof[q_] = prof_acc[q_]; } while (0)
+#define PROF_FLUSH() do { if (a.prof && tid == 0) for (int q_ = 0; q_ < 12; q_++) { if (blockIdx.x == 0) a.prof[q_] = prof_acc[q_]; atomicAdd((unsigned long long *)&a.prof[1008 + q_], (unsigned long long)prof_acc[q_]); } } while (0)
 // raw timestamp trace of the first cycles: control thread 0 -> prof[16 + 16*cyc + i], stage thread 32 -> prof[512 + 16*cyc + i]
 #define TRACE_C(i) do { if (a.prof && blockIdx.x == 0 && tid == 0 && trace_cyc < 24) a.prof[16 + 16 * trace_cyc + (i)] = clock64(); } while (0)
 #define TRACE_S(i) do { if (a.prof && blockIdx.x == 0 && tid == 32 && trace_cyc < 24) a.prof[512 + 16 * trace_cyc + (i)] = clock64(); } while (0)
@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 nx_state = NX_READY;
             }
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
+                adjoint_sweep(prm, sm, p);      // common to both branches below: keep it out of the divergence
                 if (sm.I(PI_FLAGS, p) & FL_LSQ) {
                     const int keep = ctrl_lsq_finish(prm, sm, p);
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;

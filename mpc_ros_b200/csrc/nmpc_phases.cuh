@@ -299,13 +299,16 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
 {
     for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
     for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = 0.0;
-    for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
-    for (int c = 0; c < 12; c++) sm.at(k, W_0 + c, p) = 0.0;
+    // (the D and W slots need no initialisation: every phase writes them before it reads them)
     r.uw = 0.0; r.ua = 0.0;
     r.zlw = r.zuw = r.zla = r.zua = 1.0;      // bound_mult_init_val
     r.c0 = coef4[0]; r.c1 = coef4[1]; r.c2 = coef4[2]; r.c3 = coef4[3];
-    sincos_d(sm.at(k, S_T, p), &r.sn, &r.cs);
-    sincos_d(sm.at(k, S_E, p), &r.se, &r.ce);
+    if (k == 0) {
+        sincos_d(state6[2], &r.sn, &r.cs);
+        sincos_d(state6[5], &r.se, &r.ce);
+    } else {
+        r.sn = 0.0; r.cs = 1.0; r.se = 0.0; r.ce = 1.0;
+    }
     r.duw = r.dua = 0.0;
     r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
     r.qv = r.qc = r.qe = 0.0;
@@ -962,7 +965,7 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
         const int ok = inside && (pr1 == pr1) && (phi_t == phi_t);
         int acc = 0, armijo = 0;
         if (ok && filter_acceptable(sm, c, p, pr1, phi_t)) {
-            if (th <= c.theta_min && gd < 0.0 && log(alpha) > c.sw_log) {
+            if (th <= c.theta_min && gd < 0.0 && log_pos(alpha) > c.sw_log) {
                 if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; armijo = 1; }
             } else {
                 if (pr1 <= (1.0 - NMPC_GAMMA_THETA) * th ||
@@ -982,7 +985,7 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
     const int m = 6 * N, nb = 4 * (N - 1);
     const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) * (1.0 / NMPC_S_MAX);
     const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) * (1.0 / NMPC_S_MAX);
-    const double isd = 1.0 / s_d, isc = 1.0 / s_c, isf = 1.0 / sf;
+    const double isd = fast_rcp(s_d), isc = fast_rcp(s_c), isf = fast_rcp(sf);
     const double compl0 = fmax2(fabs(vmax), fabs(vmin));
     const double du_s = duinf * isd;
     const double E0 = fmax2(fmax2(du_s, prinf), compl0 * isc);
@@ -1026,7 +1029,7 @@ MPC_HD double next_dw(const Ctrl &c, double dw)
     return (c.dw_last == 0.0) ? NMPC_KW_PLUS_BAR * dw : NMPC_KW_PLUS * dw;
 }
 
-// P6: after the step is known.  Reduces the step partials, runs the adjoint sweep, sets up the line
+// P6: after the step is known and adjoint_sweep has run.  Reduces the step partials, sets up the line
 // search.  Leaves PS_ALPHA (first trial), PS_ALPHA_Z and PS_MU_STEP.
 template <class SM>
 MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
@@ -1038,7 +1041,6 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
     const double tau = sm.P(PS_TAU, p);
     const double amax = (rmax > tau) ? tau / rmax : 1.0;      // fraction to the boundary, W&B eq. (15)
     const double az = (rzmax > tau) ? tau / rzmax : 1.0;
-    adjoint_sweep(prm, sm, p);
     c.gd = gd;
     const double th = c.theta;
     // switching condition (W&B eq. (19)) in log form:  log alpha + s_phi log(-gd) > s_theta log theta
@@ -1055,13 +1057,13 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
     sm.P(PS_MU_STEP, p) = sm.P(PS_MU, p);
 }
 
-// P6 of the first cycle: keep the least-squares multipliers unless they are huge (W&B Sec. 3.6).
+// P6 of the first cycle (after adjoint_sweep): keep the least-squares multipliers unless they are huge
+// (W&B Sec. 3.6).
 // Returns the FL_KEEP flag (or 0).
 template <class SM>
 MPC_HD int ctrl_lsq_finish(const Params &prm, const SM &sm, int p)
 {
     const int N = prm.N;
-    adjoint_sweep(prm, sm, p);
     double lmax = 0.0;
     for (int k = 0; k < N - 1; k++)
         for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.at(k, W_6 + i, p)));

@@ -124,6 +124,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             // ---- P6
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_STEP) continue;
+                adjoint_sweep(prm, sm, p);
                 if (sm.I(PI_FLAGS, p) & FL_LSQ) {
                     const int keep = ctrl_lsq_finish(prm, sm, p);
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;

@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
         const int k0 = g * SPT;
         const bool mine = k0 < N;
         StageRegs r[SPT];
+        double cf[4] = {0.0, 0.0, 0.0, 0.0};   // path polynomial of the lane's problem
         int trace_cyc = -1; (void)trace_cyc;
         for (;;) {
             trace_cyc++;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 if (idx >= 0) {
                     double s6[6], c4[4];
                     for (int i = 0; i < 6; i++) s6[i] = sm.P(PS_NX0 + i, p);
-                    for (int i = 0; i < 4; i++) c4[i] = sm.P(PS_NX6 + i, p);
+                    for (int i = 0; i < 4; i++) { c4[i] = sm.P(PS_NX6 + i, p); cf[i] = c4[i]; }
                     if (WARM && (fl & FL_WARM)) {
 #pragma unroll
                         for (int j = 0; j < SPT; j++)
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_coeffs(prm, sm, r[j], k0 + j, p, lsq);
+                        if (k0 + j < N) stage_coeffs(prm, sm, r[j], k0 + j, p, lsq, cf);
                 }
             }
             TRACE_S(4);
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 }
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_eval(prm, sm, r[j], k0 + j, p, fl, acc);
+                    if (k0 + j < N) stage_eval(prm, sm, r[j], k0 + j, p, fl, acc, cf);
                 part_store(sm, g, p, acc);
             }
             TRACE_S(8);

@@ -160,10 +160,8 @@ struct StageRegs {
     double zlw, zuw, zla, zua;  // bound multipliers of the controls (scaled problem)
     double sn, cs, se, ce;      // sin/cos(theta_k), sin/cos(etheta_k) at the iterate
     double tsn, tcs, tse, tce;  // the same at the last evaluated point
-    double qv, qc, qe;          // objective gradient wrt (v, cte, etheta) at the iterate
     double hxx, htt, htv, hee, hev;  // Lagrangian-Hessian entries of this stage
     double duw, dua;            // Newton step of the controls
-    double c0, c1, c2, c3;      // path polynomial coefficients
     double ilw, iuw, ila, iua;  // reciprocals of the four bound slacks at the iterate
 };
 
@@ -302,7 +300,7 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     // (the D and W slots need no initialisation: every phase writes them before it reads them)
     r.uw = 0.0; r.ua = 0.0;
     r.zlw = r.zuw = r.zla = r.zua = 1.0;      // bound_mult_init_val
-    r.c0 = coef4[0]; r.c1 = coef4[1]; r.c2 = coef4[2]; r.c3 = coef4[3];
+    (void)coef4;
     if (k == 0) {
         sincos_d(state6[2], &r.sn, &r.cs);
         sincos_d(state6[5], &r.se, &r.ce);
@@ -311,7 +309,6 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     }
     r.duw = r.dua = 0.0;
     r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
-    r.qv = r.qc = r.qe = 0.0;
     r.tsn = r.sn; r.tcs = r.cs; r.tse = r.se; r.tce = r.ce;
     r.ilw = r.iuw = 1.0 / relaxed(prm.max_angvel); r.ila = r.iua = 1.0 / relaxed(prm.max_throttle);
 }
@@ -411,7 +408,8 @@ MPC_HD void stage_adopt(const Params &prm, const SM &sm, int k, int p, int flags
 // sum, max|dual residual| and the extreme complementarity products with the trial multipliers
 // lambda + alpha (lambda^+ - lambda), z + alpha_z dz, plus the multiplier norms.
 template <class SM>
-MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int flags, EvalPart &acc)
+MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int flags, EvalPart &acc,
+                       const double *cf)
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
@@ -470,8 +468,8 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
     if (k < N - 1) {
         const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
         f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
-        const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
-        const double dpoly = r.c1 + x * (2.0 * r.c2 + 3.0 * r.c3 * x);
+        const double poly = cf[0] + x * (cf[1] + x * (cf[2] + x * cf[3]));
+        const double dpoly = cf[1] + x * (2.0 * cf[2] + 3.0 * cf[3] * x);
         double nx = sm.at(k + 1, S_X, p), ny = sm.at(k + 1, S_Y, p), nt = sm.at(k + 1, S_T, p);
         double nv = sm.at(k + 1, S_V, p), nc = sm.at(k + 1, S_C, p), ne = sm.at(k + 1, S_E, p);
         if (ls) {
@@ -560,19 +558,19 @@ MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, in
 }
 
 template <class SM>
-MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq)
+MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq, const double *cf)
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), mu = sm.P(PS_MU, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
     const double x = sm.at(k, S_X, p), y = sm.at(k, S_Y, p), th = sm.at(k, S_T, p);
     const double v = sm.at(k, S_V, p), ct = sm.at(k, S_C, p), e = sm.at(k, S_E, p);
-    r.qv = 2.0 * sf * prm.w_vel * (v - refv);
-    r.qc = 2.0 * sf * prm.w_cte * (ct - prm.ref_cte);
-    r.qe = 2.0 * sf * prm.w_etheta * (e - prm.ref_etheta);
+    const double qv = 2.0 * sf * prm.w_vel * (v - refv);
+    const double qc = 2.0 * sf * prm.w_cte * (ct - prm.ref_cte);
+    const double qe = 2.0 * sf * prm.w_etheta * (e - prm.ref_etheta);
     if (k < N - 1) {
-        const double poly = r.c0 + x * (r.c1 + x * (r.c2 + x * r.c3));
-        const double dpoly = r.c1 + x * (2.0 * r.c2 + 3.0 * r.c3 * x);
-        const double ddpoly = 2.0 * r.c2 + 6.0 * r.c3 * x;
+        const double poly = cf[0] + x * (cf[1] + x * (cf[2] + x * cf[3]));
+        const double dpoly = cf[1] + x * (2.0 * cf[2] + 3.0 * cf[3] * x);
+        const double ddpoly = 2.0 * cf[2] + 6.0 * cf[3] * x;
         sm.at(k, A_13, p) = -v * r.sn * dt; sm.at(k, A_14, p) = r.cs * dt;
         sm.at(k, A_23, p) = v * r.cs * dt;  sm.at(k, A_24, p) = r.sn * dt;
         sm.at(k, A_51, p) = dpoly; sm.at(k, A_54, p) = r.se * dt; sm.at(k, A_56, p) = v * r.ce * dt;
@@ -610,7 +608,7 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
         sm.at(k, W_5, p) = r.hxx; sm.at(k, W_6, p) = r.htt; sm.at(k, W_7, p) = r.htv;
         sm.at(k, W_8, p) = r.hee; sm.at(k, W_9, p) = r.hev;
     }
-    sm.at(k, W_0, p) = r.qv; sm.at(k, W_1, p) = r.qc; sm.at(k, W_2, p) = r.qe;
+    sm.at(k, W_0, p) = qv; sm.at(k, W_1, p) = qc; sm.at(k, W_2, p) = qe;
 }
 
 // ---------------------------------------------------------------- Riccati sweeps (control thread)
@@ -642,9 +640,9 @@ MPC_HD void load_coef(const SM &sm, int k, int p, StageCoef &c)
 // Backward sweep over stages N-1 .. 0.  5x5 value matrix over (x,y,theta,v,etheta); the cte
 // row/column of A is zero, so cte only contributes a rank-one term.  Returns 0 if some
 // R~_k is not positive definite (wrong KKT inertia), else 1.  Overwrites W_0..W_11 of each
-// stage k <= N-2 with the gains K (2x5) and k_ff (2).  The next stage's coefficients are
-// loaded while the current stage computes (the sweep is one long dependency chain through
-// P; everything that does not depend on P is kept off that chain).
+// stage k <= N-2 with the gains K (2x5) and k_ff (2).  The sweep is one long dependency chain
+// through P; everything that does not depend on P is kept off that chain.  (Prefetching the next
+// stage's coefficients into registers was measured slower: it costs 50 live registers.)
 template <class SM>
 MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
@@ -657,12 +655,10 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
     double qc_next = sm.at(N - 1, W_1, p);
     const double gam = hd.dc;
     int ok = 1;
-    StageCoef c, nx;
-    load_coef(sm, N - 2, p, c);
-    nx = c;
+    StageCoef c;
 #pragma unroll 1
     for (int k = N - 2; k >= 0; k--) {
-        if (k > 0) load_coef(sm, k - 1, p, nx);
+        load_coef(sm, k, p, c);
 
         // ---- R~ = R + B^T P B  (B = dt [e_theta + e_etheta | e_v]) and its inverse: the head of the
         //      critical chain, needs only P_{k+1}
@@ -754,7 +750,6 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
         pv = ((c.qv + tv) + (c.a14 * tx + c.a24 * ty)) + (c.a54 * pic + (Swv * kfw + Sav * kfa));
         pe = ((c.qe + te) + c.a56 * pic) + (Swe * kfw + Sae * kfa);
         qc_next = c.qc;
-        c = nx;
     }
     return ok;
 }
@@ -798,13 +793,17 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
 {
     const int N = prm.N;
     const double mu = sm.P(PS_MU, p), sf = sm.P(PS_SF, p);
+    // objective gradient at the iterate (recomputed: cheaper than three live registers per stage)
+    const double qv = 2.0 * sf * prm.w_vel * (sm.at(k, S_V, p) - sm.P(PS_REFV, p));
+    const double qc = 2.0 * sf * prm.w_cte * (sm.at(k, S_C, p) - prm.ref_cte);
+    const double qe = 2.0 * sf * prm.w_etheta * (sm.at(k, S_E, p) - prm.ref_etheta);
     double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
     if (k > 0) {
         dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
         dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
     }
     // fraction to the boundary (W&B eq. (15)) as the largest step / slack ratio: alpha_max = min(1, tau / ratio)
-    double rmax = 0.0, rzmax = 0.0, gd = r.qv * dsv + r.qc * dsc + r.qe * dse;
+    double rmax = 0.0, rzmax = 0.0, gd = qv * dsv + qc * dsc + qe * dse;
     if (k < N - 1) {
         r.duw = sm.at(k, W_10, p); r.dua = sm.at(k, W_11, p);
         if (!lsq) {
@@ -826,9 +825,9 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
     g6[0] = (hd.dx + r.hxx) * dsx;
     g6[1] = hd.dy * dsy;
     g6[2] = (hd.dt_ + r.htt) * dst + r.htv * dsv;
-    g6[3] = r.qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
-    g6[4] = r.qc + hd.dc * dsc;
-    g6[5] = r.qe + r.hev * dsv + (hd.de + r.hee) * dse;
+    g6[3] = qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
+    g6[4] = qc + hd.dc * dsc;
+    g6[5] = qe + r.hev * dsv + (hd.de + r.hee) * dse;
     acc.rmax = fmax2(acc.rmax, rmax); acc.rzmax = fmax2(acc.rzmax, rzmax); acc.gd += gd;
 }
 

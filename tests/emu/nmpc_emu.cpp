@@ -32,6 +32,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
     std::vector<double> mem(smem_bytes(N, NG, PB) / sizeof(double) + 8);
     Smem sm; sm.PB = PB; sm.carve(mem.data(), N, NG);
     std::vector<StageRegs> regs((size_t)N * PB);
+    std::vector<double> cfs((size_t)4 * PB);
     std::vector<Ctrl> ctrl(PB);
     std::vector<int> nreg(PB);
 #define REG(k, p) regs[(size_t)(k) * PB + (p)]
@@ -77,7 +78,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 if (idx >= 0) {
                     double s6[6], c4[4];
                     for (int c = 0; c < 6; c++) s6[c] = state[(size_t)c * batch + idx];
-                    for (int c = 0; c < 4; c++) c4[c] = coeffs[(size_t)c * batch + idx];
+                    for (int c = 0; c < 4; c++) { c4[c] = coeffs[(size_t)c * batch + idx]; cfs[(size_t)4 * p + c] = c4[c]; }
                     for (int k = 0; k < N; k++) stage_init(prm, sm, REG(k, p), k, p, s6, c4);
                 }
             }
@@ -88,7 +89,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             // ---- P3b
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_NEWTON)
-                    for (int k = 0; k < N; k++) stage_coeffs(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ);
+                    for (int k = 0; k < N; k++) stage_coeffs(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)4 * p]);
             // ---- P4
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_NEWTON) continue;
@@ -143,7 +144,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 if (fl & FL_ADOPT) for (int k = 0; k < N; k++) stage_adopt(prm, sm, k, p, fl);
                 for (int g = 0; g < NG; g++) {
                     EvalPart acc; part_reset(acc);
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval(prm, sm, REG(k, p), k, p, fl, acc);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval(prm, sm, REG(k, p), k, p, fl, acc, &cfs[(size_t)4 * p]);
                     part_store(sm, g, p, acc);
                 }
             }

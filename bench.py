@@ -42,6 +42,9 @@ UNIT = "solves/s"
 BATCH = 4096                 # BASELINE config 2
 SEED = 20261018 + 2          # seed = 20261018 + config#
 FLOP_PER_ITER_N20 = 27879.0  # SURVEY 8d algorithmic flops per interior-point iteration, N = 20
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE solve-kernel launch (4,096 problems) from the ncu --set full
+# capture in profiles/r1_solve_kernel_ncu_raw.csv (805,632 + 54,016 B); algorithmic: 80 B in + ~520 B out per problem
+NCU_DRAM_BYTES_PER_LAUNCH = 859648
 WORKLOAD = ("config2: batch of 4096 independent N=20 diff-drive NMPC problems per GPU, random poses on "
             "infinity/epitrochoid/square tracks, mpc_params.yaml weights, cold start; step = prestep "
             "(transform+polyfit+state) + solve")
@@ -285,7 +288,7 @@ def run_ours(a):
         iso.append(x.elapsed_time(y))
     iso_ms = float(np.median(iso))
     roofline = dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak,
-                    traffic=None, kernel="nmpc_solve_kernel", kernel_ms=eff_ms,
+                    traffic=NCU_DRAM_BYTES_PER_LAUNCH if B == BATCH else None, kernel="nmpc_solve_kernel", kernel_ms=eff_ms,
                     kernel_ms_isolated=iso_ms, achieved_isolated=flops_per_launch / (iso_ms * 1e-3) / 1e12,
                     streams=S, flops_per_launch=flops_per_launch,
                     peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak; "

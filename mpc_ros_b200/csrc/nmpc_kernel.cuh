@@ -78,9 +78,6 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
         c.status = 0; c.iter = 0; c.E0 = 0.0; c.obj = 0.0;
         if (lane) { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_FLAGS, p) = 0; sm.I(PI_PROB, p) = -1; sm.I(PI_NEXT, p) = -1; }
         bool fin = lane;          // every lane starts by popping a problem
-        enum { NX_NONE = 0, NX_POPPED, NX_LOADED, NX_READY, NX_EMPTY };
-        int nx_state = NX_NONE, nx_idx = -1;   // prefetch of the lane's next problem
-        double nx_v[11];
         PROF_DECL;
 #ifdef NMPC_PROFILE
         const long long prof_t0 = clock64();
@@ -89,30 +86,21 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
         for (;;) {
             trace_cyc++;
             TRACE_C(0);
-            // ---- refill the lanes that finished (fin).  A lane normally finds its next problem already staged
-            //      in shared memory (prefetched during an earlier cycle's sweeps, see P4 / P6 below); only the
-            //      first problem of a lane, or a lane that finishes before its prefetch landed, pops synchronously.
+            // ---- refill the lanes that finished (fin): one warp-aggregated pop from the work queue; the new
+            //      problem's inputs are staged in shared memory for the stage threads (P3a).
+            //      (Prefetching the next problem during the sweeps was measured: no gain.)
             {
-                const bool sync_pop = fin && nx_state != NX_READY && nx_state != NX_EMPTY;
-                const unsigned m = __ballot_sync(0xffffffffu, sync_pop);
+                const unsigned m = __ballot_sync(0xffffffffu, fin);
                 int nb = 0;
                 if (p == 0 && m) nb = atomicAdd(a.queue, __popc(m));
                 nb = __shfl_sync(0xffffffffu, nb, 0);
                 if (fin) {
-                    int nidx = -1;
-                    if (nx_state == NX_READY) {
-                        nidx = nx_idx;
-                        nx_state = NX_NONE;
-                    } else if (sync_pop) {
-                        nidx = nb + __popc(m & ((1u << p) - 1u));
-                        if (nidx >= batch) { nidx = -1; nx_state = NX_EMPTY; }
-                        else {
-                            for (int i = 0; i < 6; i++) sm.P(PS_NX0 + i, p) = a.state[(size_t)i * batch + nidx];
-                            for (int i = 0; i < 4; i++) sm.P(PS_NX6 + i, p) = a.coeffs[(size_t)i * batch + nidx];
-                            sm.P(PS_NX10, p) = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
-                            if (nx_state == NX_POPPED) { /* keep the index already popped for the following problem */ }
-                            else nx_state = NX_NONE;
-                        }
+                    int nidx = nb + __popc(m & ((1u << p) - 1u));
+                    if (nidx >= batch) nidx = -1;
+                    else {
+                        for (int i = 0; i < 6; i++) sm.P(PS_NX0 + i, p) = a.state[(size_t)i * batch + nidx];
+                        for (int i = 0; i < 4; i++) sm.P(PS_NX6 + i, p) = a.coeffs[(size_t)i * batch + nidx];
+                        sm.P(PS_NX10, p) = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
                     }
                     sm.I(PI_NEXT, p) = nidx;
                     if (nidx >= 0) {
@@ -153,13 +141,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
             __syncthreads();  // B4
             TRACE_C(3);
             PROF_MARK(2);
-            // ---- P4: Riccati sweeps.  Before them: pop the index of the lane's next problem (the atomic's
-            //      latency hides under the sweeps); after them: issue the loads of its inputs (they land
-            //      during P5 and are staged into shared memory in P6).
-            int pf_base = 0;
-            const bool pf_pop = lane && nx_state == NX_NONE && sm.I(PI_MODE, p) != MODE_IDLE;
-            const unsigned pf_mask = __ballot_sync(0xffffffffu, pf_pop);
-            if (p == 0 && pf_mask) pf_base = atomicAdd(a.queue, __popc(pf_mask));
+            // ---- P4: Riccati sweeps
             if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
                 const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
                 const double dw = sm.P(PS_DW, p);
@@ -174,17 +156,6 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     const double nd = next_dw(c, dw);
                     if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_MODE, p) = MODE_FAIL; }
                     else sm.P(PS_DW, p) = nd;       // stays MODE_NEWTON: coefficients are rewritten next cycle
-                }
-            }
-            pf_base = __shfl_sync(0xffffffffu, pf_base, 0);
-            if (pf_pop) {
-                nx_idx = pf_base + __popc(pf_mask & ((1u << p) - 1u));
-                if (nx_idx >= batch) { nx_idx = -1; nx_state = NX_EMPTY; }
-                else {
-                    nx_state = NX_LOADED;
-                    for (int i = 0; i < 6; i++) nx_v[i] = a.state[(size_t)i * batch + nx_idx];
-                    for (int i = 0; i < 4; i++) nx_v[6 + i] = a.coeffs[(size_t)i * batch + nx_idx];
-                    nx_v[10] = a.ref_vel ? a.ref_vel[nx_idx] : prm.ref_vel;
                 }
             }
             if (WARM && lane && sm.I(PI_MODE, p) == MODE_ROLLOUT) {
@@ -204,11 +175,6 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
             TRACE_C(6);
             PROF_MARK(5);
             // ---- P6: multipliers, step sizes
-            if (nx_state == NX_LOADED) {
-                // the staging slots are free: the lane's current problem was initialised from them in P3a
-                for (int i = 0; i < 11; i++) sm.P(PS_NX0 + i, p) = nx_v[i];
-                nx_state = NX_READY;
-            }
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
                 adjoint_sweep(prm, sm, p);      // common to both branches below: keep it out of the divergence
                 if (sm.I(PI_FLAGS, p) & FL_LSQ) {

@@ -55,7 +55,7 @@ enum PSlot {
     PS_AP_ALPHA, PS_AP_AZ, PS_AP_MU, PS_AP_SF,            // the step to apply in P3 (copied in P2: the lane may
                                                           // already have been re-initialised for its next problem)
     PS_NX0, PS_NX1, PS_NX2, PS_NX3, PS_NX4, PS_NX5,       // staged inputs of the lane's next problem: state (6),
-    PS_NX6, PS_NX7, PS_NX8, PS_NX9, PS_NX10,              // coeffs (4), ref_vel -- prefetched during the sweeps
+    PS_NX6, PS_NX7, PS_NX8, PS_NX9, PS_NX10,              // coeffs (4), ref_vel -- written at refill, read in P3a
     NPS
 };
 enum PISlot {

@@ -257,9 +257,7 @@ static int check_params(const mpc_b200_params *p)
     if (!p) return MPC_B200_ERR_INVALID;
     if (p->mpc_steps < 2 || p->mpc_steps > 600) return MPC_B200_ERR_INVALID;
     if (!(p->dt > 0.0) || !(p->max_angvel > 0.0) || !(p->max_throttle > 0.0)) return MPC_B200_ERR_INVALID;
-    // rate penalties couple u_k and u_{k+1} (mpc_planner.cpp:144-147): needs the augmented-state
-    // Riccati variant; not on the GPU path yet.
-    if (p->w_angvel_d != 0.0 || p->w_accel_d != 0.0) return MPC_B200_ERR_UNSUPPORTED;
+    if (p->w_angvel_d < 0.0 || p->w_accel_d < 0.0) return MPC_B200_ERR_INVALID;
     return MPC_B200_OK;
 }
 
@@ -318,10 +316,12 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     h->num_sms = sms; h->smem_optin = (size_t)optin;
 #define SET_SMEM(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)
-    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, false>));
-    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 16, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 8, false>));
-    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 4, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 1, false>));
-    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, true>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 16, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 8, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 4, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 1, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, true, false>));
+    // rate-penalty variant (w_angvel_d / w_accel_d != 0): 44 slots per stage, lanes per CTA chosen at run time
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true>));
 #undef SET_SMEM
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
@@ -379,19 +379,21 @@ int64_t mpc_b200_launch_count(const mpc_b200_handle *h) { return h ? h->launches
 
 // Problems per CTA: as many as shared memory and the thread budget allow, but spread a small
 // batch over all SMs (the CTA's latency does not depend on how many lanes are active).
-static int choose_pb(const mpc_b200_handle *h, int N, int batch)
+static int choose_pb(const mpc_b200_handle *h, int N, int batch, int nslots)
 {
     const int NG = (N + SPT - 1) / SPT;
     int pb = 32;
     if (pb > STAGE_THREADS / NG) pb = STAGE_THREADS / NG;
-    while (pb > 1 && nmpc::smem_bytes(N, NG, pb) > h->smem_optin) pb--;
+    while (pb > 1 && nmpc::smem_bytes(N, NG, pb, nslots) > h->smem_optin) pb--;
     if (h->opt_pb > 0) return h->opt_pb < pb ? h->opt_pb : pb;
     // a small batch is spread over all SMs; snap to the lane counts that have a compiled specialisation
     const int spread = (batch + h->num_sms - 1) / h->num_sms;
     if (spread < pb) {
         int want = spread < 1 ? 1 : spread;
-        if (want > 16) want = 32; else if (want > 8) want = 16; else if (want > 4) want = 8;
-        else if (want > 1) want = 4;
+        if (nslots == nmpc::NSLOTS) {
+            if (want > 16) want = 32; else if (want > 8) want = 16; else if (want > 4) want = 8;
+            else if (want > 1) want = 4;
+        }
         if (want < pb) pb = want;
     }
     return pb;
@@ -431,7 +433,10 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.prm.grp = SPT;
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
     a.batch = batch;
-    a.PB = choose_pb(h, N, batch);
+    const bool rate = P.w_angvel_d != 0.0 || P.w_accel_d != 0.0;
+    const int nslots = rate ? nmpc::NSLOTS_RATE : nmpc::NSLOTS;
+    a.prm.w_angvel_d = P.w_angvel_d; a.prm.w_accel_d = P.w_accel_d;
+    a.PB = choose_pb(h, N, batch, nslots);
     a.prof = h->d_prof;
 
     if (dev_in) {
@@ -464,20 +469,23 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     int grid = (batch + a.PB - 1) / a.PB;
     const int cap = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
     if (grid > cap) grid = cap;
-    const size_t smem = nmpc::smem_bytes(N, NG, a.PB);
+    const size_t smem = nmpc::smem_bytes(N, NG, a.PB, nslots);
     a.queue = h->d_queue + (h->launches % QUEUE_RING);
     CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     CK(cudaEventRecord(h->ev0, st));
-    if (a.warm_in) {
-        if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32, true><<<grid, threads, smem, st>>>(a);
-        else nmpc::nmpc_solve_kernel<SPT, 0, true><<<grid, threads, smem, st>>>(a);
+    if (rate) {
+        if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);
+        else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);
+    } else if (a.warm_in) {
+        if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32, true, false><<<grid, threads, smem, st>>>(a);
+        else nmpc::nmpc_solve_kernel<SPT, 0, true, false><<<grid, threads, smem, st>>>(a);
     } else switch (a.PB) {
-        case 32: nmpc::nmpc_solve_kernel<SPT, 32, false><<<grid, threads, smem, st>>>(a); break;
-        case 16: nmpc::nmpc_solve_kernel<SPT, 16, false><<<grid, threads, smem, st>>>(a); break;
-        case 8: nmpc::nmpc_solve_kernel<SPT, 8, false><<<grid, threads, smem, st>>>(a); break;
-        case 4: nmpc::nmpc_solve_kernel<SPT, 4, false><<<grid, threads, smem, st>>>(a); break;
-        case 1: nmpc::nmpc_solve_kernel<SPT, 1, false><<<grid, threads, smem, st>>>(a); break;
-        default: nmpc::nmpc_solve_kernel<SPT, 0, false><<<grid, threads, smem, st>>>(a); break;
+        case 32: nmpc::nmpc_solve_kernel<SPT, 32, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 16: nmpc::nmpc_solve_kernel<SPT, 16, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 8: nmpc::nmpc_solve_kernel<SPT, 8, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 4: nmpc::nmpc_solve_kernel<SPT, 4, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 1: nmpc::nmpc_solve_kernel<SPT, 1, false, false><<<grid, threads, smem, st>>>(a); break;
+        default: nmpc::nmpc_solve_kernel<SPT, 0, false, false><<<grid, threads, smem, st>>>(a); break;
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));

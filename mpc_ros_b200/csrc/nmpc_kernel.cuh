@@ -57,14 +57,14 @@ struct SolveArgs {
 #define TRACE_S(i)
 #endif
 
-template <int SPT, int CPB, bool WARM>
+template <int SPT, int CPB, bool WARM, bool RATE>
 __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;
     const int N = prm.N, PB = (CPB > 0) ? CPB : a.PB, batch = a.batch;
     const int NG = (N + SPT - 1) / SPT;
-    SmemT<CPB> sm;
+    SmemT<CPB, RATE ? NSLOTS_RATE : NSLOTS> sm;
     sm.PB = PB;
     sm.carve(smem_raw, N, NG);
 
@@ -146,10 +146,10 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
                 const double dw = sm.P(PS_DW, p);
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
-                const int okb = riccati_backward(prm, sm, p, hd);
+                const int okb = riccati_backward<RATE>(prm, sm, p, hd);
                 PROF_MARK(3);
                 if (okb || lsq) {
-                    riccati_forward(prm, sm, p);
+                    riccati_forward<RATE>(prm, sm, p, hd);
                     if (dw > 0.0) c.dw_last = dw;
                     sm.I(PI_MODE, p) = MODE_STEP;
                 } else {
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 if (fl & FL_APPLY) {
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_apply(prm, sm, r[j], k0 + j, p);
+                        if (k0 + j < N) stage_apply<RATE>(prm, sm, r[j], k0 + j, p);
                 }
                 if (fl & FL_FLUSH) {
                     // the last iterate whatever the status (mpc_planner.cpp:378-401)
@@ -311,11 +311,11 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     if (WARM && (fl & FL_WARM)) {
 #pragma unroll
                         for (int j = 0; j < SPT; j++)
-                            if (k0 + j < N) stage_init_warm(prm, sm, r[j], k0 + j, p, s6, c4, a.warm_in, (size_t)batch, (size_t)idx);
+                            if (k0 + j < N) stage_init_warm<RATE>(prm, sm, r[j], k0 + j, p, s6, c4, a.warm_in, (size_t)batch, (size_t)idx);
                     } else {
 #pragma unroll
                         for (int j = 0; j < SPT; j++)
-                            if (k0 + j < N) stage_init(prm, sm, r[j], k0 + j, p, s6, c4);
+                            if (k0 + j < N) stage_init<RATE>(prm, sm, r[j], k0 + j, p, s6, c4);
                     }
                 }
             }
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_coeffs(prm, sm, r[j], k0 + j, p, lsq, cf);
+                        if (k0 + j < N) stage_coeffs<RATE>(prm, sm, r[j], k0 + j, p, lsq, cf);
                 }
             }
             TRACE_S(4);
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 double gk[SPT][6];
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_step(prm, sm, r[j], k0 + j, p, hd, lsq, acc, gk[j]);
+                    if (k0 + j < N) stage_step<RATE>(prm, sm, r[j], k0 + j, p, hd, lsq, acc, gk[j]);
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
                     if (k0 + j < N)
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 }
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_eval(prm, sm, r[j], k0 + j, p, fl, acc, cf);
+                    if (k0 + j < N) stage_eval<RATE>(prm, sm, r[j], k0 + j, p, fl, acc, cf);
                 part_store(sm, g, p, acc);
             }
             TRACE_S(8);

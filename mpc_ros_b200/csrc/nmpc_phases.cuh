@@ -40,7 +40,12 @@ enum Slot {
     A_13, A_14, A_23, A_24, A_51, A_54, A_56,  // non-trivial entries of A_k = d phi / d s
     D_X, D_Y, D_T, D_V, D_C, D_E,              // d_k = -(s_{k+1} - phi_k); after the forward sweep: ds_{k+1}
     W_0, W_1, W_2, W_3, W_4, W_5, W_6, W_7, W_8, W_9, W_10, W_11,  // work slots (see phases)
-    NSLOTS
+    NSLOTS,
+    // only in the rate-penalty variant (w_angvel_d / w_accel_d != 0 couple u_k and u_{k+1}):
+    U_W = NSLOTS, U_A,          // controls of the stage, published for the neighbouring stages
+    DU_W, DU_A,                 // their Newton step
+    RI_11, RI_12, RI_22,        // inverse of the Riccati pivot R~_k (forward sweep: gain on the previous control step)
+    NSLOTS_RATE
 };
 // partial sums, one set per group of stages: [group][NPART][lane]
 enum PartSlot { PT_0 = 0, PT_1, PT_2, PT_3, PT_4, PT_5, PT_6, PT_7, PT_8, NPART };
@@ -94,22 +99,23 @@ struct Params {
     int max_iter;
     int grp;      // stages per stage thread: partial sums are pre-reduced over groups of grp stages
     double warm_mu;   // initial barrier parameter of a warm-started problem
+    double w_angvel_d, w_accel_d;   // rate penalties (mpc_planner.cpp:144-147); both 0 in the plain variant
 };
 
 #define NMPC_MAX_FILTER 8
 
 // View of the CTA's shared-memory block.  CPB > 0 fixes the lanes-per-CTA at compile time so that
 // every access is base + lane*8 + immediate (no index arithmetic in the sweeps).
-template <int CPB>
+template <int CPB, int NS = NSLOTS>
 struct SmemT {
-    double *st;   // [N][NSLOTS][PB]
+    double *st;   // [N][NS][PB]
     double *pt;   // [NG][NPART][PB]
     double *ps;   // [NPS][PB]
     double *fl;   // [2*NMPC_MAX_FILTER][PB]  filter entries (theta, phi)
     int *pi;      // [NPI][PB]
     int PB;
     MPC_HD int pb() const { return CPB > 0 ? CPB : PB; }
-    MPC_HD double &at(int k, int slot, int p) const { return st[(k * NSLOTS + slot) * pb() + p]; }
+    MPC_HD double &at(int k, int slot, int p) const { return st[(k * NS + slot) * pb() + p]; }
     MPC_HD double &part(int g, int slot, int p) const { return pt[(g * NPART + slot) * pb() + p]; }
     MPC_HD double &P(int slot, int p) const { return ps[slot * pb() + p]; }
     MPC_HD double &F(int slot, int p) const { return fl[slot * pb() + p]; }
@@ -117,7 +123,7 @@ struct SmemT {
     MPC_HD void carve(double *base, int N, int NG)
     {
         st = base;
-        pt = st + (size_t)N * NSLOTS * pb();
+        pt = st + (size_t)N * NS * pb();
         ps = pt + (size_t)NG * NPART * pb();
         fl = ps + (size_t)NPS * pb();
         pi = reinterpret_cast<int *>(fl + (size_t)2 * NMPC_MAX_FILTER * pb());
@@ -125,9 +131,9 @@ struct SmemT {
 };
 typedef SmemT<0> Smem;
 
-MPC_HD size_t smem_bytes(int N, int NG, int PB)
+MPC_HD size_t smem_bytes(int N, int NG, int PB, int nslots = NSLOTS)
 {
-    return sizeof(double) * ((size_t)N * NSLOTS + (size_t)NG * NPART + NPS + 2 * NMPC_MAX_FILTER) * PB +
+    return sizeof(double) * ((size_t)N * nslots + (size_t)NG * NPART + NPS + 2 * NMPC_MAX_FILTER) * PB +
            sizeof(int) * (size_t)NPI * PB;
 }
 
@@ -291,10 +297,11 @@ template <class SM> MPC_HD void part_store(const SM &sm, int g, int p, const Ste
 
 // ---------------------------------------------------------------- init (new problem in a lane)
 // Reference cold start (mpc_planner.cpp:288-300): zeros except stage 0 = state; z = 1; lambda = 0.
-template <class SM>
+template <bool RATE = false, class SM>
 MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int p,
                        const double *state6, const double *coef4)
 {
+    if (RATE) { sm.at(k, U_W, p) = 0.0; sm.at(k, U_A, p) = 0.0; sm.at(k, DU_W, p) = 0.0; sm.at(k, DU_A, p) = 0.0; }
     for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
     for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = 0.0;
     // (the D and W slots need no initialisation: every phase writes them before it reads them)
@@ -319,12 +326,12 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
 // zL_w, zL_a, zU_w, zU_a.  Controls and multipliers are taken from the record (controls pushed into the
 // interior of their bounds); the states are NOT taken from it: the control thread rolls the model out
 // from the given state (ctrl_rollout), so the start point satisfies the dynamics exactly.
-template <class SM>
+template <bool RATE = false, class SM>
 MPC_HD void stage_init_warm(const Params &prm, const SM &sm, StageRegs &r, int k, int p,
                             const double *state6, const double *coef4, const double *warm, size_t stride, size_t idx)
 {
     const int N = prm.N;
-    stage_init(prm, sm, r, k, p, state6, coef4);
+    stage_init<RATE>(prm, sm, r, k, p, state6, coef4);
     if (k < N - 1) {
         const double sf = sm.P(PS_SF, p), mu = prm.warm_mu;
         const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
@@ -333,6 +340,7 @@ MPC_HD void stage_init_warm(const Params &prm, const SM &sm, StageRegs &r, int k
         uw = fmax2(fmin2(uw, Uw - pw), -Uw + pw); ua = fmax2(fmin2(ua, Ua - pa), -Ua + pa);
         r.uw = uw; r.ua = ua;
         sm.at(k, W_10, p) = uw; sm.at(k, W_11, p) = ua;    // for the roll-out
+        if (RATE) { sm.at(k, U_W, p) = uw; sm.at(k, U_A, p) = ua; }
         const size_t offl = (size_t)(8 * N - 2), offz = offl + (size_t)6 * N;
         for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = sf * warm[(offl + (size_t)c * N + k + 1) * stride + idx];
         const int nu = N - 1;
@@ -402,12 +410,22 @@ MPC_HD void stage_adopt(const Params &prm, const SM &sm, int k, int p, int flags
         for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = keep ? sm.at(k, W_6 + c, p) : 0.0;
 }
 
+// Rate penalty  sum_j w_d (u_{j+1} - u_j)^2  (mpc_planner.cpp:144-147): gradient wrt u_k given its neighbours.
+// The pair (u_{k-1}, u_k) exists for 1 <= k <= N-2, the pair (u_k, u_{k+1}) for k <= N-3.
+MPC_HD double rate_grad(double wd2, double u, double up, double un, bool has_prev, bool has_next)
+{
+    double g = 0.0;
+    if (has_prev) g += wd2 * (u - up);
+    if (has_next) g -= wd2 * (un - u);
+    return g;
+}
+
 // ---------------------------------------------------------------- P1: evaluate  iterate + alpha * step
 // Everything the control thread needs to (a) run the filter line search on this point and (b), if it
 // becomes the iterate, test convergence and update mu: sum|c|, max|c|, scaled objective, log-barrier
 // sum, max|dual residual| and the extreme complementarity products with the trial multipliers
 // lambda + alpha (lambda^+ - lambda), z + alpha_z dz, plus the multiplier norms.
-template <class SM>
+template <bool RATE = false, class SM>
 MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int flags, EvalPart &acc,
                        const double *cf)
 {
@@ -505,8 +523,19 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         // stationarity wrt u_k:  grad f - B^T lambda_{k+1} - zL + zU
         double zlw, zuw, zla, zua;
         trial_z(prm, r, az, mu, uw, ua, zlw, zuw, zla, zua);
-        const double rw = 2.0 * sf * prm.w_angvel * uw - dt * (mt + me) - zlw + zuw;
-        const double ra = 2.0 * sf * prm.w_accel * ua - dt * mv - zla + zua;
+        double rw = 2.0 * sf * prm.w_angvel * uw - dt * (mt + me) - zlw + zuw;
+        double ra = 2.0 * sf * prm.w_accel * ua - dt * mv - zla + zua;
+        if (RATE) {
+            const bool hp = k >= 1, hn = k <= N - 3;
+            double upw = 0, upa = 0, unw = 0, una = 0;
+            if (hp) { upw = sm.at(k - 1, U_W, p); upa = sm.at(k - 1, U_A, p);
+                      if (ls) { upw += alpha * sm.at(k - 1, DU_W, p); upa += alpha * sm.at(k - 1, DU_A, p); } }
+            if (hn) { unw = sm.at(k + 1, U_W, p); una = sm.at(k + 1, U_A, p);
+                      if (ls) { unw += alpha * sm.at(k + 1, DU_W, p); una += alpha * sm.at(k + 1, DU_A, p); } }
+            rw += rate_grad(2.0 * sf * prm.w_angvel_d, uw, upw, unw, hp, hn);
+            ra += rate_grad(2.0 * sf * prm.w_accel_d, ua, upa, una, hp, hn);
+            if (hp) f += prm.w_angvel_d * (uw - upw) * (uw - upw) + prm.w_accel_d * (ua - upa) * (ua - upa);
+        }
         duinf = fmax2(fmax2(fmax2(fabs(rx), fabs(ry)), fmax2(fabs(rt), fabs(rv))),
                       fmax2(fmax2(fabs(rc), fabs(re)), fmax2(fabs(rw), fabs(ra))));
         l1 += fabs(mx) + fabs(my) + fabs(mt) + fabs(mv) + fabs(mc) + fabs(me);
@@ -537,7 +566,7 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
 // Must be called for ALL stages of a lane before any stage's coefficients are written when FL_APPLY is
 // set (stage k reads stage k-1's D slots and stage k+1's S slots): the caller runs apply for its whole
 // group first (apply==1), synchronises the CTA, then calls again with apply==0.
-template <class SM>
+template <bool RATE = false, class SM>
 MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, int p)
 {
     const int N = prm.N;
@@ -553,11 +582,12 @@ MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, in
         double zlw, zuw, zla, zua;
         trial_z(prm, r, az, mu, uw, ua, zlw, zuw, zla, zua);
         r.uw = uw; r.ua = ua; r.zlw = zlw; r.zuw = zuw; r.zla = zla; r.zua = zua;
+        if (RATE) { sm.at(k, U_W, p) = uw; sm.at(k, U_A, p) = ua; }
     }
     r.sn = r.tsn; r.cs = r.tcs; r.se = r.tse; r.ce = r.tce;
 }
 
-template <class SM>
+template <bool RATE = false, class SM>
 MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq, const double *cf)
 {
     const int N = prm.N;
@@ -578,7 +608,17 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
         const double ilw = fast_rcp(r.uw + Uw), iuw = fast_rcp(Uw - r.uw);
         const double ila = fast_rcp(r.ua + Ua), iua = fast_rcp(Ua - r.ua);
         r.ilw = ilw; r.iuw = iuw; r.ila = ila; r.iua = iua;
-        const double gw = 2.0 * sf * prm.w_angvel * r.uw, ga = 2.0 * sf * prm.w_accel * r.ua;
+        double gw = 2.0 * sf * prm.w_angvel * r.uw, ga = 2.0 * sf * prm.w_accel * r.ua;
+        double rdw = 0.0, rda = 0.0;     // diagonal Hessian contribution of the rate terms this control is part of
+        if (RATE) {
+            const bool hp = k >= 1, hn = k <= N - 3;
+            const double upw = hp ? sm.at(k - 1, U_W, p) : 0.0, upa = hp ? sm.at(k - 1, U_A, p) : 0.0;
+            const double unw = hn ? sm.at(k + 1, U_W, p) : 0.0, una = hn ? sm.at(k + 1, U_A, p) : 0.0;
+            gw += rate_grad(2.0 * sf * prm.w_angvel_d, r.uw, upw, unw, hp, hn);
+            ga += rate_grad(2.0 * sf * prm.w_accel_d, r.ua, upa, una, hp, hn);
+            const double cnt = (hp ? 1.0 : 0.0) + (hn ? 1.0 : 0.0);
+            rdw = 2.0 * sf * prm.w_angvel_d * cnt; rda = 2.0 * sf * prm.w_accel_d * cnt;
+        }
         if (lsq) {
             r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
             sm.at(k, W_3, p) = gw - r.zlw + r.zuw;
@@ -602,8 +642,8 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             r.hev = -mc * r.ce * dt;
             sm.at(k, W_3, p) = gw - mu * ilw + mu * iuw;     // gradient of the barrier objective
             sm.at(k, W_4, p) = ga - mu * ila + mu * iua;
-            sm.at(k, W_10, p) = 2.0 * sf * prm.w_angvel + r.zlw * ilw + r.zuw * iuw;   // R + Sigma
-            sm.at(k, W_11, p) = 2.0 * sf * prm.w_accel + r.zla * ila + r.zua * iua;
+            sm.at(k, W_10, p) = 2.0 * sf * prm.w_angvel + rdw + r.zlw * ilw + r.zuw * iuw;   // R + Sigma
+            sm.at(k, W_11, p) = 2.0 * sf * prm.w_accel + rda + r.zla * ila + r.zua * iua;
         }
         sm.at(k, W_5, p) = r.hxx; sm.at(k, W_6, p) = r.htt; sm.at(k, W_7, p) = r.htv;
         sm.at(k, W_8, p) = r.hee; sm.at(k, W_9, p) = r.hev;
@@ -613,7 +653,7 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
 
 // ---------------------------------------------------------------- Riccati sweeps (control thread)
 // Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}, u.
-struct HessDiag { double dx, dy, dt_, dv, dc, de, du; };
+struct HessDiag { double dx, dy, dt_, dv, dc, de, du; double rw, ra; /* 2 sf w_angvel_d, 2 sf w_accel_d */ };
 
 // Coefficients of one stage as the backward sweep consumes them.
 struct StageCoef {
@@ -643,7 +683,12 @@ MPC_HD void load_coef(const SM &sm, int k, int p, StageCoef &c)
 // stage k <= N-2 with the gains K (2x5) and k_ff (2).  The sweep is one long dependency chain
 // through P; everything that does not depend on P is kept off that chain.  (Prefetching the next
 // stage's coefficients into registers was measured slower: it costs 50 live registers.)
-template <class SM>
+// RATE: the rate penalties add the cross term  -du_k^T D du_{k-1}  (D = diag(hd.rw, hd.ra)) to the QP; the
+// value function then also depends on the previous control step pi = du_{k-1}:
+//   V_k = 1/2 ds'P ds + p'ds + ds'M pi + 1/2 pi'N pi + n'pi,   M_k = -K_k^T D,  N_k = -D R~_k^{-1} D,  n_k = -D kff_k,
+// so stage k needs K, R~^{-1} and kff of stage k+1 (kept in registers) and contributes
+//   R~ += B'M + M'B + N,   S~ += M'A,   r~_u += M'd + n;   forward: du_k += R~^{-1} D du_{k-1}.
+template <bool RATE = false, class SM>
 MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
     const int N = prm.N;
@@ -656,15 +701,23 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
     const double gam = hd.dc;
     int ok = 1;
     StageCoef c;
+    // RATE: M, N, n of stage k+1 (zero at the terminal stage)
+    double Mxw = 0, Myw = 0, Mtw = 0, Mvw = 0, Mew = 0, Mxa = 0, Mya = 0, Mta = 0, Mva = 0, Mea = 0;
+    double Nww = 0, Nwa = 0, Naa = 0, nw = 0, na = 0;
 #pragma unroll 1
     for (int k = N - 2; k >= 0; k--) {
         load_coef(sm, k, p, c);
 
         // ---- R~ = R + B^T P B  (B = dt [e_theta + e_etheta | e_v]) and its inverse: the head of the
         //      critical chain, needs only P_{k+1}
-        const double Rww = c.rw + hd.du + dt2 * ((Ptt + Pee) + 2.0 * Pte);
-        const double Rwa = dt2 * (Ptv + Pve);
-        const double Raa = c.ra + hd.du + dt2 * Pvv;
+        double Rww = c.rw + hd.du + dt2 * ((Ptt + Pee) + 2.0 * Pte);
+        double Rwa = dt2 * (Ptv + Pve);
+        double Raa = c.ra + hd.du + dt2 * Pvv;
+        if (RATE) {
+            Rww += 2.0 * dt * (Mtw + Mew) + Nww;
+            Rwa += dt * ((Mta + Mea) + Mvw) + Nwa;
+            Raa += 2.0 * dt * Mva + Naa;
+        }
         const double det = Rww * Raa - Rwa * Rwa;
         if (!(Rww > 0.0) || !(det > 0.0)) ok = 0;
         const double idet = fast_rcp(det);
@@ -686,9 +739,15 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
         const double Mvv = Wvv + c.a14 * Mxv + c.a24 * Myv;
 
         // ---- S~ = B^T W
-        const double Swx = dt * (Pxt + Pxe), Swy = dt * (Pyt + Pye), Swt = dt * (Wtt + Met),
-                     Swv = dt * (Wtv + Mev), Swe = dt * (Pte + Pee);
-        const double Sax = dt * Pxv, Say = dt * Pyv, Sat = dt * Wvt, Sav = dt * Wvv, Sae = dt * Pve;
+        double Swx = dt * (Pxt + Pxe), Swy = dt * (Pyt + Pye), Swt = dt * (Wtt + Met),
+               Swv = dt * (Wtv + Mev), Swe = dt * (Pte + Pee);
+        double Sax = dt * Pxv, Say = dt * Pyv, Sat = dt * Wvt, Sav = dt * Wvv, Sae = dt * Pve;
+        if (RATE) {   // S~ += M^T A5
+            Swx += Mxw; Swy += Myw; Swe += Mew;
+            Swt += Mtw + c.a13 * Mxw + c.a23 * Myw; Swv += Mvw + c.a14 * Mxw + c.a24 * Myw;
+            Sax += Mxa; Say += Mya; Sae += Mea;
+            Sat += Mta + c.a13 * Mxa + c.a23 * Mya; Sav += Mva + c.a14 * Mxa + c.a24 * Mya;
+        }
 
         // ---- vector part (uses P_{k+1}):  p~ = P d + p,  pi_c = gam d_c + q_c,k+1
         const double tx = (Pxx * c.dx + Pxy * c.dy) + (Pxt * c.dth + Pxv * c.dv) + (Pxe * c.de + px);
@@ -720,12 +779,24 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
         const double Kwv = -(i11 * Swv + i12 * Sav), Kav = -(i12 * Swv + i22 * Sav);
         const double Kwe = -(i11 * Swe + i12 * Sae), Kae = -(i12 * Swe + i22 * Sae);
         // ---- feed-forward
-        const double ruw = c.qw + dt * (tt + te), rua = c.qa + dt * tv;
+        double ruw = c.qw + dt * (tt + te), rua = c.qa + dt * tv;
+        if (RATE) {   // r~_u += M^T d + n
+            ruw += (Mxw * c.dx + Myw * c.dy) + (Mtw * c.dth + Mvw * c.dv) + (Mew * c.de + nw);
+            rua += (Mxa * c.dx + Mya * c.dy) + (Mta * c.dth + Mva * c.dv) + (Mea * c.de + na);
+        }
         const double kfw = -(i11 * ruw + i12 * rua), kfa = -(i12 * ruw + i22 * rua);
 
         sm.at(k, W_0, p) = Kwx; sm.at(k, W_1, p) = Kwy; sm.at(k, W_2, p) = Kwt; sm.at(k, W_3, p) = Kwv;
         sm.at(k, W_4, p) = Kwe; sm.at(k, W_5, p) = Kax; sm.at(k, W_6, p) = Kay; sm.at(k, W_7, p) = Kat;
         sm.at(k, W_8, p) = Kav; sm.at(k, W_9, p) = Kae; sm.at(k, W_10, p) = kfw; sm.at(k, W_11, p) = kfa;
+        if (RATE) {
+            sm.at(k, RI_11, p) = i11; sm.at(k, RI_12, p) = i12; sm.at(k, RI_22, p) = i22;
+            // M_k = -K^T D, N_k = -D R~^{-1} D, n_k = -D kff  (for stage k-1)
+            Mxw = -Kwx * hd.rw; Myw = -Kwy * hd.rw; Mtw = -Kwt * hd.rw; Mvw = -Kwv * hd.rw; Mew = -Kwe * hd.rw;
+            Mxa = -Kax * hd.ra; Mya = -Kay * hd.ra; Mta = -Kat * hd.ra; Mva = -Kav * hd.ra; Mea = -Kae * hd.ra;
+            Nww = -hd.rw * hd.rw * i11; Nwa = -hd.rw * hd.ra * i12; Naa = -hd.ra * hd.ra * i22;
+            nw = -hd.rw * kfw; na = -hd.ra * kfa;
+        }
 
         // ---- P_k = Q~ + S~^T K
         Pxx = Qxx + (Swx * Kwx + Sax * Kax);
@@ -756,18 +827,25 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
 
 // Forward sweep: ds_0 = 0 (the initial-condition rows stay satisfied).  Leaves du_k in
 // W_10/W_11 of stage k and ds_{k+1} in the D slots of stage k.
-template <class SM>
-MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p)
+template <bool RATE = false, class SM>
+MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
     const int N = prm.N;
     const double dt = prm.dt;
     double sx = 0, sy = 0, st = 0, sv = 0, sc = 0, se = 0;
-    (void)sc;
+    double pw = 0, pa = 0;      // RATE: previous control step
+    (void)sc; (void)pw; (void)pa;
     for (int k = 0; k < N - 1; k++) {
-        const double duw = sm.at(k, W_0, p) * sx + sm.at(k, W_1, p) * sy + sm.at(k, W_2, p) * st +
-                           sm.at(k, W_3, p) * sv + sm.at(k, W_4, p) * se + sm.at(k, W_10, p);
-        const double dua = sm.at(k, W_5, p) * sx + sm.at(k, W_6, p) * sy + sm.at(k, W_7, p) * st +
-                           sm.at(k, W_8, p) * sv + sm.at(k, W_9, p) * se + sm.at(k, W_11, p);
+        double duw = sm.at(k, W_0, p) * sx + sm.at(k, W_1, p) * sy + sm.at(k, W_2, p) * st +
+                     sm.at(k, W_3, p) * sv + sm.at(k, W_4, p) * se + sm.at(k, W_10, p);
+        double dua = sm.at(k, W_5, p) * sx + sm.at(k, W_6, p) * sy + sm.at(k, W_7, p) * st +
+                     sm.at(k, W_8, p) * sv + sm.at(k, W_9, p) * se + sm.at(k, W_11, p);
+        if (RATE && k >= 1) {   // + R~^{-1} D du_{k-1}
+            const double i11 = sm.at(k, RI_11, p), i12 = sm.at(k, RI_12, p), i22 = sm.at(k, RI_22, p);
+            duw += i11 * hd.rw * pw + i12 * hd.ra * pa;
+            dua += i12 * hd.rw * pw + i22 * hd.ra * pa;
+        }
+        pw = duw; pa = dua;
         const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
                      a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
                      a56 = sm.at(k, A_56, p);
@@ -787,7 +865,7 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p)
 // ---------------------------------------------------------------- P5: step-dependent stage work
 // Reads ds_k, du_k; returns g_k = q_s + Q_k ds_k (to be stored into W_0..W_5) and accumulates the partials
 // (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`.
-template <class SM>
+template <bool RATE = false, class SM>
 MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq,
                        StepPart &acc, double *g6)
 {
@@ -806,6 +884,7 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
     double rmax = 0.0, rzmax = 0.0, gd = qv * dsv + qc * dsc + qe * dse;
     if (k < N - 1) {
         r.duw = sm.at(k, W_10, p); r.dua = sm.at(k, W_11, p);
+        if (RATE) { sm.at(k, DU_W, p) = r.duw; sm.at(k, DU_A, p) = r.dua; }
         if (!lsq) {
             rmax = fmax2(fmax2(-r.duw * r.ilw, r.duw * r.iuw), fmax2(-r.dua * r.ila, r.dua * r.iua));
             const double mlw = mu * r.ilw, muw = mu * r.iuw, mla = mu * r.ila, mua = mu * r.iua;
@@ -815,8 +894,15 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
             const double dzua = mua - r.zua + r.zua * r.iua * r.dua;
             rzmax = fmax2(fmax2(-dzlw * fast_rcp(r.zlw), -dzuw * fast_rcp(r.zuw)),
                           fmax2(-dzla * fast_rcp(r.zla), -dzua * fast_rcp(r.zua)));
-            const double gw = 2.0 * sf * prm.w_angvel * r.uw - mlw + muw;
-            const double ga = 2.0 * sf * prm.w_accel * r.ua - mla + mua;
+            double gw = 2.0 * sf * prm.w_angvel * r.uw - mlw + muw;
+            double ga = 2.0 * sf * prm.w_accel * r.ua - mla + mua;
+            if (RATE) {
+                const bool hp = k >= 1, hn = k <= N - 3;
+                const double upw = hp ? sm.at(k - 1, U_W, p) : 0.0, upa = hp ? sm.at(k - 1, U_A, p) : 0.0;
+                const double unw = hn ? sm.at(k + 1, U_W, p) : 0.0, una = hn ? sm.at(k + 1, U_A, p) : 0.0;
+                gw += rate_grad(hd.rw, r.uw, upw, unw, hp, hn);
+                ga += rate_grad(hd.ra, r.ua, upa, una, hp, hn);
+            }
             gd += gw * r.duw + ga * r.dua;
         }
     }
@@ -875,7 +961,9 @@ struct Ctrl {
 MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
 {
     HessDiag h;
+    h.rw = 0.0; h.ra = 0.0;
     if (lsq) { h.dx = h.dy = h.dt_ = h.dv = h.dc = h.de = 1.0; h.du = 0.0; return h; }
+    h.rw = 2.0 * sf * prm.w_angvel_d; h.ra = 2.0 * sf * prm.w_accel_d;
     h.dx = dw; h.dy = dw; h.dt_ = dw; h.du = dw;
     h.dv = 2.0 * sf * prm.w_vel + dw;
     h.dc = 2.0 * sf * prm.w_cte + dw;

@@ -14,10 +14,11 @@
 
 using namespace nmpc;
 
-extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_iter, int PB, int batch,
-                              const double *state, const double *coeffs, const double *ref_vel,
-                              double *u0, double *pred, double *obj, int *status, int *iters, double *kkt,
-                              double *lam_out /* 6N x batch, optional */, int *n_reg /* batch, optional */)
+template <bool RATE>
+static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB, int batch,
+                   const double *state, const double *coeffs, const double *ref_vel,
+                   double *u0, double *pred, double *obj, int *status, int *iters, double *kkt,
+                   double *lam_out, int *n_reg)
 {
     Params prm;
     prm.N = N;
@@ -25,12 +26,15 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
     prm.w_cte = prm14[4]; prm.w_etheta = prm14[5]; prm.w_vel = prm14[6]; prm.w_angvel = prm14[7];
     prm.w_accel = prm14[8]; prm.max_angvel = prm14[9]; prm.max_throttle = prm14[10];
     prm.tol = tol; prm.max_iter = max_iter;
+    prm.warm_mu = 1e-3;
+    prm.w_angvel_d = prm14[11]; prm.w_accel_d = prm14[12];
     const int SPT = 3;   // same grouping of partial sums as the kernel's stage threads
     prm.grp = SPT;
     const int NG = (N + SPT - 1) / SPT;
 
-    std::vector<double> mem(smem_bytes(N, NG, PB) / sizeof(double) + 8);
-    Smem sm; sm.PB = PB; sm.carve(mem.data(), N, NG);
+    const int NS = RATE ? NSLOTS_RATE : NSLOTS;
+    std::vector<double> mem(smem_bytes(N, NG, PB, NS) / sizeof(double) + 8);
+    SmemT<0, RATE ? NSLOTS_RATE : NSLOTS> sm; sm.PB = PB; sm.carve(mem.data(), N, NG);
     std::vector<StageRegs> regs((size_t)N * PB);
     std::vector<double> cfs((size_t)4 * PB);
     std::vector<Ctrl> ctrl(PB);
@@ -58,7 +62,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             // ---- P3a
             for (int p = 0; p < np; p++) {
                 const int fl = sm.I(PI_FLAGS, p);
-                if (fl & FL_APPLY) for (int k = 0; k < N; k++) stage_apply(prm, sm, REG(k, p), k, p);
+                if (fl & FL_APPLY) for (int k = 0; k < N; k++) stage_apply<RATE>(prm, sm, REG(k, p), k, p);
                 if (fl & FL_FLUSH) {
                     const size_t i = (size_t)sm.I(PI_PROB, p);
                     u0[i] = REG(0, p).uw; u0[(size_t)batch + i] = REG(0, p).ua;
@@ -79,7 +83,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                     double s6[6], c4[4];
                     for (int c = 0; c < 6; c++) s6[c] = state[(size_t)c * batch + idx];
                     for (int c = 0; c < 4; c++) { c4[c] = coeffs[(size_t)c * batch + idx]; cfs[(size_t)4 * p + c] = c4[c]; }
-                    for (int k = 0; k < N; k++) stage_init(prm, sm, REG(k, p), k, p, s6, c4);
+                    for (int k = 0; k < N; k++) stage_init<RATE>(prm, sm, REG(k, p), k, p, s6, c4);
                 }
             }
             for (int p = 0; p < np; p++) {
@@ -89,7 +93,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
             // ---- P3b
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_NEWTON)
-                    for (int k = 0; k < N; k++) stage_coeffs(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)4 * p]);
+                    for (int k = 0; k < N; k++) stage_coeffs<RATE>(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)4 * p]);
             // ---- P4
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_NEWTON) continue;
@@ -97,8 +101,8 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
                 const double dw = sm.P(PS_DW, p);
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
-                if (riccati_backward(prm, sm, p, hd) || lsq) {
-                    riccati_forward(prm, sm, p);
+                if (riccati_backward<RATE>(prm, sm, p, hd) || lsq) {
+                    riccati_forward<RATE>(prm, sm, p, hd);
                     if (dw > 0.0) c.dw_last = dw;
                     sm.I(PI_MODE, p) = MODE_STEP;
                 } else {
@@ -116,7 +120,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 for (int g = 0; g < NG; g++) {
                     StepPart acc; part_reset(acc);
                     double gk[SPT][6];
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT]);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step<RATE>(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT]);
                     for (int k = g * SPT; k < g * SPT + SPT && k < N; k++)
                         for (int q = 0; q < 6; q++) sm.at(k, W_0 + q, p) = gk[k - g * SPT][q];
                     part_store(sm, g, p, acc);
@@ -144,7 +148,7 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
                 if (fl & FL_ADOPT) for (int k = 0; k < N; k++) stage_adopt(prm, sm, k, p, fl);
                 for (int g = 0; g < NG; g++) {
                     EvalPart acc; part_reset(acc);
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval(prm, sm, REG(k, p), k, p, fl, acc, &cfs[(size_t)4 * p]);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval<RATE>(prm, sm, REG(k, p), k, p, fl, acc, &cfs[(size_t)4 * p]);
                     part_store(sm, g, p, acc);
                 }
             }
@@ -192,4 +196,17 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
         }
     }
     return 0;
+}
+
+extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_iter, int PB, int batch,
+                              const double *state, const double *coeffs, const double *ref_vel,
+                              double *u0, double *pred, double *obj, int *status, int *iters, double *kkt,
+                              double *lam_out /* 6N x batch, optional */, int *n_reg /* batch, optional */)
+{
+    // prm14[11], prm14[12]: w_angvel_d, w_accel_d (rate penalties) select the augmented-Riccati variant
+    if (prm14[11] != 0.0 || prm14[12] != 0.0)
+        return emu_run<true>(N, prm14, tol, max_iter, PB, batch, state, coeffs, ref_vel, u0, pred, obj, status, iters, kkt,
+                             lam_out, n_reg);
+    return emu_run<false>(N, prm14, tol, max_iter, PB, batch, state, coeffs, ref_vel, u0, pred, obj, status, iters, kkt,
+                          lam_out, n_reg);
 }

@@ -74,8 +74,8 @@ def test_create_validates_and_fails_loudly_without_gpu():
     assert L.mpc_b200_create(C.byref(h), C.byref(p), 0, 0) == -1            # max_batch < 1
     bad = capi.yaml_default_params(); bad.mpc_steps = 1
     assert L.mpc_b200_create(C.byref(h), C.byref(bad), 8, 0) == -1
-    rate = capi.yaml_default_params(); rate.w_accel_d = 10.0
-    assert L.mpc_b200_create(C.byref(h), C.byref(rate), 8, 0) == -3         # unsupported on the GPU path (documented)
+    neg = capi.yaml_default_params(); neg.w_accel_d = -1.0
+    assert L.mpc_b200_create(C.byref(h), C.byref(neg), 8, 0) == -1          # negative rate weight
     if not has_gpu():
         assert L.mpc_b200_device_count() == 0
         assert L.mpc_b200_create(C.byref(h), C.byref(p), 8, 0) == -2        # no CPU fallback

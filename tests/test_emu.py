@@ -19,7 +19,8 @@ def emu_solve(pm, state, coeffs, PB=4, tol=1e-8, max_iter=200, ref_vel=None):
     dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
     N = int(pm["STEPS"]); B = state.shape[1]
     prm = np.array([pm["DT"], pm["REF_CTE"], pm["REF_ETHETA"], pm["REF_V"], pm["W_CTE"], pm["W_EPSI"], pm["W_V"],
-                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], 0, 0, 0], dtype=np.float64)
+                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], pm.get("W_DANGVEL", 0.0), pm.get("W_DA", 0.0), 0],
+                   dtype=np.float64)
     state = np.ascontiguousarray(state, dtype=np.float64); coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
     u0 = np.zeros((2, B)); pred = np.zeros((3 * N, B)); obj = np.zeros(B); kkt = np.zeros(B); lam = np.zeros((6 * N, B))
     st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32); nreg = np.zeros(B, dtype=np.int32)
@@ -73,6 +74,23 @@ def test_emu_cfg_weights(oracle):
         assert r["status"][i] == 1 and o["status"] == 1
         assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5
         assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"])
+
+
+def test_emu_rate_penalties(oracle):
+    """w_angvel_d / w_accel_d != 0 (the reference's cfg defaults, MPCPlanner.cfg:31-33): augmented Riccati."""
+    for pm in (dict(CFG_DEFAULT), dict(YAML_DEFAULT, W_DANGVEL=30.0, W_DA=5.0), dict(YAML_DEFAULT, W_DANGVEL=200.0, W_DA=0.0)):
+        state, coeffs = mild(26, 10)
+        r = emu_solve(pm, state, coeffs, PB=3)
+        nobound = dict(pm, BOUND=1e19)
+        for i in range(10):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert r["status"][i] == 1 and o["status"] == 1
+            assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5
+            assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"])
+            assert r["kkt"][i] <= 1e-8
+            o2 = oracle.solve(nobound, state[:, i], coeffs[:, i])
+            assert r["iters"][i] == o2["iters"]
+            assert np.abs(r["u0"][:, i] - o2["u0"]).max() <= 1e-9
 
 
 def test_emu_long_horizon(oracle):

@@ -185,6 +185,22 @@ def test_cfg_weights(oracle):
         assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
 
 
+def test_rate_penalties_cfg_defaults(oracle):
+    """The reference's dynamic_reconfigure defaults (MPCPlanner.cfg:22-37) include w_accel_d = 10: the rate
+    terms couple u_k and u_{k+1} (mpc_planner.cpp:144-147) and run through the augmented Riccati variant."""
+    for pm, seed in ((dict(CFG_DEFAULT), 45), (dict(YAML_DEFAULT, W_DANGVEL=30.0, W_DA=5.0), 46)):
+        state, coeffs = mild(seed, 48)
+        sv = _solver(pm, 48)
+        out = sv.solve(state, coeffs)
+        sv.close()
+        for i in range(48):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert out["status"][i] == 1 and o["status"] == 1
+            assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
+            assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+            assert out["kkt"][i] <= KKT_TOL
+
+
 def test_long_horizon(oracle):
     """BASELINE config 4 (N = 100) on a small batch."""
     pm = dict(YAML_DEFAULT, STEPS=100)

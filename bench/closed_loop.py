@@ -5,9 +5,11 @@ Per tick (the reference's control tick, SURVEY section 3A, with the ROS plumbing
   -> pre-step: transform + polyfit + delay-compensated state (driving_state.cpp:196-256)   [GPU, K1]
   -> MPC::Solve, warm-started from the previous tick's shifted solution                     [GPU, K3]
   -> speed command clamp (driving_state.cpp:263-269) -> unicycle plant step.
-The windowing and the plant are a few numpy lines on the host (SURVEY 8f-2 / 8f-1 are "next" rows).
+run_gpu drives the loop from the host (windowing and plant in numpy); run_gpu_device keeps everything on the
+device: windowing (mpc_b200_window_batch), post-step (mpc_b200_poststep_batch) and the warm-start shift are
+kernels too, robots are split over independent streams.
 
-    python bench/closed_loop.py [robots] [ticks] [--cold] [--oracle-subset K]
+    python bench/closed_loop.py [robots] [ticks] [--cold] [--oracle-subset K] [--device]
 """
 import json
 import os
@@ -55,9 +57,11 @@ class Fleet:
         for i in range(R):
             px, py = self.paths[self.kind[i]]
             n = len(px)
-            cand = (self.idx[i] + np.arange(0, 60)) % n
+            # getCutOffPlan: drop plan points while the distance to the robot keeps shrinking
+            cand = (self.idx[i] + np.arange(0, 64)) % n
             d2 = (px[cand] - self.pose[0, i]) ** 2 + (py[cand] - self.pose[1, i]) ** 2
-            self.idx[i] = cand[int(np.argmin(d2))]
+            grow = np.nonzero(d2[1:] > d2[:-1])[0]
+            self.idx[i] = cand[int(grow[0])] if len(grow) else cand[-1]
             sel = list(range(0, self.win, self.step)) + [self.win - 1]
             q = (self.idx[i] + np.array(sel)) % n
             wx[:, i] = px[q]; wy[:, i] = py[q]
@@ -123,6 +127,83 @@ def run_gpu(R, T, warm=True, seed=20261018 + 5, record_solver=False):
     return out
 
 
+def run_gpu_device(R, T, groups=8, seed=20261018 + 5, max_iter=100, trace=True):
+    """Device-resident loop: windowing, pre-step, warm-started solve, warm shift and post-step are C-ABI
+    kernels; the unicycle plant (simulation, not part of the reference) is three torch element-wise ops.
+    Robots are split into `groups` independent streams so that a slow solve only delays its own group."""
+    import torch
+    from mpc_ros_b200 import capi
+    prm = capi.yaml_default_params()
+    prm.max_iter = max_iter
+    N = prm.mpc_steps; dt = prm.dt
+    dev = torch.device("cuda:0")
+    fleet = Fleet(R, seed)
+    M = capi.lib().mpc_b200_num_waypoints(prm)
+    assert M == fleet.M
+    f64 = dict(dtype=torch.float64, device=dev); i32 = dict(dtype=torch.int32, device=dev)
+    lens = [len(p[0]) for p in fleet.paths]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    d_px = torch.from_numpy(np.concatenate([p[0] for p in fleet.paths])).to(dev)
+    d_py = torch.from_numpy(np.concatenate([p[1] for p in fleet.paths])).to(dev)
+    d_off = torch.from_numpy(offs).to(dev); d_len = torch.tensor(lens, **i32)
+    ws = capi.lib().mpc_b200_warm_size(N)
+    G = max(1, min(groups, R))
+    bounds = [(g * R // G, (g + 1) * R // G) for g in range(G)]
+    sv = capi.Solver(prm, max(hi - lo for lo, hi in bounds), 0)
+    sv.set_option("max_ctas", max(1, 148 // G))
+    grp = []
+    for lo, hi in bounds:
+        B = hi - lo
+        st = torch.cuda.Stream()
+        grp.append(dict(B=B, st=st, sp=st.cuda_stream,
+                        tid=torch.from_numpy(fleet.kind[lo:hi].astype(np.int32)).to(dev),
+                        idx=torch.from_numpy(fleet.idx[lo:hi].astype(np.int32)).to(dev),
+                        pose=torch.from_numpy(np.ascontiguousarray(fleet.pose[:, lo:hi])).to(dev),
+                        vel=torch.from_numpy(np.ascontiguousarray(fleet.vel()[:, lo:hi])).to(dev),
+                        wx=torch.zeros((M, B), **f64), wy=torch.zeros((M, B), **f64), coef=torch.zeros((4, B), **f64),
+                        state=torch.zeros((6, B), **f64), u0=torch.zeros((2, B), **f64), pred=torch.zeros((3 * N, B), **f64),
+                        cmd=torch.zeros((2, B), **f64), wa=torch.zeros((ws, B), **f64), wb=torch.zeros((ws, B), **f64),
+                        it=torch.zeros(B, **i32), stt=torch.zeros(B, **i32), ce=torch.zeros((2, B), **f64),
+                        cte=[], iters=[], conv=[]))
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for g in grp:
+        g["st"].wait_event(e0)
+    for t in range(T):
+        for g in grp:
+            B, sp = g["B"], g["sp"]
+            with torch.cuda.stream(g["st"]):
+                sv.window_raw(B, d_px, d_py, d_off, d_len, g["tid"], g["idx"], g["pose"], g["wx"], g["wy"], stream=sp)
+                if trace:
+                    sv.polyfit_raw(B, M, g["wx"], g["wy"], g["pose"], g["coef"], g["ce"], stream=sp)
+                sv.prestep_raw(B, M, g["wx"], g["wy"], g["pose"], g["vel"], g["coef"], g["state"], stream=sp)
+                sv.solve_raw(B, g["state"], g["coef"], g["u0"], g["pred"], warm_in=g["wa"] if t > 0 else None,
+                             status=g["stt"], iters=g["it"], warm_out=g["wb"], stream=sp)
+                sv.warm_shift(B, g["wb"], g["wa"], stream=sp)
+                sv.poststep_raw(B, g["u0"], g["vel"], None, g["cmd"], stream=sp)
+                # plant (simulation): unicycle driven by the command
+                speed = g["cmd"][0]; w = g["cmd"][1]
+                g["pose"][0] += speed * torch.cos(g["pose"][2]) * dt
+                g["pose"][1] += speed * torch.sin(g["pose"][2]) * dt
+                g["pose"][2] = torch.remainder(g["pose"][2] + w * dt + np.pi, 2 * np.pi) - np.pi
+                g["vel"][0] = speed
+                if trace:
+                    g["cte"].append(g["ce"][0].clone()); g["iters"].append(g["it"].clone()); g["conv"].append(g["stt"] == 1)
+    for g in grp:
+        torch.cuda.current_stream().wait_stream(g["st"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = dict(loop_ms=ms, robot_ticks_per_s=R * T / (ms * 1e-3))
+    if trace:
+        out["cte"] = torch.cat([torch.stack(g["cte"]) for g in grp], dim=1).cpu().numpy()
+        out["iters"] = torch.cat([torch.stack(g["iters"]) for g in grp], dim=1).cpu().numpy()
+        out["conv"] = torch.cat([torch.stack(g["conv"]) for g in grp], dim=1).cpu().numpy()
+    sv.close()
+    return out
+
+
 def run_oracle(R, T, seed=20261018 + 5):
     """The reference loop: cold-started CPU solve every tick (oracle restatement of MPC::Solve)."""
     from oracle.oracle_py import Oracle, YAML_DEFAULT
@@ -152,6 +233,14 @@ def main():
     K = 0
     if "--oracle-subset" in sys.argv:
         K = int(sys.argv[sys.argv.index("--oracle-subset") + 1])
+    if "--device" in sys.argv:
+        d = run_gpu_device(R, T, trace=False)
+        dt_ = run_gpu_device(R, min(T, 100), trace=True)
+        print(json.dumps(dict(robots=R, ticks=T, mode="device-resident loop, 8 streams", loop_ms=d["loop_ms"],
+                              robot_ticks_per_s=d["robot_ticks_per_s"], mean_abs_cte_100=float(np.abs(dt_["cte"]).mean()),
+                              median_abs_cte_100=float(np.median(np.abs(dt_["cte"]))),
+                              mean_iters_100=float(dt_["iters"].mean()), converged_100=float(dt_["conv"].mean()))))
+        return
     g = run_gpu(R, T, warm=not cold)
     res = dict(robots=R, ticks=T, warm=not cold, solve_s=g["solve_s"], solves_per_s=R * T / g["solve_s"],
                mean_abs_cte=float(np.abs(g["cte"]).mean()), max_abs_cte=float(np.abs(g["cte"]).max()),

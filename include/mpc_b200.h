@@ -143,6 +143,29 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
                          double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
                          double *kkt_res, double *warm_out, void *stream);
 
+/*
+ * Plan windowing for a device-resident closed loop (all pointers DEVICE memory): cut the plan at the
+ * nearest point ahead of the robot (MPCPlannerROS::getCutOffPlan, mpc_ros/src/mpc_planner_ros.cpp:266-291)
+ * and down-sample the next params.path_length metres (downSamplePlan, :365-391; waypoint spacing =
+ * params.waypoints_dist, or 0.05 m when that is <= 0).  Plans are closed tracks stored back to back:
+ * track t occupies path_x/path_y[track_off[t] .. track_off[t] + track_len[t]).
+ *   track_id  batch      track of each robot          idx_inout  batch   plan index of the cut (updated)
+ *   pose      3 x batch                               wx_out, wy_out   mpc_b200_num_waypoints(params) x batch
+ */
+int mpc_b200_window_batch(mpc_b200_handle *h, int32_t batch, const double *path_x, const double *path_y,
+                          const int32_t *track_off, const int32_t *track_len, const int32_t *track_id,
+                          int32_t *idx_inout, const double *pose, double *wx_out, double *wy_out, void *stream);
+int mpc_b200_num_waypoints(const mpc_b200_params *p);
+
+/*
+ * Result post-step of Tracking::findBestPath (mpc_ros/src/driving_state.cpp:263-269), device memory:
+ * speed = v + throttle * dt clamped above at REF_V; cmd_out (2 x batch) = {linear.x, angular.z}
+ * (:115-116); vel_inout (3 x batch: v, previous w, previous throttle) gets the new w and throttle for the
+ * next tick's delay compensation (the caller supplies the new feedback speed v).
+ */
+int mpc_b200_poststep_batch(mpc_b200_handle *h, int32_t batch, const double *u0, double *vel_inout,
+                            const double *ref_vel, double *cmd_out, void *stream);
+
 /* Next tick's warm start from this tick's solution (device buffers): every block of the record moves
  * one stage forward, the last entry is repeated. */
 int mpc_b200_warm_shift(mpc_b200_handle *h, int32_t batch, const double *warm_prev, double *warm_next, void *stream);

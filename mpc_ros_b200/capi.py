@@ -37,7 +37,8 @@ EXPORTS = [
     "mpc_b200_params_default", "mpc_b200_params_yaml_default", "mpc_b200_params_from_yaml",
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
     "mpc_b200_get_params", "mpc_b200_set_option", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
-    "mpc_b200_prestep_batch", "mpc_b200_warm_shift",
+    "mpc_b200_prestep_batch", "mpc_b200_warm_shift", "mpc_b200_window_batch", "mpc_b200_poststep_batch",
+    "mpc_b200_num_waypoints",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
 ]
@@ -76,6 +77,12 @@ def lib():
     L.mpc_b200_polyfit_batch.restype = C.c_int
     L.mpc_b200_prestep_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.mpc_b200_prestep_batch.restype = C.c_int
+    L.mpc_b200_window_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10
+    L.mpc_b200_window_batch.restype = C.c_int
+    L.mpc_b200_poststep_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+    L.mpc_b200_poststep_batch.restype = C.c_int
+    L.mpc_b200_num_waypoints.argtypes = [C.POINTER(Params)]
+    L.mpc_b200_num_waypoints.restype = C.c_int
     L.mpc_b200_warm_shift.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mpc_b200_warm_shift.restype = C.c_int
     L.mpc_b200_last_kernel_seconds.argtypes = [C.c_void_p]
@@ -218,6 +225,17 @@ class Solver:
                                           _addr(cte_etheta), stream)
         if rc != 0:
             raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def window_raw(self, batch, path_x, path_y, track_off, track_len, track_id, idx, pose, wx, wy, stream=None):
+        rc = lib().mpc_b200_window_batch(self._h, batch, _addr(path_x), _addr(path_y), _addr(track_off), _addr(track_len),
+                                         _addr(track_id), _addr(idx), _addr(pose), _addr(wx), _addr(wy), stream)
+        if rc != 0:
+            raise MpcError(rc)
+
+    def poststep_raw(self, batch, u0, vel, ref_vel, cmd, stream=None):
+        rc = lib().mpc_b200_poststep_batch(self._h, batch, _addr(u0), _addr(vel), _addr(ref_vel), _addr(cmd), stream)
+        if rc != 0:
+            raise MpcError(rc)
 
     def warm_shift(self, batch, prev, nxt, stream=None):
         rc = lib().mpc_b200_warm_shift(self._h, batch, _addr(prev), _addr(nxt), stream)

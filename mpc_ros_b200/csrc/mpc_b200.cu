@@ -115,6 +115,64 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
     }
 }
 
+// ================================================================ plan windowing
+// Reference: MPCPlannerROS::getCutOffPlan (mpc_ros/src/mpc_planner_ros.cpp:266-291) drops plan points while
+// the distance to the robot keeps shrinking, i.e. advances to the first local minimum of the distance along
+// the plan; downSamplePlan (:365-391) then keeps every `step`-th point of the window plus its last point
+// (with path_length / waypoints_dist taken from the parameters instead of the reference's uninitialised
+// members).  Closed tracks: indices wrap.  One thread per robot.
+__global__ void window_kernel(int batch, const double *__restrict__ px, const double *__restrict__ py,
+                              const int *__restrict__ track_off, const int *__restrict__ track_len,
+                              const int *__restrict__ track_id, int *__restrict__ idx_io,
+                              const double *__restrict__ pose, int win, int step, int max_advance,
+                              double *__restrict__ wx, double *__restrict__ wy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const int t = track_id[i], off = track_off[t], n = track_len[t];
+    const double rx = pose[i], ry = pose[(size_t)batch + i];
+    int j = idx_io[i] % n;
+    double best = 1e300;
+    for (int a = 0; a < max_advance; a++) {
+        const int q = (j + a) % n;
+        const double dx = rx - px[off + q], dy = ry - py[off + q];
+        const double d2 = dx * dx + dy * dy;
+        if (best < d2) { j = (j + a - 1) % n; break; }     // distance started to grow: previous point is the cut
+        best = d2;
+        if (a == max_advance - 1) j = q;
+    }
+    idx_io[i] = j;
+    int m = 0;
+    for (int a = 0; a < win; a += step, m++) {
+        const int q = (j + a) % n;
+        wx[(size_t)m * batch + i] = px[off + q]; wy[(size_t)m * batch + i] = py[off + q];
+    }
+    const int q = (j + win - 1) % n;
+    wx[(size_t)m * batch + i] = px[off + q]; wy[(size_t)m * batch + i] = py[off + q];
+}
+
+// ================================================================ result post-step (SURVEY 8a last row, 8f-1)
+// Reference: Tracking::findBestPath after the solve, mpc_ros/src/driving_state.cpp:263-269:
+//   w = res[0]; throttle = res[1]; speed = v + throttle * dt, clamped ABOVE at REF_V only.
+// vel (3 x batch: v, previous w, previous throttle) is updated in place for the next tick's delay
+// compensation (:191-193, :245-251); cmd (2 x batch) = {linear.x, angular.z} (:115-116).
+__global__ void poststep_kernel(int batch, const double *__restrict__ u0, double *__restrict__ vel,
+                                const double *__restrict__ ref_vel, double ref_vel_all, double dt,
+                                double *__restrict__ cmd)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const double w = u0[i], thr = u0[(size_t)batch + i];
+    const double v = vel[i];
+    const double rv = ref_vel ? ref_vel[i] : ref_vel_all;
+    double speed = v + thr * dt;
+    if (speed >= rv) speed = rv;
+    vel[(size_t)batch + i] = w;
+    vel[2 * (size_t)batch + i] = thr;
+    cmd[i] = speed;
+    cmd[(size_t)batch + i] = w;
+}
+
 // ================================================================ warm-start shift
 // Next tick's warm start from this tick's solution: every block of the record (6 state components,
 // 2 controls, 6 multiplier components, 4 bound multipliers) moves one stage forward, the last entry is
@@ -618,6 +676,56 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
     }
     return MPC_B200_OK;
+}
+
+int mpc_b200_window_batch(mpc_b200_handle *h, int32_t batch, const double *path_x, const double *path_y,
+                          const int32_t *track_off, const int32_t *track_len, const int32_t *track_id,
+                          int32_t *idx_inout, const double *pose, double *wx_out, double *wy_out, void *stream_v)
+{
+    if (!h || batch < 0 || !path_x || !path_y || !track_off || !track_len || !track_id || !idx_inout || !pose ||
+        !wx_out || !wy_out) return MPC_B200_ERR_INVALID;
+    if (!is_device_ptr(path_x) || !is_device_ptr(idx_inout) || !is_device_ptr(pose) || !is_device_ptr(wx_out))
+        return MPC_B200_ERR_UNSUPPORTED;     // device-resident closed loop only
+    const mpc_b200_params &P = h->params;
+    const double wd = P.waypoints_dist > 0.0 ? P.waypoints_dist : 0.05;
+    const int win = (int)lround(P.path_length / wd);
+    const int step = (int)(P.path_length / 10.0 / wd);     // mpc_planner_ros.cpp:374
+    if (win < 4 || step < 1 || (win + step - 1) / step + 1 > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    window_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, path_x, path_y, track_off, track_len, track_id, idx_inout,
+                                                        pose, win, step, 64, wx_out, wy_out);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (!stream_v) CK(cudaStreamSynchronize(st));
+    return MPC_B200_OK;
+}
+
+int mpc_b200_poststep_batch(mpc_b200_handle *h, int32_t batch, const double *u0, double *vel_inout,
+                            const double *ref_vel, double *cmd_out, void *stream_v)
+{
+    if (!h || batch < 0 || !u0 || !vel_inout || !cmd_out) return MPC_B200_ERR_INVALID;
+    if (!is_device_ptr(u0) || !is_device_ptr(vel_inout) || !is_device_ptr(cmd_out) || (ref_vel && !is_device_ptr(ref_vel)))
+        return MPC_B200_ERR_UNSUPPORTED;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    poststep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, u0, vel_inout, ref_vel, h->params.ref_vel, h->params.dt, cmd_out);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (!stream_v) CK(cudaStreamSynchronize(st));
+    return MPC_B200_OK;
+}
+
+int mpc_b200_num_waypoints(const mpc_b200_params *p)
+{
+    if (!p) return MPC_B200_ERR_INVALID;
+    const double wd = p->waypoints_dist > 0.0 ? p->waypoints_dist : 0.05;
+    const int win = (int)lround(p->path_length / wd);
+    const int step = (int)(p->path_length / 10.0 / wd);
+    if (step < 1) return MPC_B200_ERR_INVALID;
+    return (win + step - 1) / step + 1;
 }
 
 int mpc_b200_warm_shift(mpc_b200_handle *h, int32_t batch, const double *warm_prev, double *warm_next, void *stream_v)

@@ -297,3 +297,16 @@ def test_closed_loop_tracks_like_the_reference_loop():
     assert abs(np.abs(g["cte"]).mean() - np.abs(o["cte"]).mean()) <= 0.01
     assert np.abs(g["cte"][-10:]).mean() <= 0.12          # the order of the reference's own trace (assets/mpc.csv)
     assert g["iters"][1:].mean() < o["iters"][1:].mean()  # warm start pays
+
+
+def test_device_resident_loop_matches_host_loop():
+    """windowing (mpc_planner_ros.cpp:266-291, :365-391) and post-step
+    (driving_state.cpp:263-269) as kernels; the device-resident loop tracks like the host-driven one."""
+    from bench import closed_loop
+    R, T = 24, 30
+    h = closed_loop.run_gpu(R, T, warm=True)
+    d = closed_loop.run_gpu_device(R, T, groups=3)
+    assert d["conv"].mean() >= 0.99
+    # same robots, same rule for the cut, same solver: identical tracking errors while round-off has not diverged
+    assert np.abs(d["cte"][:3] - h["cte"][:3]).max() <= 1e-6
+    assert abs(np.median(np.abs(d["cte"])) - np.median(np.abs(h["cte"]))) <= 0.01

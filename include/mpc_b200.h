@@ -109,7 +109,9 @@ int mpc_b200_set_params(mpc_b200_handle *h, const mpc_b200_params *p);
 int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p);
 /* Launch tuning, no reference counterpart.  "max_ctas": cap on the persistent grid (0 = one CTA per SM;
  * smaller values leave SMs to batches in flight on other streams and make each lane work through
- * several problems); "problems_per_cta": 0 = auto (up to 32).  Unknown name: MPC_B200_ERR_INVALID. */
+ * several problems); "problems_per_cta": 0 = auto (up to 32); "hard_first": 1 (default) serves the work queue
+ * in descending order of |c1|+|c2|+|c3| so that the slow problems of a batch start first (results do not
+ * depend on it).  Unknown name: MPC_B200_ERR_INVALID. */
 int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value);
 
 /* Size in doubles of one problem's warm-start record: primal (8N-2, the reference's variable

@@ -14,6 +14,7 @@ using nmpc::SolveArgs;
 
 #define MAX_WAYPOINTS 64
 #define QUEUE_RING 1024
+#define ORDER_RING 64
 // stages per stage thread: 1 control warp + 7 stage warps = 256 threads, so that the kernel may use
 // 255 registers per thread (the serial Riccati sweep wants ~110 live doubles)
 #define SPT 3
@@ -112,6 +113,37 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
             state_out[3 * (size_t)batch + i] = s3; state_out[4 * (size_t)batch + i] = s4;
             state_out[5 * (size_t)batch + i] = s5;
         }
+    }
+}
+
+// ================================================================ hard-first queue order
+// Iteration counts range from 5 to the cap; the few slow problems are almost always the ones whose fitted
+// path polynomial is wild (a 5 m window wrapped around a sharp corner gives |c2|, |c3| in the tens or
+// thousands).  The work queue is therefore served in descending order of |c1|+|c2|+|c3| (bucketed by binary
+// exponent): slow problems start first and the tail of a launch is filled with quick ones.  Results do not
+// depend on the order (lanes are independent).  One CTA, counting sort with shared-memory atomics.
+__global__ void queue_order_kernel(int batch, const double *__restrict__ coeffs, int *__restrict__ order)
+{
+    __shared__ int hist[32], offs[32];
+    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+        const double s = fabs(coeffs[(size_t)batch + i]) + fabs(coeffs[2 * (size_t)batch + i]) + fabs(coeffs[3 * (size_t)batch + i]);
+        int b = 0;
+        if (s == s) { int e; frexp(s + 1e-12, &e); b = min(31, max(0, e + 12)); } else b = 31;
+        atomicAdd(&hist[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 31; b >= 0; b--) { offs[b] = acc; acc += hist[b]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+        const double s = fabs(coeffs[(size_t)batch + i]) + fabs(coeffs[2 * (size_t)batch + i]) + fabs(coeffs[3 * (size_t)batch + i]);
+        int b = 0;
+        if (s == s) { int e; frexp(s + 1e-12, &e); b = min(31, max(0, e + 12)); } else b = 31;
+        order[atomicAdd(&offs[b], 1)] = i;
     }
 }
 
@@ -239,6 +271,8 @@ struct mpc_b200_handle {
     long long launches;
     long long *d_prof;
     int *d_queue;          // ring of work-queue heads, one per in-flight launch
+    int *d_order;          // ring of hard-first queue orders (ORDER_RING x max_batch)
+    int opt_order;         // option: serve the queue hard-first (default on)
     int max_ctas;          // option: cap on the persistent grid (0 = one CTA per SM)
     int opt_pb;            // option: problems per CTA (0 = auto)
     std::string last_err;
@@ -278,6 +312,7 @@ static void free_scratch(mpc_b200_handle *h)
     cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
     if (h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
     if (h->d_queue) { cudaFree(h->d_queue); h->d_queue = NULL; }
+    if (h->d_order) { cudaFree(h->d_order); h->d_order = NULL; }
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL;
     h->h_in = h->h_out = NULL;
@@ -302,6 +337,7 @@ static int alloc_scratch(mpc_b200_handle *h)
     CK(cudaMalloc(&h->d_cte, sizeof(double) * 2 * B));
     CK(cudaMalloc(&h->d_vel, sizeof(double) * 3 * B));
     CK(cudaMalloc(&h->d_queue, sizeof(int) * QUEUE_RING));
+    CK(cudaMalloc(&h->d_order, sizeof(int) * ORDER_RING * B));
     h->d_warm_out = NULL;
     h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
     h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 1 + 6) * B;
@@ -363,7 +399,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
-    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0;
+    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->d_order = NULL; h->opt_order = 1;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -428,6 +464,7 @@ int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value)
     if (!h || !name) return MPC_B200_ERR_INVALID;
     if (!strcmp(name, "max_ctas")) h->max_ctas = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "problems_per_cta")) h->opt_pb = value > 0 ? (int)value : 0;
+    else if (!strcmp(name, "hard_first")) h->opt_order = value != 0.0;
     else return MPC_B200_ERR_INVALID;
     return MPC_B200_OK;
 }
@@ -530,6 +567,12 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     const size_t smem = nmpc::smem_bytes(N, NG, a.PB, nslots);
     a.queue = h->d_queue + (h->launches % QUEUE_RING);
     CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
+    a.order = NULL;
+    if (h->opt_order && batch > grid * a.PB) {      // only matters when lanes work through several problems
+        a.order = h->d_order + (size_t)(h->launches % ORDER_RING) * h->max_batch;
+        queue_order_kernel<<<1, 1024, 0, st>>>(batch, a.coeffs, (int *)a.order);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(h->ev0, st));
     if (rate) {
         if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);

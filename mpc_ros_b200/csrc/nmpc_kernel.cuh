@@ -39,6 +39,7 @@ struct SolveArgs {
     double *warm_out;       // warm_size x batch or NULL
     const double *warm_in;  // warm_size x batch or NULL (cold start)
     int *queue;             // work-queue head (zeroed by the host before the launch)
+    const int *order;       // queue position -> problem index (hard-first order) or NULL (identity)
     long long *prof;        // NMPC_PROFILE builds only: per-phase cycle counters of CTA 0
 };
 
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                     int nidx = nb + __popc(m & ((1u << p) - 1u));
                     if (nidx >= batch) nidx = -1;
                     else {
+                        if (a.order) nidx = a.order[nidx];
                         for (int i = 0; i < 6; i++) sm.P(PS_NX0 + i, p) = a.state[(size_t)i * batch + nidx];
                         for (int i = 0; i < 4; i++) sm.P(PS_NX6 + i, p) = a.coeffs[(size_t)i * batch + nidx];
                         sm.P(PS_NX10, p) = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;

@@ -137,7 +137,8 @@ int32_t mpc_b200_warm_size(int32_t mpc_steps);
  *   warm_out warm_size x batch, optional, DEVICE memory
  *   stream   cudaStream_t, or NULL for the handle's own stream.  The call returns after the
  *            results are in the caller's buffers (synchronous, like MPC::Solve) unless every
- *            buffer is device memory AND a stream is given, in which case it only enqueues.
+ *            buffer is device memory AND a stream is given, in which case it only enqueues; one handle
+ *            may have max(16, min(1024, 4M / max_batch)) such launches in flight on different streams.
  */
 int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
                          const double *state, const double *coeffs, const double *ref_vel,

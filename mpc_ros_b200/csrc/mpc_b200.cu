@@ -14,7 +14,6 @@ using nmpc::SolveArgs;
 
 #define MAX_WAYPOINTS 64
 #define QUEUE_RING 1024
-#define ORDER_RING 64
 // stages per stage thread: 1 control warp + 7 stage warps = 256 threads, so that the kernel may use
 // 255 registers per thread (the serial Riccati sweep wants ~110 live doubles)
 #define SPT 3
@@ -271,7 +270,8 @@ struct mpc_b200_handle {
     long long launches;
     long long *d_prof;
     int *d_queue;          // ring of work-queue heads, one per in-flight launch
-    int *d_order;          // ring of hard-first queue orders (ORDER_RING x max_batch)
+    int *d_order;          // ring of hard-first queue orders (order_ring x max_batch)
+    int order_ring;        // launches that may be in flight on this handle at once (16 .. 1024)
     int opt_order;         // option: serve the queue hard-first (default on)
     int max_ctas;          // option: cap on the persistent grid (0 = one CTA per SM)
     int opt_pb;            // option: problems per CTA (0 = auto)
@@ -337,7 +337,10 @@ static int alloc_scratch(mpc_b200_handle *h)
     CK(cudaMalloc(&h->d_cte, sizeof(double) * 2 * B));
     CK(cudaMalloc(&h->d_vel, sizeof(double) * 3 * B));
     CK(cudaMalloc(&h->d_queue, sizeof(int) * QUEUE_RING));
-    CK(cudaMalloc(&h->d_order, sizeof(int) * ORDER_RING * B));
+    h->order_ring = (int)((size_t)(1 << 22) / B);
+    if (h->order_ring < 16) h->order_ring = 16;
+    if (h->order_ring > QUEUE_RING) h->order_ring = QUEUE_RING;
+    CK(cudaMalloc(&h->d_order, sizeof(int) * (size_t)h->order_ring * B));
     h->d_warm_out = NULL;
     h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
     h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 1 + 6) * B;
@@ -569,7 +572,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     a.order = NULL;
     if (h->opt_order && batch > grid * a.PB) {      // only matters when lanes work through several problems
-        a.order = h->d_order + (size_t)(h->launches % ORDER_RING) * h->max_batch;
+        a.order = h->d_order + (size_t)(h->launches % h->order_ring) * h->max_batch;
         queue_order_kernel<<<1, 1024, 0, st>>>(batch, a.coeffs, (int *)a.order);
         CK(cudaGetLastError());
     }

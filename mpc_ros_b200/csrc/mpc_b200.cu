@@ -267,7 +267,8 @@ struct mpc_b200_handle {
     size_t h_in_bytes, h_out_bytes;
     int pred_steps;        // horizon the scratch was sized for
     double last_kernel_s;
-    long long launches;
+    long long launches;    // API calls that launched work (also drives the queue / order rings)
+    long long kernels;     // kernels launched by this handle
     long long *d_prof;
     int *d_queue;          // ring of work-queue heads, one per in-flight launch
     int *d_order;          // ring of hard-first queue orders (order_ring x max_batch)
@@ -399,7 +400,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     }
     mpc_b200_handle *h = new (std::nothrow) mpc_b200_handle();
     if (!h) return MPC_B200_ERR_NOMEM;
-    h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0;
+    h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0; h->kernels = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
     h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->d_order = NULL; h->opt_order = 1;
@@ -473,7 +474,7 @@ int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value)
 }
 
 double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h) { return h ? h->last_kernel_s : 0.0; }
-int64_t mpc_b200_launch_count(const mpc_b200_handle *h) { return h ? h->launches : 0; }
+int64_t mpc_b200_launch_count(const mpc_b200_handle *h) { return h ? h->kernels : 0; }
 
 // Problems per CTA: as many as shared memory and the thread budget allow, but spread a small
 // batch over all SMs (the CTA's latency does not depend on how many lanes are active).
@@ -575,6 +576,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         a.order = h->d_order + (size_t)(h->launches % h->order_ring) * h->max_batch;
         queue_order_kernel<<<1, 1024, 0, st>>>(batch, a.coeffs, (int *)a.order);
         CK(cudaGetLastError());
+        h->kernels++;
     }
     CK(cudaEventRecord(h->ev0, st));
     if (rate) {
@@ -593,7 +595,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
-    h->launches++;
+    h->launches++; h->kernels++;
 
     if (!dev_out) {
         double *ho = h->h_out;
@@ -654,7 +656,7 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
     prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, dce, NULL, NULL, 0, 0.0);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
-    h->launches++;
+    h->launches++; h->kernels++;
     if (!dev_out) {
         double *ho = h->h_out;
         CK(cudaMemcpyAsync(ho, dco, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
@@ -706,7 +708,7 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                                                          h->params.delay_mode, h->params.dt);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
-    h->launches++;
+    h->launches++; h->kernels++;
     if (!dev_out) {
         double *ho = h->h_out;
         CK(cudaMemcpyAsync(ho, dco, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
@@ -743,7 +745,7 @@ int mpc_b200_window_batch(mpc_b200_handle *h, int32_t batch, const double *path_
     window_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, path_x, path_y, track_off, track_len, track_id, idx_inout,
                                                         pose, win, step, 64, wx_out, wy_out);
     CK(cudaGetLastError());
-    h->launches++;
+    h->launches++; h->kernels++;
     if (!stream_v) CK(cudaStreamSynchronize(st));
     return MPC_B200_OK;
 }
@@ -759,7 +761,7 @@ int mpc_b200_poststep_batch(mpc_b200_handle *h, int32_t batch, const double *u0,
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
     poststep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, u0, vel_inout, ref_vel, h->params.ref_vel, h->params.dt, cmd_out);
     CK(cudaGetLastError());
-    h->launches++;
+    h->launches++; h->kernels++;
     if (!stream_v) CK(cudaStreamSynchronize(st));
     return MPC_B200_OK;
 }
@@ -783,7 +785,7 @@ int mpc_b200_warm_shift(mpc_b200_handle *h, int32_t batch, const double *warm_pr
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
     warm_shift_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, h->params.mpc_steps, warm_prev, warm_next);
     CK(cudaGetLastError());
-    h->launches++;
+    h->launches++; h->kernels++;
     if (!stream_v) CK(cudaStreamSynchronize(st));
     return MPC_B200_OK;
 }

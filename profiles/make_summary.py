@@ -1,0 +1,116 @@
+"""profiles/make_summary.py -- builds profiles/rN_summary.md from the files a gpurun evidence run left in
+gpurun_out/ (bench outputs, ncu launch list, ncu --set full report).  Usage: python profiles/make_summary.py r1"""
+import collections, csv, json, os, shutil, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+shutil.copy(os.path.join(G, "launches_%s.csv" % tag), os.path.join(P, "%s_launches.csv" % tag))
+raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof_%s_solve.ncu-rep" % tag), "--page", "raw", "--csv"],
+                     capture_output=True, text=True).stdout
+open(os.path.join(P, "%s_solve_kernel_ncu_raw.csv" % tag), "w").write(raw)
+for src, dst in (("bench_default_%s.json", "%s_bench_default.json"), ("bench_reference_%s.json", "%s_bench_reference.json"),
+                 ("config4_%s.json", "%s_config4.json"), ("config5_%s.json", "%s_config5.json"),
+                 ("config5_device_%s.json", "%s_config5_device.json")):
+    if os.path.exists(os.path.join(G, src % tag)):
+        shutil.copy(os.path.join(G, src % tag), os.path.join(P, dst % tag))
+lat = [ln for ln in open(os.path.join(G, "latency_%s.json" % tag)) if ln.startswith("{")][-1]
+open(os.path.join(P, "%s_config1_latency.json" % tag), "w").write(lat)
+
+rows = [r for r in csv.reader(open(os.path.join(P, "%s_launches.csv" % tag))) if len(r) > 5]
+hdr = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+H = rows[hdr]; data = rows[hdr + 1:]
+ik = H.index("Kernel Name"); iv = H.index("Metric Value"); iu = H.index("Metric Unit")
+agg = collections.defaultdict(list)
+for r in data:
+    try:
+        v = float(r[iv].replace(",", ""))
+    except ValueError:
+        continue
+    u = r[iu]
+    v = v / 1e3 if u in ("ns", "nsecond") else v * 1e3 if u in ("ms", "msecond") else v
+    agg[r[ik][:80]].append(v)
+tot = sum(sum(v) for v in agg.values())
+lines = ["| `%s` | %d | %.2f | %.1f %% | %.1f |" % (k, len(v), sum(v) / 1e3, 100 * sum(v) / tot, sum(v) / len(v))
+         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))]
+rr = list(csv.reader(raw.splitlines()))
+h, u, v = rr[0], rr[1], rr[2]
+keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sass__inst_executed_register_spilling", "smsp__inst_executed.sum",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__sass_inst_executed_op_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+met = ["| `%s` | %s | %s |" % (k, v[h.index(k)], u[h.index(k)]) for k in keys if k in h]
+d = json.load(open(os.path.join(P, "%s_bench_default.json" % tag)))
+ref = json.load(open(os.path.join(P, "%s_bench_reference.json" % tag)))
+c1 = json.loads(lat); c4 = json.load(open(os.path.join(P, "%s_config4.json" % tag)))
+c5 = json.load(open(os.path.join(P, "%s_config5.json" % tag)))
+c5d = json.load(open(os.path.join(P, "%s_config5_device.json" % tag))) if os.path.exists(os.path.join(P, "%s_config5_device.json" % tag)) else None
+spill = v[h.index("sass__inst_executed_register_spilling")]; inst = v[h.index("smsp__inst_executed.sum")]
+md = """# Round %s profile summary (B200, gpurun)
+
+All files in this directory come from `gpurun` runs of the committed tree (`profiles/make_summary.py %s`).
+
+## Headline (`%s_bench_default.json`, `python bench.py`, no flags)
+
+* value **%.2f M converged solves/s** on 1xB200 (%.3f ms per 4,096-problem step, %d streams, persistent grid of
+  %d CTAs per launch), converged fraction %.5f, mean %.2f iterations, clocks %.0f/%.0f MHz, throttle reasons %s.
+* e2e (host buffers, H2D+D2H inside, %d host threads) **%.2f M solves/s**.
+* roofline (FP64 pipe): %.2f TFLOP/s algorithmic (SURVEY 8d count) of %.1f measured peak = **%.1f %%**;
+  DRAM traffic of one launch %.2f MB (ncu) vs %.2f MB algorithmic (the results are still in L2 when the kernel ends).
+* CPU baseline: %.0f solves/s on %d host cores (`oracle/_ref`: reference `mpc_planner.cpp` + CppAD, stand-in IPM);
+  reference arm (`%s_bench_reference.json`): %.0f solves/s.
+
+## Other BASELINE configs
+
+* config 1 (`%s_config1_latency.json`): one solve through the C++ `MPC` adapter, host buffers: p50 %.1f us, p99 %.1f us (10,000 calls).
+* config 4 (`%s_config4.json`): N=100, batch 16,384: %.0f converged solves/s, %.1f mean iterations, converged fraction %.4f.
+* config 5 (`%s_config5.json`): 1,024 robots x 500 ticks, warm start: %.2f mean iterations (oracle loop, cold: %.2f), converged
+  fraction %.5f; host-driven loop %.0f solves/s%s.
+
+## Launch list (`%s_launches.csv`)
+
+`ncu --metrics gpu__time_duration.sum --clock-control none -c 600` on
+`python bench.py --steps 40 --warmup 8 --streams 8 --no-cpu-baseline --e2e-steps 16 --e2e-threads 2` (serialised, cold).
+
+| kernel | launches | total ms | share | avg us |
+|---|---|---|---|---|
+%s
+
+`dfma_kernel<8>` is bench.py's own FP64-peak probe (outside the timed region); `queue_order_kernel` is the
+hard-first work-queue ordering.  Inside a step the solve kernel is > 99 %% of the device time, in line with the
+CUDA-event shares bench.py reports (`roofline.kernel_ms` vs `ms_per_step`).
+
+## Solve kernel, `ncu --set full` (`%s_solve_kernel_ncu_raw.csv`, one launch of 4,096 problems, launch alone)
+
+| metric | value | unit |
+|---|---|---|
+%s
+
+Reading: 255 registers/thread and 219 KB dynamic shared memory give one 8-warp CTA per SM by design (the
+per-problem working set lives in shared memory: 37 fp64 slots x 20 stages x 32 lanes).  A lone launch of one
+batch leaves most SMs idle most of the time (the tail of a batch is a handful of problems that need 10-20x
+the median iteration count), which is why throughput is measured with many batches in flight.  Within active
+cycles the FP64 pipe is busy a fifth of the time: the serial Riccati sweep runs on ONE warp per SM (32 problems
+per instruction) and is bound by FP64 issue latency, not by throughput.  DRAM traffic per launch is the
+algorithmic input + output; nothing is re-read.  Register spilling: 80 B/thread in the stage threads
+(`ptxas -v`), %s of %s executed warp instructions (%.2f %%).  compute-sanitizer is closed on this pool
+(`gpurun` refuses it), so race freedom is argued from the barrier structure and checked by the bit-reproducibility
+and lane-permutation tests.
+""" % (tag, tag, tag, d["value"] / 1e6, d["ms_per_step"], d["config"]["streams"], d["config"]["max_ctas"],
+       d["config"]["converged_fraction"], d["config"]["mean_iters_converged"], d["clocks"]["sm_mhz"], d["clocks"]["sm_max_mhz"],
+       d["clocks"]["reasons"], d["e2e"]["threads"], d["e2e"]["value"] / 1e6, d["roofline"]["achieved"], d["roofline"]["peak"],
+       100 * d["roofline"]["frac"], (float(v[h.index("dram__bytes_read.sum")]) * (1e3 if u[h.index("dram__bytes_read.sum")] == "Kbyte" else 1e6 if u[h.index("dram__bytes_read.sum")] == "Mbyte" else 1) +
+                                     float(v[h.index("dram__bytes_write.sum")]) * (1e3 if u[h.index("dram__bytes_write.sum")] == "Kbyte" else 1e6 if u[h.index("dram__bytes_write.sum")] == "Mbyte" else 1)) / 1e6,
+       4096 * (88 + 520) / 1e6, d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], tag, ref["value"],
+       tag, c1["p50_us"], c1["p99_us"], tag, c4["solves_per_s"], c4["mean_iters"], c4["converged_fraction"],
+       tag, c5["mean_iters"], c5["oracle_subset"]["mean_iters_oracle"], c5["converged_fraction"], c5["solves_per_s"],
+       ("; device-resident loop (`%s_config5_device.json`) %.0f robot-ticks/s" % (tag, c5d["robot_ticks_per_s"])) if c5d else "",
+       tag, "\n".join(lines), tag, "\n".join(met), spill, inst, 100.0 * float(spill) / float(inst))
+open(os.path.join(P, "%s_summary.md" % tag), "w").write(md)
+print(md[:1800])

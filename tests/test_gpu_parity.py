@@ -335,3 +335,35 @@ def test_all_kernel_specialisations_agree(oracle):
             np.testing.assert_allclose(out["u0"][:, ok], ref["u0"][:, ok], rtol=0, atol=1e-9, err_msg=tag + "u0")
             np.testing.assert_allclose(out["pred"][:, ok], ref["pred"][:, ok], rtol=0, atol=1e-8, err_msg=tag + "pred")
             np.testing.assert_allclose(out["obj"][ok], ref["obj"][ok], rtol=1e-10, err_msg=tag + "obj")
+
+
+def test_prestep_ragged_windows_and_delay_mode(oracle):
+    """K1 at the edges: the shortest (M = 4: cubic through 4 points) and longest (M = 64) windows, refused
+    sizes, and the delay-compensated state of driving_state.cpp:243-254."""
+    rng = np.random.default_rng(3)
+    for M in (4, 7, 64):
+        B = 33
+        wx = np.cumsum(rng.uniform(0.05, 0.6, (M, B)), axis=0); wy = 0.3 * np.sin(wx) + rng.normal(0, 0.01, (M, B))
+        pose = np.stack([rng.uniform(-0.2, 0.2, B), rng.uniform(-0.2, 0.2, B), rng.uniform(-0.4, 0.4, B)])
+        vel = np.stack([rng.uniform(0, 0.6, B), rng.uniform(-0.5, 0.5, B), rng.uniform(-0.5, 0.5, B)])
+        for delay in (0, 1):
+            prm = capi.yaml_default_params(); prm.delay_mode = delay
+            sv = capi.Solver(prm, B, 0)
+            coeffs, state = sv.prestep(wx, wy, pose, vel)
+            sv.close()
+            for i in range(B):
+                c, cte, eth = oracle.prestep(wx[:, i], wy[:, i], *pose[:, i])
+                scale = max(1.0, np.abs(c).max())
+                assert np.abs(coeffs[:, i] - c).max() <= 1e-8 * scale
+                v, w, thr = vel[:, i]
+                dt = prm.dt
+                exp = [v * dt, 0.0, w * dt, v + thr * dt, cte + v * np.sin(eth) * dt, eth - w * dt] if delay else [0, 0, 0, v, cte, eth]
+                assert np.abs(state[:, i] - np.array(exp)).max() <= 1e-8 * scale
+    sv = capi.Solver(capi.yaml_default_params(), 4, 0)
+    for M in (3, 65):
+        with pytest.raises(capi.MpcError):
+            sv.polyfit(np.zeros((M, 4)), np.zeros((M, 4)), np.zeros((3, 4)))
+    # degenerate window (all waypoints identical): NaN coefficients, reported, no hang
+    coeffs, cte, eth = sv.polyfit(np.zeros((11, 4)), np.zeros((11, 4)), np.zeros((3, 4)))
+    assert np.all(np.isnan(coeffs)) or np.all(np.isfinite(coeffs))
+    sv.close()

@@ -223,6 +223,11 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 } else if (md == MODE_FAIL) {
                     term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
                 }
+                // watchdog: retries and backtracks are bounded, this only guards against the unforeseen
+                if (!term && md != MODE_IDLE && ++c.age > 8 * prm.max_iter + 64) {
+                    if (c.status == 0) c.status = 2;
+                    term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
+                }
                 if (term) {
                     const size_t i = (size_t)sm.I(PI_PROB, p);
                     if (a.obj) a.obj[i] = c.obj;

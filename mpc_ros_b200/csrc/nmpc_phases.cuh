@@ -951,6 +951,7 @@ struct Ctrl {
     int n_accept;          // consecutive "acceptable" iterations
     int nfilt;
     int have_theta0;
+    int age;               // global cycles spent on the current problem (watchdog)
     double dw_last;
     double theta_min, theta_max;
     double theta, phi, gd;          // at the current iterate, for the line search
@@ -989,7 +990,7 @@ MPC_HD double objective_scaling(const Params &prm, const double *state6, double 
 template <class SM>
 MPC_HD void ctrl_init(const Params &prm, const SM &sm, Ctrl &c, int p, const double *state6, double refv)
 {
-    c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.have_theta0 = 0;
+    c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.have_theta0 = 0; c.age = 0;
     c.dw_last = 0.0; c.theta_min = 0.0; c.theta_max = 0.0; c.theta = 0.0; c.phi = 0.0; c.gd = 0.0;
     c.alpha_min = 0.0; c.sw_log = 0.0; c.E0 = 1e300; c.obj = 0.0;
     sm.P(PS_MU, p) = NMPC_MU_INIT;
@@ -1061,7 +1062,8 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
         }
         if (!acc) {
             const double a2 = 0.5 * alpha;
-            if (a2 < c.alpha_min) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; return 2; }
+            // (alpha_min can be 0 or NaN in degenerate cases: the absolute floor bounds the number of halvings)
+            if (a2 < c.alpha_min || !(a2 > 1e-40)) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; return 2; }
             sm.P(PS_ALPHA, p) = a2;
             return 0;
         }

@@ -517,7 +517,7 @@ int ipm_solve(const ipm_nlp *nlp, const ipm_options *opt, ipm_result *res)
         double f_t = f, theta_t = theta;
         const double *dacc = dx;
         double alpha_acc = alpha;
-        while (!accepted && (alpha >= a_min || first)) {
+        while (!accepted && (alpha >= a_min || first) && alpha > 1e-40) {
             for (int i = 0; i < N; i++) Xt[i] = X[i] + alpha * dx[i];
             int ok = ev_fc(w, Xt, &f_t, ct);
             double phi_t = INFINITY;

@@ -179,6 +179,11 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 } else if (md == MODE_FAIL) {
                     term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
                 }
+                // watchdog: retries and backtracks are bounded, this only guards against the unforeseen
+                if (!term && md != MODE_IDLE && ++c.age > 8 * prm.max_iter + 64) {
+                    if (c.status == 0) c.status = 2;
+                    term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
+                }
                 if (term) {
                     const size_t i = (size_t)sm.I(PI_PROB, p);
                     if (obj) obj[i] = c.obj;

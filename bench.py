@@ -313,16 +313,16 @@ def run_ours(a):
             for j in range(Rh):
                 q = (t * Rh + j) % R
                 self.wx[j].copy_(d_wx[q]); self.wy[j].copy_(d_wy[q]); self.pose[j].copy_(d_pose[q]); self.vel[j].copy_(d_vel[q])
-            self.coef = pinned((4, B)); self.state = pinned((6, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
+            self.cmd = pinned((2, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
             self.obj = pinned(B); self.kkt = pinned(B); self.stat = pinned(B, torch.int32); self.it = pinned(B, torch.int32)
             self.conv = 0
 
         def step(self, j):
             j %= Rh
             s = self.solver
-            s.prestep_raw(B, M, self.wx[j].numpy(), self.wy[j].numpy(), self.pose[j].numpy(), self.vel[j].numpy(),
-                          self.coef.numpy(), self.state.numpy())
-            s.solve_raw(B, self.state.numpy(), self.coef.numpy(), self.u0.numpy(), self.pred.numpy(), obj=self.obj.numpy(),
+            # one control tick per robot: pre-step -> solve -> post-step, host buffers in and out
+            s.track_raw(B, M, self.wx[j].numpy(), self.wy[j].numpy(), self.pose[j].numpy(), self.vel[j].numpy(),
+                        self.u0.numpy(), self.pred.numpy(), cmd=self.cmd.numpy(), obj=self.obj.numpy(),
                         status=self.stat.numpy(), iters=self.it.numpy(), kkt=self.kkt.numpy())
             return int(((self.stat.numpy() == 1) & (self.kkt.numpy() <= 1e-8)).sum())
 
@@ -349,11 +349,11 @@ def run_ours(a):
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev); ce = torch.tensor([float(conv_h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce, op=dist.ReduceOp.SUM)
-    h2d = (2 * M + 6) * B * 8 + 10 * B * 8          # prestep inputs + (state, coeffs) re-sent to the solve call
-    d2h = 10 * B * 8 + (2 + 3 * N + 2) * B * 8 + 2 * B * 4
+    h2d = (2 * M + 6) * B * 8                       # waypoints, pose, (v, previous w, previous throttle)
+    d2h = (3 + 2 + 3 * N + 2 + 2) * B * 8 + 2 * B * 4   # vel, u0, pred, cmd, obj, kkt, status, iters
     e2e = dict(value=float(ce.item()) / float(te.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                steps=e2e_steps, threads=T,
-               note="synchronous C-ABI calls with host buffers (pinned staging, H2D and D2H inside the timed region) "
+               note="synchronous mpc_b200_track_batch calls with host buffers (pinned staging, H2D and D2H inside the timed region) "
                     "from %d host threads, one handle + stream each; host wall clock" % T)
     for w in workers:
         w.solver.close()

@@ -196,6 +196,19 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                            const double *wx, const double *wy, const double *pose, const double *vel,
                            double *coeffs_out, double *state_out, void *stream);
 
+/*
+ * The whole control tick of Tracking::findBestPath (mpc_ros/src/driving_state.cpp:175-271) for `batch` robots,
+ * HOST buffers in and out, one synchronous call: pre-step (:196-256) -> MPC::Solve (:260) -> post-step
+ * (:263-269).  The fitted coefficients and the assembled state never leave the device.
+ *   wx, wy  M x batch; pose 3 x batch; vel_inout 3 x batch (v, previous w, previous throttle; w and
+ *   throttle are updated); ref_vel batch or NULL; u0 2 x batch; pred 3N x batch;
+ *   cmd_out 2 x batch {linear.x, angular.z} (:115-116), optional; obj/status/iters/kkt_res optional.
+ */
+int mpc_b200_track_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                         const double *wx, const double *wy, const double *pose, double *vel_inout,
+                         const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                         double *obj, int32_t *status, int32_t *iters, double *kkt_res);
+
 /* Seconds spent on the device by the last solve_batch / polyfit_batch on this handle
  * (CUDA events on the launching stream around the kernel only; no copies). */
 double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h);

@@ -38,7 +38,7 @@ EXPORTS = [
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
     "mpc_b200_get_params", "mpc_b200_set_option", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
     "mpc_b200_prestep_batch", "mpc_b200_warm_shift", "mpc_b200_window_batch", "mpc_b200_poststep_batch",
-    "mpc_b200_num_waypoints",
+    "mpc_b200_num_waypoints", "mpc_b200_track_batch",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
 ]
@@ -83,6 +83,8 @@ def lib():
     L.mpc_b200_poststep_batch.restype = C.c_int
     L.mpc_b200_num_waypoints.argtypes = [C.POINTER(Params)]
     L.mpc_b200_num_waypoints.restype = C.c_int
+    L.mpc_b200_track_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 12
+    L.mpc_b200_track_batch.restype = C.c_int
     L.mpc_b200_warm_shift.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mpc_b200_warm_shift.restype = C.c_int
     L.mpc_b200_last_kernel_seconds.argtypes = [C.c_void_p]
@@ -236,6 +238,30 @@ class Solver:
         rc = lib().mpc_b200_poststep_batch(self._h, batch, _addr(u0), _addr(vel), _addr(ref_vel), _addr(cmd), stream)
         if rc != 0:
             raise MpcError(rc)
+
+    def track_raw(self, batch, M, wx, wy, pose, vel, u0, pred, ref_vel=None, cmd=None, obj=None, status=None, iters=None,
+                  kkt=None):
+        rc = lib().mpc_b200_track_batch(self._h, batch, M, _addr(wx), _addr(wy), _addr(pose), _addr(vel), _addr(ref_vel),
+                                        _addr(u0), _addr(pred), _addr(cmd), _addr(obj), _addr(status), _addr(iters), _addr(kkt))
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def track(self, wx, wy, pose, vel, ref_vel=None):
+        """One control tick for B robots, host numpy in/out (Tracking::findBestPath, driving_state.cpp:175-271).
+        vel (3 x B: v, previous w, previous throttle) is updated in place for the next tick."""
+        wx = np.ascontiguousarray(wx, dtype=np.float64); wy = np.ascontiguousarray(wy, dtype=np.float64)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        if not (isinstance(vel, np.ndarray) and vel.dtype == np.float64 and vel.flags.c_contiguous):
+            raise TypeError("vel must be a C-contiguous float64 array (it is updated in place)")
+        M, B = wx.shape
+        N = self.N
+        out = dict(u0=np.zeros((2, B)), pred=np.zeros((3 * N, B)), cmd=np.zeros((2, B)), obj=np.zeros(B),
+                   status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32), kkt=np.zeros(B))
+        if ref_vel is not None:
+            ref_vel = np.ascontiguousarray(ref_vel, dtype=np.float64)
+        self.track_raw(B, M, wx, wy, pose, vel, out["u0"], out["pred"], ref_vel=ref_vel, cmd=out["cmd"], obj=out["obj"],
+                       status=out["status"], iters=out["iters"], kkt=out["kkt"])
+        return out
 
     def warm_shift(self, batch, prev, nxt, stream=None):
         rc = lib().mpc_b200_warm_shift(self._h, batch, _addr(prev), _addr(nxt), stream)

@@ -498,31 +498,13 @@ static int choose_pb(const mpc_b200_handle *h, int N, int batch, int nslots)
     return pb;
 }
 
-int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
-                         const double *state, const double *coeffs, const double *ref_vel,
-                         const double *warm_in,
-                         double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
-                         double *kkt_res, double *warm_out, void *stream_v)
+// Enqueue one batched solve on `st`; every pointer is DEVICE memory.
+static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_state, const double *d_coeffs,
+                         const double *d_refv, const double *d_warm_in, double *d_u0, double *d_pred, double *d_obj,
+                         int32_t *d_status, int32_t *d_iters, double *d_kkt, double *d_warm_out, cudaStream_t st)
 {
-    if (!h || batch < 0 || batch > h->max_batch || !state || !coeffs || !u0 || !pred) return MPC_B200_ERR_INVALID;
-    if (batch == 0) return MPC_B200_OK;
-    CK(cudaSetDevice(h->device));
     const mpc_b200_params &P = h->params;
     const int N = P.mpc_steps;
-    const size_t B = (size_t)batch;
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
-
-    const bool dev_in = is_device_ptr(state);
-    const bool dev_out = is_device_ptr(u0);
-    if (is_device_ptr(coeffs) != dev_in || (ref_vel && is_device_ptr(ref_vel) != dev_in)) return MPC_B200_ERR_INVALID;
-    // warm-start records are large and meant to stay on the device between ticks
-    if (warm_in && !is_device_ptr(warm_in)) return MPC_B200_ERR_UNSUPPORTED;
-    if (is_device_ptr(pred) != dev_out || (obj && is_device_ptr(obj) != dev_out) ||
-        (status && is_device_ptr(status) != dev_out) || (iters && is_device_ptr(iters) != dev_out) ||
-        (kkt_res && is_device_ptr(kkt_res) != dev_out))
-        return MPC_B200_ERR_INVALID;
-    if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
-
     SolveArgs a;
     a.prm.N = N; a.prm.dt = P.dt; a.prm.ref_cte = P.ref_cte; a.prm.ref_etheta = P.ref_etheta; a.prm.ref_vel = P.ref_vel;
     a.prm.w_cte = P.w_cte; a.prm.w_etheta = P.w_etheta; a.prm.w_vel = P.w_vel; a.prm.w_angvel = P.w_angvel;
@@ -537,29 +519,8 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     a.prm.w_angvel_d = P.w_angvel_d; a.prm.w_accel_d = P.w_accel_d;
     a.PB = choose_pb(h, N, batch, nslots);
     a.prof = h->d_prof;
-
-    if (dev_in) {
-        a.state = state; a.coeffs = coeffs; a.ref_vel = ref_vel;
-    } else {
-        if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
-        double *hi = h->h_in;
-        const double *src_s = state, *src_c = coeffs, *src_r = ref_vel;
-        if (!is_pinned_host(state)) { memcpy(hi, state, sizeof(double) * 6 * B); src_s = hi; }
-        if (!is_pinned_host(coeffs)) { memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B); src_c = hi + 6 * B; }
-        if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + 10 * B, ref_vel, sizeof(double) * B); src_r = hi + 10 * B; }
-        // state and coeffs scratch are separate allocations: two copies (three with ref_vel)
-        CK(cudaMemcpyAsync(h->d_state, src_s, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(h->d_coeffs, src_c, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, st));
-        if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, src_r, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-        a.state = h->d_state; a.coeffs = h->d_coeffs; a.ref_vel = ref_vel ? h->d_refv : NULL;
-    }
-    a.warm_in = warm_in;
-    if (dev_out) {
-        a.u0 = u0; a.pred = pred; a.obj = obj; a.status = status; a.iters = iters; a.kkt = kkt_res; a.warm_out = warm_out;
-    } else {
-        a.u0 = h->d_u0; a.pred = h->d_pred; a.obj = h->d_obj; a.status = h->d_status; a.iters = h->d_iters;
-        a.kkt = h->d_kkt; a.warm_out = warm_out;
-    }
+    a.state = d_state; a.coeffs = d_coeffs; a.ref_vel = d_refv; a.warm_in = d_warm_in;
+    a.u0 = d_u0; a.pred = d_pred; a.obj = d_obj; a.status = d_status; a.iters = d_iters; a.kkt = d_kkt; a.warm_out = d_warm_out;
 
     const int NG = (N + SPT - 1) / SPT;
     const int stage_threads = ((NG * a.PB + 31) / 32) * 32;
@@ -596,26 +557,84 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++; h->kernels++;
+    return MPC_B200_OK;
+}
+
+// D2H of the solve results into host buffers (direct when they are page-locked), then synchronise.
+static int fetch_results(mpc_b200_handle *h, int32_t batch, double *u0, double *pred, double *obj, int32_t *status,
+                         int32_t *iters, double *kkt_res, double *cmd, cudaStream_t st)
+{
+    const size_t B = (size_t)batch, N = (size_t)h->params.mpc_steps;
+    double *ho = h->h_out;
+    double *ho_u0 = ho, *ho_pred = ho + 2 * B, *ho_obj = ho_pred + 3 * N * B, *ho_kkt = ho_obj + B, *ho_cmd = ho_kkt + B;
+    int *ho_status = reinterpret_cast<int *>(ho_cmd + 2 * B), *ho_iters = ho_status + B;
+    const bool pu = is_pinned_host(u0), pp = is_pinned_host(pred), po = is_pinned_host(obj), pk = is_pinned_host(kkt_res),
+               ps = is_pinned_host(status), pi = is_pinned_host(iters), pc = is_pinned_host(cmd);
+    CK(cudaMemcpyAsync(pu ? u0 : ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pp ? pred : ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
+    if (obj) CK(cudaMemcpyAsync(po ? obj : ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (kkt_res) CK(cudaMemcpyAsync(pk ? kkt_res : ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(ps ? status : ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(pi ? iters : ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (cmd) CK(cudaMemcpyAsync(pc ? cmd : ho_cmd, h->d_cte, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!pu) memcpy(u0, ho_u0, sizeof(double) * 2 * B);
+    if (!pp) memcpy(pred, ho_pred, sizeof(double) * 3 * N * B);
+    if (obj && !po) memcpy(obj, ho_obj, sizeof(double) * B);
+    if (kkt_res && !pk) memcpy(kkt_res, ho_kkt, sizeof(double) * B);
+    if (status && !ps) memcpy(status, ho_status, sizeof(int) * B);
+    if (iters && !pi) memcpy(iters, ho_iters, sizeof(int) * B);
+    if (cmd && !pc) memcpy(cmd, ho_cmd, sizeof(double) * 2 * B);
+    return MPC_B200_OK;
+}
+
+int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
+                         const double *state, const double *coeffs, const double *ref_vel,
+                         const double *warm_in,
+                         double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
+                         double *kkt_res, double *warm_out, void *stream_v)
+{
+    if (!h || batch < 0 || batch > h->max_batch || !state || !coeffs || !u0 || !pred) return MPC_B200_ERR_INVALID;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t B = (size_t)batch;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+
+    const bool dev_in = is_device_ptr(state);
+    const bool dev_out = is_device_ptr(u0);
+    if (is_device_ptr(coeffs) != dev_in || (ref_vel && is_device_ptr(ref_vel) != dev_in)) return MPC_B200_ERR_INVALID;
+    // warm-start records are large and meant to stay on the device between ticks
+    if (warm_in && !is_device_ptr(warm_in)) return MPC_B200_ERR_UNSUPPORTED;
+    if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
+    if (is_device_ptr(pred) != dev_out || (obj && is_device_ptr(obj) != dev_out) ||
+        (status && is_device_ptr(status) != dev_out) || (iters && is_device_ptr(iters) != dev_out) ||
+        (kkt_res && is_device_ptr(kkt_res) != dev_out))
+        return MPC_B200_ERR_INVALID;
+
+    const double *ds = state, *dc = coeffs, *dr = ref_vel;
+    if (!dev_in) {
+        double *hi = h->h_in;
+        const double *src_s = state, *src_c = coeffs, *src_r = ref_vel;
+        if (!is_pinned_host(state)) { memcpy(hi, state, sizeof(double) * 6 * B); src_s = hi; }
+        if (!is_pinned_host(coeffs)) { memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B); src_c = hi + 6 * B; }
+        if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + 10 * B, ref_vel, sizeof(double) * B); src_r = hi + 10 * B; }
+        // state and coeffs scratch are separate allocations: two copies (three with ref_vel)
+        CK(cudaMemcpyAsync(h->d_state, src_s, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_coeffs, src_c, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, st));
+        if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, src_r, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+        ds = h->d_state; dc = h->d_coeffs; dr = ref_vel ? h->d_refv : NULL;
+    }
+    int rc;
+    if (dev_out)
+        rc = enqueue_solve(h, batch, ds, dc, dr, warm_in, u0, pred, obj, status, iters, kkt_res, warm_out, st);
+    else
+        rc = enqueue_solve(h, batch, ds, dc, dr, warm_in, h->d_u0, h->d_pred, h->d_obj, h->d_status, h->d_iters, h->d_kkt,
+                           warm_out, st);
+    if (rc != MPC_B200_OK) return rc;
 
     if (!dev_out) {
-        double *ho = h->h_out;
-        double *ho_u0 = ho, *ho_pred = ho + 2 * B, *ho_obj = ho_pred + 3 * (size_t)N * B, *ho_kkt = ho_obj + B;
-        int *ho_status = reinterpret_cast<int *>(ho_kkt + B), *ho_iters = ho_status + B;
-        const bool pu = is_pinned_host(u0), pp = is_pinned_host(pred), po = is_pinned_host(obj), pk = is_pinned_host(kkt_res),
-                   ps = is_pinned_host(status), pi = is_pinned_host(iters);
-        CK(cudaMemcpyAsync(pu ? u0 : ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(pp ? pred : ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
-        if (obj) CK(cudaMemcpyAsync(po ? obj : ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        if (kkt_res) CK(cudaMemcpyAsync(pk ? kkt_res : ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        if (status) CK(cudaMemcpyAsync(ps ? status : ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-        if (iters) CK(cudaMemcpyAsync(pi ? iters : ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (!pu) memcpy(u0, ho_u0, sizeof(double) * 2 * B);
-        if (!pp) memcpy(pred, ho_pred, sizeof(double) * 3 * N * B);
-        if (obj && !po) memcpy(obj, ho_obj, sizeof(double) * B);
-        if (kkt_res && !pk) memcpy(kkt_res, ho_kkt, sizeof(double) * B);
-        if (status && !ps) memcpy(status, ho_status, sizeof(int) * B);
-        if (iters && !pi) memcpy(iters, ho_iters, sizeof(int) * B);
+        rc = fetch_results(h, batch, u0, pred, obj, status, iters, kkt_res, NULL, st);
+        if (rc != MPC_B200_OK) return rc;
     } else if (!(dev_in && stream_v)) {
         CK(cudaStreamSynchronize(st));
     }
@@ -623,6 +642,52 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
     }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_track_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                         const double *wx, const double *wy, const double *pose, double *vel_inout,
+                         const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                         double *obj, int32_t *status, int32_t *iters, double *kkt_res)
+{
+    if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !vel_inout || !u0 || !pred) return MPC_B200_ERR_INVALID;
+    if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
+    if (is_device_ptr(wx) || is_device_ptr(u0)) return MPC_B200_ERR_UNSUPPORTED;   // host entry point; device callers chain the
+                                                                                 // prestep / solve / poststep calls themselves
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t B = (size_t)batch;
+    cudaStream_t st = h->stream;
+    double *hi = h->h_in;
+    const double *sx = wx, *sy = wy, *sp = pose, *sv = vel_inout, *sr = ref_vel;
+    if (!is_pinned_host(wx)) { memcpy(hi, wx, sizeof(double) * M * B); sx = hi; }
+    if (!is_pinned_host(wy)) { memcpy(hi + (size_t)M * B, wy, sizeof(double) * M * B); sy = hi + (size_t)M * B; }
+    if (!is_pinned_host(pose)) { memcpy(hi + 2 * (size_t)M * B, pose, sizeof(double) * 3 * B); sp = hi + 2 * (size_t)M * B; }
+    if (!is_pinned_host(vel_inout)) { memcpy(hi + 2 * (size_t)M * B + 3 * B, vel_inout, sizeof(double) * 3 * B); sv = hi + 2 * (size_t)M * B + 3 * B; }
+    if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + 2 * (size_t)M * B + 6 * B, ref_vel, sizeof(double) * B); sr = hi + 2 * (size_t)M * B + 6 * B; }
+    CK(cudaMemcpyAsync(h->d_wx, sx, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_wy, sy, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_pose, sp, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_vel, sv, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
+    if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, sr, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, h->d_wx, h->d_wy, h->d_pose, h->d_coeffs, NULL, h->d_vel,
+                                                         h->d_state, h->params.delay_mode, h->params.dt);
+    CK(cudaGetLastError());
+    h->kernels++;
+    int rc = enqueue_solve(h, batch, h->d_state, h->d_coeffs, ref_vel ? h->d_refv : NULL, NULL, h->d_u0, h->d_pred, h->d_obj,
+                           h->d_status, h->d_iters, h->d_kkt, NULL, st);
+    if (rc != MPC_B200_OK) return rc;
+    poststep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, h->d_u0, h->d_vel, ref_vel ? h->d_refv : NULL, h->params.ref_vel,
+                                                          h->params.dt, h->d_cte);
+    CK(cudaGetLastError());
+    h->kernels++;
+    // previous w / throttle for the next tick's delay compensation go back into the caller's vel buffer
+    CK(cudaMemcpyAsync(is_pinned_host(vel_inout) ? vel_inout : hi, h->d_vel, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, st));
+    rc = fetch_results(h, batch, u0, pred, obj, status, iters, kkt_res, cmd_out, st);
+    if (rc != MPC_B200_OK) return rc;
+    if (!is_pinned_host(vel_inout)) memcpy(vel_inout, hi, sizeof(double) * 3 * B);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
     return MPC_B200_OK;
 }
 

@@ -367,3 +367,37 @@ def test_prestep_ragged_windows_and_delay_mode(oracle):
     coeffs, cte, eth = sv.polyfit(np.zeros((11, 4)), np.zeros((11, 4)), np.zeros((3, 4)))
     assert np.all(np.isnan(coeffs)) or np.all(np.isfinite(coeffs))
     sv.close()
+
+
+def test_track_batch_equals_prestep_solve_poststep(oracle):
+    """mpc_b200_track_batch (the whole findBestPath tick, driving_state.cpp:175-271) must give exactly what
+    the three separate calls give, with and without delay compensation and per-robot reference speeds."""
+    from bench import gen_py
+    B = 777
+    g = gen_py.problems(4242, B)
+    rng = np.random.default_rng(9)
+    for delay, per_robot in ((0, False), (1, True)):
+        prm = capi.yaml_default_params(); prm.delay_mode = delay
+        vel = g["vel"].copy()
+        vel[1] = rng.uniform(-0.5, 0.5, B); vel[2] = rng.uniform(-0.5, 0.5, B)
+        refv = rng.uniform(0.3, 1.0, B) if per_robot else None
+        sv = capi.Solver(prm, B, 0)
+        coeffs, state = sv.prestep(g["wx"], g["wy"], g["pose"], vel)
+        a = sv.solve(state, coeffs, ref_vel=refv)
+        v2 = vel.copy()
+        b = sv.track(g["wx"], g["wy"], g["pose"], v2, ref_vel=refv)
+        sv.close()
+        for k in ("u0", "pred", "obj", "kkt", "status", "iters"):
+            np.testing.assert_array_equal(a[k], b[k])
+        # post-step (driving_state.cpp:263-269): speed clamped above at the reference speed only
+        rv = refv if per_robot else np.full(B, prm.ref_vel)
+        speed = np.minimum(vel[0] + a["u0"][1] * prm.dt, rv)
+        np.testing.assert_allclose(b["cmd"][0], speed, rtol=0, atol=1e-15)   # v + thr*dt is one FMA on the device
+        np.testing.assert_array_equal(b["cmd"][1], a["u0"][0])
+        np.testing.assert_array_equal(v2[0], vel[0])
+        np.testing.assert_array_equal(v2[1], a["u0"][0])
+        np.testing.assert_array_equal(v2[2], a["u0"][1])
+        # the oracle's own pre-step + solve on a few of them
+        for i in range(0, B, 97):
+            c, ct, e = oracle.prestep(g["wx"][:, i], g["wy"][:, i], *g["pose"][:, i])
+            assert np.abs(coeffs[:, i] - c).max() <= 1e-9 * max(1.0, np.abs(c).max())

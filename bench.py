@@ -203,28 +203,35 @@ def run_ours(a):
     # Steps are independent batches: they are issued round-robin on S streams so that the tail of one
     # batch (a few problems need 10-25x the median iteration count) overlaps the next batches.
     S = max(1, min(a.streams, a.steps))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    # torch.cuda.Stream() hands out at most 32 distinct streams per device (a pool): the library creates them
+    raw_streams = [capi.stream_create(local) for _ in range(S)]
+    streams = [torch.cuda.ExternalStream(p, device=dev) for p in raw_streams]
     # persistent-grid size per launch: with many batches in flight each launch takes a slice of the SMs and
     # every lane works through several problems; with few steps a launch must cover the machine by itself
-    max_ctas = a.max_ctas if a.max_ctas > 0 else max(8, min(128, -(-256 // S)))
+    max_ctas = a.max_ctas if a.max_ctas > 0 else max(4, min(128, -(-512 // S)))
     solver.set_option("max_ctas", max_ctas)
 
     # pre-marshalled C-ABI argument tuples (the timed loop is launches only, ~10 us of host time each)
     pre_f = L.mpc_b200_prestep_batch; sol_f = L.mpc_b200_solve_batch
-    pre_args = [(solver._h, B, M, d_wx[j].data_ptr(), d_wy[j].data_ptr(), d_pose[j].data_ptr(), d_vel[j].data_ptr(),
+    H = max(1, min(a.handles, S))
+    solvers = [solver] + [capi.Solver(prm, B, local) for _ in range(H - 1)]
+    for s_ in solvers:
+        s_.set_option("max_ctas", max_ctas)
+    hs = [s_._h for s_ in solvers]                # stream k always uses handle k % H
+    pre_args = [(B, M, d_wx[j].data_ptr(), d_wy[j].data_ptr(), d_pose[j].data_ptr(), d_vel[j].data_ptr(),
                  d_coef[j].data_ptr(), d_state[j].data_ptr()) for j in range(R)]
-    sol_args = [(solver._h, B, d_state[j].data_ptr(), d_coef[j].data_ptr(), None, None, d_u0[j].data_ptr(),
+    sol_args = [(B, d_state[j].data_ptr(), d_coef[j].data_ptr(), None, None, d_u0[j].data_ptr(),
                  d_pred[j].data_ptr(), d_obj[j].data_ptr(), d_stat[j].data_ptr(), d_it[j].data_ptr(),
                  d_kkt[j].data_ptr(), None) for j in range(R)]
-    sptr = [st.cuda_stream for st in streams]
+    sptr = raw_streams
 
     def step_dev(j, ev=None):
-        sp = sptr[j % S]; st = streams[j % S]
+        sp = sptr[j % S]; st = streams[j % S]; hh = hs[(j % S) % H]
         j %= R
-        rc = pre_f(*pre_args[j], sp)
+        rc = pre_f(hh, *pre_args[j], sp)
         if ev is not None:
             ev[0].record(st)
-        rc |= sol_f(*sol_args[j], sp)
+        rc |= sol_f(hh, *sol_args[j], sp)
         if ev is not None:
             ev[1].record(st)
         if rc != 0:
@@ -245,7 +252,7 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    n0 = solver.launch_count
+    n0 = sum(s_.launch_count for s_ in solvers)
     main = torch.cuda.current_stream()
     e0.record(main)
     for st in streams:
@@ -256,7 +263,7 @@ def run_ours(a):
         main.wait_stream(st)
     e1.record(main)
     barrier()
-    launches = solver.launch_count - n0
+    launches = sum(s_.launch_count for s_ in solvers) - n0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
 
@@ -296,45 +303,61 @@ def run_ours(a):
                     peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak; "
                                 "MEASURED_PEAKS.json has no FP64 entry")
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  T host threads, each with
-    # its own handle (a handle is not re-entrant), stream and pinned buffers, issue synchronous calls --
-    # the way a server feeding the solver from several request queues would.
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  T host threads, each keeping
+    # K ticks in flight on K handles (a handle owns a stream and its device scratch) through
+    # mpc_b200_track_submit / _wait -- the way a server feeding the solver from request queues would.
     def pinned(shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype).pin_memory()
     T = max(1, a.e2e_threads)
-    Rh = 4
+    K = max(1, a.e2e_inflight // T)
+    sub_f = L.mpc_b200_track_submit; wait_f = L.mpc_b200_track_wait
+
+    class Slot:
+        def __init__(self, q):
+            self.solver = capi.Solver(prm, B, local)
+            self.solver.set_option("max_ctas", a.e2e_max_ctas if a.e2e_max_ctas > 0 else max(4, min(128, -(-512 // (T * K)))))
+            self.wx = pinned((M, B)); self.wy = pinned((M, B)); self.pose = pinned((3, B)); self.vel = pinned((3, B))
+            self.wx.copy_(d_wx[q]); self.wy.copy_(d_wy[q]); self.pose.copy_(d_pose[q]); self.vel.copy_(d_vel[q])
+            self.cmd = pinned((2, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
+            self.obj = pinned(B); self.kkt = pinned(B); self.stat = pinned(B, torch.int32); self.it = pinned(B, torch.int32)
+            self.stat_np = self.stat.numpy(); self.kkt_np = self.kkt.numpy()
+            # one control tick per robot: pre-step -> solve -> post-step, host buffers in and out
+            self.args = (self.solver._h, B, M, self.wx.data_ptr(), self.wy.data_ptr(), self.pose.data_ptr(),
+                         self.vel.data_ptr(), None, self.u0.data_ptr(), self.pred.data_ptr(), self.cmd.data_ptr(),
+                         self.obj.data_ptr(), self.stat.data_ptr(), self.it.data_ptr(), self.kkt.data_ptr())
+            self.busy = False
+
+        def submit(self):
+            if sub_f(*self.args) != 0:
+                raise RuntimeError("mpc_b200_track_submit failed")
+            self.busy = True
+
+        def wait(self):
+            if not self.busy:
+                return 0
+            if wait_f(self.solver._h) != 0:
+                raise RuntimeError("mpc_b200_track_wait failed")
+            self.busy = False
+            return int(((self.stat_np == 1) & (self.kkt_np <= 1e-8)).sum())
 
     class Worker:
         def __init__(self, t):
-            self.solver = capi.Solver(prm, B, local)
-            self.solver.set_option("max_ctas", max(8, min(128, -(-256 // T))))
-            self.wx = [pinned((M, B)) for _ in range(Rh)]; self.wy = [pinned((M, B)) for _ in range(Rh)]
-            self.pose = [pinned((3, B)) for _ in range(Rh)]; self.vel = [pinned((3, B)) for _ in range(Rh)]
-            for j in range(Rh):
-                q = (t * Rh + j) % R
-                self.wx[j].copy_(d_wx[q]); self.wy[j].copy_(d_wy[q]); self.pose[j].copy_(d_pose[q]); self.vel[j].copy_(d_vel[q])
-            self.cmd = pinned((2, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
-            self.obj = pinned(B); self.kkt = pinned(B); self.stat = pinned(B, torch.int32); self.it = pinned(B, torch.int32)
+            self.slots = [Slot((t * K + k) % R) for k in range(K)]
             self.conv = 0
-
-        def step(self, j):
-            j %= Rh
-            s = self.solver
-            # one control tick per robot: pre-step -> solve -> post-step, host buffers in and out
-            s.track_raw(B, M, self.wx[j].numpy(), self.wy[j].numpy(), self.pose[j].numpy(), self.vel[j].numpy(),
-                        self.u0.numpy(), self.pred.numpy(), cmd=self.cmd.numpy(), obj=self.obj.numpy(),
-                        status=self.stat.numpy(), iters=self.it.numpy(), kkt=self.kkt.numpy())
-            return int(((self.stat.numpy() == 1) & (self.kkt.numpy() <= 1e-8)).sum())
 
         def run(self, n):
             self.conv = 0
             for j in range(n):
-                self.conv += self.step(j)
+                s = self.slots[j % K]
+                self.conv += s.wait()
+                s.submit()
+            for s in self.slots:
+                self.conv += s.wait()
 
     workers = [Worker(t) for t in range(T)]
     per_thread = max(2, a.e2e_steps // T)
     for w in workers:
-        w.step(0)
+        w.run(K)
     barrier()
     t0 = time.perf_counter()
     ths = [threading.Thread(target=w.run, args=(per_thread,)) for w in workers]
@@ -352,11 +375,12 @@ def run_ours(a):
     h2d = (2 * M + 6) * B * 8                       # waypoints, pose, (v, previous w, previous throttle)
     d2h = (3 + 2 + 3 * N + 2 + 2) * B * 8 + 2 * B * 4   # vel, u0, pred, cmd, obj, kkt, status, iters
     e2e = dict(value=float(ce.item()) / float(te.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-               steps=e2e_steps, threads=T,
-               note="synchronous mpc_b200_track_batch calls with host buffers (pinned staging, H2D and D2H inside the timed region) "
-                    "from %d host threads, one handle + stream each; host wall clock" % T)
+               steps=e2e_steps, threads=T, in_flight=T * K,
+               note="mpc_b200_track_submit/_wait with page-locked host buffers (H2D and D2H inside the timed region), "
+                    "%d host thread(s) x %d handles in flight each; host wall clock" % (T, K))
     for w in workers:
-        w.solver.close()
+        for s in w.slots:
+            s.solver.close()
 
     if rank == 0:
         cpu = None
@@ -376,22 +400,26 @@ def run_ours(a):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    solver.close()
+    for s_ in solvers:
+        s_.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=128)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--sets", type=int, default=48)
     ap.add_argument("--max-iter", type=int, default=100)
-    ap.add_argument("--streams", type=int, default=32)
+    ap.add_argument("--streams", type=int, default=128)
     ap.add_argument("--max-ctas", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=512)
-    ap.add_argument("--e2e-threads", type=int, default=16)
+    ap.add_argument("--handles", type=int, default=1, help="solver handles the device-resident loop spreads its streams over")
+    ap.add_argument("--e2e-steps", type=int, default=2048)
+    ap.add_argument("--e2e-threads", type=int, default=2)
+    ap.add_argument("--e2e-max-ctas", type=int, default=0)
+    ap.add_argument("--e2e-inflight", type=int, default=128, help="ticks in flight over all e2e threads")
     ap.add_argument("--ref-per-core", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

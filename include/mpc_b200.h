@@ -197,6 +197,15 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                            double *coeffs_out, double *state_out, void *stream);
 
 /*
+ * CUDA streams for hosts that do not link the CUDA runtime themselves (cgo / JNI / ctypes callers): the
+ * `stream` argument of the *_batch calls takes what _stream_create returns (a cudaStream_t, non-blocking).
+ * Independent batches issued on different streams overlap on the device.
+ */
+int mpc_b200_stream_create(int32_t device, void **stream_out);
+int mpc_b200_stream_destroy(void *stream);
+int mpc_b200_stream_synchronize(void *stream);
+
+/*
  * The whole control tick of Tracking::findBestPath (mpc_ros/src/driving_state.cpp:175-271) for `batch` robots,
  * HOST buffers in and out, one synchronous call: pre-step (:196-256) -> MPC::Solve (:260) -> post-step
  * (:263-269).  The fitted coefficients and the assembled state never leave the device.
@@ -208,6 +217,18 @@ int mpc_b200_track_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                          const double *wx, const double *wy, const double *pose, double *vel_inout,
                          const double *ref_vel, double *u0, double *pred, double *cmd_out,
                          double *obj, int32_t *status, int32_t *iters, double *kkt_res);
+/*
+ * The same tick split in two so that one host thread can keep several handles busy: _submit enqueues the
+ * copies and kernels on the handle's own stream and returns; _wait blocks until the results are in the
+ * caller's buffers.  Page-locked buffers are read and written by DMA while the tick is in flight; pageable
+ * ones are staged (inputs copied inside _submit, outputs inside _wait).  One tick in flight per handle:
+ * a second _submit before _wait returns MPC_B200_ERR_INVALID.  track_batch == _submit followed by _wait.
+ */
+int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
+                          const double *wx, const double *wy, const double *pose, double *vel_inout,
+                          const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                          double *obj, int32_t *status, int32_t *iters, double *kkt_res);
+int mpc_b200_track_wait(mpc_b200_handle *h);
 
 /* Seconds spent on the device by the last solve_batch / polyfit_batch on this handle
  * (CUDA events on the launching stream around the kernel only; no copies). */

@@ -38,7 +38,7 @@ EXPORTS = [
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
     "mpc_b200_get_params", "mpc_b200_set_option", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
     "mpc_b200_prestep_batch", "mpc_b200_warm_shift", "mpc_b200_window_batch", "mpc_b200_poststep_batch",
-    "mpc_b200_num_waypoints", "mpc_b200_track_batch",
+    "mpc_b200_num_waypoints", "mpc_b200_stream_create", "mpc_b200_stream_destroy", "mpc_b200_stream_synchronize", "mpc_b200_track_batch", "mpc_b200_track_submit", "mpc_b200_track_wait",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
 ]
@@ -83,8 +83,18 @@ def lib():
     L.mpc_b200_poststep_batch.restype = C.c_int
     L.mpc_b200_num_waypoints.argtypes = [C.POINTER(Params)]
     L.mpc_b200_num_waypoints.restype = C.c_int
+    L.mpc_b200_stream_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+    L.mpc_b200_stream_create.restype = C.c_int
+    L.mpc_b200_stream_destroy.argtypes = [C.c_void_p]
+    L.mpc_b200_stream_destroy.restype = C.c_int
+    L.mpc_b200_stream_synchronize.argtypes = [C.c_void_p]
+    L.mpc_b200_stream_synchronize.restype = C.c_int
     L.mpc_b200_track_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 12
     L.mpc_b200_track_batch.restype = C.c_int
+    L.mpc_b200_track_submit.argtypes = L.mpc_b200_track_batch.argtypes
+    L.mpc_b200_track_submit.restype = C.c_int
+    L.mpc_b200_track_wait.argtypes = [C.c_void_p]
+    L.mpc_b200_track_wait.restype = C.c_int
     L.mpc_b200_warm_shift.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mpc_b200_warm_shift.restype = C.c_int
     L.mpc_b200_last_kernel_seconds.argtypes = [C.c_void_p]
@@ -134,6 +144,19 @@ def params_from_yaml(path, base=None):
     if rc != 0:
         raise MpcError(rc, path)
     return p
+
+
+def stream_create(device=0):
+    """A non-blocking CUDA stream owned by the library (an integer cudaStream_t)."""
+    s = C.c_void_p()
+    rc = lib().mpc_b200_stream_create(device, C.byref(s))
+    if rc != 0:
+        raise MpcError(rc)
+    return s.value
+
+
+def stream_destroy(stream):
+    lib().mpc_b200_stream_destroy(stream)
 
 
 def params_from_map(pm, base=None):
@@ -243,6 +266,18 @@ class Solver:
                   kkt=None):
         rc = lib().mpc_b200_track_batch(self._h, batch, M, _addr(wx), _addr(wy), _addr(pose), _addr(vel), _addr(ref_vel),
                                         _addr(u0), _addr(pred), _addr(cmd), _addr(obj), _addr(status), _addr(iters), _addr(kkt))
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def track_submit_raw(self, batch, M, wx, wy, pose, vel, u0, pred, ref_vel=None, cmd=None, obj=None, status=None,
+                         iters=None, kkt=None):
+        rc = lib().mpc_b200_track_submit(self._h, batch, M, _addr(wx), _addr(wy), _addr(pose), _addr(vel), _addr(ref_vel),
+                                         _addr(u0), _addr(pred), _addr(cmd), _addr(obj), _addr(status), _addr(iters), _addr(kkt))
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
+
+    def track_wait(self):
+        rc = lib().mpc_b200_track_wait(self._h)
         if rc != 0:
             raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
 

@@ -250,6 +250,15 @@ __global__ void dfma_kernel(double *out, int iters, int active_lanes, long long 
 }
 
 // ================================================================ handle
+// host-buffer results of a tick that is still in flight (mpc_b200_track_submit / _wait)
+struct Fetch {
+    bool active;
+    int32_t batch;
+    double *u0, *pred, *obj, *kkt, *cmd, *vel;
+    int32_t *status, *iters;
+    bool pu, pp, po, pk, pc, ps, pi, pv;
+};
+
 struct mpc_b200_handle {
     mpc_b200_params params;
     int device;
@@ -276,6 +285,7 @@ struct mpc_b200_handle {
     int opt_order;         // option: serve the queue hard-first (default on)
     int max_ctas;          // option: cap on the persistent grid (0 = one CTA per SM)
     int opt_pb;            // option: problems per CTA (0 = auto)
+    Fetch pending;
     std::string last_err;
 };
 
@@ -344,7 +354,7 @@ static int alloc_scratch(mpc_b200_handle *h)
     CK(cudaMalloc(&h->d_order, sizeof(int) * (size_t)h->order_ring * B));
     h->d_warm_out = NULL;
     h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
-    h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 1 + 6) * B;
+    h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 2 + 3 + 1 + 6) * B;   // u0 pred obj kkt cmd vel status/iters + slack
     CK(cudaMallocHost(&h->h_in, h->h_in_bytes));
     CK(cudaMallocHost(&h->h_out, h->h_out_bytes));
     return MPC_B200_OK;
@@ -440,11 +450,37 @@ void mpc_b200_destroy(mpc_b200_handle *h)
     delete h;
 }
 
+int mpc_b200_stream_create(int32_t device, void **stream_out)
+{
+    if (!stream_out) return MPC_B200_ERR_INVALID;
+    cudaStream_t s = NULL;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return MPC_B200_ERR_CUDA;
+    }
+    *stream_out = (void *)s;
+    return MPC_B200_OK;
+}
+
+int mpc_b200_stream_destroy(void *stream)
+{
+    if (!stream) return MPC_B200_ERR_INVALID;
+    if (cudaStreamDestroy((cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return MPC_B200_ERR_CUDA; }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_stream_synchronize(void *stream)
+{
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return MPC_B200_ERR_CUDA; }
+    return MPC_B200_OK;
+}
+
 int mpc_b200_set_params(mpc_b200_handle *h, const mpc_b200_params *p)
 {
     if (!h) return MPC_B200_ERR_INVALID;
     int rc = check_params(p);
     if (rc != MPC_B200_OK) return rc;
+    if (h->pending.active) return MPC_B200_ERR_INVALID;      // a submitted tick must be waited for first
     const bool regrow = p->mpc_steps > h->pred_steps;
     h->params = *p;
     if (regrow) {
@@ -501,7 +537,8 @@ static int choose_pb(const mpc_b200_handle *h, int N, int batch, int nslots)
 // Enqueue one batched solve on `st`; every pointer is DEVICE memory.
 static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_state, const double *d_coeffs,
                          const double *d_refv, const double *d_warm_in, double *d_u0, double *d_pred, double *d_obj,
-                         int32_t *d_status, int32_t *d_iters, double *d_kkt, double *d_warm_out, cudaStream_t st)
+                         int32_t *d_status, int32_t *d_iters, double *d_kkt, double *d_warm_out, cudaStream_t st,
+                         bool timed = true)
 {
     const mpc_b200_params &P = h->params;
     const int N = P.mpc_steps;
@@ -539,7 +576,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         CK(cudaGetLastError());
         h->kernels++;
     }
-    CK(cudaEventRecord(h->ev0, st));
+    if (timed) CK(cudaEventRecord(h->ev0, st));
     if (rate) {
         if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);
@@ -555,36 +592,60 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         default: nmpc::nmpc_solve_kernel<SPT, 0, false, false><<<grid, threads, smem, st>>>(a); break;
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, st));
+    if (timed) CK(cudaEventRecord(h->ev1, st));
     h->launches++; h->kernels++;
     return MPC_B200_OK;
 }
 
-// D2H of the solve results into host buffers (direct when they are page-locked), then synchronise.
-static int fetch_results(mpc_b200_handle *h, int32_t batch, double *u0, double *pred, double *obj, int32_t *status,
-                         int32_t *iters, double *kkt_res, double *cmd, cudaStream_t st)
+// D2H of the solve results into host buffers (direct when they are page-locked): the copies are enqueued
+// by fetch_enqueue; fetch_finish synchronises and moves what went through the staging buffer.
+
+static void fetch_layout(mpc_b200_handle *h, size_t B, double **u0, double **pred, double **obj, double **kkt, double **cmd,
+                         double **vel, int **status, int **iters)
 {
-    const size_t B = (size_t)batch, N = (size_t)h->params.mpc_steps;
+    const size_t N = (size_t)h->params.mpc_steps;
     double *ho = h->h_out;
-    double *ho_u0 = ho, *ho_pred = ho + 2 * B, *ho_obj = ho_pred + 3 * N * B, *ho_kkt = ho_obj + B, *ho_cmd = ho_kkt + B;
-    int *ho_status = reinterpret_cast<int *>(ho_cmd + 2 * B), *ho_iters = ho_status + B;
-    const bool pu = is_pinned_host(u0), pp = is_pinned_host(pred), po = is_pinned_host(obj), pk = is_pinned_host(kkt_res),
-               ps = is_pinned_host(status), pi = is_pinned_host(iters), pc = is_pinned_host(cmd);
-    CK(cudaMemcpyAsync(pu ? u0 : ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pp ? pred : ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
-    if (obj) CK(cudaMemcpyAsync(po ? obj : ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    if (kkt_res) CK(cudaMemcpyAsync(pk ? kkt_res : ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    if (status) CK(cudaMemcpyAsync(ps ? status : ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    if (iters) CK(cudaMemcpyAsync(pi ? iters : ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    if (cmd) CK(cudaMemcpyAsync(pc ? cmd : ho_cmd, h->d_cte, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+    *u0 = ho; *pred = ho + 2 * B; *obj = *pred + 3 * N * B; *kkt = *obj + B; *cmd = *kkt + B; *vel = *cmd + 2 * B;
+    *status = reinterpret_cast<int *>(*vel + 3 * B); *iters = *status + B;
+}
+
+static int fetch_enqueue(mpc_b200_handle *h, Fetch &f, cudaStream_t st)
+{
+    const size_t B = (size_t)f.batch, N = (size_t)h->params.mpc_steps;
+    double *ho_u0, *ho_pred, *ho_obj, *ho_kkt, *ho_cmd, *ho_vel; int *ho_status, *ho_iters;
+    fetch_layout(h, B, &ho_u0, &ho_pred, &ho_obj, &ho_kkt, &ho_cmd, &ho_vel, &ho_status, &ho_iters);
+    f.pu = is_pinned_host(f.u0); f.pp = is_pinned_host(f.pred); f.po = is_pinned_host(f.obj); f.pk = is_pinned_host(f.kkt);
+    f.ps = is_pinned_host(f.status); f.pi = is_pinned_host(f.iters); f.pc = is_pinned_host(f.cmd); f.pv = is_pinned_host(f.vel);
+    CK(cudaMemcpyAsync(f.pu ? f.u0 : ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(f.pp ? f.pred : ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
+    if (f.obj) CK(cudaMemcpyAsync(f.po ? f.obj : ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (f.kkt) CK(cudaMemcpyAsync(f.pk ? f.kkt : ho_kkt, h->d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (f.status) CK(cudaMemcpyAsync(f.ps ? f.status : ho_status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (f.iters) CK(cudaMemcpyAsync(f.pi ? f.iters : ho_iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (f.cmd) CK(cudaMemcpyAsync(f.pc ? f.cmd : ho_cmd, h->d_cte, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+    if (f.vel) CK(cudaMemcpyAsync(f.pv ? f.vel : ho_vel, h->d_vel, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, st));
+    f.active = true;
+    return MPC_B200_OK;
+}
+
+static int fetch_finish(mpc_b200_handle *h, Fetch &f, cudaStream_t st)
+{
+    if (!f.active) return MPC_B200_OK;
+    f.active = false;
+    const size_t B = (size_t)f.batch, N = (size_t)h->params.mpc_steps;
+    double *ho_u0, *ho_pred, *ho_obj, *ho_kkt, *ho_cmd, *ho_vel; int *ho_status, *ho_iters;
+    fetch_layout(h, B, &ho_u0, &ho_pred, &ho_obj, &ho_kkt, &ho_cmd, &ho_vel, &ho_status, &ho_iters);
     CK(cudaStreamSynchronize(st));
-    if (!pu) memcpy(u0, ho_u0, sizeof(double) * 2 * B);
-    if (!pp) memcpy(pred, ho_pred, sizeof(double) * 3 * N * B);
-    if (obj && !po) memcpy(obj, ho_obj, sizeof(double) * B);
-    if (kkt_res && !pk) memcpy(kkt_res, ho_kkt, sizeof(double) * B);
-    if (status && !ps) memcpy(status, ho_status, sizeof(int) * B);
-    if (iters && !pi) memcpy(iters, ho_iters, sizeof(int) * B);
-    if (cmd && !pc) memcpy(cmd, ho_cmd, sizeof(double) * 2 * B);
+    if (!f.pu) memcpy(f.u0, ho_u0, sizeof(double) * 2 * B);
+    if (!f.pp) memcpy(f.pred, ho_pred, sizeof(double) * 3 * N * B);
+    if (f.obj && !f.po) memcpy(f.obj, ho_obj, sizeof(double) * B);
+    if (f.kkt && !f.pk) memcpy(f.kkt, ho_kkt, sizeof(double) * B);
+    if (f.status && !f.ps) memcpy(f.status, ho_status, sizeof(int) * B);
+    if (f.iters && !f.pi) memcpy(f.iters, ho_iters, sizeof(int) * B);
+    if (f.cmd && !f.pc) memcpy(f.cmd, ho_cmd, sizeof(double) * 2 * B);
+    if (f.vel && !f.pv) memcpy(f.vel, ho_vel, sizeof(double) * 3 * B);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
     return MPC_B200_OK;
 }
 
@@ -626,34 +687,38 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     }
     int rc;
     if (dev_out)
-        rc = enqueue_solve(h, batch, ds, dc, dr, warm_in, u0, pred, obj, status, iters, kkt_res, warm_out, st);
+        rc = enqueue_solve(h, batch, ds, dc, dr, warm_in, u0, pred, obj, status, iters, kkt_res, warm_out, st,
+                           !(dev_in && stream_v));      // asynchronous calls are not timed (last_kernel_seconds)
     else
         rc = enqueue_solve(h, batch, ds, dc, dr, warm_in, h->d_u0, h->d_pred, h->d_obj, h->d_status, h->d_iters, h->d_kkt,
                            warm_out, st);
     if (rc != MPC_B200_OK) return rc;
 
     if (!dev_out) {
-        rc = fetch_results(h, batch, u0, pred, obj, status, iters, kkt_res, NULL, st);
+        Fetch f = {};
+        f.batch = batch; f.u0 = u0; f.pred = pred; f.obj = obj; f.kkt = kkt_res; f.status = status; f.iters = iters;
+        rc = fetch_enqueue(h, f, st);
         if (rc != MPC_B200_OK) return rc;
-    } else if (!(dev_in && stream_v)) {
-        CK(cudaStreamSynchronize(st));
+        return fetch_finish(h, f, st);
     }
-    if (!(dev_in && dev_out && stream_v)) {
+    if (!(dev_in && stream_v)) {
+        CK(cudaStreamSynchronize(st));
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
     }
     return MPC_B200_OK;
 }
 
-int mpc_b200_track_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
-                         const double *wx, const double *wy, const double *pose, double *vel_inout,
-                         const double *ref_vel, double *u0, double *pred, double *cmd_out,
-                         double *obj, int32_t *status, int32_t *iters, double *kkt_res)
+int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
+                          const double *wx, const double *wy, const double *pose, double *vel_inout,
+                          const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                          double *obj, int32_t *status, int32_t *iters, double *kkt_res)
 {
     if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !vel_inout || !u0 || !pred) return MPC_B200_ERR_INVALID;
     if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
     if (is_device_ptr(wx) || is_device_ptr(u0)) return MPC_B200_ERR_UNSUPPORTED;   // host entry point; device callers chain the
                                                                                  // prestep / solve / poststep calls themselves
+    if (h->pending.active) return MPC_B200_ERR_INVALID;                         // one tick in flight per handle
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
     const size_t B = (size_t)batch;
@@ -682,13 +747,29 @@ int mpc_b200_track_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
     CK(cudaGetLastError());
     h->kernels++;
     // previous w / throttle for the next tick's delay compensation go back into the caller's vel buffer
-    CK(cudaMemcpyAsync(is_pinned_host(vel_inout) ? vel_inout : hi, h->d_vel, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, st));
-    rc = fetch_results(h, batch, u0, pred, obj, status, iters, kkt_res, cmd_out, st);
+    Fetch &f = h->pending;
+    f.batch = batch; f.u0 = u0; f.pred = pred; f.obj = obj; f.kkt = kkt_res; f.status = status; f.iters = iters;
+    f.cmd = cmd_out; f.vel = vel_inout;
+    return fetch_enqueue(h, f, st);
+}
+
+int mpc_b200_track_wait(mpc_b200_handle *h)
+{
+    if (!h) return MPC_B200_ERR_INVALID;
+    if (!h->pending.active) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    return fetch_finish(h, h->pending, h->stream);
+}
+
+int mpc_b200_track_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
+                         const double *wx, const double *wy, const double *pose, double *vel_inout,
+                         const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                         double *obj, int32_t *status, int32_t *iters, double *kkt_res)
+{
+    const int rc = mpc_b200_track_submit(h, batch, M, wx, wy, pose, vel_inout, ref_vel, u0, pred, cmd_out, obj, status, iters,
+                                         kkt_res);
     if (rc != MPC_B200_OK) return rc;
-    if (!is_pinned_host(vel_inout)) memcpy(vel_inout, hi, sizeof(double) * 3 * B);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
-    return MPC_B200_OK;
+    return mpc_b200_track_wait(h);
 }
 
 int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,

@@ -401,3 +401,35 @@ def test_track_batch_equals_prestep_solve_poststep(oracle):
         for i in range(0, B, 97):
             c, ct, e = oracle.prestep(g["wx"][:, i], g["wy"][:, i], *g["pose"][:, i])
             assert np.abs(coeffs[:, i] - c).max() <= 1e-9 * max(1.0, np.abs(c).max())
+
+
+def test_track_submit_wait_pipelined():
+    """Two handles with a tick in flight each give the results of the synchronous call; a second submit on a
+    busy handle is refused."""
+    from bench import gen_py
+    B = 512
+    N = 20
+    g = [gen_py.problems(900 + k, B) for k in range(2)]
+    prm = capi.yaml_default_params()
+    ref = []
+    sv = capi.Solver(prm, B, 0)
+    for k in range(2):
+        ref.append(sv.track(g[k]["wx"], g[k]["wy"], g[k]["pose"], g[k]["vel"].copy()))
+    sv.close()
+    hs = [capi.Solver(prm, B, 0) for _ in range(2)]
+    outs = []
+    for k in range(2):
+        o = dict(u0=np.zeros((2, B)), pred=np.zeros((3 * N, B)), cmd=np.zeros((2, B)), status=np.zeros(B, dtype=np.int32),
+                 vel=g[k]["vel"].copy())
+        M = g[k]["wx"].shape[0]
+        hs[k].track_submit_raw(B, M, g[k]["wx"], g[k]["wy"], g[k]["pose"], o["vel"], o["u0"], o["pred"], cmd=o["cmd"],
+                               status=o["status"])
+        outs.append(o)
+    with pytest.raises(capi.MpcError):
+        hs[0].track_submit_raw(B, M, g[0]["wx"], g[0]["wy"], g[0]["pose"], outs[0]["vel"], outs[0]["u0"], outs[0]["pred"])
+    for k in (1, 0):
+        hs[k].track_wait()
+        hs[k].track_wait()          # idempotent
+        for key in ("u0", "pred", "cmd", "status"):
+            np.testing.assert_array_equal(outs[k][key], ref[k][key])
+        hs[k].close()

@@ -304,7 +304,8 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     if (RATE) { sm.at(k, U_W, p) = 0.0; sm.at(k, U_A, p) = 0.0; sm.at(k, DU_W, p) = 0.0; sm.at(k, DU_A, p) = 0.0; }
     for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
     for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = 0.0;
-    // (the D and W slots need no initialisation: every phase writes them before it reads them)
+    // the step slots are read (times a zero step length) by plain evaluations before any sweep wrote them
+    for (int c = 0; c < 6; c++) { sm.at(k, D_X + c, p) = 0.0; sm.at(k, W_6 + c, p) = 0.0; }
     r.uw = 0.0; r.ua = 0.0;
     r.zlw = r.zuw = r.zla = r.zua = 1.0;      // bound_mult_init_val
     (void)coef4;
@@ -387,15 +388,18 @@ MPC_HD void trial_z(const Params &prm, const StageRegs &r, double az, double mu,
                     double &zlw, double &zuw, double &zla, double &zua)
 {
     const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
-    if (az != 0.0) {
-        zlw = r.zlw + az * (mu * r.ilw - r.zlw - r.zlw * r.ilw * r.duw);
-        zuw = r.zuw + az * (mu * r.iuw - r.zuw + r.zuw * r.iuw * r.duw);
-        zla = r.zla + az * (mu * r.ila - r.zla - r.zla * r.ila * r.dua);
-        zua = r.zua + az * (mu * r.iua - r.zua + r.zua * r.iua * r.dua);
-        zlw = zsafe(zlw, mu, uw + Uw); zuw = zsafe(zuw, mu, Uw - uw);
-        zla = zsafe(zla, mu, ua + Ua); zua = zsafe(zua, mu, Ua - ua);
-    } else {
-        zlw = r.zlw; zuw = r.zuw; zla = r.zla; zua = r.zua;
+    // az == 0 (plain evaluation) leaves the multipliers bit-for-bit unchanged and skips the safeguard
+    zlw = r.zlw + az * (mu * r.ilw - r.zlw - r.zlw * r.ilw * r.duw);
+    zuw = r.zuw + az * (mu * r.iuw - r.zuw + r.zuw * r.iuw * r.duw);
+    zla = r.zla + az * (mu * r.ila - r.zla - r.zla * r.ila * r.dua);
+    zua = r.zua + az * (mu * r.iua - r.zua + r.zua * r.iua * r.dua);
+    const double slw = uw + Uw, suw = Uw - uw, sla = ua + Ua, sua = Ua - ua;
+    const double hi = NMPC_KAPPA_SIGMA * mu, lo = (1.0 / NMPC_KAPPA_SIGMA) * mu;
+    const double p1 = zlw * slw, p2 = zuw * suw, p3 = zla * sla, p4 = zua * sua;
+    const bool out = (fmax2(fmax2(p1, p2), fmax2(p3, p4)) > hi) || (fmin2(fmin2(p1, p2), fmin2(p3, p4)) < lo);
+    if (az != 0.0 && out) {
+        zlw = zsafe(zlw, mu, slw); zuw = zsafe(zuw, mu, suw);
+        zla = zsafe(zla, mu, sla); zua = zsafe(zua, mu, sua);
     }
 }
 
@@ -429,71 +433,52 @@ template <bool RATE = false, class SM>
 MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int flags, EvalPart &acc,
                        const double *cf)
 {
+    // Written without lane-dependent branches (one rare one excepted) so that the compiler sees one long
+    // basic block per stage: a plain evaluation is a trial point with alpha = 0 (the step slots always hold
+    // finite numbers: stage_init zeroes them), and the multipliers to adopt after the least-squares solve
+    // are the trial multipliers with base 0 and step length 1.
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
     const bool ls = (flags & FL_LS) != 0;
+    const bool adopt = (flags & FL_ADOPT) != 0;
     const double alpha = ls ? sm.P(PS_ALPHA, p) : 0.0;
     const double az = ls ? sm.P(PS_ALPHA_Z, p) : 0.0;
+    const double lcoef = adopt ? (((flags & FL_KEEP) != 0) ? 1.0 : 0.0) : alpha;   // step length of lambda_k
     const double mu = sm.P(PS_MU_STEP, p);
-    double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
-    if (k > 0 && ls) {
-        dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
-        dsv = sm.at(k - 1, D_V, p); dsc = sm.at(k - 1, D_C, p); dse = sm.at(k - 1, D_E, p);
-    }
-    const double x = sm.at(k, S_X, p) + alpha * dsx, y = sm.at(k, S_Y, p) + alpha * dsy;
-    const double th = sm.at(k, S_T, p) + alpha * dst, v = sm.at(k, S_V, p) + alpha * dsv;
-    const double ct = sm.at(k, S_C, p) + alpha * dsc, e = sm.at(k, S_E, p) + alpha * dse;
+    const int km = k > 0 ? k - 1 : 0;
+    const double dmask = k > 0 ? alpha : 0.0;        // ds_0 = 0
+    const double x = sm.at(k, S_X, p) + dmask * sm.at(km, D_X, p), y = sm.at(k, S_Y, p) + dmask * sm.at(km, D_Y, p);
+    const double th = sm.at(k, S_T, p) + dmask * sm.at(km, D_T, p), v = sm.at(k, S_V, p) + dmask * sm.at(km, D_V, p);
+    const double ct = sm.at(k, S_C, p) + dmask * sm.at(km, D_C, p), e = sm.at(k, S_E, p) + dmask * sm.at(km, D_E, p);
     sincos_d(th, &r.tsn, &r.tcs);
     sincos_d(e, &r.tse, &r.tce);
     // objective part of this stage (mpc_planner.cpp:122-140) and its gradient
     const double ec = ct - prm.ref_cte, ee = e - prm.ref_etheta, ev = v - refv;
     double f = prm.w_cte * ec * ec + prm.w_etheta * ee * ee + prm.w_vel * ev * ev;
     const double qv = 2.0 * sf * prm.w_vel * ev, qc = 2.0 * sf * prm.w_cte * ec, qe = 2.0 * sf * prm.w_etheta * ee;
-    // lambda_k (multiplier of the rows that define s_k) lives with stage k-1 (lambda_0: per-lane scalars)
-    double lkx, lky, lkt, lkv, lkc, lke, l1 = 0.0;
-    if (k == 0) {
-        if (flags & FL_ADOPT) {
-            const bool keep = (flags & FL_KEEP) != 0;
-            lkx = keep ? sm.P(PS_N0X, p) : 0.0; lky = keep ? sm.P(PS_N0Y, p) : 0.0; lkt = keep ? sm.P(PS_N0T, p) : 0.0;
-            lkv = keep ? sm.P(PS_N0V, p) : 0.0; lkc = keep ? sm.P(PS_N0C, p) : 0.0; lke = keep ? sm.P(PS_N0E, p) : 0.0;
-        } else {
-            lkx = sm.P(PS_L0X, p); lky = sm.P(PS_L0Y, p); lkt = sm.P(PS_L0T, p);
-            lkv = sm.P(PS_L0V, p); lkc = sm.P(PS_L0C, p); lke = sm.P(PS_L0E, p);
-            if (ls) {
-                lkx += alpha * (sm.P(PS_N0X, p) - lkx); lky += alpha * (sm.P(PS_N0Y, p) - lky);
-                lkt += alpha * (sm.P(PS_N0T, p) - lkt); lkv += alpha * (sm.P(PS_N0V, p) - lkv);
-                lkc += alpha * (sm.P(PS_N0C, p) - lkc); lke += alpha * (sm.P(PS_N0E, p) - lke);
-            }
-        }
-        l1 += fabs(lkx) + fabs(lky) + fabs(lkt) + fabs(lkv) + fabs(lkc) + fabs(lke);
-    } else {
-        if (flags & FL_ADOPT) {
-            const bool keep = (flags & FL_KEEP) != 0;
-            lkx = keep ? sm.at(k - 1, W_6, p) : 0.0; lky = keep ? sm.at(k - 1, W_7, p) : 0.0;
-            lkt = keep ? sm.at(k - 1, W_8, p) : 0.0; lkv = keep ? sm.at(k - 1, W_9, p) : 0.0;
-            lkc = keep ? sm.at(k - 1, W_10, p) : 0.0; lke = keep ? sm.at(k - 1, W_11, p) : 0.0;
-        } else {
-            lkx = sm.at(k - 1, L_X, p); lky = sm.at(k - 1, L_Y, p); lkt = sm.at(k - 1, L_T, p);
-            lkv = sm.at(k - 1, L_V, p); lkc = sm.at(k - 1, L_C, p); lke = sm.at(k - 1, L_E, p);
-            if (ls) {
-                lkx += alpha * (sm.at(k - 1, W_6, p) - lkx); lky += alpha * (sm.at(k - 1, W_7, p) - lky);
-                lkt += alpha * (sm.at(k - 1, W_8, p) - lkt); lkv += alpha * (sm.at(k - 1, W_9, p) - lkv);
-                lkc += alpha * (sm.at(k - 1, W_10, p) - lkc); lke += alpha * (sm.at(k - 1, W_11, p) - lke);
-            }
-        }
+    // lambda_k (multiplier of the rows that define s_k) lives with stage k-1 (lambda_0: per-lane scalars):
+    // current value in L (PS_L0*), the Newton / least-squares value in W_6.. (PS_N0*)
+    const double *lcur = (k == 0) ? &sm.P(PS_L0X, p) : &sm.at(k - 1, L_X, p);
+    const double *lnew = (k == 0) ? &sm.P(PS_N0X, p) : &sm.at(k - 1, W_6, p);
+    const int ld = sm.pb();
+    double lk[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        const double b = adopt ? 0.0 : lcur[c * ld];
+        lk[c] = b + lcoef * (lnew[c * ld] - b);
     }
+    const double lkx = lk[0], lky = lk[1], lkt = lk[2], lkv = lk[3], lkc = lk[4], lke = lk[5];
+    double l1 = 0.0;
+    if (k == 0) l1 = fabs(lkx) + fabs(lky) + fabs(lkt) + fabs(lkv) + fabs(lkc) + fabs(lke);
     double prinf = 0.0, pr1 = 0.0, duinf, vmax = -1e300, vmin = 1e300, z1 = 0.0, lnsum = 0.0;
     if (k < N - 1) {
         const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
         f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
         const double poly = cf[0] + x * (cf[1] + x * (cf[2] + x * cf[3]));
         const double dpoly = cf[1] + x * (2.0 * cf[2] + 3.0 * cf[3] * x);
-        double nx = sm.at(k + 1, S_X, p), ny = sm.at(k + 1, S_Y, p), nt = sm.at(k + 1, S_T, p);
-        double nv = sm.at(k + 1, S_V, p), nc = sm.at(k + 1, S_C, p), ne = sm.at(k + 1, S_E, p);
-        if (ls) {
-            nx += alpha * sm.at(k, D_X, p); ny += alpha * sm.at(k, D_Y, p); nt += alpha * sm.at(k, D_T, p);
-            nv += alpha * sm.at(k, D_V, p); nc += alpha * sm.at(k, D_C, p); ne += alpha * sm.at(k, D_E, p);
-        }
+        const double nx = sm.at(k + 1, S_X, p) + alpha * sm.at(k, D_X, p), ny = sm.at(k + 1, S_Y, p) + alpha * sm.at(k, D_Y, p);
+        const double nt = sm.at(k + 1, S_T, p) + alpha * sm.at(k, D_T, p), nv = sm.at(k + 1, S_V, p) + alpha * sm.at(k, D_V, p);
+        const double nc = sm.at(k + 1, S_C, p) + alpha * sm.at(k, D_C, p), ne = sm.at(k + 1, S_E, p) + alpha * sm.at(k, D_E, p);
         // defect of the dynamics interval k -> k+1 (mpc_planner.cpp:208-215)
         const double cx = nx - (x + v * r.tcs * dt);
         const double cy = ny - (y + v * r.tsn * dt);
@@ -503,14 +488,12 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         const double ce_ = ne - (e + uw * dt);
         prinf = fmax2(fmax2(fmax2(fabs(cx), fabs(cy)), fmax2(fabs(cth), fabs(cv))), fmax2(fabs(cc), fabs(ce_)));
         pr1 = fabs(cx) + fabs(cy) + fabs(cth) + fabs(cv) + fabs(cc) + fabs(ce_);
-        // trial lambda_{k+1}
+        // trial lambda_{k+1} (after an adoption stage_adopt has already put it into L)
         double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mt = sm.at(k, L_T, p);
         double mv = sm.at(k, L_V, p), mc = sm.at(k, L_C, p), me = sm.at(k, L_E, p);
-        if (ls) {
-            mx += alpha * (sm.at(k, W_6, p) - mx); my += alpha * (sm.at(k, W_7, p) - my);
-            mt += alpha * (sm.at(k, W_8, p) - mt); mv += alpha * (sm.at(k, W_9, p) - mv);
-            mc += alpha * (sm.at(k, W_10, p) - mc); me += alpha * (sm.at(k, W_11, p) - me);
-        }
+        mx += alpha * (sm.at(k, W_6, p) - mx); my += alpha * (sm.at(k, W_7, p) - my);
+        mt += alpha * (sm.at(k, W_8, p) - mt); mv += alpha * (sm.at(k, W_9, p) - mv);
+        mc += alpha * (sm.at(k, W_10, p) - mc); me += alpha * (sm.at(k, W_11, p) - me);
         // stationarity wrt s_k:  grad f + lambda_k - A_k^T lambda_{k+1}
         const double a13 = -v * r.tsn * dt, a14 = r.tcs * dt, a23 = v * r.tcs * dt, a24 = r.tsn * dt;
         const double a51 = dpoly, a54 = r.tse * dt, a56 = v * r.tce * dt;
@@ -528,10 +511,8 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         if (RATE) {
             const bool hp = k >= 1, hn = k <= N - 3;
             double upw = 0, upa = 0, unw = 0, una = 0;
-            if (hp) { upw = sm.at(k - 1, U_W, p); upa = sm.at(k - 1, U_A, p);
-                      if (ls) { upw += alpha * sm.at(k - 1, DU_W, p); upa += alpha * sm.at(k - 1, DU_A, p); } }
-            if (hn) { unw = sm.at(k + 1, U_W, p); una = sm.at(k + 1, U_A, p);
-                      if (ls) { unw += alpha * sm.at(k + 1, DU_W, p); una += alpha * sm.at(k + 1, DU_A, p); } }
+            if (hp) { upw = sm.at(k - 1, U_W, p) + alpha * sm.at(k - 1, DU_W, p); upa = sm.at(k - 1, U_A, p) + alpha * sm.at(k - 1, DU_A, p); }
+            if (hn) { unw = sm.at(k + 1, U_W, p) + alpha * sm.at(k + 1, DU_W, p); una = sm.at(k + 1, U_A, p) + alpha * sm.at(k + 1, DU_A, p); }
             rw += rate_grad(2.0 * sf * prm.w_angvel_d, uw, upw, unw, hp, hn);
             ra += rate_grad(2.0 * sf * prm.w_accel_d, ua, upa, una, hp, hn);
             if (hp) f += prm.w_angvel_d * (uw - upw) * (uw - upw) + prm.w_accel_d * (ua - upa) * (ua - upa);
@@ -546,7 +527,7 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         vmax = fmax2(fmax2(p1, p2), fmax2(p3, p4));
         vmin = fmin2(fmin2(p1, p2), fmin2(p3, p4));
         const bool in_ = slw > 0.0 && suw > 0.0 && sla > 0.0 && sua > 0.0;
-        lnsum = in_ ? log_pos((slw * suw) * (sla * sua)) : 0.0;
+        lnsum = log_pos(in_ ? (slw * suw) * (sla * sua) : 1.0);      // log_pos(1) == 0 exactly
         if (!in_) acc.inside = 0;
     } else {
         // last stage: no dynamics, no control

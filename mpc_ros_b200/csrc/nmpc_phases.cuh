@@ -779,28 +779,28 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
             nw = -hd.rw * kfw; na = -hd.ra * kfa;
         }
 
-        // ---- P_k = Q~ + S~^T K
-        Pxx = Qxx + (Swx * Kwx + Sax * Kax);
-        Pxy = Qxy + (Swx * Kwy + Sax * Kay);
-        Pxt = Mxt + (Swx * Kwt + Sax * Kat);
-        Pxv = Qxv + (Swx * Kwv + Sax * Kav);
-        Pxe = Qxe + (Swx * Kwe + Sax * Kae);
-        Pyy = Qyy + (Swy * Kwy + Say * Kay);
-        Pyt = Myt + (Swy * Kwt + Say * Kat);
-        Pyv = Qyv + (Swy * Kwv + Say * Kav);
-        Pye = Qye + (Swy * Kwe + Say * Kae);
-        Ptt = Qtt + (Swt * Kwt + Sat * Kat);
-        Ptv = Qtv + (Swt * Kwv + Sat * Kav);
-        Pte = Met + (Swt * Kwe + Sat * Kae);
-        Pvv = Qvv + (Swv * Kwv + Sav * Kav);
-        Pve = Qve + (Swv * Kwe + Sav * Kae);
-        Pee = Qee + (Swe * Kwe + Sae * Kae);
+        // ---- P_k = Q~ + S~^T K   (two fused operations per entry)
+        Pxx = fma(Swx, Kwx, fma(Sax, Kax, Qxx));
+        Pxy = fma(Swx, Kwy, fma(Sax, Kay, Qxy));
+        Pxt = fma(Swx, Kwt, fma(Sax, Kat, Mxt));
+        Pxv = fma(Swx, Kwv, fma(Sax, Kav, Qxv));
+        Pxe = fma(Swx, Kwe, fma(Sax, Kae, Qxe));
+        Pyy = fma(Swy, Kwy, fma(Say, Kay, Qyy));
+        Pyt = fma(Swy, Kwt, fma(Say, Kat, Myt));
+        Pyv = fma(Swy, Kwv, fma(Say, Kav, Qyv));
+        Pye = fma(Swy, Kwe, fma(Say, Kae, Qye));
+        Ptt = fma(Swt, Kwt, fma(Sat, Kat, Qtt));
+        Ptv = fma(Swt, Kwv, fma(Sat, Kav, Qtv));
+        Pte = fma(Swt, Kwe, fma(Sat, Kae, Met));
+        Pvv = fma(Swv, Kwv, fma(Sav, Kav, Qvv));
+        Pve = fma(Swv, Kwe, fma(Sav, Kae, Qve));
+        Pee = fma(Swe, Kwe, fma(Sae, Kae, Qee));
         // ---- p_k = q_s + A^T p~ + S~^T k_ff
-        px = (tx + c.a51 * pic) + (Swx * kfw + Sax * kfa);
-        py = (ty - pic) + (Swy * kfw + Say * kfa);
-        pt = (tt + c.a13 * tx + c.a23 * ty) + (Swt * kfw + Sat * kfa);
-        pv = ((c.qv + tv) + (c.a14 * tx + c.a24 * ty)) + (c.a54 * pic + (Swv * kfw + Sav * kfa));
-        pe = ((c.qe + te) + c.a56 * pic) + (Swe * kfw + Sae * kfa);
+        px = fma(Swx, kfw, fma(Sax, kfa, fma(c.a51, pic, tx)));
+        py = fma(Swy, kfw, fma(Say, kfa, ty - pic));
+        pt = fma(Swt, kfw, fma(Sat, kfa, fma(c.a23, ty, fma(c.a13, tx, tt))));
+        pv = fma(Swv, kfw, fma(Sav, kfa, fma(c.a54, pic, fma(c.a24, ty, fma(c.a14, tx, c.qv + tv)))));
+        pe = fma(Swe, kfw, fma(Sae, kfa, fma(c.a56, pic, c.qe + te)));
         qc_next = c.qc;
     }
     return ok;
@@ -816,11 +816,13 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDi
     double sx = 0, sy = 0, st = 0, sv = 0, sc = 0, se = 0;
     double pw = 0, pa = 0;      // RATE: previous control step
     (void)sc; (void)pw; (void)pa;
+#pragma unroll 4
     for (int k = 0; k < N - 1; k++) {
-        double duw = sm.at(k, W_0, p) * sx + sm.at(k, W_1, p) * sy + sm.at(k, W_2, p) * st +
-                     sm.at(k, W_3, p) * sv + sm.at(k, W_4, p) * se + sm.at(k, W_10, p);
-        double dua = sm.at(k, W_5, p) * sx + sm.at(k, W_6, p) * sy + sm.at(k, W_7, p) * st +
-                     sm.at(k, W_8, p) * sv + sm.at(k, W_9, p) * se + sm.at(k, W_11, p);
+        // du_k = K ds_k + k_ff as a depth-3 tree (this is the loop-carried chain)
+        double duw = fma(sm.at(k, W_0, p), sx, sm.at(k, W_1, p) * sy) + fma(sm.at(k, W_2, p), st, sm.at(k, W_3, p) * sv) +
+                     fma(sm.at(k, W_4, p), se, sm.at(k, W_10, p));
+        double dua = fma(sm.at(k, W_5, p), sx, sm.at(k, W_6, p) * sy) + fma(sm.at(k, W_7, p), st, sm.at(k, W_8, p) * sv) +
+                     fma(sm.at(k, W_9, p), se, sm.at(k, W_11, p));
         if (RATE && k >= 1) {   // + R~^{-1} D du_{k-1}
             const double i11 = sm.at(k, RI_11, p), i12 = sm.at(k, RI_12, p), i22 = sm.at(k, RI_22, p);
             duw += i11 * hd.rw * pw + i12 * hd.ra * pa;
@@ -906,6 +908,7 @@ MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
     const int N = prm.N;
     double lx = -sm.at(N - 1, W_0, p), ly = -sm.at(N - 1, W_1, p), lt = -sm.at(N - 1, W_2, p);
     double lv = -sm.at(N - 1, W_3, p), lc = -sm.at(N - 1, W_4, p), le = -sm.at(N - 1, W_5, p);
+#pragma unroll 4
     for (int k = N - 2; k >= 0; k--) {
         sm.at(k, W_6, p) = lx; sm.at(k, W_7, p) = ly; sm.at(k, W_8, p) = lt;
         sm.at(k, W_9, p) = lv; sm.at(k, W_10, p) = lc; sm.at(k, W_11, p) = le;

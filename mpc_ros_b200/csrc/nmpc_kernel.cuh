@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
             TRACE_C(6);
             PROF_MARK(5);
             // ---- P6: multipliers, step sizes
+            bool late = false;
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
                 adjoint_sweep(prm, sm, p);      // common to both branches below: keep it out of the divergence
                 if (sm.I(PI_FLAGS, p) & FL_LSQ) {
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 } else {
                     ctrl_step(prm, sm, c, p, NG);
                     sm.I(PI_FLAGS, p) = FL_LS;
+                    late = true;
                 }
                 sm.I(PI_MODE, p) = MODE_EVAL;
             }
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
             TRACE_C(7);
             __syncthreads();  // B7
             TRACE_C(8);
-            // ---- P1: stage threads evaluate
+            // ---- P1: stage threads evaluate; meanwhile the part of the line-search set-up only P2 needs
+            if (late) ctrl_step_late(c);
             __syncthreads();  // B1
             TRACE_C(9);
             PROF_MARK(7);

@@ -1102,8 +1102,8 @@ MPC_HD double next_dw(const Ctrl &c, double dw)
     return (c.dw_last == 0.0) ? NMPC_KW_PLUS_BAR * dw : NMPC_KW_PLUS * dw;
 }
 
-// P6: after the step is known and adjoint_sweep has run.  Reduces the step partials, sets up the line
-// search.  Leaves PS_ALPHA (first trial), PS_ALPHA_Z and PS_MU_STEP.
+// P6: after the step is known and adjoint_sweep has run.  Reduces the step partials and leaves PS_ALPHA
+// (first trial), PS_ALPHA_Z and PS_MU_STEP: all the evaluation in P1 needs.
 template <class SM>
 MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
 {
@@ -1115,8 +1115,17 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
     const double amax = (rmax > tau) ? tau / rmax : 1.0;      // fraction to the boundary, W&B eq. (15)
     const double az = (rzmax > tau) ? tau / rzmax : 1.0;
     c.gd = gd;
-    const double th = c.theta;
-    // switching condition (W&B eq. (19)) in log form:  log alpha + s_phi log(-gd) > s_theta log theta
+    sm.P(PS_ALPHA, p) = amax;
+    sm.P(PS_ALPHA_Z, p) = az;
+    sm.P(PS_MU_STEP, p) = sm.P(PS_MU, p);
+}
+
+// The rest of the line-search set-up (only the decision in P2 needs it, so the control thread computes it
+// while the stage threads evaluate the first trial point): switching condition (W&B eq. (19)) in log form,
+//   log alpha + s_phi log(-gd) > s_theta log theta,   and the minimal step size (eq. (23)).
+MPC_HD void ctrl_step_late(Ctrl &c)
+{
+    const double gd = c.gd, th = c.theta;
     c.sw_log = 0.0;
     if (gd < 0.0 && th <= c.theta_min) {
         c.sw_log = NMPC_S_THETA * log(th) - NMPC_S_PHI * log(-gd);      // -inf when theta == 0
@@ -1125,9 +1134,6 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
         c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd));
     else
         c.alpha_min = NMPC_GAMMA_ALPHA * NMPC_GAMMA_THETA;
-    sm.P(PS_ALPHA, p) = amax;
-    sm.P(PS_ALPHA_Z, p) = az;
-    sm.P(PS_MU_STEP, p) = sm.P(PS_MU, p);
 }
 
 // P6 of the first cycle (after adjoint_sweep): keep the least-squares multipliers unless they are huge

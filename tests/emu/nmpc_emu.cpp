@@ -135,6 +135,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
                 } else {
                     ctrl_step(prm, sm, ctrl[p], p, NG);
+                    ctrl_step_late(ctrl[p]);
                     sm.I(PI_FLAGS, p) = FL_LS;
                 }
                 sm.I(PI_MODE, p) = MODE_EVAL;

@@ -43,10 +43,10 @@ BATCH = 4096                 # BASELINE config 2
 SEED = 20261018 + 2          # seed = 20261018 + config#
 FLOP_PER_ITER_N20 = 27879.0  # SURVEY 8d algorithmic flops per interior-point iteration, N = 20
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE solve-kernel launch (4,096 problems) from the ncu --set full
-# capture in profiles/r1_solve_kernel_ncu_raw.csv (820,736 + 29,184 B).  Algorithmic: 88 B in + ~520 B out per
+# capture in profiles/r1_solve_kernel_ncu_raw.csv (934,912 + 12,032 B).  Algorithmic: 88 B in + ~520 B out per
 # problem = 2.5 MB per launch; the 2.1 MB of results are still in the 126 MB L2 when the kernel ends, so DRAM
 # sees less than the algorithmic bytes -- nothing is re-read.
-NCU_DRAM_BYTES_PER_LAUNCH = 849920
+NCU_DRAM_BYTES_PER_LAUNCH = 946944
 WORKLOAD = ("config2: batch of 4096 independent N=20 diff-drive NMPC problems per GPU, random poses on "
             "infinity/epitrochoid/square tracks, mpc_params.yaml weights, cold start; step = prestep "
             "(transform+polyfit+state) + solve")
@@ -315,7 +315,7 @@ def run_ours(a):
     class Slot:
         def __init__(self, q):
             self.solver = capi.Solver(prm, B, local)
-            self.solver.set_option("max_ctas", a.e2e_max_ctas if a.e2e_max_ctas > 0 else max(4, min(128, -(-512 // (T * K)))))
+            self.solver.set_option("max_ctas", a.e2e_max_ctas if a.e2e_max_ctas > 0 else max(8, min(128, -(-512 // (T * K)))))
             self.wx = pinned((M, B)); self.wy = pinned((M, B)); self.pose = pinned((3, B)); self.vel = pinned((3, B))
             self.wx.copy_(d_wx[q]); self.wy.copy_(d_wy[q]); self.pose.copy_(d_pose[q]); self.vel.copy_(d_vel[q])
             self.cmd = pinned((2, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
@@ -416,10 +416,10 @@ def main():
     ap.add_argument("--streams", type=int, default=128)
     ap.add_argument("--max-ctas", type=int, default=0)
     ap.add_argument("--handles", type=int, default=1, help="solver handles the device-resident loop spreads its streams over")
-    ap.add_argument("--e2e-steps", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=8192)
     ap.add_argument("--e2e-threads", type=int, default=2)
     ap.add_argument("--e2e-max-ctas", type=int, default=0)
-    ap.add_argument("--e2e-inflight", type=int, default=128, help="ticks in flight over all e2e threads")
+    ap.add_argument("--e2e-inflight", type=int, default=96, help="ticks in flight over all e2e threads")
     ap.add_argument("--ref-per-core", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

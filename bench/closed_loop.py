@@ -129,7 +129,7 @@ def run_gpu(R, T, warm=True, seed=20261018 + 5, record_solver=False):
 
 def run_gpu_device(R, T, groups=8, seed=20261018 + 5, max_iter=100, trace=True):
     """Device-resident loop: windowing, pre-step, warm-started solve, warm shift and post-step are C-ABI
-    kernels; the unicycle plant (simulation, not part of the reference) is three torch element-wise ops.
+    kernels, the unicycle plant (simulation, not part of the reference) included.
     Robots are split into `groups` independent streams so that a slow solve only delays its own group."""
     import torch
     from mpc_ros_b200 import capi
@@ -183,11 +183,7 @@ def run_gpu_device(R, T, groups=8, seed=20261018 + 5, max_iter=100, trace=True):
                 sv.warm_shift(B, g["wb"], g["wa"], stream=sp)
                 sv.poststep_raw(B, g["u0"], g["vel"], None, g["cmd"], stream=sp)
                 # plant (simulation): unicycle driven by the command
-                speed = g["cmd"][0]; w = g["cmd"][1]
-                g["pose"][0] += speed * torch.cos(g["pose"][2]) * dt
-                g["pose"][1] += speed * torch.sin(g["pose"][2]) * dt
-                g["pose"][2] = torch.remainder(g["pose"][2] + w * dt + np.pi, 2 * np.pi) - np.pi
-                g["vel"][0] = speed
+                sv.plant_step_raw(B, g["cmd"], g["pose"], g["vel"], stream=sp)
                 if trace:
                     g["cte"].append(g["ce"][0].clone()); g["iters"].append(g["it"].clone()); g["conv"].append(g["stt"] == 1)
     for g in grp:

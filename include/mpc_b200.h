@@ -161,6 +161,26 @@ int mpc_b200_window_batch(mpc_b200_handle *h, int32_t batch, const double *path_
 int mpc_b200_num_waypoints(const mpc_b200_params *p);
 
 /*
+ * Reference-speed schedule near the goal (Tracking::deceleration, mpc_ros/src/driving_state.cpp:121-141),
+ * device memory: inside the braking distance v^2 / max_throttle of its goal a robot's REF_V becomes
+ * max_throttle * distance (not below min_speed; the reference's `speed > REF_V -> max_speed` branch is kept).
+ * pose 3 x batch, goal 2 x batch, vel 3 x batch (row 0 = feedback speed), ref_vel_inout batch: the value
+ * persists from tick to tick and is what solve_batch / poststep_batch take as `ref_vel`.
+ * max_throttle (floored at 0.1, :61-63) and max_speed come from the handle's params; min_speed is the
+ * reference's context member (0.05, :29).
+ */
+int mpc_b200_decel_batch(mpc_b200_handle *h, int32_t batch, const double *pose, const double *goal, const double *vel,
+                         double min_speed, double *ref_vel_inout, void *stream);
+
+/*
+ * Plant step for closed-loop simulation (the reference has no plant, the robot is):
+ * unicycle x += v cos(theta) dt, y += v sin(theta) dt, theta += w dt wrapped to [-pi, pi), with
+ * {v, w} = cmd (2 x batch, from poststep_batch); vel_inout row 0 becomes the new feedback speed.  Device memory.
+ */
+int mpc_b200_plant_step_batch(mpc_b200_handle *h, int32_t batch, const double *cmd, double *pose_inout, double *vel_inout,
+                              void *stream);
+
+/*
  * Result post-step of Tracking::findBestPath (mpc_ros/src/driving_state.cpp:263-269), device memory:
  * speed = v + throttle * dt clamped above at REF_V; cmd_out (2 x batch) = {linear.x, angular.z}
  * (:115-116); vel_inout (3 x batch: v, previous w, previous throttle) gets the new w and throttle for the

@@ -38,7 +38,7 @@ EXPORTS = [
     "mpc_b200_params_set", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_set_params",
     "mpc_b200_get_params", "mpc_b200_set_option", "mpc_b200_warm_size", "mpc_b200_solve_batch", "mpc_b200_polyfit_batch",
     "mpc_b200_prestep_batch", "mpc_b200_warm_shift", "mpc_b200_window_batch", "mpc_b200_poststep_batch",
-    "mpc_b200_num_waypoints", "mpc_b200_stream_create", "mpc_b200_stream_destroy", "mpc_b200_stream_synchronize", "mpc_b200_track_batch", "mpc_b200_track_submit", "mpc_b200_track_wait",
+    "mpc_b200_num_waypoints", "mpc_b200_decel_batch", "mpc_b200_plant_step_batch", "mpc_b200_stream_create", "mpc_b200_stream_destroy", "mpc_b200_stream_synchronize", "mpc_b200_track_batch", "mpc_b200_track_submit", "mpc_b200_track_wait",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
 ]
@@ -83,6 +83,10 @@ def lib():
     L.mpc_b200_poststep_batch.restype = C.c_int
     L.mpc_b200_num_waypoints.argtypes = [C.POINTER(Params)]
     L.mpc_b200_num_waypoints.restype = C.c_int
+    L.mpc_b200_decel_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    L.mpc_b200_decel_batch.restype = C.c_int
+    L.mpc_b200_plant_step_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mpc_b200_plant_step_batch.restype = C.c_int
     L.mpc_b200_stream_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
     L.mpc_b200_stream_create.restype = C.c_int
     L.mpc_b200_stream_destroy.argtypes = [C.c_void_p]
@@ -259,6 +263,16 @@ class Solver:
 
     def poststep_raw(self, batch, u0, vel, ref_vel, cmd, stream=None):
         rc = lib().mpc_b200_poststep_batch(self._h, batch, _addr(u0), _addr(vel), _addr(ref_vel), _addr(cmd), stream)
+        if rc != 0:
+            raise MpcError(rc)
+
+    def decel_raw(self, batch, pose, goal, vel, min_speed, ref_vel, stream=None):
+        rc = lib().mpc_b200_decel_batch(self._h, batch, _addr(pose), _addr(goal), _addr(vel), min_speed, _addr(ref_vel), stream)
+        if rc != 0:
+            raise MpcError(rc)
+
+    def plant_step_raw(self, batch, cmd, pose, vel, stream=None):
+        rc = lib().mpc_b200_plant_step_batch(self._h, batch, _addr(cmd), _addr(pose), _addr(vel), stream)
         if rc != 0:
             raise MpcError(rc)
 

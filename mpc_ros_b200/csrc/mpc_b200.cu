@@ -204,6 +204,49 @@ __global__ void poststep_kernel(int batch, const double *__restrict__ u0, double
     cmd[(size_t)batch + i] = w;
 }
 
+// ================================================================ reference-speed schedule near the goal (8f-1)
+// Reference: Tracking::deceleration, mpc_ros/src/driving_state.cpp:121-141.  Inside the braking distance
+// v^2 / max_throttle of the goal REF_V becomes max_throttle * distance, limited below at min_speed; the
+// reference's first branch (speed > REF_V -> max_speed) is kept as it is written.  REF_V persists per robot.
+__global__ void decel_kernel(int batch, const double *__restrict__ pose, const double *__restrict__ goal,
+                             const double *__restrict__ vel, double max_throttle, double max_speed, double min_speed,
+                             double *__restrict__ ref_vel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const double dist = hypot(pose[i] - goal[i], pose[(size_t)batch + i] - goal[(size_t)batch + i]);
+    const double v = vel[i];
+    if (dist <= v * v / max_throttle) {
+        const double speed = max_throttle * dist;
+        double rv = ref_vel[i];
+        if (speed > rv) rv = max_speed;
+        else if (speed < min_speed) rv = min_speed;
+        else rv = speed;
+        ref_vel[i] = rv;
+    }
+}
+
+// ================================================================ plant step
+// Not in the reference (there the robot or Gazebo is the plant): unicycle driven by the command,
+//   x += v cos(theta) dt, y += v sin(theta) dt, theta += w dt (wrapped to [-pi, pi)), v = commanded speed.
+__global__ void plant_kernel(int batch, const double *__restrict__ cmd, double *__restrict__ pose, double *__restrict__ vel,
+                             double dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const double speed = cmd[i], w = cmd[(size_t)batch + i];
+    double th = pose[2 * (size_t)batch + i];
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    pose[i] += speed * cs * dt;
+    pose[(size_t)batch + i] += speed * sn * dt;
+    const double kPi = 3.14159265358979323846;
+    th += w * dt + kPi;
+    th -= 2.0 * kPi * floor(th / (2.0 * kPi));
+    pose[2 * (size_t)batch + i] = th - kPi;
+    vel[i] = speed;
+}
+
 // ================================================================ warm-start shift
 // Next tick's warm start from this tick's solution: every block of the record (6 state components,
 // 2 controls, 6 multiplier components, 4 bound multipliers) moves one stage forward, the last entry is
@@ -906,6 +949,38 @@ int mpc_b200_poststep_batch(mpc_b200_handle *h, int32_t batch, const double *u0,
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
     poststep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, u0, vel_inout, ref_vel, h->params.ref_vel, h->params.dt, cmd_out);
+    CK(cudaGetLastError());
+    h->launches++; h->kernels++;
+    if (!stream_v) CK(cudaStreamSynchronize(st));
+    return MPC_B200_OK;
+}
+
+int mpc_b200_decel_batch(mpc_b200_handle *h, int32_t batch, const double *pose, const double *goal, const double *vel,
+                         double min_speed, double *ref_vel_inout, void *stream_v)
+{
+    if (!h || batch < 0 || !pose || !goal || !vel || !ref_vel_inout) return MPC_B200_ERR_INVALID;
+    if (!is_device_ptr(pose) || !is_device_ptr(goal) || !is_device_ptr(vel) || !is_device_ptr(ref_vel_inout))
+        return MPC_B200_ERR_UNSUPPORTED;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    const double thr = h->params.max_throttle < 0.1 ? 0.1 : h->params.max_throttle;      // driving_state.cpp:63
+    decel_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, pose, goal, vel, thr, h->params.max_speed, min_speed, ref_vel_inout);
+    CK(cudaGetLastError());
+    h->launches++; h->kernels++;
+    if (!stream_v) CK(cudaStreamSynchronize(st));
+    return MPC_B200_OK;
+}
+
+int mpc_b200_plant_step_batch(mpc_b200_handle *h, int32_t batch, const double *cmd, double *pose_inout, double *vel_inout,
+                              void *stream_v)
+{
+    if (!h || batch < 0 || !cmd || !pose_inout || !vel_inout) return MPC_B200_ERR_INVALID;
+    if (!is_device_ptr(cmd) || !is_device_ptr(pose_inout) || !is_device_ptr(vel_inout)) return MPC_B200_ERR_UNSUPPORTED;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    plant_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, cmd, pose_inout, vel_inout, h->params.dt);
     CK(cudaGetLastError());
     h->launches++; h->kernels++;
     if (!stream_v) CK(cudaStreamSynchronize(st));

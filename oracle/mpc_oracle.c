@@ -358,3 +358,17 @@ void mpc_oracle_prestep(const double *wx, const double *wy, int M,
     *etheta = eth;
     free(xv); free(yv);
 }
+
+/* Tracking::deceleration, driving_state.cpp:121-141 */
+double mpc_oracle_decel(double px, double py, double gx, double gy, double v,
+                        double max_throttle, double max_speed, double min_speed, double ref_v)
+{
+    const double dist_to_goal = hypot(px - gx, py - gy);                 /* :125-126 */
+    if (dist_to_goal <= pow(v, 2) / max_throttle) {                      /* :127 */
+        const double speed = max_throttle * dist_to_goal;                /* :129 */
+        if (speed > ref_v) ref_v = max_speed;                            /* :130-132 */
+        else if (speed < min_speed) ref_v = min_speed;                   /* :133-135 */
+        else ref_v = speed;                                              /* :136-138 */
+    }
+    return ref_v;
+}

@@ -71,6 +71,12 @@ void mpc_oracle_prestep(const double *wx, const double *wy, int M,
                         double px, double py, double theta,
                         double *coeffs4, double *cte, double *etheta);
 
+/* Reference-speed schedule near the goal (Tracking::deceleration, driving_state.cpp:121-141): returns the
+ * new REF_V (the map entry persists from tick to tick, so the caller passes the previous value in).
+ * max_throttle is the context member floored at 0.1 (driving_state.cpp:61-63). */
+double mpc_oracle_decel(double px, double py, double gx, double gy, double v,
+                        double max_throttle, double max_speed, double min_speed, double ref_v);
+
 #ifdef __cplusplus
 }
 #endif

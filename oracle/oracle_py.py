@@ -95,6 +95,8 @@ class Oracle:
         L.mpc_oracle_eval_hess_dense.argtypes = [C.POINTER(OracleParams), _dp, C.c_int, _dp, C.c_double, _dp, _dp]
         L.mpc_oracle_polyfit.restype = C.c_int
         L.mpc_oracle_polyfit.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp]
+        L.mpc_oracle_decel.argtypes = [C.c_double] * 9
+        L.mpc_oracle_decel.restype = C.c_double
         L.mpc_oracle_prestep.argtypes = [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp]
         L.ipm_default_options.argtypes = [C.POINTER(IpmOptions)]
 
@@ -144,6 +146,9 @@ class Oracle:
         c = np.zeros(4); cte = C.c_double(); eth = C.c_double()
         self.lib.mpc_oracle_prestep(_ptr(wx), _ptr(wy), len(wx), px, py, theta, _ptr(c), C.byref(cte), C.byref(eth))
         return c, cte.value, eth.value
+
+    def decel(self, px, py, gx, gy, v, max_throttle, max_speed, min_speed, ref_v):
+        return self.lib.mpc_oracle_decel(px, py, gx, gy, v, max_throttle, max_speed, min_speed, ref_v)
 
 
 def ref_available():

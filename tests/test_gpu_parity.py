@@ -433,3 +433,37 @@ def test_track_submit_wait_pipelined():
         for key in ("u0", "pred", "cmd", "status"):
             np.testing.assert_array_equal(outs[k][key], ref[k][key])
         hs[k].close()
+
+
+def test_decel_and_plant_kernels(oracle):
+    """8f-1: the REF_V schedule near the goal (driving_state.cpp:121-141) against the oracle, and the plant step."""
+    import torch
+    B = 5000
+    rng = np.random.default_rng(31)
+    prm = capi.yaml_default_params()
+    pose = np.vstack([rng.uniform(-2, 2, B), rng.uniform(-2, 2, B), rng.uniform(-np.pi, np.pi, B)])
+    goal = pose[:2] + rng.uniform(-0.6, 0.6, (2, B))
+    vel = np.vstack([rng.uniform(0, 1.0, B), rng.uniform(-0.5, 0.5, B), rng.uniform(-0.5, 0.5, B)])
+    refv = rng.uniform(0.2, 0.7, B)
+    dev = torch.device("cuda:0")
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    sv = capi.Solver(prm, B, 0)
+    d_pose, d_goal, d_vel, d_ref = d(pose), d(goal), d(vel), d(refv)
+    sv.decel_raw(B, d_pose, d_goal, d_vel, 0.05, d_ref)
+    got = d_ref.cpu().numpy()
+    thr = max(prm.max_throttle, 0.1)
+    want = np.array([oracle.decel(pose[0, i], pose[1, i], goal[0, i], goal[1, i], vel[0, i], thr, prm.max_speed, 0.05, refv[i])
+                     for i in range(B)])
+    assert (want != refv).sum() > B // 10          # the schedule is exercised
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-15)
+    # plant: unicycle driven by the command
+    cmd = np.vstack([rng.uniform(0, 0.7, B), rng.uniform(-1.5, 1.5, B)])
+    d_cmd = d(cmd)
+    sv.plant_step_raw(B, d_cmd, d_pose, d_vel)
+    p2 = d_pose.cpu().numpy(); v2 = d_vel.cpu().numpy()
+    sv.close()
+    np.testing.assert_allclose(p2[0], pose[0] + cmd[0] * np.cos(pose[2]) * prm.dt, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(p2[1], pose[1] + cmd[0] * np.sin(pose[2]) * prm.dt, rtol=0, atol=1e-14)
+    th = np.remainder(pose[2] + cmd[1] * prm.dt + np.pi, 2 * np.pi) - np.pi
+    np.testing.assert_allclose(p2[2], th, rtol=0, atol=1e-14)
+    np.testing.assert_array_equal(v2[0], cmd[0]); np.testing.assert_array_equal(v2[1:], vel[1:])

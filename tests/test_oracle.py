@@ -167,3 +167,18 @@ def test_generated_set_statistics(oracle):
     np.testing.assert_array_equal(state, state2)
     assert set(g["kind"].tolist()) == {0, 1, 2}
     assert np.all(state[3] >= 0) and np.all(state[3] <= 0.6)
+
+
+def test_decel_known_answers(oracle):
+    """Tracking::deceleration (driving_state.cpp:121-141) worked by hand."""
+    thr, vmax, vmin = 1.0, 0.7, 0.05
+    # outside the braking distance: REF_V untouched
+    assert oracle.decel(0, 0, 1.0, 0, 0.5, thr, vmax, vmin, 0.5) == 0.5
+    # inside, speed = thr * dist = 1.0 > REF_V -> max_speed (the reference's branch, as written)
+    assert oracle.decel(0, 0, 1.0, 0, 1.2, thr, vmax, vmin, 0.5) == 0.7
+    # inside, min_speed <= speed <= REF_V -> speed
+    assert abs(oracle.decel(0, 0, 0.3, 0, 0.6, thr, vmax, vmin, 0.5) - 0.3) < 1e-16
+    # inside, speed < min_speed -> min_speed
+    assert oracle.decel(0, 0, 0.0, 0.02, 0.2, thr, vmax, vmin, 0.5) == 0.05
+    # boundary: dist == v^2 / thr counts as inside
+    assert oracle.decel(0, 0, 0.25, 0, 0.5, thr, vmax, vmin, 0.5) == 0.25

@@ -11,7 +11,7 @@ raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof_%s_solve.ncu-rep" % tag
 open(os.path.join(P, "%s_solve_kernel_ncu_raw.csv" % tag), "w").write(raw)
 for src, dst in (("bench_default_%s.json", "%s_bench_default.json"), ("bench_reference_%s.json", "%s_bench_reference.json"),
                  ("config4_%s.json", "%s_config4.json"), ("config5_%s.json", "%s_config5.json"),
-                 ("config5_device_%s.json", "%s_config5_device.json")):
+                 ("config5_device_%s.json", "%s_config5_device.json"), ("parity_sweep_%s.json", "%s_parity_sweep.json")):
     if os.path.exists(os.path.join(G, src % tag)):
         shutil.copy(os.path.join(G, src % tag), os.path.join(P, dst % tag))
 lat = [ln for ln in open(os.path.join(G, "latency_%s.json" % tag)) if ln.startswith("{")][-1]
@@ -76,7 +76,8 @@ All files in this directory come from `gpurun` runs of the committed tree (`prof
 ## Launch list (`%s_launches.csv`)
 
 `ncu --metrics gpu__time_duration.sum --clock-control none -c 600` on
-`python bench.py --steps 40 --warmup 8 --streams 8 --no-cpu-baseline --e2e-steps 16 --e2e-threads 2` (serialised, cold).
+`python bench.py --steps 40 --warmup 8 --streams 8 --no-cpu-baseline --e2e-steps 16 --e2e-threads 2 --e2e-inflight 4`
+(serialised, cold; the whole sequence is `profiles/evidence_run.sh`).
 
 | kernel | launches | total ms | share | avg us |
 |---|---|---|---|---|
@@ -112,5 +113,14 @@ and lane-permutation tests.
        tag, c5["mean_iters"], c5["oracle_subset"]["mean_iters_oracle"], c5["converged_fraction"], c5["solves_per_s"],
        ("; device-resident loop (`%s_config5_device.json`) %.0f robot-ticks/s" % (tag, c5d["robot_ticks_per_s"])) if c5d else "",
        tag, "\n".join(lines), tag, "\n".join(met), spill, inst, 100.0 * float(spill) / float(inst))
+ps = os.path.join(P, "%s_parity_sweep.json" % tag)
+if os.path.exists(ps):
+    md += "\n## Parity sweep (`%s_parity_sweep.json`, `tests/parity_sweep.py`: GPU through the C ABI vs the oracle)\n\n" % tag
+    md += "| weights | problems | converged GPU / oracle | within 1e-5 (u0) and 1e-6 (obj) of both-converged | p99.9 abs du0 | same iteration count | mean iterations GPU / oracle |\n|---|---|---|---|---|---|---|\n"
+    for r in json.load(open(ps)):
+        md += "| %s | %d | %d / %d | %d of %d | %.1e | %d | %.2f / %.2f |\n" % (
+            r["weights"], r["problems"], r["gpu_converged"], r["oracle_converged"], min(r["within_1e5_du0"], r["within_1e6_dobj"]),
+            r["both_converged"], r["p999_abs_du0"], r["iters_equal_among_both"], r["mean_iters_gpu"], r["mean_iters_oracle"])
+    md += "\nSee DESIGN.md section 7 for the reading (the GPU path leaves out the never-active state bounds).\n"
 open(os.path.join(P, "%s_summary.md" % tag), "w").write(md)
 print(md[:1800])

@@ -14,6 +14,8 @@
 
 using namespace nmpc;
 
+static long long g_lane_cycles = 0;
+
 template <bool RATE>
 static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB, int batch,
                    const double *state, const double *coeffs, const double *ref_vel,
@@ -59,6 +61,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
             int active = 0;
             for (int p = 0; p < np; p++) active |= (sm.I(PI_MODE, p) != MODE_IDLE) || (sm.I(PI_FLAGS, p) & FL_FLUSH);
             if (!active) break;
+            for (int p = 0; p < np; p++) g_lane_cycles += (sm.I(PI_MODE, p) != MODE_IDLE);
             // ---- P3a
             for (int p = 0; p < np; p++) {
                 const int fl = sm.I(PI_FLAGS, p);
@@ -203,6 +206,9 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     }
     return 0;
 }
+
+// lane-cycles (one lane busy for one global cycle) spent since the last reset: utilisation studies
+extern "C" long long nmpc_emu_lane_cycles(int reset) { const long long v = g_lane_cycles; if (reset) g_lane_cycles = 0; return v; }
 
 extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_iter, int PB, int batch,
                               const double *state, const double *coeffs, const double *ref_vel,

@@ -86,6 +86,27 @@ def test_create_validates_and_fails_loudly_without_gpu():
     assert b"no CPU path" in L.mpc_b200_strerror(-2)
 
 
+def test_null_handle_is_rejected_everywhere():
+    """Every batched entry point validates its handle before touching CUDA (returns MPC_B200_ERR_INVALID)."""
+    L = capi.lib()
+    z = None
+    assert L.mpc_b200_solve_batch(z, 1, z, z, z, z, z, z, z, z, z, z, z, z) == -1
+    assert L.mpc_b200_track_batch(z, 1, 11, z, z, z, z, z, z, z, z, z, z, z, z) == -1
+    assert L.mpc_b200_track_submit(z, 1, 11, z, z, z, z, z, z, z, z, z, z, z, z) == -1
+    assert L.mpc_b200_track_wait(z) == -1
+    assert L.mpc_b200_decel_batch(z, 1, z, z, z, 0.05, z, z) == -1
+    assert L.mpc_b200_plant_step_batch(z, 1, z, z, z, z) == -1
+    assert L.mpc_b200_poststep_batch(z, 1, z, z, z, z, z) == -1
+    assert L.mpc_b200_warm_shift(z, 1, z, z, z) == -1
+    assert L.mpc_b200_stream_create(0, None) == -1
+    assert L.mpc_b200_stream_destroy(None) == -1
+    if not has_gpu():
+        s = C.c_void_p()
+        assert L.mpc_b200_stream_create(0, C.byref(s)) == -2               # no device, no stream
+    p = capi.yaml_default_params()
+    assert L.mpc_b200_num_waypoints(C.byref(p)) == 11                      # 5 m window, every 10th of 100 points + the last
+
+
 def test_product_library_has_no_oracle_or_emulator_symbols():
     """The product .so must not contain the oracle / emulator (no CPU fallback inside)."""
     import subprocess

@@ -17,5 +17,6 @@ mpc_ros_b200/lib/mpc_bench latency 10000 > $O/latency_$T.json
 python bench/config4.py 16384 100 > $O/config4_$T.json
 python bench/closed_loop.py 1024 500 --oracle-subset 32 > $O/config5_$T.json
 python bench/closed_loop.py 1024 500 --device > $O/config5_device_$T.json
+# (config 3, multi-GPU: gpurun --gpus 4 -- torchrun ... bench/config3.py; see profiles/r1_config3.json)
 python tests/parity_sweep.py 16384 > $O/parity_sweep_$T.json 2> $O/parity_sweep.err
 cut -c1-300 $O/bench_default_$T.json

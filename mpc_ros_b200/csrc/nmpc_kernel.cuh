@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
                 double gk[SPT][6];
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_step<RATE>(prm, sm, r[j], k0 + j, p, hd, lsq, acc, gk[j]);
+                    if (k0 + j < N) stage_step<RATE>(prm, sm, r[j], k0 + j, p, hd, lsq, acc, gk[j], cf);
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
                     if (k0 + j < N)

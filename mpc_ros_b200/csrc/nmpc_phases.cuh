@@ -166,7 +166,6 @@ struct StageRegs {
     double zlw, zuw, zla, zua;  // bound multipliers of the controls (scaled problem)
     double sn, cs, se, ce;      // sin/cos(theta_k), sin/cos(etheta_k) at the iterate
     double tsn, tcs, tse, tce;  // the same at the last evaluated point
-    double hxx, htt, htv, hee, hev;  // Lagrangian-Hessian entries of this stage
     double duw, dua;            // Newton step of the controls
     double ilw, iuw, ila, iua;  // reciprocals of the four bound slacks at the iterate
 };
@@ -316,7 +315,6 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
         r.sn = 0.0; r.cs = 1.0; r.se = 0.0; r.ce = 1.0;
     }
     r.duw = r.dua = 0.0;
-    r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
     r.tsn = r.sn; r.tcs = r.cs; r.tse = r.se; r.tce = r.ce;
     r.ilw = r.iuw = 1.0 / relaxed(prm.max_angvel); r.ila = r.iua = 1.0 / relaxed(prm.max_throttle);
 }
@@ -600,8 +598,8 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             const double cnt = (hp ? 1.0 : 0.0) + (hn ? 1.0 : 0.0);
             rdw = 2.0 * sf * prm.w_angvel_d * cnt; rda = 2.0 * sf * prm.w_accel_d * cnt;
         }
+        double hxx = 0.0, htt = 0.0, htv = 0.0, hee = 0.0, hev = 0.0;
         if (lsq) {
-            r.hxx = r.htt = r.htv = r.hee = r.hev = 0.0;
             sm.at(k, W_3, p) = gw - r.zlw + r.zuw;
             sm.at(k, W_4, p) = ga - r.zla + r.zua;
             sm.at(k, W_10, p) = 1.0; sm.at(k, W_11, p) = 1.0;
@@ -616,18 +614,19 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             sm.at(k, D_E, p) = (e + r.uw * dt) - sm.at(k + 1, S_E, p);
             const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mc = sm.at(k, L_C, p);
             // second derivatives of the constraint rows weighted by lambda_{k+1}
-            r.hxx = -mc * ddpoly;
-            r.htt = (mx * r.cs + my * r.sn) * v * dt;
-            r.htv = (mx * r.sn - my * r.cs) * dt;
-            r.hee = mc * v * r.se * dt;
-            r.hev = -mc * r.ce * dt;
+            // (stage_step recomputes these five instead of keeping them in registers across the cycle)
+            hxx = -mc * ddpoly;
+            htt = (mx * r.cs + my * r.sn) * v * dt;
+            htv = (mx * r.sn - my * r.cs) * dt;
+            hee = mc * v * r.se * dt;
+            hev = -mc * r.ce * dt;
             sm.at(k, W_3, p) = gw - mu * ilw + mu * iuw;     // gradient of the barrier objective
             sm.at(k, W_4, p) = ga - mu * ila + mu * iua;
             sm.at(k, W_10, p) = 2.0 * sf * prm.w_angvel + rdw + r.zlw * ilw + r.zuw * iuw;   // R + Sigma
             sm.at(k, W_11, p) = 2.0 * sf * prm.w_accel + rda + r.zla * ila + r.zua * iua;
         }
-        sm.at(k, W_5, p) = r.hxx; sm.at(k, W_6, p) = r.htt; sm.at(k, W_7, p) = r.htv;
-        sm.at(k, W_8, p) = r.hee; sm.at(k, W_9, p) = r.hev;
+        sm.at(k, W_5, p) = hxx; sm.at(k, W_6, p) = htt; sm.at(k, W_7, p) = htv;
+        sm.at(k, W_8, p) = hee; sm.at(k, W_9, p) = hev;
     }
     sm.at(k, W_0, p) = qv; sm.at(k, W_1, p) = qc; sm.at(k, W_2, p) = qe;
 }
@@ -850,12 +849,13 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDi
 // (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`.
 template <bool RATE = false, class SM>
 MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq,
-                       StepPart &acc, double *g6)
+                       StepPart &acc, double *g6, const double *cf)
 {
     const int N = prm.N;
-    const double mu = sm.P(PS_MU, p), sf = sm.P(PS_SF, p);
+    const double mu = sm.P(PS_MU, p), sf = sm.P(PS_SF, p), dt = prm.dt;
+    const double v = sm.at(k, S_V, p);
     // objective gradient at the iterate (recomputed: cheaper than three live registers per stage)
-    const double qv = 2.0 * sf * prm.w_vel * (sm.at(k, S_V, p) - sm.P(PS_REFV, p));
+    const double qv = 2.0 * sf * prm.w_vel * (v - sm.P(PS_REFV, p));
     const double qc = 2.0 * sf * prm.w_cte * (sm.at(k, S_C, p) - prm.ref_cte);
     const double qe = 2.0 * sf * prm.w_etheta * (sm.at(k, S_E, p) - prm.ref_etheta);
     double dsx = 0, dsy = 0, dst = 0, dsv = 0, dsc = 0, dse = 0;
@@ -889,14 +889,27 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
             gd += gw * r.duw + ga * r.dua;
         }
     }
+    // the five lambda-weighted Hessian entries, exactly as stage_coeffs formed them for the sweep (same
+    // operands: the iterate has not moved since); recomputed here so that they do not occupy ten registers
+    // per stage for the whole cycle
+    double hxx = 0.0, htt = 0.0, htv = 0.0, hee = 0.0, hev = 0.0;
+    if (k < N - 1 && !lsq) {
+        const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mc = sm.at(k, L_C, p);
+        const double ddpoly = 2.0 * cf[2] + 6.0 * cf[3] * sm.at(k, S_X, p);
+        hxx = -mc * ddpoly;
+        htt = (mx * r.cs + my * r.sn) * v * dt;
+        htv = (mx * r.sn - my * r.cs) * dt;
+        hee = mc * v * r.se * dt;
+        hev = -mc * r.ce * dt;
+    }
     // g_k = q_s,k + Q_k ds_k  (Q_k = diag + the five lambda-weighted entries)
     // (returned in g6; the caller stores W_0..W_5 after all of its stages are computed)
-    g6[0] = (hd.dx + r.hxx) * dsx;
+    g6[0] = (hd.dx + hxx) * dsx;
     g6[1] = hd.dy * dsy;
-    g6[2] = (hd.dt_ + r.htt) * dst + r.htv * dsv;
-    g6[3] = qv + r.htv * dst + hd.dv * dsv + r.hev * dse;
+    g6[2] = (hd.dt_ + htt) * dst + htv * dsv;
+    g6[3] = qv + htv * dst + hd.dv * dsv + hev * dse;
     g6[4] = qc + hd.dc * dsc;
-    g6[5] = qe + r.hev * dsv + (hd.de + r.hee) * dse;
+    g6[5] = qe + hev * dsv + (hd.de + hee) * dse;
     acc.rmax = fmax2(acc.rmax, rmax); acc.rzmax = fmax2(acc.rzmax, rzmax); acc.gd += gd;
 }
 

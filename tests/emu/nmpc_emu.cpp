@@ -123,7 +123,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 for (int g = 0; g < NG; g++) {
                     StepPart acc; part_reset(acc);
                     double gk[SPT][6];
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step<RATE>(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT]);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step<RATE>(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT], &cfs[(size_t)4 * p]);
                     for (int k = g * SPT; k < g * SPT + SPT && k < N; k++)
                         for (int q = 0; q < 6; q++) sm.at(k, W_0 + q, p) = gk[k - g * SPT][q];
                     part_store(sm, g, p, acc);

@@ -160,14 +160,18 @@ MPC_HD size_t smem_bytes(int N, int NG, int PB, int nslots = NSLOTS)
 #define NMPC_KW_PLUS_BAR 100.0
 #define NMPC_EPS_MACH 2.220446049250313e-16
 
+// Roles of the work slots between the sweeps and the next coefficient phase:
+//   W_LAM..+5  g_k (P5), then lambda_{k+1}^+ (adjoint sweep, in place);
+//   W_ISL..+3  reciprocal slacks of the control bounds at the iterate (P5), read by P1 / P3a;
+//   W_DU, +1   Newton step of the controls (forward sweep), read by P5 / P1 / P3a.
+enum { W_LAM = W_0, W_ISL = W_6, W_DU = W_10 };
+
 // ---------------------------------------------------------------- per-(lane, stage) registers
 struct StageRegs {
     double uw, ua;              // controls of this stage (k <= N-2)
     double zlw, zuw, zla, zua;  // bound multipliers of the controls (scaled problem)
     double sn, cs, se, ce;      // sin/cos(theta_k), sin/cos(etheta_k) at the iterate
     double tsn, tcs, tse, tce;  // the same at the last evaluated point
-    double duw, dua;            // Newton step of the controls
-    double ilw, iuw, ila, iua;  // reciprocals of the four bound slacks at the iterate
 };
 
 MPC_HD double fmax2(double a, double b) { return a > b ? a : b; }
@@ -304,7 +308,7 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) = (k == 0) ? state6[c] : 0.0;
     for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = 0.0;
     // the step slots are read (times a zero step length) by plain evaluations before any sweep wrote them
-    for (int c = 0; c < 6; c++) { sm.at(k, D_X + c, p) = 0.0; sm.at(k, W_6 + c, p) = 0.0; }
+    for (int c = 0; c < 6; c++) { sm.at(k, D_X + c, p) = 0.0; sm.at(k, W_0 + c, p) = 0.0; sm.at(k, W_6 + c, p) = 0.0; }
     r.uw = 0.0; r.ua = 0.0;
     r.zlw = r.zuw = r.zla = r.zua = 1.0;      // bound_mult_init_val
     (void)coef4;
@@ -314,9 +318,7 @@ MPC_HD void stage_init(const Params &prm, const SM &sm, StageRegs &r, int k, int
     } else {
         r.sn = 0.0; r.cs = 1.0; r.se = 0.0; r.ce = 1.0;
     }
-    r.duw = r.dua = 0.0;
     r.tsn = r.sn; r.tcs = r.cs; r.tse = r.se; r.tce = r.ce;
-    r.ilw = r.iuw = 1.0 / relaxed(prm.max_angvel); r.ila = r.iua = 1.0 / relaxed(prm.max_throttle);
 }
 
 // Warm start (new capability; the reference cold-starts every call, solve_callback.hpp:595-597).
@@ -382,15 +384,18 @@ MPC_HD double zsafe(double z, double mu, double slack)
     if (prod > NMPC_KAPPA_SIGMA * mu || prod < (1.0 / NMPC_KAPPA_SIGMA) * mu) z = zclamp(z, mu, 1.0 / slack);
     return z;
 }
-MPC_HD void trial_z(const Params &prm, const StageRegs &r, double az, double mu, double uw, double ua,
+template <class SM>
+MPC_HD void trial_z(const Params &prm, const SM &sm, const StageRegs &r, int k, int p, double az, double mu, double uw, double ua,
                     double &zlw, double &zuw, double &zla, double &zua)
 {
     const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+    const double duw = sm.at(k, W_DU, p), dua = sm.at(k, W_DU + 1, p);
+    const double ilw = sm.at(k, W_ISL, p), iuw = sm.at(k, W_ISL + 1, p), ila = sm.at(k, W_ISL + 2, p), iua = sm.at(k, W_ISL + 3, p);
     // az == 0 (plain evaluation) leaves the multipliers bit-for-bit unchanged and skips the safeguard
-    zlw = r.zlw + az * (mu * r.ilw - r.zlw - r.zlw * r.ilw * r.duw);
-    zuw = r.zuw + az * (mu * r.iuw - r.zuw + r.zuw * r.iuw * r.duw);
-    zla = r.zla + az * (mu * r.ila - r.zla - r.zla * r.ila * r.dua);
-    zua = r.zua + az * (mu * r.iua - r.zua + r.zua * r.iua * r.dua);
+    zlw = r.zlw + az * (mu * ilw - r.zlw - r.zlw * ilw * duw);
+    zuw = r.zuw + az * (mu * iuw - r.zuw + r.zuw * iuw * duw);
+    zla = r.zla + az * (mu * ila - r.zla - r.zla * ila * dua);
+    zua = r.zua + az * (mu * iua - r.zua + r.zua * iua * dua);
     const double slw = uw + Uw, suw = Uw - uw, sla = ua + Ua, sua = Ua - ua;
     const double hi = NMPC_KAPPA_SIGMA * mu, lo = (1.0 / NMPC_KAPPA_SIGMA) * mu;
     const double p1 = zlw * slw, p2 = zuw * suw, p3 = zla * sla, p4 = zua * sua;
@@ -409,7 +414,7 @@ MPC_HD void stage_adopt(const Params &prm, const SM &sm, int k, int p, int flags
 {
     const bool keep = (flags & FL_KEEP) != 0;
     if (k < prm.N - 1)
-        for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = keep ? sm.at(k, W_6 + c, p) : 0.0;
+        for (int c = 0; c < 6; c++) sm.at(k, L_X + c, p) = keep ? sm.at(k, W_LAM + c, p) : 0.0;
 }
 
 // Rate penalty  sum_j w_d (u_{j+1} - u_j)^2  (mpc_planner.cpp:144-147): gradient wrt u_k given its neighbours.
@@ -455,9 +460,9 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
     double f = prm.w_cte * ec * ec + prm.w_etheta * ee * ee + prm.w_vel * ev * ev;
     const double qv = 2.0 * sf * prm.w_vel * ev, qc = 2.0 * sf * prm.w_cte * ec, qe = 2.0 * sf * prm.w_etheta * ee;
     // lambda_k (multiplier of the rows that define s_k) lives with stage k-1 (lambda_0: per-lane scalars):
-    // current value in L (PS_L0*), the Newton / least-squares value in W_6.. (PS_N0*)
+    // current value in L (PS_L0*), the Newton / least-squares value in W_LAM.. (PS_N0*)
     const double *lcur = (k == 0) ? &sm.P(PS_L0X, p) : &sm.at(k - 1, L_X, p);
-    const double *lnew = (k == 0) ? &sm.P(PS_N0X, p) : &sm.at(k - 1, W_6, p);
+    const double *lnew = (k == 0) ? &sm.P(PS_N0X, p) : &sm.at(k - 1, W_LAM, p);
     const int ld = sm.pb();
     double lk[6];
 #pragma unroll
@@ -470,7 +475,7 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
     if (k == 0) l1 = fabs(lkx) + fabs(lky) + fabs(lkt) + fabs(lkv) + fabs(lkc) + fabs(lke);
     double prinf = 0.0, pr1 = 0.0, duinf, vmax = -1e300, vmin = 1e300, z1 = 0.0, lnsum = 0.0;
     if (k < N - 1) {
-        const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
+        const double uw = r.uw + alpha * sm.at(k, W_DU, p), ua = r.ua + alpha * sm.at(k, W_DU + 1, p);
         f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
         const double poly = cf[0] + x * (cf[1] + x * (cf[2] + x * cf[3]));
         const double dpoly = cf[1] + x * (2.0 * cf[2] + 3.0 * cf[3] * x);
@@ -489,9 +494,9 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         // trial lambda_{k+1} (after an adoption stage_adopt has already put it into L)
         double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mt = sm.at(k, L_T, p);
         double mv = sm.at(k, L_V, p), mc = sm.at(k, L_C, p), me = sm.at(k, L_E, p);
-        mx += alpha * (sm.at(k, W_6, p) - mx); my += alpha * (sm.at(k, W_7, p) - my);
-        mt += alpha * (sm.at(k, W_8, p) - mt); mv += alpha * (sm.at(k, W_9, p) - mv);
-        mc += alpha * (sm.at(k, W_10, p) - mc); me += alpha * (sm.at(k, W_11, p) - me);
+        mx += alpha * (sm.at(k, W_LAM, p) - mx); my += alpha * (sm.at(k, W_LAM + 1, p) - my);
+        mt += alpha * (sm.at(k, W_LAM + 2, p) - mt); mv += alpha * (sm.at(k, W_LAM + 3, p) - mv);
+        mc += alpha * (sm.at(k, W_LAM + 4, p) - mc); me += alpha * (sm.at(k, W_LAM + 5, p) - me);
         // stationarity wrt s_k:  grad f + lambda_k - A_k^T lambda_{k+1}
         const double a13 = -v * r.tsn * dt, a14 = r.tcs * dt, a23 = v * r.tcs * dt, a24 = r.tsn * dt;
         const double a51 = dpoly, a54 = r.tse * dt, a56 = v * r.tce * dt;
@@ -503,7 +508,7 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         const double re = qe + lke - (a56 * mc + me);
         // stationarity wrt u_k:  grad f - B^T lambda_{k+1} - zL + zU
         double zlw, zuw, zla, zua;
-        trial_z(prm, r, az, mu, uw, ua, zlw, zuw, zla, zua);
+        trial_z(prm, sm, r, k, p, az, mu, uw, ua, zlw, zuw, zla, zua);
         double rw = 2.0 * sf * prm.w_angvel * uw - dt * (mt + me) - zlw + zuw;
         double ra = 2.0 * sf * prm.w_accel * ua - dt * mv - zla + zua;
         if (RATE) {
@@ -555,11 +560,11 @@ MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, in
     if (k < N - 1) {
         for (int c = 0; c < 6; c++) {
             const double l = sm.at(k, L_X + c, p);
-            sm.at(k, L_X + c, p) = l + alpha * (sm.at(k, W_6 + c, p) - l);
+            sm.at(k, L_X + c, p) = l + alpha * (sm.at(k, W_LAM + c, p) - l);
         }
-        const double uw = r.uw + alpha * r.duw, ua = r.ua + alpha * r.dua;
+        const double uw = r.uw + alpha * sm.at(k, W_DU, p), ua = r.ua + alpha * sm.at(k, W_DU + 1, p);
         double zlw, zuw, zla, zua;
-        trial_z(prm, r, az, mu, uw, ua, zlw, zuw, zla, zua);
+        trial_z(prm, sm, r, k, p, az, mu, uw, ua, zlw, zuw, zla, zua);
         r.uw = uw; r.ua = ua; r.zlw = zlw; r.zuw = zuw; r.zla = zla; r.zua = zua;
         if (RATE) { sm.at(k, U_W, p) = uw; sm.at(k, U_A, p) = ua; }
     }
@@ -586,7 +591,6 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
         const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
         const double ilw = fast_rcp(r.uw + Uw), iuw = fast_rcp(Uw - r.uw);
         const double ila = fast_rcp(r.ua + Ua), iua = fast_rcp(Ua - r.ua);
-        r.ilw = ilw; r.iuw = iuw; r.ila = ila; r.iua = iua;
         double gw = 2.0 * sf * prm.w_angvel * r.uw, ga = 2.0 * sf * prm.w_accel * r.ua;
         double rdw = 0.0, rda = 0.0;     // diagonal Hessian contribution of the rate terms this control is part of
         if (RATE) {
@@ -866,15 +870,21 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
     // fraction to the boundary (W&B eq. (15)) as the largest step / slack ratio: alpha_max = min(1, tau / ratio)
     double rmax = 0.0, rzmax = 0.0, gd = qv * dsv + qc * dsc + qe * dse;
     if (k < N - 1) {
-        r.duw = sm.at(k, W_10, p); r.dua = sm.at(k, W_11, p);
-        if (RATE) { sm.at(k, DU_W, p) = r.duw; sm.at(k, DU_A, p) = r.dua; }
+        const double duw = sm.at(k, W_DU, p), dua = sm.at(k, W_DU + 1, p);
+        if (RATE) { sm.at(k, DU_W, p) = duw; sm.at(k, DU_A, p) = dua; }
+        // reciprocal slacks at the iterate, the same values stage_coeffs used; left in W_ISL.. for the trial
+        // multipliers of P1 / P3a (the gains that occupied these slots were consumed by the forward sweep)
+        const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+        const double ilw = fast_rcp(r.uw + Uw), iuw = fast_rcp(Uw - r.uw);
+        const double ila = fast_rcp(r.ua + Ua), iua = fast_rcp(Ua - r.ua);
+        sm.at(k, W_ISL, p) = ilw; sm.at(k, W_ISL + 1, p) = iuw; sm.at(k, W_ISL + 2, p) = ila; sm.at(k, W_ISL + 3, p) = iua;
         if (!lsq) {
-            rmax = fmax2(fmax2(-r.duw * r.ilw, r.duw * r.iuw), fmax2(-r.dua * r.ila, r.dua * r.iua));
-            const double mlw = mu * r.ilw, muw = mu * r.iuw, mla = mu * r.ila, mua = mu * r.iua;
-            const double dzlw = mlw - r.zlw - r.zlw * r.ilw * r.duw;
-            const double dzuw = muw - r.zuw + r.zuw * r.iuw * r.duw;
-            const double dzla = mla - r.zla - r.zla * r.ila * r.dua;
-            const double dzua = mua - r.zua + r.zua * r.iua * r.dua;
+            rmax = fmax2(fmax2(-duw * ilw, duw * iuw), fmax2(-dua * ila, dua * iua));
+            const double mlw = mu * ilw, muw = mu * iuw, mla = mu * ila, mua = mu * iua;
+            const double dzlw = mlw - r.zlw - r.zlw * ilw * duw;
+            const double dzuw = muw - r.zuw + r.zuw * iuw * duw;
+            const double dzla = mla - r.zla - r.zla * ila * dua;
+            const double dzua = mua - r.zua + r.zua * iua * dua;
             rzmax = fmax2(fmax2(-dzlw * fast_rcp(r.zlw), -dzuw * fast_rcp(r.zuw)),
                           fmax2(-dzla * fast_rcp(r.zla), -dzua * fast_rcp(r.zua)));
             double gw = 2.0 * sf * prm.w_angvel * r.uw - mlw + muw;
@@ -886,7 +896,7 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
                 gw += rate_grad(hd.rw, r.uw, upw, unw, hp, hn);
                 ga += rate_grad(hd.ra, r.ua, upa, una, hp, hn);
             }
-            gd += gw * r.duw + ga * r.dua;
+            gd += gw * duw + ga * dua;
         }
     }
     // the five lambda-weighted Hessian entries, exactly as stage_coeffs formed them for the sweep (same
@@ -914,7 +924,7 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
 }
 
 // Adjoint sweep (control thread): lambda_k^+ = A_k^T lambda_{k+1}^+ - g_k, k = N-1 .. 0.
-// lambda_{k+1}^+ is left in W_6..W_11 of stage k; lambda_0^+ in PS_N0*.
+// lambda_{k+1}^+ replaces g_k in W_LAM..+5 of stage k (stage N-1 keeps g_{N-1}); lambda_0^+ goes to PS_N0*.
 template <class SM>
 MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
 {
@@ -923,17 +933,19 @@ MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
     double lv = -sm.at(N - 1, W_3, p), lc = -sm.at(N - 1, W_4, p), le = -sm.at(N - 1, W_5, p);
 #pragma unroll 4
     for (int k = N - 2; k >= 0; k--) {
-        sm.at(k, W_6, p) = lx; sm.at(k, W_7, p) = ly; sm.at(k, W_8, p) = lt;
-        sm.at(k, W_9, p) = lv; sm.at(k, W_10, p) = lc; sm.at(k, W_11, p) = le;
+        const double g0 = sm.at(k, W_0, p), g1 = sm.at(k, W_1, p), g2 = sm.at(k, W_2, p);
+        const double g3 = sm.at(k, W_3, p), g4 = sm.at(k, W_4, p), g5 = sm.at(k, W_5, p);
+        sm.at(k, W_LAM, p) = lx; sm.at(k, W_LAM + 1, p) = ly; sm.at(k, W_LAM + 2, p) = lt;
+        sm.at(k, W_LAM + 3, p) = lv; sm.at(k, W_LAM + 4, p) = lc; sm.at(k, W_LAM + 5, p) = le;
         const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
                      a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
                      a56 = sm.at(k, A_56, p);
-        const double nx = lx + a51 * lc - sm.at(k, W_0, p);
-        const double ny = ly - lc - sm.at(k, W_1, p);
-        const double nt = a13 * lx + a23 * ly + lt - sm.at(k, W_2, p);
-        const double nv = a14 * lx + a24 * ly + lv + a54 * lc - sm.at(k, W_3, p);
-        const double nc = -sm.at(k, W_4, p);
-        const double ne = a56 * lc + le - sm.at(k, W_5, p);
+        const double nx = lx + a51 * lc - g0;
+        const double ny = ly - lc - g1;
+        const double nt = a13 * lx + a23 * ly + lt - g2;
+        const double nv = a14 * lx + a24 * ly + lv + a54 * lc - g3;
+        const double nc = -g4;
+        const double ne = a56 * lc + le - g5;
         lx = nx; ly = ny; lt = nt; lv = nv; lc = nc; le = ne;
     }
     sm.P(PS_N0X, p) = lx; sm.P(PS_N0Y, p) = ly; sm.P(PS_N0T, p) = lt;
@@ -1158,7 +1170,7 @@ MPC_HD int ctrl_lsq_finish(const Params &prm, const SM &sm, int p)
     const int N = prm.N;
     double lmax = 0.0;
     for (int k = 0; k < N - 1; k++)
-        for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.at(k, W_6 + i, p)));
+        for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.at(k, W_LAM + i, p)));
     for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.P(PS_N0X + i, p)));
     const int keep = (lmax <= NMPC_LAM_MAX) ? 1 : 0;   // NaN compares false -> 0
     for (int i = 0; i < 6; i++) sm.P(PS_L0X + i, p) = keep ? sm.P(PS_N0X + i, p) : 0.0;

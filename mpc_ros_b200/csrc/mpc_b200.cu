@@ -16,8 +16,8 @@ using nmpc::SolveArgs;
 #define QUEUE_RING 1024
 // stages per stage thread: 1 control warp + 7 stage warps = 256 threads, so that the kernel may use
 // 255 registers per thread (the serial Riccati sweep wants ~110 live doubles)
-#define SPT 3
-#define STAGE_THREADS 224
+#define SPT 2
+#define STAGE_THREADS 320
 
 // ================================================================ K1: transform + polyfit
 // Reference: Tracking::findBestPath, mpc_ros/src/driving_state.cpp:196-235, polyfit :283-300

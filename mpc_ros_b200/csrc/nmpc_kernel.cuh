@@ -6,7 +6,8 @@
 // shuffles in the recursions).  The other warps are stage threads: thread (g, p) owns stages
 // g*SPT .. g*SPT+SPT-1 of lane p's problem and does everything that is parallel over the horizon
 // (sin/cos, model derivatives, residual norms, trial-point evaluation, step application).
-// All exchange goes through shared memory [stage][slot][lane].
+// All exchange goes through shared memory [stage][slot][lane].  SPT = 2 at N = 20: 1 + 10 warps, 352 threads at
+// 168 registers (the register file); SPT = 3 would be 8 warps at 255.
 //
 // One global cycle = the fixed phase sequence
 //   P3a apply / flush / init | P3b coefficients | P4 sweeps | P5 step work | P6 multipliers, step sizes |
@@ -59,7 +60,7 @@ struct SolveArgs {
 #endif
 
 template <int SPT, int CPB, bool WARM, bool RATE>
-__global__ void __launch_bounds__(256, 1) nmpc_solve_kernel(const SolveArgs a)
+__global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;

@@ -93,7 +93,7 @@ CUDA-event shares bench.py reports (`roofline.kernel_ms` vs `ms_per_step`).
 |---|---|---|
 %s
 
-Reading: 255 registers/thread and 219 KB dynamic shared memory give one 8-warp CTA per SM by design (the
+Reading: registers (352 threads x 168) and 219 KB dynamic shared memory give one 11-warp CTA per SM by design (the
 per-problem working set lives in shared memory: 37 fp64 slots x 20 stages x 32 lanes).  A lone launch of one
 batch leaves most SMs idle most of the time (the tail of a batch is a handful of problems that need 10-20x
 the median iteration count), which is why throughput is measured with many batches in flight.  Within active

@@ -30,7 +30,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     prm.tol = tol; prm.max_iter = max_iter;
     prm.warm_mu = 1e-3;
     prm.w_angvel_d = prm14[11]; prm.w_accel_d = prm14[12];
-    const int SPT = 3;   // same grouping of partial sums as the kernel's stage threads
+    const int SPT = 2;   // same grouping of partial sums as the kernel's stage threads
     prm.grp = SPT;
     const int NG = (N + SPT - 1) / SPT;
 

@@ -13,6 +13,9 @@ def main():
     sv = capi.Solver(prm, B, 0)
     if hasattr(L, 'mpc_b200_debug_profile'): L.mpc_b200_debug_profile(sv._h, None)
     if maxc: sv.set_option("max_ctas", maxc)
+    pbo = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    if pbo: sv.set_option("problems_per_cta", pbo)
+    if len(sys.argv) > 6: sv.set_option("hard_first", int(sys.argv[6]))
     R = 8
     g = gen_py.problems(20261020, B * R)
     M = g["M"]
@@ -22,7 +25,9 @@ def main():
     coef = [torch.zeros((4, B), **f64) for _ in range(R)]; state = [torch.zeros((6, B), **f64) for _ in range(R)]
     u0 = [torch.zeros((2, B), **f64) for _ in range(R)]; pred = [torch.zeros((60, B), **f64) for _ in range(R)]
     stat = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(R)]
-    streams = [torch.cuda.Stream() for _ in range(S)]
+    # (torch.cuda.Stream() hands out at most 32 distinct streams per device: the library creates real ones)
+    raw = [capi.stream_create(0) for _ in range(S)]
+    streams = [torch.cuda.ExternalStream(q, device=dev) for q in raw]
     for j in range(R):
         sv.prestep_raw(B, M, wx[j], wy[j], pose[j], vel[j], coef[j], state[j])
     torch.cuda.synchronize()
@@ -30,7 +35,7 @@ def main():
     for j in range(R):
         args.append((sv._h, B, state[j].data_ptr(), coef[j].data_ptr(), None, None, u0[j].data_ptr(), pred[j].data_ptr(),
                      None, stat[j].data_ptr(), None, None, None))
-    sp = [s.cuda_stream for s in streams]
+    sp = raw
     f = L.mpc_b200_solve_batch
     for j in range(S):
         f(*args[j % R], sp[j % S])
@@ -49,8 +54,11 @@ def main():
         buf = (C.c_longlong * 1024)()
         if L.mpc_b200_debug_profile(sv._h, buf) and buf[1000] > 0:
             print("   avg global cycle: %.0f SM cycles (%d cycles total over all CTAs of all launches)" % (buf[1001] / buf[1000], buf[1000]))
-            names = ["-", "refill", "P3_apply_coeffs", "P4_backward", "P4_forward(+rollout,prefetch)", "P5_step", "P6", "P1_eval", "P2_decide"]
-            print("   per-cycle breakdown (control thread 0 of every CTA): " + ", ".join("%s %.0f" % (names[i], buf[1008 + i] / buf[1000]) for i in range(1, 9)))
+            if buf[1002] > 0: print("   busy lanes per cycle: %.2f" % (buf[1002] / buf[1000]))
+            names = ["-", "refill", "P3_apply_coeffs", "P4_backward", "P4_forward(+rollout,prefetch)", "P5_step", "P6", "P1_eval", "P2_rest", "P6_adjoint", "P2_ctrl_decide"]
+            print("   per-cycle breakdown (control thread 0 of every CTA): " + ", ".join("%s %.0f" % (names[i], buf[1008 + i] / buf[1000]) for i in range(1, 11)))
+    conv = sum(int((t == 1).sum()) for t in stat)
+    print("   converged in the %d result sets: %d of %d" % (R, conv, R * B))
     print("B %d S %d K %d maxctas %d: host issue %.1f us/launch, device %.3f ms/launch, %.2f M solves/s" %
           (B, S, K, maxc, (t1 - t0) / K * 1e6, ms / K, B * K / ms / 1e3))
 main()

@@ -121,9 +121,14 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
 // thousands).  The work queue is therefore served in descending order of |c1|+|c2|+|c3| (bucketed by binary
 // exponent): slow problems start first and the tail of a launch is filled with quick ones.  Results do not
 // depend on the order (lanes are independent).  One CTA, counting sort with shared-memory atomics.
-__global__ void queue_order_kernel(int batch, const double *__restrict__ coeffs, int *__restrict__ order)
+// Small on purpose (128 threads, few registers): it has to fit on an SM NEXT TO a resident solve CTA, or every
+// launch would wait for an SM to drain completely before its solve kernel could even be queued.  Also resets the
+// launch's work-queue head.
+__global__ void __launch_bounds__(128) queue_order_kernel(int batch, const double *__restrict__ coeffs, int *__restrict__ order,
+                                                          int *__restrict__ queue)
 {
     __shared__ int hist[32], offs[32];
+    if (threadIdx.x == 0) *queue = 0;
     if (threadIdx.x < 32) hist[threadIdx.x] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < batch; i += blockDim.x) {
@@ -611,13 +616,14 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     if (grid > cap) grid = cap;
     const size_t smem = nmpc::smem_bytes(N, NG, a.PB, nslots);
     a.queue = h->d_queue + (h->launches % QUEUE_RING);
-    CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     a.order = NULL;
     if (h->opt_order && batch > grid * a.PB) {      // only matters when lanes work through several problems
         a.order = h->d_order + (size_t)(h->launches % h->order_ring) * h->max_batch;
-        queue_order_kernel<<<1, 1024, 0, st>>>(batch, a.coeffs, (int *)a.order);
+        queue_order_kernel<<<1, 128, 0, st>>>(batch, a.coeffs, (int *)a.order, a.queue);
         CK(cudaGetLastError());
         h->kernels++;
+    } else {
+        CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     }
     if (timed) CK(cudaEventRecord(h->ev0, st));
     if (rate) {

@@ -131,6 +131,12 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             PROF_MARK(1);
             int active = 0;
             if (lane) active = (sm.I(PI_MODE, p) != MODE_IDLE) || (sm.I(PI_FLAGS, p) & FL_FLUSH);
+#ifdef NMPC_PROFILE
+            {   // busy lanes of this cycle
+                const unsigned bz = __ballot_sync(0xffffffffu, lane && sm.I(PI_MODE, p) != MODE_IDLE);
+                if (a.prof && p == 0) atomicAdd((unsigned long long *)&a.prof[1002], (unsigned long long)__popc(bz));
+            }
+#endif
             if (!__syncthreads_or(active)) break;   // B2 (vote)
             TRACE_C(1);
             // ---- P3a: stage threads apply / flush / init
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             bool late = false;
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
                 adjoint_sweep(prm, sm, p);      // common to both branches below: keep it out of the divergence
+                PROF_MARK(9);
                 if (sm.I(PI_FLAGS, p) & FL_LSQ) {
                     const int keep = ctrl_lsq_finish(prm, sm, p);
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
@@ -207,6 +214,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
                 if (md == MODE_EVAL) {
                     const int fl = sm.I(PI_FLAGS, p);
                     const int r = ctrl_decide(prm, sm, c, p, fl, NG);
+                    PROF_MARK(10);
                     if (r == 0) {
                         sm.I(PI_FLAGS, p) = FL_LS;
                     } else {

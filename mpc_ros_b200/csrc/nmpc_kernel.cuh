@@ -183,15 +183,11 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             __syncthreads();  // B6
             TRACE_C(6);
             PROF_MARK(5);
-            // ---- P6: multipliers, step sizes
+            // ---- P6: step sizes; meanwhile the lane's stage thread of group 0 runs the adjoint sweep (multipliers),
+            //      which nothing here depends on.  A least-squares lane (FL_LSQ) gets its flags from that thread.
             bool late = false;
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
-                adjoint_sweep(prm, sm, p);      // common to both branches below: keep it out of the divergence
-                PROF_MARK(9);
-                if (sm.I(PI_FLAGS, p) & FL_LSQ) {
-                    const int keep = ctrl_lsq_finish(prm, sm, p);
-                    sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
-                } else {
+                if (!(sm.I(PI_FLAGS, p) & FL_LSQ)) {
                     ctrl_step(prm, sm, c, p, NG);
                     sm.I(PI_FLAGS, p) = FL_LS;
                     late = true;
@@ -356,8 +352,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             __syncthreads();  // B5
             TRACE_S(5);
             // ---- P5: step-dependent work
-            if (mine && sm.I(PI_MODE, p) == MODE_STEP) {
-                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+            const bool stepping = mine && sm.I(PI_MODE, p) == MODE_STEP;     // (sampled before B6: the control thread
+            const int step_lsq = stepping ? (sm.I(PI_FLAGS, p) & FL_LSQ) : 0;  //  rewrites mode and flags in P6)
+            if (stepping) {
+                const int lsq = step_lsq;
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
                 StepPart acc;
                 part_reset(acc);
@@ -373,7 +371,11 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             }
             TRACE_S(6);
             __syncthreads();  // B6
-            // ---- P6: control
+            // ---- P6: the control thread sets the step sizes; thread (0, p) runs lane p's adjoint sweep
+            if (g == 0 && stepping) {
+                const int big = adjoint_sweep(prm, sm, p);
+                if (step_lsq) sm.I(PI_FLAGS, p) = FL_ADOPT | ctrl_lsq_finish(prm, sm, p, big);
+            }
             __syncthreads();  // B7
             TRACE_S(7);
             // ---- P1: evaluate

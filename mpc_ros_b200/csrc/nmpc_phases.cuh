@@ -151,7 +151,6 @@ MPC_HD size_t smem_bytes(int N, int NG, int PB, int nslots = NSLOTS)
 #define NMPC_KAPPA_SIGMA 1e10
 #define NMPC_MU_INIT 0.1
 #define NMPC_BOUND_RELAX 1e-8
-#define NMPC_LAM_MAX 1e3
 #define NMPC_DW_MIN 1e-20
 #define NMPC_DW_0 1e-4
 #define NMPC_DW_MAX 1e40
@@ -923,20 +922,28 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
     acc.rmax = fmax2(acc.rmax, rmax); acc.rzmax = fmax2(acc.rzmax, rzmax); acc.gd += gd;
 }
 
-// Adjoint sweep (control thread): lambda_k^+ = A_k^T lambda_{k+1}^+ - g_k, k = N-1 .. 0.
+// Adjoint sweep: lambda_k^+ = A_k^T lambda_{k+1}^+ - g_k, k = N-1 .. 0.
 // lambda_{k+1}^+ replaces g_k in W_LAM..+5 of stage k (stage N-1 keeps g_{N-1}); lambda_0^+ goes to PS_N0*.
+// Runs on the lane's stage thread of group 0 while the control thread sets the step sizes (it needs only the
+// P5 results).  Returns 1 if some multiplier exceeds NMPC_LAM_MAX in magnitude (or is NaN): the test the
+// least-squares start makes (W&B Sec. 3.6), folded into the sweep so that it costs no extra pass.
+#define NMPC_LAM_MAX 1e3
 template <class SM>
-MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
+MPC_HD int adjoint_sweep(const Params &prm, const SM &sm, int p)
 {
     const int N = prm.N;
     double lx = -sm.at(N - 1, W_0, p), ly = -sm.at(N - 1, W_1, p), lt = -sm.at(N - 1, W_2, p);
     double lv = -sm.at(N - 1, W_3, p), lc = -sm.at(N - 1, W_4, p), le = -sm.at(N - 1, W_5, p);
+    int big = 0;
+#define NMPC_BIG6() big |= !(fabs(lx) <= NMPC_LAM_MAX) | !(fabs(ly) <= NMPC_LAM_MAX) | !(fabs(lt) <= NMPC_LAM_MAX) | \
+                           !(fabs(lv) <= NMPC_LAM_MAX) | !(fabs(lc) <= NMPC_LAM_MAX) | !(fabs(le) <= NMPC_LAM_MAX)
 #pragma unroll 4
     for (int k = N - 2; k >= 0; k--) {
         const double g0 = sm.at(k, W_0, p), g1 = sm.at(k, W_1, p), g2 = sm.at(k, W_2, p);
         const double g3 = sm.at(k, W_3, p), g4 = sm.at(k, W_4, p), g5 = sm.at(k, W_5, p);
         sm.at(k, W_LAM, p) = lx; sm.at(k, W_LAM + 1, p) = ly; sm.at(k, W_LAM + 2, p) = lt;
         sm.at(k, W_LAM + 3, p) = lv; sm.at(k, W_LAM + 4, p) = lc; sm.at(k, W_LAM + 5, p) = le;
+        NMPC_BIG6();
         const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
                      a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
                      a56 = sm.at(k, A_56, p);
@@ -948,8 +955,11 @@ MPC_HD void adjoint_sweep(const Params &prm, const SM &sm, int p)
         const double ne = a56 * lc + le - g5;
         lx = nx; ly = ny; lt = nt; lv = nv; lc = nc; le = ne;
     }
+    NMPC_BIG6();
+#undef NMPC_BIG6
     sm.P(PS_N0X, p) = lx; sm.P(PS_N0Y, p) = ly; sm.P(PS_N0T, p) = lt;
     sm.P(PS_N0V, p) = lv; sm.P(PS_N0C, p) = lc; sm.P(PS_N0E, p) = le;
+    return big;
 }
 
 // ---------------------------------------------------------------- control thread state + logic
@@ -1161,18 +1171,13 @@ MPC_HD void ctrl_step_late(Ctrl &c)
         c.alpha_min = NMPC_GAMMA_ALPHA * NMPC_GAMMA_THETA;
 }
 
-// P6 of the first cycle (after adjoint_sweep): keep the least-squares multipliers unless they are huge
-// (W&B Sec. 3.6).
+// P6 of the first cycle (after adjoint_sweep, `big` = its result): keep the least-squares multipliers unless
+// they are huge (W&B Sec. 3.6).
 // Returns the FL_KEEP flag (or 0).
 template <class SM>
-MPC_HD int ctrl_lsq_finish(const Params &prm, const SM &sm, int p)
+MPC_HD int ctrl_lsq_finish(const Params &prm, const SM &sm, int p, int big)
 {
-    const int N = prm.N;
-    double lmax = 0.0;
-    for (int k = 0; k < N - 1; k++)
-        for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.at(k, W_LAM + i, p)));
-    for (int i = 0; i < 6; i++) lmax = fmax2(lmax, fabs(sm.P(PS_N0X + i, p)));
-    const int keep = (lmax <= NMPC_LAM_MAX) ? 1 : 0;   // NaN compares false -> 0
+    const int keep = big ? 0 : 1;
     for (int i = 0; i < 6; i++) sm.P(PS_L0X + i, p) = keep ? sm.P(PS_N0X + i, p) : 0.0;
     return keep ? FL_KEEP : 0;
 }

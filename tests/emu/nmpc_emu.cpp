@@ -132,9 +132,9 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
             // ---- P6
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_STEP) continue;
-                adjoint_sweep(prm, sm, p);
+                const int big = adjoint_sweep(prm, sm, p);
                 if (sm.I(PI_FLAGS, p) & FL_LSQ) {
-                    const int keep = ctrl_lsq_finish(prm, sm, p);
+                    const int keep = ctrl_lsq_finish(prm, sm, p, big);
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
                 } else {
                     ctrl_step(prm, sm, ctrl[p], p, NG);

@@ -54,6 +54,7 @@ def main():
         buf = (C.c_longlong * 1024)()
         if L.mpc_b200_debug_profile(sv._h, buf) and buf[1000] > 0:
             print("   avg global cycle: %.0f SM cycles (%d cycles total over all CTAs of all launches)" % (buf[1001] / buf[1000], buf[1000]))
+            print("   ctrl_decide parts (thread 0): reduce %.0f, line search %.0f, error+tests %.0f, mu+rest %.0f" % tuple(buf[1020 + i] / buf[1000] for i in range(4)))
             if buf[1002] > 0: print("   busy lanes per cycle: %.2f" % (buf[1002] / buf[1000]))
             names = ["-", "refill", "P3_apply_coeffs", "P4_backward", "P4_forward(+rollout,prefetch)", "P5_step", "P6", "P1_eval", "P2_rest", "P6_adjoint", "P2_ctrl_decide"]
             print("   per-cycle breakdown (control thread 0 of every CTA): " + ", ".join("%s %.0f" % (names[i], buf[1008 + i] / buf[1000]) for i in range(1, 11)))

@@ -1059,7 +1059,10 @@ int mpc_b200_debug_profile(mpc_b200_handle *h, long long *out12)
         cudaMemset(h->d_prof, 0, sizeof(long long) * 1024);
         return 1;
     }
-    if (out12) cudaMemcpy(out12, h->d_prof, sizeof(long long) * 1024, cudaMemcpyDeviceToHost);
+    if (out12) {
+        cudaMemcpy(out12, h->d_prof, sizeof(long long) * 1024, cudaMemcpyDeviceToHost);
+        cudaMemcpyFromSymbol(out12 + 1020, nmpc::nmpc_dec_acc, sizeof(long long) * 4);      // ctrl_decide sub-phases
+    }
     return 1;
 #else
     (void)h; (void)out12;

@@ -974,7 +974,7 @@ struct Ctrl {
     double dw_last;
     double theta_min, theta_max;
     double theta, phi, gd;          // at the current iterate, for the line search
-    double alpha_min, sw_log;
+    double alpha_min, sw_log, sw_alpha;
     double E0, obj;
 };
 
@@ -1011,7 +1011,7 @@ MPC_HD void ctrl_init(const Params &prm, const SM &sm, Ctrl &c, int p, const dou
 {
     c.iter = 0; c.status = 0; c.n_accept = 0; c.nfilt = 0; c.have_theta0 = 0; c.age = 0;
     c.dw_last = 0.0; c.theta_min = 0.0; c.theta_max = 0.0; c.theta = 0.0; c.phi = 0.0; c.gd = 0.0;
-    c.alpha_min = 0.0; c.sw_log = 0.0; c.E0 = 1e300; c.obj = 0.0;
+    c.alpha_min = 0.0; c.sw_log = 0.0; c.sw_alpha = 1.0; c.E0 = 1e300; c.obj = 0.0;
     sm.P(PS_MU, p) = NMPC_MU_INIT;
     sm.P(PS_MU_STEP, p) = NMPC_MU_INIT;
     sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - NMPC_MU_INIT);
@@ -1049,9 +1049,20 @@ MPC_HD void filter_add(const SM &sm, Ctrl &c, int p, double theta, double phi)
 // iterate: convergence test (W&B eq. (5), (6)) and monotone barrier update (eq. (7)).
 // Returns: 0 = evaluate again (alpha halved), 1 = iterate accepted, continue with a Newton step,
 //          2 = terminated (c.status set; the step, if any, still has to be applied before flushing).
+#if defined(NMPC_PROFILE) && defined(__CUDACC__)
+__device__ long long nmpc_dec_acc[8];
+#endif
+#if defined(NMPC_PROFILE) && defined(__CUDA_ARCH__)
+#define DEC_MARK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long *)&nmpc_dec_acc[i], (unsigned long long)(t_ - nmpc_dec_t)); nmpc_dec_t = t_; } } while (0)
+#define DEC_START() long long nmpc_dec_t = clock64()
+#else
+#define DEC_MARK(i)
+#define DEC_START()
+#endif
 template <class SM>
 MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flags, int NG)
 {
+    DEC_START();
     const int N = prm.N;
     double prinf = 0, pr1 = 0, duinf = 0, vmax = -1e300, vmin = 1e300, l1 = 0, z1 = 0, f = 0, lnsum = 0;
     int inside = 1;
@@ -1065,6 +1076,10 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
     }
     double mu = sm.P(PS_MU, p);
     const double sf = sm.P(PS_SF, p);
+    DEC_MARK(0);
+    // The function is written without early returns (ret < 0 = still undecided) so that the lanes of the warp
+    // reconverge after every block instead of running the common tail once per path.
+    int ret = -1;
     if (flags & FL_LS) {
         const double alpha = sm.P(PS_ALPHA, p);
         const double phi_t = f - mu * lnsum;
@@ -1072,7 +1087,9 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
         const int ok = inside && (pr1 == pr1) && (phi_t == phi_t);
         int acc = 0, armijo = 0;
         if (ok && filter_acceptable(sm, c, p, pr1, phi_t)) {
-            if (th <= c.theta_min && gd < 0.0 && log_pos(alpha) > c.sw_log) {
+            // switching condition (W&B eq. (19)): alpha (-gd)^s_phi > theta^s_theta, with the right-hand side
+            // brought over in ctrl_step_late (c.sw_alpha)
+            if (th <= c.theta_min && gd < 0.0 && alpha > c.sw_alpha) {
                 if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; armijo = 1; }
             } else {
                 if (pr1 <= (1.0 - NMPC_GAMMA_THETA) * th ||
@@ -1082,52 +1099,62 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
         if (!acc) {
             const double a2 = 0.5 * alpha;
             // (alpha_min can be 0 or NaN in degenerate cases: the absolute floor bounds the number of halvings)
-            if (a2 < c.alpha_min || !(a2 > 1e-40)) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; return 2; }
-            sm.P(PS_ALPHA, p) = a2;
-            return 0;
+            if (a2 < c.alpha_min || !(a2 > 1e-40)) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; ret = 2; }
+            else { sm.P(PS_ALPHA, p) = a2; ret = 0; }
+        } else {
+            if (!armijo) filter_add(sm, c, p, th, phi);
+            c.iter++;
         }
-        if (!armijo) filter_add(sm, c, p, th, phi);
-        c.iter++;
     }
+    DEC_MARK(1);
     // ---- the evaluated point is now the iterate
-    const int m = 6 * N, nb = 4 * (N - 1);
-    const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) * (1.0 / NMPC_S_MAX);
-    const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) * (1.0 / NMPC_S_MAX);
-    const double isd = fast_rcp(s_d), isc = fast_rcp(s_c), isf = fast_rcp(sf);
-    const double compl0 = fmax2(fabs(vmax), fabs(vmin));
-    const double du_s = duinf * isd;
-    const double E0 = fmax2(fmax2(du_s, prinf), compl0 * isc);
-    c.E0 = E0; c.obj = f * isf;
-    if (!(E0 == E0) || !(f == f)) { c.status = 11; return 2; }
-    if (E0 <= prm.tol && duinf * isf <= 1.0 && prinf <= 1e-4 && compl0 * isf <= 1e-4) { c.status = 1; return 2; }
-    if (E0 <= 1e-6 && prinf <= 1e-2 && compl0 * isf <= 1e-2) c.n_accept++; else c.n_accept = 0;
-    if (c.n_accept >= 15) { c.status = 4; return 2; }
-    if (c.iter >= prm.max_iter) { c.status = 2; return 2; }
-    // monotone barrier update (W&B eq. (7)); repeated while the barrier problem is already solved
-    int changed = 0;
-    const double base_err = fmax2(du_s, prinf);
-    const double floor_ = fmin2(prm.tol, 1e-4) * (1.0 / (NMPC_KAPPA_EPS + 1.0));
-    for (;;) {
-        const double cmu = fmax2(fabs(vmax - mu), fabs(vmin - mu));
-        const double Emu = fmax2(base_err, cmu * isc);
-        if (!(Emu <= NMPC_KAPPA_EPS * mu)) break;
-        const double mun = fmax2(floor_, fmin2(NMPC_KAPPA_MU * mu, mu * sqrt(mu)));   // theta_mu = 1.5
-        if (!(mun < mu)) break;
-        mu = mun; changed = 1;
+    double base_err = 0.0, isc = 0.0;
+    if (ret < 0) {
+        const int m = 6 * N, nb = 4 * (N - 1);
+        const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) * (1.0 / NMPC_S_MAX);
+        const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) * (1.0 / NMPC_S_MAX);
+        const double isd = fast_rcp(s_d), isf = fast_rcp(sf);
+        isc = fast_rcp(s_c);
+        const double compl0 = fmax2(fabs(vmax), fabs(vmin));
+        const double du_s = duinf * isd;
+        const double E0 = fmax2(fmax2(du_s, prinf), compl0 * isc);
+        base_err = fmax2(du_s, prinf);
+        c.E0 = E0; c.obj = f * isf;
+        if (E0 <= 1e-6 && prinf <= 1e-2 && compl0 * isf <= 1e-2) c.n_accept++; else c.n_accept = 0;
+        if (!(E0 == E0) || !(f == f)) { c.status = 11; ret = 2; }
+        else if (E0 <= prm.tol && duinf * isf <= 1.0 && prinf <= 1e-4 && compl0 * isf <= 1e-4) { c.status = 1; ret = 2; }
+        else if (c.n_accept >= 15) { c.status = 4; ret = 2; }
+        else if (c.iter >= prm.max_iter) { c.status = 2; ret = 2; }
     }
-    if (changed) {
-        c.nfilt = 0;
-        sm.P(PS_MU, p) = mu;
-        sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - mu);
+    DEC_MARK(2);
+    if (ret < 0) {
+        // monotone barrier update (W&B eq. (7)); repeated while the barrier problem is already solved
+        int changed = 0;
+        const double floor_ = fmin2(prm.tol, 1e-4) * (1.0 / (NMPC_KAPPA_EPS + 1.0));
+        for (;;) {
+            const double cmu = fmax2(fabs(vmax - mu), fabs(vmin - mu));
+            const double Emu = fmax2(base_err, cmu * isc);
+            if (!(Emu <= NMPC_KAPPA_EPS * mu)) break;
+            const double mun = fmax2(floor_, fmin2(NMPC_KAPPA_MU * mu, mu * sqrt(mu)));   // theta_mu = 1.5
+            if (!(mun < mu)) break;
+            mu = mun; changed = 1;
+        }
+        if (changed) {
+            c.nfilt = 0;
+            sm.P(PS_MU, p) = mu;
+            sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - mu);
+        }
+        c.theta = pr1;
+        c.phi = f - mu * lnsum;
+        if (!c.have_theta0) {
+            c.have_theta0 = 1;
+            c.theta_max = 1e4 * fmax2(1.0, pr1);
+            c.theta_min = 1e-4 * fmax2(1.0, pr1);
+        }
+        ret = 1;
     }
-    c.theta = pr1;
-    c.phi = f - mu * lnsum;
-    if (!c.have_theta0) {
-        c.have_theta0 = 1;
-        c.theta_max = 1e4 * fmax2(1.0, pr1);
-        c.theta_min = 1e-4 * fmax2(1.0, pr1);
-    }
-    return 1;
+    DEC_MARK(3);
+    return ret;
 }
 
 // Next regularisation value of the inertia-correction sequence (W&B Algorithm IC).
@@ -1161,10 +1188,11 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
 MPC_HD void ctrl_step_late(Ctrl &c)
 {
     const double gd = c.gd, th = c.theta;
-    c.sw_log = 0.0;
+    c.sw_log = 0.0; c.sw_alpha = 1.0;
     if (gd < 0.0 && th <= c.theta_min) {
         c.sw_log = NMPC_S_THETA * log(th) - NMPC_S_PHI * log(-gd);      // -inf when theta == 0
-        c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd)), exp(c.sw_log));
+        c.sw_alpha = exp(c.sw_log);                                      // 0 .. inf
+        c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd)), c.sw_alpha);
     } else if (gd < 0.0)
         c.alpha_min = NMPC_GAMMA_ALPHA * fmin2(NMPC_GAMMA_THETA, NMPC_GAMMA_PHI * th / (-gd));
     else

@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             }
             PROF_MARK(8);
             TRACE_C(10);
+            __syncthreads();  // B1b: the stage threads apply / flush while the lanes are refilled
         }
         PROF_FLUSH();
 #ifdef NMPC_PROFILE
@@ -277,47 +278,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             TRACE_S(0);
             if (!__syncthreads_or(0)) break;   // B2 (vote)
             TRACE_S(1);
-            // ---- P3a: apply the accepted step, flush a finished problem, start the next one
+            // ---- P3a: start the lane's next problem (the accepted step was applied and a finished problem flushed
+            //      before the vote, while the control thread fetched the next problems)
             if (mine) {
                 const int fl = sm.I(PI_FLAGS, p);
-                if (fl & FL_APPLY) {
-#pragma unroll
-                    for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_apply<RATE>(prm, sm, r[j], k0 + j, p);
-                }
-                if (fl & FL_FLUSH) {
-                    // the last iterate whatever the status (mpc_planner.cpp:378-401)
-                    const size_t i = (size_t)sm.I(PI_PROB, p);
-#pragma unroll
-                    for (int j = 0; j < SPT; j++) {
-                        const int k = k0 + j;
-                        if (k >= N) continue;
-                        a.pred[((size_t)0 * N + k) * batch + i] = sm.at(k, S_X, p);
-                        a.pred[((size_t)1 * N + k) * batch + i] = sm.at(k, S_Y, p);
-                        a.pred[((size_t)2 * N + k) * batch + i] = sm.at(k, S_T, p);
-                        if (k == 0) { a.u0[i] = r[j].uw; a.u0[(size_t)batch + i] = r[j].ua; }
-                        if (a.warm_out) {
-                            // primal in the reference's variable layout (mpc_planner.cpp:232-239), then equality
-                            // multipliers (row layout of :153-158, unscaled), then zL, zU of w and a.
-                            double *wo = a.warm_out;
-                            const double isf = 1.0 / sm.P(PS_AP_SF, p);
-                            for (int cc = 0; cc < 6; cc++) wo[((size_t)cc * N + k) * batch + i] = sm.at(k, S_X + cc, p);
-                            const size_t offl = (size_t)(8 * N - 2);
-                            if (k < N - 1) {
-                                wo[((size_t)6 * N + k) * batch + i] = r[j].uw;
-                                wo[((size_t)7 * N - 1 + k) * batch + i] = r[j].ua;
-                                for (int cc = 0; cc < 6; cc++)
-                                    wo[(offl + (size_t)cc * N + k + 1) * batch + i] = sm.at(k, L_X + cc, p) * isf;
-                                const size_t offz = offl + (size_t)6 * N;
-                                const int nu = N - 1;
-                                wo[(offz + k) * batch + i] = r[j].zlw * isf;
-                                wo[(offz + nu + k) * batch + i] = r[j].zla * isf;
-                                wo[(offz + 2 * nu + k) * batch + i] = r[j].zuw * isf;
-                                wo[(offz + 3 * nu + k) * batch + i] = r[j].zua * isf;
-                            }
-                        }
-                    }
-                }
                 const int idx = sm.I(PI_NEXT, p);
                 if (idx >= 0) {
                     double s6[6], c4[4];
@@ -397,6 +361,50 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             __syncthreads();  // B1
             TRACE_S(9);
             // ---- P2: control
+            __syncthreads();  // B1b
+            // ---- P3a0: apply the accepted step, flush a finished problem -- while the control thread refills the
+            //      lanes (neither touches what the other reads: the step to apply was copied to PS_AP_* in P2)
+            if (mine) {
+                const int fl = sm.I(PI_FLAGS, p);
+                if (fl & FL_APPLY) {
+#pragma unroll
+                    for (int j = 0; j < SPT; j++)
+                        if (k0 + j < N) stage_apply<RATE>(prm, sm, r[j], k0 + j, p);
+                }
+                if (fl & FL_FLUSH) {
+                    // the last iterate whatever the status (mpc_planner.cpp:378-401)
+                    const size_t i = (size_t)sm.I(PI_PROB, p);
+#pragma unroll
+                    for (int j = 0; j < SPT; j++) {
+                        const int k = k0 + j;
+                        if (k >= N) continue;
+                        a.pred[((size_t)0 * N + k) * batch + i] = sm.at(k, S_X, p);
+                        a.pred[((size_t)1 * N + k) * batch + i] = sm.at(k, S_Y, p);
+                        a.pred[((size_t)2 * N + k) * batch + i] = sm.at(k, S_T, p);
+                        if (k == 0) { a.u0[i] = r[j].uw; a.u0[(size_t)batch + i] = r[j].ua; }
+                        if (a.warm_out) {
+                            // primal in the reference's variable layout (mpc_planner.cpp:232-239), then equality
+                            // multipliers (row layout of :153-158, unscaled), then zL, zU of w and a.
+                            double *wo = a.warm_out;
+                            const double isf = 1.0 / sm.P(PS_AP_SF, p);
+                            for (int cc = 0; cc < 6; cc++) wo[((size_t)cc * N + k) * batch + i] = sm.at(k, S_X + cc, p);
+                            const size_t offl = (size_t)(8 * N - 2);
+                            if (k < N - 1) {
+                                wo[((size_t)6 * N + k) * batch + i] = r[j].uw;
+                                wo[((size_t)7 * N - 1 + k) * batch + i] = r[j].ua;
+                                for (int cc = 0; cc < 6; cc++)
+                                    wo[(offl + (size_t)cc * N + k + 1) * batch + i] = sm.at(k, L_X + cc, p) * isf;
+                                const size_t offz = offl + (size_t)6 * N;
+                                const int nu = N - 1;
+                                wo[(offz + k) * batch + i] = r[j].zlw * isf;
+                                wo[(offz + nu + k) * batch + i] = r[j].zla * isf;
+                                wo[(offz + 2 * nu + k) * batch + i] = r[j].zuw * isf;
+                                wo[(offz + 3 * nu + k) * batch + i] = r[j].zua * isf;
+                            }
+                        }
+                    }
+                }
+            }
         }
     }
 }

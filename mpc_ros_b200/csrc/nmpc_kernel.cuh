@@ -10,13 +10,15 @@
 // 168 registers (the register file); SPT = 3 would be 8 warps at 255.
 //
 // One global cycle = the fixed phase sequence
-//   P3a apply / flush / init | P3b coefficients | P4 sweeps | P5 step work | P6 multipliers, step sizes |
-//   P1 evaluate | P2 decide
+//   P3a init | P3b coefficients | P4 sweeps | P5 step work | P6 step sizes + adjoint sweep | P1 evaluate |
+//   P2 decide | P3a0 apply / flush + refill
 // separated by CTA barriers; each lane is a state machine (nmpc::Mode) and takes part in the phases its
 // state asks for.  A lane that needs another factorisation (inertia correction) or a shorter trial step
 // simply repeats on the next cycle; it never stalls the other lanes.  When a lane's problem terminates,
 // its results are written out and the lane pops the next problem from the queue, so lanes never wait
 // for the slowest problem of a batch (iteration counts range from 5 to the cap).
+// The control warp's serial chain bounds the cycle, so what need not be on it runs beside it: the adjoint
+// sweep on the lane's stage thread of group 0 (P6), apply / flush on the stage threads during the refill.
 //
 // Replaces, per problem: CppAD::ipopt::solve + Ipopt (mpc_ros/src/mpc_planner.cpp:373-375).
 #pragma once

@@ -97,10 +97,11 @@ Reading: registers (352 threads x 168) and 219 KB dynamic shared memory give one
 per-problem working set lives in shared memory: 37 fp64 slots x 20 stages x 32 lanes).  A lone launch of one
 batch leaves most SMs idle most of the time (the tail of a batch is a handful of problems that need 10-20x
 the median iteration count), which is why throughput is measured with many batches in flight.  Within active
-cycles the FP64 pipe is busy a fifth of the time: the serial Riccati sweep runs on ONE warp per SM (32 problems
-per instruction) and is bound by FP64 issue latency, not by throughput.  DRAM traffic per launch is the
-algorithmic input + output; nothing is re-read.  Register spilling: 80 B/thread in the stage threads
-(`ptxas -v`), %s of %s executed warp instructions (%.2f %%).  compute-sanitizer is closed on this pool
+cycles the FP64 pipe is busy about a fifth of the time: the serial Riccati sweeps run on ONE warp per SM (32
+problems per instruction; the backward sweep is bound by the FP64 issue rate of that warp's sub-partition, 2.13
+cycles per instruction, the other phases by dependent-issue latency).  DRAM traffic per launch is the
+algorithmic input + output; nothing is re-read.  Register spilling: 24 B/thread (`ptxas -v`,
+`mpc_ros_b200/lib/ptxas_info.txt`), %s of %s executed warp instructions (%.2f %%).  compute-sanitizer is closed on this pool
 (`gpurun` refuses it), so race freedom is argued from the barrier structure and checked by the bit-reproducibility
 and lane-permutation tests.
 """ % (tag, tag, tag, d["value"] / 1e6, d["ms_per_step"], d["config"]["streams"], d["config"]["max_ctas"],

@@ -114,6 +114,12 @@ and lane-permutation tests.
        tag, c5["mean_iters"], c5["oracle_subset"]["mean_iters_oracle"], c5["converged_fraction"], c5["solves_per_s"],
        ("; device-resident loop (`%s_config5_device.json`) %.0f robot-ticks/s" % (tag, c5d["robot_ticks_per_s"])) if c5d else "",
        tag, "\n".join(lines), tag, "\n".join(met), spill, inst, 100.0 * float(spill) / float(inst))
+n8 = os.path.join(P, "%s_bench_n8.json" % tag)
+if os.path.exists(n8):
+    d8 = json.load(open(n8))
+    md += "\n## Eight GPUs (`%s_bench_n8.json`, `torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 3000 --warmup 128 --e2e-steps 4096`)\n\n" % tag
+    md += "* value **%.1f M converged solves/s** over 8 B200 (weak scaling, 4,096 problems per GPU per step, max over ranks; %.1f %% of 8 x the one-GPU value), e2e %.1f M solves/s.\n" % (
+        d8["value"] / 1e6, 100 * d8["value"] / (8 * d["value"]), d8["e2e"]["value"] / 1e6)
 ps = os.path.join(P, "%s_parity_sweep.json" % tag)
 if os.path.exists(ps):
     md += "\n## Parity sweep (`%s_parity_sweep.json`, `tests/parity_sweep.py`: GPU through the C ABI vs the oracle)\n\n" % tag

@@ -124,3 +124,25 @@ def test_emu_ref_vel_override(oracle):
     for i in range(4):
         o = oracle.solve(dict(YAML_DEFAULT, REF_V=rv[i]), state[:, i], coeffs[:, i])
         assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5
+
+
+def test_emu_small_weights_keep_lsq_multipliers(oracle):
+    """With small weights the least-squares multiplier start stays below 1e3 and is KEPT (W&B Sec. 3.6); with
+    the YAML weights it is discarded (test_emu_matches_oracle_mild).  The size test is folded into the adjoint
+    sweep: both outcomes must reproduce the oracle's iterates."""
+    pm = dict(YAML_DEFAULT, W_CTE=2.0, W_V=5.0, W_ANGVEL=1.0, W_A=1.0, BOUND=1e19)
+    state, coeffs = mild(23, 16)
+    r = emu_solve(pm, state, coeffs, PB=7)
+    big = dict(YAML_DEFAULT, BOUND=1e19)
+    rb = emu_solve(big, state, coeffs, PB=7)
+    kept = 0
+    for i in range(16):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert r["status"][i] == 1 and o["status"] == 1
+        assert r["iters"][i] == o["iters"]
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-9
+        assert np.abs(r["lam"][:, i] - o["lam"]).max() <= 1e-8 * max(1.0, np.abs(o["lam"]).max())
+        ob = oracle.solve(big, state[:, i], coeffs[:, i])
+        assert rb["iters"][i] == ob["iters"]
+        kept += int(np.abs(o["lam"]).max() < 1e3)
+    assert kept == 16      # (the converged multipliers are small too: the start was not the discarded kind)

@@ -467,3 +467,18 @@ def test_decel_and_plant_kernels(oracle):
     th = np.remainder(pose[2] + cmd[1] * prm.dt + np.pi, 2 * np.pi) - np.pi
     np.testing.assert_allclose(p2[2], th, rtol=0, atol=1e-14)
     np.testing.assert_array_equal(v2[0], cmd[0]); np.testing.assert_array_equal(v2[1:], vel[1:])
+
+
+def test_small_weights_keep_lsq_multipliers(oracle):
+    """Both outcomes of the least-squares multiplier size test (folded into the adjoint sweep, which runs on a
+    stage thread) reproduce the oracle's iterates: small weights -> multipliers kept, YAML weights -> discarded."""
+    state, coeffs = mild(23, 96)
+    for pm in (dict(YAML_DEFAULT, W_CTE=2.0, W_V=5.0, W_ANGVEL=1.0, W_A=1.0, BOUND=1e19), dict(YAML_DEFAULT, BOUND=1e19)):
+        sv = _solver(pm, 96)
+        out = sv.solve(state, coeffs)
+        sv.close()
+        for i in range(0, 96, 3):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert out["status"][i] == 1 and o["status"] == 1
+            assert out["iters"][i] == o["iters"]
+            assert np.abs(out["u0"][:, i] - o["u0"]).max() <= 1e-9

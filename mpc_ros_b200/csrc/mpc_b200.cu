@@ -609,7 +609,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
 
     const int NG = (N + SPT - 1) / SPT;
     const int stage_threads = ((NG * a.PB + 31) / 32) * 32;
-    const int threads = 32 + stage_threads;
+    const int threads = NMPC_CTRL_THREADS + stage_threads;
     // persistent grid: at most one CTA per SM (or the max_ctas option); lanes refill from the queue
     int grid = (batch + a.PB - 1) / a.PB;
     const int cap = h->max_ctas > 0 ? h->max_ctas : h->num_sms;

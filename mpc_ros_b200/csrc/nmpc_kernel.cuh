@@ -52,7 +52,7 @@ struct SolveArgs {
 #define PROF_FLUSH() do { if (a.prof && tid == 0) for (int q_ = 0; q_ < 12; q_++) { if (blockIdx.x == 0) a.prof[q_] = prof_acc[q_]; atomicAdd((unsigned long long *)&a.prof[1008 + q_], (unsigned long long)prof_acc[q_]); } } while (0)
 // raw timestamp trace of the first cycles: control thread 0 -> prof[16 + 16*cyc + i], stage thread 32 -> prof[512 + 16*cyc + i]
 #define TRACE_C(i) do { if (a.prof && blockIdx.x == 0 && tid == 0 && trace_cyc < 24) a.prof[16 + 16 * trace_cyc + (i)] = clock64(); } while (0)
-#define TRACE_S(i) do { if (a.prof && blockIdx.x == 0 && tid == 32 && trace_cyc < 24) a.prof[512 + 16 * trace_cyc + (i)] = clock64(); } while (0)
+#define TRACE_S(i) do { if (a.prof && blockIdx.x == 0 && tid == NMPC_CTRL_THREADS && trace_cyc < 24) a.prof[512 + 16 * trace_cyc + (i)] = clock64(); } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(i)
@@ -61,8 +61,14 @@ struct SolveArgs {
 #define TRACE_S(i)
 #endif
 
+// Two control warps of 16 lanes each (on different SM sub-partitions): a warp instruction costs the FP64 pipe the
+// same whether 16 or 32 lanes are active, but a 64-bit shared-memory access of 16 lanes is one wavefront instead of
+// two, and each warp's divergent P2 logic covers half as many different problems.
+#define NMPC_CTRL_WARPS 2
+#define NMPC_CTRL_LANES 16
+#define NMPC_CTRL_THREADS (32 * NMPC_CTRL_WARPS)
 template <int SPT, int CPB, bool WARM, bool RATE>
-__global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(const SolveArgs a)
+__global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;
@@ -74,10 +80,11 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
 
     const int tid = threadIdx.x;
 
-    if (tid < 32) {
-        // ------------------------------------------------------------ control warp
-        const int p = tid;
-        const bool lane = p < PB;
+    if (tid < NMPC_CTRL_THREADS) {
+        // ------------------------------------------------------------ control warps
+        const int p = (tid & 31) % NMPC_CTRL_LANES + NMPC_CTRL_LANES * (tid >> 5);
+        const int wl = tid & 31;      // lane within the warp (ballots, shuffles)
+        const bool lane = wl < NMPC_CTRL_LANES && p < PB;
         Ctrl c;
         c.status = 0; c.iter = 0; c.E0 = 0.0; c.obj = 0.0;
         if (lane) { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_FLAGS, p) = 0; sm.I(PI_PROB, p) = -1; sm.I(PI_NEXT, p) = -1; }
@@ -96,10 +103,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
             {
                 const unsigned m = __ballot_sync(0xffffffffu, fin);
                 int nb = 0;
-                if (p == 0 && m) nb = atomicAdd(a.queue, __popc(m));
+                if (wl == 0 && m) nb = atomicAdd(a.queue, __popc(m));
                 nb = __shfl_sync(0xffffffffu, nb, 0);
                 if (fin) {
-                    int nidx = nb + __popc(m & ((1u << p) - 1u));
+                    int nidx = nb + __popc(m & ((1u << wl) - 1u));
                     if (nidx >= batch) nidx = -1;
                     else {
                         if (a.order) nidx = a.order[nidx];
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
 #ifdef NMPC_PROFILE
             {   // busy lanes of this cycle
                 const unsigned bz = __ballot_sync(0xffffffffu, lane && sm.I(PI_MODE, p) != MODE_IDLE);
-                if (a.prof && p == 0) atomicAdd((unsigned long long *)&a.prof[1002], (unsigned long long)__popc(bz));
+                if (a.prof && wl == 0) atomicAdd((unsigned long long *)&a.prof[1002], (unsigned long long)__popc(bz));
             }
 #endif
             if (!__syncthreads_or(active)) break;   // B2 (vote)
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 352, 1) nmpc_solve_kernel(con
 #endif
     } else {
         // ------------------------------------------------------------ stage threads
-        const int t = tid - 32;
+        const int t = tid - NMPC_CTRL_THREADS;
         const int p = t % PB;
         const int g = t / PB;
         const int k0 = g * SPT;

@@ -570,6 +570,21 @@ MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, in
     r.sn = r.tsn; r.cs = r.tcs; r.se = r.tse; r.ce = r.tce;
 }
 
+// Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}, u.
+struct HessDiag { double dx, dy, dt_, dv, dc, de, du; double rw, ra; /* 2 sf w_angvel_d, 2 sf w_accel_d */ };
+MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
+{
+    HessDiag h;
+    h.rw = 0.0; h.ra = 0.0;
+    if (lsq) { h.dx = h.dy = h.dt_ = h.dv = h.dc = h.de = 1.0; h.du = 0.0; return h; }
+    h.rw = 2.0 * sf * prm.w_angvel_d; h.ra = 2.0 * sf * prm.w_accel_d;
+    h.dx = dw; h.dy = dw; h.dt_ = dw; h.du = dw;
+    h.dv = 2.0 * sf * prm.w_vel + dw;
+    h.dc = 2.0 * sf * prm.w_cte + dw;
+    h.de = 2.0 * sf * prm.w_etheta + dw;
+    return h;
+}
+
 template <bool RATE = false, class SM>
 MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq, const double *cf)
 {
@@ -602,10 +617,12 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             rdw = 2.0 * sf * prm.w_angvel_d * cnt; rda = 2.0 * sf * prm.w_accel_d * cnt;
         }
         double hxx = 0.0, htt = 0.0, htv = 0.0, hee = 0.0, hev = 0.0;
+        // the constant diagonal of the stage Hessian (hess_diag) is added here, not in the backward sweep
+        const HessDiag hd = hess_diag(prm, sf, sm.P(PS_DW, p), lsq);
         if (lsq) {
             sm.at(k, W_3, p) = gw - r.zlw + r.zuw;
             sm.at(k, W_4, p) = ga - r.zla + r.zua;
-            sm.at(k, W_10, p) = 1.0; sm.at(k, W_11, p) = 1.0;
+            sm.at(k, W_10, p) = 1.0 + hd.du; sm.at(k, W_11, p) = 1.0 + hd.du;
             for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
         } else {
             // d_k = -(s_{k+1} - phi(s_k, u_k))  (mpc_planner.cpp:208-215)
@@ -625,18 +642,16 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             hev = -mc * r.ce * dt;
             sm.at(k, W_3, p) = gw - mu * ilw + mu * iuw;     // gradient of the barrier objective
             sm.at(k, W_4, p) = ga - mu * ila + mu * iua;
-            sm.at(k, W_10, p) = 2.0 * sf * prm.w_angvel + rdw + r.zlw * ilw + r.zuw * iuw;   // R + Sigma
-            sm.at(k, W_11, p) = 2.0 * sf * prm.w_accel + rda + r.zla * ila + r.zua * iua;
+            sm.at(k, W_10, p) = (2.0 * sf * prm.w_angvel + rdw + r.zlw * ilw + r.zuw * iuw) + hd.du;   // R + Sigma + delta
+            sm.at(k, W_11, p) = (2.0 * sf * prm.w_accel + rda + r.zla * ila + r.zua * iua) + hd.du;
         }
-        sm.at(k, W_5, p) = hxx; sm.at(k, W_6, p) = htt; sm.at(k, W_7, p) = htv;
-        sm.at(k, W_8, p) = hee; sm.at(k, W_9, p) = hev;
+        sm.at(k, W_5, p) = hxx + hd.dx; sm.at(k, W_6, p) = htt + hd.dt_; sm.at(k, W_7, p) = htv;
+        sm.at(k, W_8, p) = hee + hd.de; sm.at(k, W_9, p) = hev;
     }
     sm.at(k, W_0, p) = qv; sm.at(k, W_1, p) = qc; sm.at(k, W_2, p) = qe;
 }
 
 // ---------------------------------------------------------------- Riccati sweeps (control thread)
-// Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}, u.
-struct HessDiag { double dx, dy, dt_, dv, dc, de, du; double rw, ra; /* 2 sf w_angvel_d, 2 sf w_accel_d */ };
 
 // Coefficients of one stage as the backward sweep consumes them.
 struct StageCoef {
@@ -693,9 +708,9 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
 
         // ---- R~ = R + B^T P B  (B = dt [e_theta + e_etheta | e_v]) and its inverse: the head of the
         //      critical chain, needs only P_{k+1}
-        double Rww = c.rw + hd.du + dt2 * ((Ptt + Pee) + 2.0 * Pte);
+        double Rww = c.rw + dt2 * ((Ptt + Pee) + 2.0 * Pte);      // (c.rw, c.ra, c.hxx, c.htt, c.hee include hess_diag)
         double Rwa = dt2 * (Ptv + Pve);
-        double Raa = c.ra + hd.du + dt2 * Pvv;
+        double Raa = c.ra + dt2 * Pvv;
         if (RATE) {
             Rww += 2.0 * dt * (Mtw + Mew) + Nww;
             Rwa += dt * ((Mta + Mea) + Mvw) + Nwa;
@@ -733,27 +748,28 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
         }
 
         // ---- vector part (uses P_{k+1}):  p~ = P d + p,  pi_c = gam d_c + q_c,k+1
-        const double tx = (Pxx * c.dx + Pxy * c.dy) + (Pxt * c.dth + Pxv * c.dv) + (Pxe * c.de + px);
-        const double ty = (Pxy * c.dx + Pyy * c.dy) + (Pyt * c.dth + Pyv * c.dv) + (Pye * c.de + py);
-        const double tt = (Pxt * c.dx + Pyt * c.dy) + (Ptt * c.dth + Ptv * c.dv) + (Pte * c.de + pt);
-        const double tv = (Pxv * c.dx + Pyv * c.dy) + (Ptv * c.dth + Pvv * c.dv) + (Pve * c.de + pv);
-        const double te = (Pxe * c.dx + Pye * c.dy) + (Pte * c.dth + Pve * c.dv) + (Pee * c.de + pe);
+        // (five independent FMA chains: the sweep is bound by FP64 issue, not by the depth of these sums)
+        const double tx = fma(Pxx, c.dx, fma(Pxy, c.dy, fma(Pxt, c.dth, fma(Pxv, c.dv, fma(Pxe, c.de, px)))));
+        const double ty = fma(Pxy, c.dx, fma(Pyy, c.dy, fma(Pyt, c.dth, fma(Pyv, c.dv, fma(Pye, c.de, py)))));
+        const double tt = fma(Pxt, c.dx, fma(Pyt, c.dy, fma(Ptt, c.dth, fma(Ptv, c.dv, fma(Pte, c.de, pt)))));
+        const double tv = fma(Pxv, c.dx, fma(Pyv, c.dy, fma(Ptv, c.dth, fma(Pvv, c.dv, fma(Pve, c.de, pv)))));
+        const double te = fma(Pxe, c.dx, fma(Pye, c.dy, fma(Pte, c.dth, fma(Pve, c.dv, fma(Pee, c.de, pe)))));
         const double pic = gam * c.dc + qc_next;
 
         // ---- Q~ = Q + M + gam a_c a_c^T   (a_c = [a51, -1, 0, a54, a56] over x,y,theta,v,etheta)
         const double g1 = gam * c.a51, g4 = gam * c.a54, g6 = gam * c.a56;
-        const double Qxx = Pxx + (g1 * c.a51 + (c.hxx + hd.dx));
+        const double Qxx = Pxx + (g1 * c.a51 + c.hxx);
         const double Qxy = Pxy - g1;
         const double Qxv = Mxv + g1 * c.a54;
         const double Qxe = Pxe + g1 * c.a56;
         const double Qyy = Pyy + (gam + hd.dy);
         const double Qyv = Myv - g4;
         const double Qye = Pye - g6;
-        const double Qtt = Mtt + (c.htt + hd.dt_);
+        const double Qtt = Mtt + c.htt;
         const double Qtv = Mtv + c.htv;
         const double Qvv = Mvv + (g4 * c.a54 + hd.dv);
         const double Qve = Mev + (g4 * c.a56 + c.hev);
-        const double Qee = Pee + (g6 * c.a56 + (c.hee + hd.de));
+        const double Qee = Pee + (g6 * c.a56 + c.hee);
 
         // ---- gains  K = -R~^{-1} S~
         const double Kwx = -(i11 * Swx + i12 * Sax), Kax = -(i12 * Swx + i22 * Sax);
@@ -978,18 +994,6 @@ struct Ctrl {
     double E0, obj;
 };
 
-MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
-{
-    HessDiag h;
-    h.rw = 0.0; h.ra = 0.0;
-    if (lsq) { h.dx = h.dy = h.dt_ = h.dv = h.dc = h.de = 1.0; h.du = 0.0; return h; }
-    h.rw = 2.0 * sf * prm.w_angvel_d; h.ra = 2.0 * sf * prm.w_accel_d;
-    h.dx = dw; h.dy = dw; h.dt_ = dw; h.du = dw;
-    h.dv = 2.0 * sf * prm.w_vel + dw;
-    h.dc = 2.0 * sf * prm.w_cte + dw;
-    h.de = 2.0 * sf * prm.w_etheta + dw;
-    return h;
-}
 
 // Gradient-based objective scaling at the start point (Ipopt nlp_scaling_max_gradient = 100).
 MPC_HD double objective_scaling(const Params &prm, const double *state6, double refv)

@@ -1059,6 +1059,9 @@ __device__ long long nmpc_dec_acc[8];
 #if defined(NMPC_PROFILE) && defined(__CUDA_ARCH__)
 #define DEC_MARK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long *)&nmpc_dec_acc[i], (unsigned long long)(t_ - nmpc_dec_t)); nmpc_dec_t = t_; } } while (0)
 #define DEC_START() long long nmpc_dec_t = clock64()
+#elif defined(__CUDA_ARCH__)
+#define DEC_MARK(i) asm volatile("" ::: "memory")     /* compiler-level fence between the blocks (see PROF_MARK) */
+#define DEC_START()
 #else
 #define DEC_MARK(i)
 #define DEC_START()

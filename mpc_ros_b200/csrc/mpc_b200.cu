@@ -597,6 +597,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
     a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 100;
     a.prm.grp = SPT;
+    a.prm.idt = 1.0 / P.dt;
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
     a.batch = batch;
     const bool rate = P.w_angvel_d != 0.0 || P.w_accel_d != 0.0;

@@ -100,6 +100,7 @@ struct Params {
     int grp;      // stages per stage thread: partial sums are pre-reduced over groups of grp stages
     double warm_mu;   // initial barrier parameter of a warm-started problem
     double w_angvel_d, w_accel_d;   // rate penalties (mpc_planner.cpp:144-147); both 0 in the plain variant
+    double idt;       // 1 / dt
 };
 
 #define NMPC_MAX_FILTER 8
@@ -619,10 +620,12 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
         double hxx = 0.0, htt = 0.0, htv = 0.0, hee = 0.0, hev = 0.0;
         // the constant diagonal of the stage Hessian (hess_diag) is added here, not in the backward sweep
         const HessDiag hd = hess_diag(prm, sf, sm.P(PS_DW, p), lsq);
+        // plain variant: the sweeps work with the control step scaled by dt (riccati_backward): q_u / dt, R / dt^2
+        const double su = RATE ? 1.0 : prm.idt, su2 = su * su;
         if (lsq) {
-            sm.at(k, W_3, p) = gw - r.zlw + r.zuw;
-            sm.at(k, W_4, p) = ga - r.zla + r.zua;
-            sm.at(k, W_10, p) = 1.0 + hd.du; sm.at(k, W_11, p) = 1.0 + hd.du;
+            sm.at(k, W_3, p) = (gw - r.zlw + r.zuw) * su;
+            sm.at(k, W_4, p) = (ga - r.zla + r.zua) * su;
+            sm.at(k, W_10, p) = (1.0 + hd.du) * su2; sm.at(k, W_11, p) = (1.0 + hd.du) * su2;
             for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
         } else {
             // d_k = -(s_{k+1} - phi(s_k, u_k))  (mpc_planner.cpp:208-215)
@@ -640,10 +643,10 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             htv = (mx * r.sn - my * r.cs) * dt;
             hee = mc * v * r.se * dt;
             hev = -mc * r.ce * dt;
-            sm.at(k, W_3, p) = gw - mu * ilw + mu * iuw;     // gradient of the barrier objective
-            sm.at(k, W_4, p) = ga - mu * ila + mu * iua;
-            sm.at(k, W_10, p) = (2.0 * sf * prm.w_angvel + rdw + r.zlw * ilw + r.zuw * iuw) + hd.du;   // R + Sigma + delta
-            sm.at(k, W_11, p) = (2.0 * sf * prm.w_accel + rda + r.zla * ila + r.zua * iua) + hd.du;
+            sm.at(k, W_3, p) = (gw - mu * ilw + mu * iuw) * su;     // gradient of the barrier objective
+            sm.at(k, W_4, p) = (ga - mu * ila + mu * iua) * su;
+            sm.at(k, W_10, p) = ((2.0 * sf * prm.w_angvel + rdw + r.zlw * ilw + r.zuw * iuw) + hd.du) * su2;   // R + Sigma + delta
+            sm.at(k, W_11, p) = ((2.0 * sf * prm.w_accel + rda + r.zla * ila + r.zua * iua) + hd.du) * su2;
         }
         sm.at(k, W_5, p) = hxx + hd.dx; sm.at(k, W_6, p) = htt + hd.dt_; sm.at(k, W_7, p) = htv;
         sm.at(k, W_8, p) = hee + hd.de; sm.at(k, W_9, p) = hev;
@@ -708,9 +711,12 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
 
         // ---- R~ = R + B^T P B  (B = dt [e_theta + e_etheta | e_v]) and its inverse: the head of the
         //      critical chain, needs only P_{k+1}
-        double Rww = c.rw + dt2 * ((Ptt + Pee) + 2.0 * Pte);      // (c.rw, c.ra, c.hxx, c.htt, c.hee include hess_diag)
-        double Rwa = dt2 * (Ptv + Pve);
-        double Raa = c.ra + dt2 * Pvv;
+        // (c.rw, c.ra, c.hxx, c.htt, c.hee include hess_diag.  Plain variant: the sweeps work with the control step
+        //  scaled by dt, du~ = dt du, so that B has unit entries and R~, S~, r~_u need no multiplications by dt:
+        //  c.rw, c.ra are R / dt^2 and c.qw, c.qa are q_u / dt; the gains are those of du~.)
+        double Rww = RATE ? c.rw + dt2 * ((Ptt + Pee) + 2.0 * Pte) : c.rw + ((Ptt + Pee) + 2.0 * Pte);
+        double Rwa = RATE ? dt2 * (Ptv + Pve) : Ptv + Pve;
+        double Raa = RATE ? c.ra + dt2 * Pvv : c.ra + Pvv;
         if (RATE) {
             Rww += 2.0 * dt * (Mtw + Mew) + Nww;
             Rwa += dt * ((Mta + Mea) + Mvw) + Nwa;
@@ -737,9 +743,10 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
         const double Mvv = Wvv + c.a14 * Mxv + c.a24 * Myv;
 
         // ---- S~ = B^T W
-        double Swx = dt * (Pxt + Pxe), Swy = dt * (Pyt + Pye), Swt = dt * (Wtt + Met),
-               Swv = dt * (Wtv + Mev), Swe = dt * (Pte + Pee);
-        double Sax = dt * Pxv, Say = dt * Pyv, Sat = dt * Wvt, Sav = dt * Wvv, Sae = dt * Pve;
+        const double sB = RATE ? dt : 1.0;      // (compile-time 1 in the plain variant: the products vanish)
+        double Swx = sB * (Pxt + Pxe), Swy = sB * (Pyt + Pye), Swt = sB * (Wtt + Met),
+               Swv = sB * (Wtv + Mev), Swe = sB * (Pte + Pee);
+        double Sax = sB * Pxv, Say = sB * Pyv, Sat = sB * Wvt, Sav = sB * Wvv, Sae = sB * Pve;
         if (RATE) {   // S~ += M^T A5
             Swx += Mxw; Swy += Myw; Swe += Mew;
             Swt += Mtw + c.a13 * Mxw + c.a23 * Myw; Swv += Mvw + c.a14 * Mxw + c.a24 * Myw;
@@ -778,7 +785,7 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
         const double Kwv = -(i11 * Swv + i12 * Sav), Kav = -(i12 * Swv + i22 * Sav);
         const double Kwe = -(i11 * Swe + i12 * Sae), Kae = -(i12 * Swe + i22 * Sae);
         // ---- feed-forward
-        double ruw = c.qw + dt * (tt + te), rua = c.qa + dt * tv;
+        double ruw = c.qw + sB * (tt + te), rua = c.qa + sB * tv;
         if (RATE) {   // r~_u += M^T d + n
             ruw += (Mxw * c.dx + Myw * c.dy) + (Mtw * c.dth + Mvw * c.dv) + (Mew * c.de + nw);
             rua += (Mxa * c.dx + Mya * c.dy) + (Mta * c.dth + Mva * c.dv) + (Mea * c.de + na);
@@ -830,7 +837,8 @@ template <bool RATE = false, class SM>
 MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
     const int N = prm.N;
-    const double dt = prm.dt;
+    const double dt = prm.dt, idt = prm.idt;
+    (void)idt;
     double sx = 0, sy = 0, st = 0, sv = 0, sc = 0, se = 0;
     double pw = 0, pa = 0;      // RATE: previous control step
     (void)sc; (void)pw; (void)pa;
@@ -852,11 +860,13 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDi
                      a56 = sm.at(k, A_56, p);
         const double nx = sx + a13 * st + a14 * sv + sm.at(k, D_X, p);
         const double ny = sy + a23 * st + a24 * sv + sm.at(k, D_Y, p);
-        const double nt = st + dt * duw + sm.at(k, D_T, p);
-        const double nv = sv + dt * dua + sm.at(k, D_V, p);
+        // (plain variant: duw, dua are the scaled steps dt du; the true step is stored for the stage threads)
+        const double bw = RATE ? dt * duw : duw, ba = RATE ? dt * dua : dua;
+        const double nt = st + bw + sm.at(k, D_T, p);
+        const double nv = sv + ba + sm.at(k, D_V, p);
         const double nc = a51 * sx - sy + a54 * sv + a56 * se + sm.at(k, D_C, p);
-        const double ne = se + dt * duw + sm.at(k, D_E, p);
-        sm.at(k, W_10, p) = duw; sm.at(k, W_11, p) = dua;
+        const double ne = se + bw + sm.at(k, D_E, p);
+        sm.at(k, W_10, p) = RATE ? duw : duw * idt; sm.at(k, W_11, p) = RATE ? dua : dua * idt;
         sm.at(k, D_X, p) = nx; sm.at(k, D_Y, p) = ny; sm.at(k, D_T, p) = nt;
         sm.at(k, D_V, p) = nv; sm.at(k, D_C, p) = nc; sm.at(k, D_E, p) = ne;
         sx = nx; sy = ny; st = nt; sv = nv; sc = nc; se = ne;

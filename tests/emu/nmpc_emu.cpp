@@ -32,6 +32,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     prm.w_angvel_d = prm14[11]; prm.w_accel_d = prm14[12];
     const int SPT = 2;   // same grouping of partial sums as the kernel's stage threads
     prm.grp = SPT;
+    prm.idt = 1.0 / prm.dt;
     const int NG = (N + SPT - 1) / SPT;
 
     const int NS = RATE ? NSLOTS_RATE : NSLOTS;

@@ -1,13 +1,13 @@
 // nmpc_kernel.cuh -- the batched NMPC solve kernel for sm_100a.
 //
-// Persistent CTAs over a global work queue.  A CTA has PB <= 32 problem lanes.  Warp 0 is the control
-// warp: lane p runs the interior-point logic and the serial Riccati sweeps of the problem currently in
-// lane p -- one thread per problem, 32 different problems per warp instruction (no idle lanes, no
+// Persistent CTAs over a global work queue.  A CTA has PB <= 32 problem lanes.  Warps 0 and 1 are the control
+// warps (16 lanes each): lane p runs the interior-point logic and the serial Riccati sweeps of the problem
+// currently in lane p -- one thread per problem, a different problem in every lane of a warp instruction (no
 // shuffles in the recursions).  The other warps are stage threads: thread (g, p) owns stages
 // g*SPT .. g*SPT+SPT-1 of lane p's problem and does everything that is parallel over the horizon
 // (sin/cos, model derivatives, residual norms, trial-point evaluation, step application).
-// All exchange goes through shared memory [stage][slot][lane].  SPT = 2 at N = 20: 1 + 10 warps, 352 threads at
-// 168 registers (the register file); SPT = 3 would be 8 warps at 255.
+// All exchange goes through shared memory [stage][slot][lane].  SPT = 2 at N = 20: 2 + 10 warps, 384 threads at
+// 168 registers (the register file).
 //
 // One global cycle = the fixed phase sequence
 //   P3a init | P3b coefficients | P4 sweeps | P5 step work | P6 step sizes + adjoint sweep | P1 evaluate |

@@ -51,7 +51,8 @@ ref = json.load(open(os.path.join(P, "%s_bench_reference.json" % tag)))
 c1 = json.loads(lat); c4 = json.load(open(os.path.join(P, "%s_config4.json" % tag)))
 c5 = json.load(open(os.path.join(P, "%s_config5.json" % tag)))
 c5d = json.load(open(os.path.join(P, "%s_config5_device.json" % tag))) if os.path.exists(os.path.join(P, "%s_config5_device.json" % tag)) else None
-spill = v[h.index("sass__inst_executed_register_spilling")]; inst = v[h.index("smsp__inst_executed.sum")]
+spill = v[h.index("sass__inst_executed_register_spilling")] if "sass__inst_executed_register_spilling" in h else "0"
+inst = v[h.index("smsp__inst_executed.sum")]
 md = """# Round %s profile summary (B200, gpurun)
 
 All files in this directory come from `gpurun` runs of the committed tree (`profiles/make_summary.py %s`).
@@ -93,15 +94,15 @@ CUDA-event shares bench.py reports (`roofline.kernel_ms` vs `ms_per_step`).
 |---|---|---|
 %s
 
-Reading: registers (352 threads x 168) and 219 KB dynamic shared memory give one 11-warp CTA per SM by design (the
+Reading: registers (384 threads x 168) and 226 KB dynamic shared memory give one 12-warp CTA per SM by design (the
 per-problem working set lives in shared memory: 37 fp64 slots x 20 stages x 32 lanes).  A lone launch of one
 batch leaves most SMs idle most of the time (the tail of a batch is a handful of problems that need 10-20x
 the median iteration count), which is why throughput is measured with many batches in flight.  Within active
 cycles the FP64 pipe is busy about a fifth of the time: the serial Riccati sweeps run on ONE warp per SM (32
 problems per instruction; the backward sweep is bound by the FP64 issue rate of that warp's sub-partition, 2.13
 cycles per instruction, the other phases by dependent-issue latency).  DRAM traffic per launch is the
-algorithmic input + output; nothing is re-read.  Register spilling: 24 B/thread (`ptxas -v`,
-`mpc_ros_b200/lib/ptxas_info.txt`), %s of %s executed warp instructions (%.2f %%).  compute-sanitizer is closed on this pool
+algorithmic input + output; nothing is re-read.  Register spilling: none in this specialisation (`ptxas -v`,
+`mpc_ros_b200/lib/ptxas_info.txt`: 168 registers, 0 B), %s of %s executed warp instructions (%.2f %%).  compute-sanitizer is closed on this pool
 (`gpurun` refuses it), so race freedom is argued from the barrier structure and checked by the bit-reproducibility
 and lane-permutation tests.
 """ % (tag, tag, tag, d["value"] / 1e6, d["ms_per_step"], d["config"]["streams"], d["config"]["max_ctas"],

@@ -598,6 +598,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 100;
     a.prm.grp = SPT;
     a.prm.idt = 1.0 / P.dt;
+    a.prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); a.prm.i_nb = 1.0 / (double)(4 * (N - 1));
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
     a.batch = batch;
     const bool rate = P.w_angvel_d != 0.0 || P.w_accel_d != 0.0;

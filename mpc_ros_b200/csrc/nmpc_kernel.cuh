@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             }
             TRACE_S(6);
             __syncthreads();  // B6
-            // ---- P6: the control thread sets the step sizes; thread (0, p) runs lane p's adjoint sweep
-            if (g == 0 && stepping) {
+            // ---- P6: the control thread sets the step sizes; a stage thread of lane p runs its adjoint sweep
+            // (lanes 0..15 on the thread of group 0, lanes 16..31 on that of group 1: a 64-bit shared-memory access of
+            //  16 lanes is one wavefront, and the two half-warps sit on different sub-partitions)
+            if (g == ((NG >= 2) ? (p >> 4) : 0) && stepping) {
                 const int big = adjoint_sweep(prm, sm, p);
                 if (step_lsq) sm.I(PI_FLAGS, p) = FL_ADOPT | ctrl_lsq_finish(prm, sm, p, big);
             }

@@ -101,6 +101,7 @@ struct Params {
     double warm_mu;   // initial barrier parameter of a warm-started problem
     double w_angvel_d, w_accel_d;   // rate penalties (mpc_planner.cpp:144-147); both 0 in the plain variant
     double idt;       // 1 / dt
+    double i_mnb, i_nb;   // 1 / (6N + 4(N-1)), 1 / (4(N-1)): reciprocal counts of all / of the bound multipliers
 };
 
 #define NMPC_MAX_FILTER 8
@@ -1127,9 +1128,9 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
     // ---- the evaluated point is now the iterate
     double base_err = 0.0, isc = 0.0;
     if (ret < 0) {
-        const int m = 6 * N, nb = 4 * (N - 1);
-        const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) / (double)(m + nb)) * (1.0 / NMPC_S_MAX);
-        const double s_c = fmax2(NMPC_S_MAX, z1 / (double)nb) * (1.0 / NMPC_S_MAX);
+        // (s_d, s_c of W&B eq. (6); the means over the m + nb and nb multipliers as products with prm.i_mnb, prm.i_nb)
+        const double s_d = fmax2(NMPC_S_MAX, (l1 + z1) * prm.i_mnb) * (1.0 / NMPC_S_MAX);
+        const double s_c = fmax2(NMPC_S_MAX, z1 * prm.i_nb) * (1.0 / NMPC_S_MAX);
         const double isd = fast_rcp(s_d), isf = fast_rcp(sf);
         isc = fast_rcp(s_c);
         const double compl0 = fmax2(fabs(vmax), fabs(vmin));

@@ -33,6 +33,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     const int SPT = 2;   // same grouping of partial sums as the kernel's stage threads
     prm.grp = SPT;
     prm.idt = 1.0 / prm.dt;
+    prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); prm.i_nb = 1.0 / (double)(4 * (N - 1));
     const int NG = (N + SPT - 1) / SPT;
 
     const int NS = RATE ? NSLOTS_RATE : NSLOTS;

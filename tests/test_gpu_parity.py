@@ -482,3 +482,25 @@ def test_small_weights_keep_lsq_multipliers(oracle):
             assert out["status"][i] == 1 and o["status"] == 1
             assert out["iters"][i] == o["iters"]
             assert np.abs(out["u0"][:, i] - o["u0"]).max() <= 1e-9
+
+
+def test_rate_penalties_full_width_ctas(oracle):
+    """The rate-penalty variant with as many lanes per CTA as fit (28: both control warps, both half-warps of the
+    adjoint sweep, queue refill) agrees with the narrow launch of the same problems and with the oracle."""
+    pm = dict(CFG_DEFAULT)
+    state, coeffs = mild(47, 224)
+    outs = []
+    for pb, ctas in ((28, 2), (4, 0)):
+        sv = _solver(pm, 224)
+        sv.set_option("problems_per_cta", pb); sv.set_option("max_ctas", ctas)
+        outs.append(sv.solve(state, coeffs))
+        sv.close()
+    wide, narrow = outs
+    assert (wide["status"] == 1).all() and (narrow["status"] == 1).all()
+    assert (wide["iters"] == narrow["iters"]).all()
+    np.testing.assert_allclose(wide["u0"], narrow["u0"], rtol=0, atol=1e-9)
+    for i in range(0, 224, 7):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert o["status"] == 1
+        assert np.abs(wide["u0"][:, i] - o["u0"]).max() <= U_TOL
+        assert abs(wide["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])

@@ -1081,7 +1081,6 @@ template <class SM>
 MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flags, int NG)
 {
     DEC_START();
-    const int N = prm.N;
     double prinf = 0, pr1 = 0, duinf = 0, vmax = -1e300, vmin = 1e300, l1 = 0, z1 = 0, f = 0, lnsum = 0;
     int inside = 1;
     for (int g = 0; g < NG; g++) {

@@ -14,8 +14,8 @@ using nmpc::SolveArgs;
 
 #define MAX_WAYPOINTS 64
 #define QUEUE_RING 1024
-// stages per stage thread: 1 control warp + 7 stage warps = 256 threads, so that the kernel may use
-// 255 registers per thread (the serial Riccati sweep wants ~110 live doubles)
+// stages per stage thread: at N = 20, 2 control warps + 10 stage warps = 384 threads at 168 registers (the whole
+// register file; the serial Riccati sweep keeps ~70 doubles live)
 #define SPT 2
 #define STAGE_THREADS 320
 

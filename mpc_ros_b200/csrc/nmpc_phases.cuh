@@ -11,8 +11,8 @@
 //     block-tridiagonal KKT system solved by a sparsity-exploiting Riccati recursion.
 //
 // Execution model (see nmpc_kernel.cuh): a CTA has PB problem lanes.  "Stage threads" own a few
-// (lane, stage) pairs each in the stage-parallel phases; one "control thread" per lane (lane ==
-// thread of warp 0) runs the per-problem logic and the serial Riccati sweeps.  All cross-thread data
+// (lane, stage) pairs each in the stage-parallel phases; one "control thread" per lane (16 lanes per
+// control warp) runs the per-problem logic and the serial Riccati sweeps.  All cross-thread data
 // goes through the CTA's shared memory, indexed [stage][slot][lane] so that a warp touches 32
 // consecutive doubles.  Every lane is a small state machine (enum Mode); one global cycle runs the six
 // phases P1..P6 once and each lane does the work its state asks for, so a lane that needs an extra

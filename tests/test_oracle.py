@@ -182,3 +182,23 @@ def test_decel_known_answers(oracle):
     assert oracle.decel(0, 0, 0.0, 0.02, 0.2, thr, vmax, vmin, 0.5) == 0.05
     # boundary: dist == v^2 / thr counts as inside
     assert oracle.decel(0, 0, 0.25, 0, 0.5, thr, vmax, vmin, 0.5) == 0.25
+
+
+def test_oracle_solution_satisfies_the_reference_kkt_conditions(oracle):
+    """grad f + J^T lambda - zL + zU = 0, g = g_target at the oracle's solutions, with f, g, J from the restatement
+    of FG_eval that the golden vectors pin to the reference's CppAD output (the same check runs on the GPU results
+    in tests/test_gpu_parity.py::test_kkt_conditions_in_the_reference_formulation)."""
+    pm = YAML_DEFAULT
+    N = int(pm["STEPS"]); m = 6 * N
+    state, coeffs = mild(61, 8)
+    for i in range(8):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert o["status"] == 1
+        ev = oracle.eval_all(pm, coeffs[:, i], o["sol"], o["lam"], 1.0)
+        target = np.zeros(m)
+        for c in range(6):
+            target[c * N] = state[c, i]
+        assert np.abs(ev["g"] - target).max() <= 1e-8
+        r = ev["grad"] + ev["J"].T @ o["lam"] - o["zl"] + o["zu"]
+        assert np.abs(r).max() <= 1e-6          # unscaled; the scaled error is o["kkt_error"] <= 1e-8
+        assert o["kkt_error"] <= 1e-8

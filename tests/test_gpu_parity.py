@@ -504,3 +504,56 @@ def test_rate_penalties_full_width_ctas(oracle):
         assert o["status"] == 1
         assert np.abs(wide["u0"][:, i] - o["u0"]).max() <= U_TOL
         assert abs(wide["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+
+
+def test_kkt_conditions_in_the_reference_formulation(oracle):
+    """Independent of the kernel's own error computation: the returned point with its multipliers (the record of
+    mpc_b200_warm_size doubles, laid out like the reference's variables mpc_planner.cpp:232-239 and constraint rows
+    :153-158) satisfies the first-order conditions of the REFERENCE's NLP, evaluated by the oracle's restatement of
+    FG_eval (pinned to the reference's CppAD output by tests/golden/fg_eval_golden.json), to Ipopt's tolerance
+    (W&B eq. (5)-(6): 1e-8 on the scaled error)."""
+    torch = pytest.importorskip("torch")
+    B = 32; N = 20; n = 8 * N - 2; m = 6 * N; nu = N - 1
+    pm = YAML_DEFAULT
+    state, coeffs = mild(61, B)
+    dev = torch.device("cuda:0")
+    sv = _solver(pm, B)
+    ws = capi.lib().mpc_b200_warm_size(N)
+    assert ws == n + m + 4 * nu
+    f64 = dict(dtype=torch.float64, device=dev)
+    u0 = torch.zeros((2, B), **f64); pred = torch.zeros((3 * N, B), **f64); wo = torch.zeros((ws, B), **f64)
+    st = torch.zeros(B, dtype=torch.int32, device=dev)
+    sv.solve_raw(B, torch.from_numpy(state).to(dev), torch.from_numpy(coeffs).to(dev), u0, pred, status=st, warm_out=wo)
+    torch.cuda.synchronize()
+    sv.close()
+    assert bool((st == 1).all())
+    rec = wo.cpu().numpy()
+    Uw = pm["ANGVEL"]; Ua = pm["MAXTHR"]
+    for i in range(B):
+        x = rec[:n, i].copy(); lam = rec[n:n + m, i].copy()
+        zlw, zla, zuw, zua = (rec[n + m + j * nu: n + m + (j + 1) * nu, i] for j in range(4))
+        ev = oracle.eval_all(pm, coeffs[:, i], x, lam, 1.0)
+        # primal feasibility: initial-condition rows equal the state, dynamics rows vanish
+        target = np.zeros(m)
+        for c in range(6):
+            target[c * N] = state[c, i]
+        assert np.abs(ev["g"] - target).max() <= 1e-8
+        # the objective scaling Ipopt applies (nlp_scaling_max_gradient = 100) and the multiplier scaling s_d, s_c
+        g0 = max(abs(2 * pm["W_CTE"] * (state[4, i] - pm["REF_CTE"])), abs(2 * pm["W_EPSI"] * (state[5, i] - pm["REF_ETHETA"])),
+                 abs(2 * pm["W_V"] * (state[3, i] - pm["REF_V"])), abs(2 * pm["W_V"] * pm["REF_V"]),
+                 abs(2 * pm["W_CTE"] * pm["REF_CTE"]), abs(2 * pm["W_EPSI"] * pm["REF_ETHETA"]))
+        sf = 100.0 / g0 if g0 > 100.0 else 1.0
+        z1 = sf * (zlw.sum() + zla.sum() + zuw.sum() + zua.sum())
+        s_d = max(100.0, (sf * np.abs(lam).sum() + z1) / (m + 4 * nu)) / 100.0
+        s_c = max(100.0, z1 / (4 * nu)) / 100.0
+        # stationarity: grad f + J^T lambda - zL + zU = 0 (only the controls carry bound multipliers on this path)
+        r = ev["grad"] + ev["J"].T @ lam
+        r[6 * N:7 * N - 1] += zuw - zlw
+        r[7 * N - 1:] += zua - zla
+        assert sf * np.abs(r).max() <= 1e-8 * s_d * 1.001
+        # bounds, multiplier signs, complementarity
+        w = x[6 * N:7 * N - 1]; a = x[7 * N - 1:]
+        assert np.abs(w).max() <= Uw * (1 + 1e-8) and np.abs(a).max() <= Ua * (1 + 1e-8)
+        assert min(zlw.min(), zla.min(), zuw.min(), zua.min()) > 0.0
+        compl = max((zlw * (w + Uw)).max(), (zuw * (Uw - w)).max(), (zla * (a + Ua)).max(), (zua * (Ua - a)).max())
+        assert sf * compl <= 1e-8 * s_c * 1.001 + 1e-8 * sf * max(zlw.max(), zla.max(), zuw.max(), zua.max())   # (+ the 1e-8 bound relaxation)

@@ -61,8 +61,14 @@ std::vector<double> MPC::Solve(Eigen::VectorXd state, Eigen::VectorXd coeffs)
     // the only caller fits a cubic (driving_state.cpp:210); lower orders are padded with zeros
     double co[4] = { 0, 0, 0, 0 };
     for (int i = 0; i < 4 && i < coeffs.size(); i++) co[i] = coeffs[i];
-    if (coeffs.size() > 4)
-        std::cerr << "[mpc_b200] polynomial order " << coeffs.size() - 1 << " > 3: higher coefficients ignored" << std::endl;
+    // a polynomial of order > 3 with non-zero higher coefficients is not on the GPU path: refuse
+    // loudly rather than solve a different problem
+    for (int i = 4; i < coeffs.size(); i++)
+        if (coeffs[i] != 0.0) {
+            std::cerr << "[mpc_b200] fatal: path polynomial of order " << coeffs.size() - 1
+                      << " (non-zero coefficient " << i << "); the GPU path takes cubics" << std::endl;
+            std::abort();
+        }
     double u0[2] = { 0.0, 0.0 };
     pred_.assign(3 * (size_t)N, 0.0);
     int32_t status = 0, iters = 0;

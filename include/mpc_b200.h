@@ -111,7 +111,11 @@ int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p);
  * smaller values leave SMs to batches in flight on other streams and make each lane work through
  * several problems); "problems_per_cta": 0 = auto (up to 32); "hard_first": 1 (default) serves the work queue
  * in descending order of |c1|+|c2|+|c3| so that the slow problems of a batch start first (results do not
- * depend on it).  Unknown name: MPC_B200_ERR_INVALID. */
+ * depend on it).  "poly_coeffs": rows of the coeffs arrays of mpc_b200_solve_batch = order of the path
+ * polynomial + 1, 4 (default, the cubic of driving_state.cpp:210) .. 8; FG_eval takes any order
+ * (mpc_planner.cpp:186-190: coeffs.size()).  Orders above 3: cold start, no rate penalties, and not through the
+ * pre-step / tick entry points (they fit a cubic) -- MPC_B200_ERR_UNSUPPORTED otherwise.
+ * Unknown name or value: MPC_B200_ERR_INVALID. */
 int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value);
 
 /* Size in doubles of one problem's warm-start record: primal (8N-2, the reference's variable

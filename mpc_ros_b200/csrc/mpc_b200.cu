@@ -333,6 +333,7 @@ struct mpc_b200_handle {
     int opt_order;         // option: serve the queue hard-first (default on)
     int max_ctas;          // option: cap on the persistent grid (0 = one CTA per SM)
     int opt_pb;            // option: problems per CTA (0 = auto)
+    int opt_nc;            // option: rows of the coeffs arrays = polynomial order + 1 (4 .. NMPC_MAX_COEFFS; default 4)
     Fetch pending;
     std::string last_err;
 };
@@ -382,7 +383,7 @@ static int alloc_scratch(mpc_b200_handle *h)
     const size_t B = (size_t)h->max_batch, N = (size_t)h->params.mpc_steps;
     h->pred_steps = (int)N;
     CK(cudaMalloc(&h->d_state, sizeof(double) * 6 * B));
-    CK(cudaMalloc(&h->d_coeffs, sizeof(double) * 4 * B));
+    CK(cudaMalloc(&h->d_coeffs, sizeof(double) * NMPC_MAX_COEFFS * B));
     CK(cudaMalloc(&h->d_refv, sizeof(double) * B));
     CK(cudaMalloc(&h->d_u0, sizeof(double) * 2 * B));
     CK(cudaMalloc(&h->d_pred, sizeof(double) * 3 * N * B));
@@ -461,7 +462,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0; h->kernels = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
-    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->d_order = NULL; h->opt_order = 1;
+    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->opt_nc = 4; h->d_order = NULL; h->opt_order = 1;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -478,6 +479,8 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, true, false>));
     // rate-penalty variant (w_angvel_d / w_accel_d != 0): 44 slots per stage, lanes per CTA chosen at run time
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true>));
+    // path polynomial of order 4..7 (cold start, no rate penalties)
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>));
 #undef SET_SMEM
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
@@ -553,6 +556,12 @@ int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value)
     if (!strcmp(name, "max_ctas")) h->max_ctas = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "problems_per_cta")) h->opt_pb = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "hard_first")) h->opt_order = value != 0.0;
+    else if (!strcmp(name, "poly_coeffs")) {
+        // rows of the coeffs arrays of mpc_b200_solve_batch: order of the path polynomial + 1 (mpc_planner.cpp:186-190
+        // takes any order; the pre-step entry points always fit and write a cubic, 4 rows)
+        if (value < 4 || value > NMPC_MAX_COEFFS) return MPC_B200_ERR_INVALID;
+        h->opt_nc = (int)value;
+    }
     else return MPC_B200_ERR_INVALID;
     return MPC_B200_OK;
 }
@@ -601,7 +610,9 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); a.prm.i_nb = 1.0 / (double)(4 * (N - 1));
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
     a.batch = batch;
+    a.ncoef = h->opt_nc;
     const bool rate = P.w_angvel_d != 0.0 || P.w_accel_d != 0.0;
+    if (a.ncoef > 4 && (rate || d_warm_in)) return MPC_B200_ERR_UNSUPPORTED;     // higher order: cold, plain variant only
     const int nslots = rate ? nmpc::NSLOTS_RATE : nmpc::NSLOTS;
     a.prm.w_angvel_d = P.w_angvel_d; a.prm.w_accel_d = P.w_accel_d;
     a.PB = choose_pb(h, N, batch, nslots);
@@ -628,7 +639,9 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     }
     if (timed) CK(cudaEventRecord(h->ev0, st));
-    if (rate) {
+    if (a.ncoef > 4) {
+        nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
+    } else if (rate) {
         if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);
     } else if (a.warm_in) {
@@ -728,11 +741,12 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         double *hi = h->h_in;
         const double *src_s = state, *src_c = coeffs, *src_r = ref_vel;
         if (!is_pinned_host(state)) { memcpy(hi, state, sizeof(double) * 6 * B); src_s = hi; }
-        if (!is_pinned_host(coeffs)) { memcpy(hi + 6 * B, coeffs, sizeof(double) * 4 * B); src_c = hi + 6 * B; }
-        if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + 10 * B, ref_vel, sizeof(double) * B); src_r = hi + 10 * B; }
+        const size_t nc = (size_t)h->opt_nc;
+        if (!is_pinned_host(coeffs)) { memcpy(hi + 6 * B, coeffs, sizeof(double) * nc * B); src_c = hi + 6 * B; }
+        if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + (6 + nc) * B, ref_vel, sizeof(double) * B); src_r = hi + (6 + nc) * B; }
         // state and coeffs scratch are separate allocations: two copies (three with ref_vel)
         CK(cudaMemcpyAsync(h->d_state, src_s, sizeof(double) * 6 * B, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(h->d_coeffs, src_c, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_coeffs, src_c, sizeof(double) * nc * B, cudaMemcpyHostToDevice, st));
         if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, src_r, sizeof(double) * B, cudaMemcpyHostToDevice, st));
         ds = h->d_state; dc = h->d_coeffs; dr = ref_vel ? h->d_refv : NULL;
     }
@@ -770,6 +784,7 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
     if (is_device_ptr(wx) || is_device_ptr(u0)) return MPC_B200_ERR_UNSUPPORTED;   // host entry point; device callers chain the
                                                                                  // prestep / solve / poststep calls themselves
     if (h->pending.active) return MPC_B200_ERR_INVALID;                         // one tick in flight per handle
+    if (h->opt_nc != 4) return MPC_B200_ERR_UNSUPPORTED;                        // the pre-step fits a cubic
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
     const size_t B = (size_t)batch;

@@ -30,8 +30,9 @@ struct SolveArgs {
     Params prm;
     int PB;
     int batch;
+    int ncoef;              // rows of coeffs: 4 (cubic) .. NMPC_MAX_COEFFS
     const double *state;    // 6 x batch
-    const double *coeffs;   // 4 x batch
+    const double *coeffs;   // ncoef x batch
     const double *ref_vel;  // batch or NULL
     double *u0;             // 2 x batch
     double *pred;           // 3N x batch
@@ -69,7 +70,9 @@ struct SolveArgs {
 #define NMPC_CTRL_WARPS 2
 #define NMPC_CTRL_LANES 16
 #define NMPC_CTRL_THREADS (32 * NMPC_CTRL_WARPS)
-template <int SPT, int CPB, bool WARM, bool RATE>
+// NC: coefficients of the path polynomial the instantiation carries (4 = the cubic of the reference's only caller;
+// 8 serves orders 4..7, rows beyond a.ncoef read as zero).
+template <int SPT, int CPB, bool WARM, bool RATE, int NC = 4>
 __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
@@ -114,6 +117,9 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                         if (a.order) nidx = a.order[nidx];
                         for (int i = 0; i < 6; i++) sm.P(PS_NX0 + i, p) = a.state[(size_t)i * batch + nidx];
                         for (int i = 0; i < 4; i++) sm.P(PS_NX6 + i, p) = a.coeffs[(size_t)i * batch + nidx];
+                        if (NC > 4)
+                            for (int i = 4; i < NC; i++)
+                                sm.P(PS_NXC4 + (i - 4), p) = i < a.ncoef ? a.coeffs[(size_t)i * batch + nidx] : 0.0;
                         sm.P(PS_NX10, p) = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
                     }
                     sm.I(PI_NEXT, p) = nidx;
@@ -282,7 +288,9 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
         const int k0 = g * SPT;
         const bool mine = k0 < N;
         StageRegs r[SPT];
-        double cf[4] = {0.0, 0.0, 0.0, 0.0};   // path polynomial of the lane's problem
+        double cf[NC];                         // path polynomial of the lane's problem
+#pragma unroll
+        for (int i = 0; i < NC; i++) cf[i] = 0.0;
         int trace_cyc = -1; (void)trace_cyc;
         for (;;) {
             trace_cyc++;
@@ -298,6 +306,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                     double s6[6], c4[4];
                     for (int i = 0; i < 6; i++) s6[i] = sm.P(PS_NX0 + i, p);
                     for (int i = 0; i < 4; i++) { c4[i] = sm.P(PS_NX6 + i, p); cf[i] = c4[i]; }
+                    if (NC > 4) {
+#pragma unroll
+                        for (int i = 4; i < NC; i++) cf[i] = sm.P(PS_NXC4 + (i - 4), p);
+                    }
                     if (WARM && (fl & FL_WARM)) {
 #pragma unroll
                         for (int j = 0; j < SPT; j++)
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                     const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_coeffs<RATE>(prm, sm, r[j], k0 + j, p, lsq, cf);
+                        if (k0 + j < N) stage_coeffs<RATE, NC>(prm, sm, r[j], k0 + j, p, lsq, cf);
                 }
             }
             TRACE_S(4);
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                 double gk[SPT][6];
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_step<RATE>(prm, sm, r[j], k0 + j, p, hd, lsq, acc, gk[j], cf);
+                    if (k0 + j < N) stage_step<RATE, NC>(prm, sm, r[j], k0 + j, p, hd, lsq, acc, gk[j], cf);
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
                     if (k0 + j < N)
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                 }
 #pragma unroll
                 for (int j = 0; j < SPT; j++)
-                    if (k0 + j < N) stage_eval<RATE>(prm, sm, r[j], k0 + j, p, fl, acc, cf);
+                    if (k0 + j < N) stage_eval<RATE, NC>(prm, sm, r[j], k0 + j, p, fl, acc, cf);
                 part_store(sm, g, p, acc);
             }
             TRACE_S(8);

@@ -61,6 +61,7 @@ enum PSlot {
                                                           // already have been re-initialised for its next problem)
     PS_NX0, PS_NX1, PS_NX2, PS_NX3, PS_NX4, PS_NX5,       // staged inputs of the lane's next problem: state (6),
     PS_NX6, PS_NX7, PS_NX8, PS_NX9, PS_NX10,              // coeffs (4), ref_vel -- written at refill, read in P3a
+    PS_NXC4, PS_NXC5, PS_NXC6, PS_NXC7,                   // coefficients 4..7 of a path polynomial of order > 3
     NPS
 };
 enum PISlot {
@@ -428,12 +429,29 @@ MPC_HD double rate_grad(double wd2, double u, double up, double un, bool has_pre
     return g;
 }
 
+// Path polynomial p(x) = sum_i cf[i] x^i (mpc_planner.cpp:186-190; the order is coeffs.size() - 1 there) with its
+// first two derivatives, by Horner's rule.  NC = 4 is the cubic the reference's only caller fits
+// (driving_state.cpp:210); the forms below then reduce to the closed cubic expressions.
+#define NMPC_MAX_COEFFS 8
+template <int NC>
+MPC_HD void path_poly(const double *cf, double x, double &p0, double &p1, double &p2)
+{
+    double a = cf[NC - 1], b = (double)(NC - 1) * cf[NC - 1], c = (double)((NC - 1) * (NC - 2)) * cf[NC - 1];
+#pragma unroll
+    for (int i = NC - 2; i >= 0; i--) a = cf[i] + x * a;
+#pragma unroll
+    for (int i = NC - 2; i >= 1; i--) b = (double)i * cf[i] + x * b;
+#pragma unroll
+    for (int i = NC - 2; i >= 2; i--) c = (double)(i * (i - 1)) * cf[i] + x * c;
+    p0 = a; p1 = b; p2 = c;
+}
+
 // ---------------------------------------------------------------- P1: evaluate  iterate + alpha * step
 // Everything the control thread needs to (a) run the filter line search on this point and (b), if it
 // becomes the iterate, test convergence and update mu: sum|c|, max|c|, scaled objective, log-barrier
 // sum, max|dual residual| and the extreme complementarity products with the trial multipliers
 // lambda + alpha (lambda^+ - lambda), z + alpha_z dz, plus the multiplier norms.
-template <bool RATE = false, class SM>
+template <bool RATE = false, int NC = 4, class SM>
 MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int flags, EvalPart &acc,
                        const double *cf)
 {
@@ -478,8 +496,9 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
     if (k < N - 1) {
         const double uw = r.uw + alpha * sm.at(k, W_DU, p), ua = r.ua + alpha * sm.at(k, W_DU + 1, p);
         f += prm.w_angvel * uw * uw + prm.w_accel * ua * ua;
-        const double poly = cf[0] + x * (cf[1] + x * (cf[2] + x * cf[3]));
-        const double dpoly = cf[1] + x * (2.0 * cf[2] + 3.0 * cf[3] * x);
+        double poly, dpoly, ddpoly_unused;
+        path_poly<NC>(cf, x, poly, dpoly, ddpoly_unused);
+        (void)ddpoly_unused;
         const double nx = sm.at(k + 1, S_X, p) + alpha * sm.at(k, D_X, p), ny = sm.at(k + 1, S_Y, p) + alpha * sm.at(k, D_Y, p);
         const double nt = sm.at(k + 1, S_T, p) + alpha * sm.at(k, D_T, p), nv = sm.at(k + 1, S_V, p) + alpha * sm.at(k, D_V, p);
         const double nc = sm.at(k + 1, S_C, p) + alpha * sm.at(k, D_C, p), ne = sm.at(k + 1, S_E, p) + alpha * sm.at(k, D_E, p);
@@ -587,7 +606,7 @@ MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
     return h;
 }
 
-template <bool RATE = false, class SM>
+template <bool RATE = false, int NC = 4, class SM>
 MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq, const double *cf)
 {
     const int N = prm.N;
@@ -598,9 +617,8 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
     const double qc = 2.0 * sf * prm.w_cte * (ct - prm.ref_cte);
     const double qe = 2.0 * sf * prm.w_etheta * (e - prm.ref_etheta);
     if (k < N - 1) {
-        const double poly = cf[0] + x * (cf[1] + x * (cf[2] + x * cf[3]));
-        const double dpoly = cf[1] + x * (2.0 * cf[2] + 3.0 * cf[3] * x);
-        const double ddpoly = 2.0 * cf[2] + 6.0 * cf[3] * x;
+        double poly, dpoly, ddpoly;
+        path_poly<NC>(cf, x, poly, dpoly, ddpoly);
         sm.at(k, A_13, p) = -v * r.sn * dt; sm.at(k, A_14, p) = r.cs * dt;
         sm.at(k, A_23, p) = v * r.cs * dt;  sm.at(k, A_24, p) = r.sn * dt;
         sm.at(k, A_51, p) = dpoly; sm.at(k, A_54, p) = r.se * dt; sm.at(k, A_56, p) = v * r.ce * dt;
@@ -877,7 +895,7 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDi
 // ---------------------------------------------------------------- P5: step-dependent stage work
 // Reads ds_k, du_k; returns g_k = q_s + Q_k ds_k (to be stored into W_0..W_5) and accumulates the partials
 // (primal fraction-to-boundary limit, dual limit, grad(phi_mu)^T d) into `acc`.
-template <bool RATE = false, class SM>
+template <bool RATE = false, int NC = 4, class SM>
 MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const HessDiag &hd, int lsq,
                        StepPart &acc, double *g6, const double *cf)
 {
@@ -931,7 +949,9 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
     double hxx = 0.0, htt = 0.0, htv = 0.0, hee = 0.0, hev = 0.0;
     if (k < N - 1 && !lsq) {
         const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mc = sm.at(k, L_C, p);
-        const double ddpoly = 2.0 * cf[2] + 6.0 * cf[3] * sm.at(k, S_X, p);
+        double poly_unused, dpoly_unused, ddpoly;
+        path_poly<NC>(cf, sm.at(k, S_X, p), poly_unused, dpoly_unused, ddpoly);
+        (void)poly_unused; (void)dpoly_unused;
         hxx = -mc * ddpoly;
         htt = (mx * r.cs + my * r.sn) * v * dt;
         htv = (mx * r.sn - my * r.cs) * dt;

@@ -58,23 +58,27 @@ std::vector<double> MPC::Solve(Eigen::VectorXd state, Eigen::VectorXd coeffs)
     const int N = handle_steps_;
     double st[6] = { 0, 0, 0, 0, 0, 0 };
     for (int i = 0; i < 6 && i < state.size(); i++) st[i] = state[i];
-    // the only caller fits a cubic (driving_state.cpp:210); lower orders are padded with zeros
-    double co[4] = { 0, 0, 0, 0 };
-    for (int i = 0; i < 4 && i < coeffs.size(); i++) co[i] = coeffs[i];
-    // a polynomial of order > 3 with non-zero higher coefficients is not on the GPU path: refuse
-    // loudly rather than solve a different problem
-    for (int i = 4; i < coeffs.size(); i++)
-        if (coeffs[i] != 0.0) {
+    // the only caller fits a cubic (driving_state.cpp:210); lower orders are padded with zeros, orders 4..7 go through
+    // the library's higher-order instantiation (option "poly_coeffs"), anything beyond is refused loudly rather than
+    // solved as a different problem
+    double co[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    int nco = 4;
+    for (int i = 0; i < coeffs.size(); i++) {
+        if (i < 8) { co[i] = coeffs[i]; if (i >= 4 && coeffs[i] != 0.0) nco = i + 1; }
+        else if (coeffs[i] != 0.0) {
             std::cerr << "[mpc_b200] fatal: path polynomial of order " << coeffs.size() - 1
-                      << " (non-zero coefficient " << i << "); the GPU path takes cubics" << std::endl;
+                      << " (non-zero coefficient " << i << "); the GPU path takes orders up to 7" << std::endl;
             std::abort();
         }
+    }
+    if (nco > 4 && mpc_b200_set_option(handle_, "poly_coeffs", (double)nco) != MPC_B200_OK) std::abort();
     double u0[2] = { 0.0, 0.0 };
     pred_.assign(3 * (size_t)N, 0.0);
     int32_t status = 0, iters = 0;
     double obj = 0.0, kkt = 0.0;
     const int rc = mpc_b200_solve_batch(handle_, 1, st, co, nullptr, nullptr, u0, pred_.data(), &obj, &status, &iters,
                                         &kkt, nullptr, nullptr);
+    if (nco > 4) mpc_b200_set_option(handle_, "poly_coeffs", 4.0);
     if (rc != MPC_B200_OK)
         std::cerr << "[mpc_b200] solve failed: " << mpc_b200_strerror(rc) << " (" << mpc_b200_last_cuda_error(handle_)
                   << ")" << std::endl;

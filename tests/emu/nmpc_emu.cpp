@@ -16,8 +16,8 @@ using namespace nmpc;
 
 static long long g_lane_cycles = 0;
 
-template <bool RATE>
-static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB, int batch,
+template <bool RATE, int NC = 4>
+static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB, int batch, int ncoef,
                    const double *state, const double *coeffs, const double *ref_vel,
                    double *u0, double *pred, double *obj, int *status, int *iters, double *kkt,
                    double *lam_out, int *n_reg)
@@ -40,7 +40,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     std::vector<double> mem(smem_bytes(N, NG, PB, NS) / sizeof(double) + 8);
     SmemT<0, RATE ? NSLOTS_RATE : NSLOTS> sm; sm.PB = PB; sm.carve(mem.data(), N, NG);
     std::vector<StageRegs> regs((size_t)N * PB);
-    std::vector<double> cfs((size_t)4 * PB);
+    std::vector<double> cfs((size_t)NC * PB);
     std::vector<Ctrl> ctrl(PB);
     std::vector<int> nreg(PB);
 #define REG(k, p) regs[(size_t)(k) * PB + (p)]
@@ -87,7 +87,8 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 if (idx >= 0) {
                     double s6[6], c4[4];
                     for (int c = 0; c < 6; c++) s6[c] = state[(size_t)c * batch + idx];
-                    for (int c = 0; c < 4; c++) { c4[c] = coeffs[(size_t)c * batch + idx]; cfs[(size_t)4 * p + c] = c4[c]; }
+                    for (int c = 0; c < 4; c++) c4[c] = coeffs[(size_t)c * batch + idx];
+                    for (int c = 0; c < NC; c++) cfs[(size_t)NC * p + c] = c < ncoef ? coeffs[(size_t)c * batch + idx] : 0.0;
                     for (int k = 0; k < N; k++) stage_init<RATE>(prm, sm, REG(k, p), k, p, s6, c4);
                 }
             }
@@ -98,7 +99,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
             // ---- P3b
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_NEWTON)
-                    for (int k = 0; k < N; k++) stage_coeffs<RATE>(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)4 * p]);
+                    for (int k = 0; k < N; k++) stage_coeffs<RATE, NC>(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)NC * p]);
             // ---- P4
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_NEWTON) continue;
@@ -125,7 +126,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 for (int g = 0; g < NG; g++) {
                     StepPart acc; part_reset(acc);
                     double gk[SPT][6];
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step<RATE>(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT], &cfs[(size_t)4 * p]);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_step<RATE, NC>(prm, sm, REG(k, p), k, p, hd, lsq, acc, gk[k - g * SPT], &cfs[(size_t)NC * p]);
                     for (int k = g * SPT; k < g * SPT + SPT && k < N; k++)
                         for (int q = 0; q < 6; q++) sm.at(k, W_0 + q, p) = gk[k - g * SPT][q];
                     part_store(sm, g, p, acc);
@@ -154,7 +155,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 if (fl & FL_ADOPT) for (int k = 0; k < N; k++) stage_adopt(prm, sm, k, p, fl);
                 for (int g = 0; g < NG; g++) {
                     EvalPart acc; part_reset(acc);
-                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval<RATE>(prm, sm, REG(k, p), k, p, fl, acc, &cfs[(size_t)4 * p]);
+                    for (int k = g * SPT; k < g * SPT + SPT && k < N; k++) stage_eval<RATE, NC>(prm, sm, REG(k, p), k, p, fl, acc, &cfs[(size_t)NC * p]);
                     part_store(sm, g, p, acc);
                 }
             }
@@ -219,8 +220,19 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
 {
     // prm14[11], prm14[12]: w_angvel_d, w_accel_d (rate penalties) select the augmented-Riccati variant
     if (prm14[11] != 0.0 || prm14[12] != 0.0)
-        return emu_run<true>(N, prm14, tol, max_iter, PB, batch, state, coeffs, ref_vel, u0, pred, obj, status, iters, kkt,
+        return emu_run<true>(N, prm14, tol, max_iter, PB, batch, 4, state, coeffs, ref_vel, u0, pred, obj, status, iters, kkt,
                              lam_out, n_reg);
-    return emu_run<false>(N, prm14, tol, max_iter, PB, batch, state, coeffs, ref_vel, u0, pred, obj, status, iters, kkt,
+    return emu_run<false>(N, prm14, tol, max_iter, PB, batch, 4, state, coeffs, ref_vel, u0, pred, obj, status, iters, kkt,
                           lam_out, n_reg);
+}
+
+// Path polynomial of order ncoef - 1 in 4 .. NMPC_MAX_COEFFS - 1 (coeffs: ncoef x batch): the instantiation the
+// kernel uses for orders above 3 (cold start, no rate penalties).
+extern "C" int nmpc_emu_solve_poly(int N, const double *prm14, double tol, int max_iter, int PB, int batch, int ncoef,
+                                   const double *state, const double *coeffs, double *u0, double *pred, double *obj,
+                                   int *status, int *iters, double *kkt)
+{
+    if (ncoef < 4 || ncoef > NMPC_MAX_COEFFS || prm14[11] != 0.0 || prm14[12] != 0.0) return -1;
+    return emu_run<false, NMPC_MAX_COEFFS>(N, prm14, tol, max_iter, PB, batch, ncoef, state, coeffs, nullptr, u0, pred, obj,
+                                           status, iters, kkt, nullptr, nullptr);
 }

@@ -146,3 +146,45 @@ def test_emu_small_weights_keep_lsq_multipliers(oracle):
         assert rb["iters"][i] == ob["iters"]
         kept += int(np.abs(o["lam"]).max() < 1e3)
     assert kept == 16      # (the converged multipliers are small too: the start was not the discarded kind)
+
+
+def emu_solve_poly(pm, state, coeffs, PB=4, tol=1e-8, max_iter=200):
+    """Path polynomial of order coeffs.shape[0] - 1 in 4..7 (the kernel's higher-order instantiation)."""
+    emu_solve(pm, state[:, :1], coeffs[:4, :1])      # (loads the library)
+    dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
+    N = int(pm["STEPS"]); B = state.shape[1]; nc = coeffs.shape[0]
+    prm = np.array([pm["DT"], pm["REF_CTE"], pm["REF_ETHETA"], pm["REF_V"], pm["W_CTE"], pm["W_EPSI"], pm["W_V"],
+                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], 0.0, 0.0, 0], dtype=np.float64)
+    state = np.ascontiguousarray(state, dtype=np.float64); coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    u0 = np.zeros((2, B)); pred = np.zeros((3 * N, B)); obj = np.zeros(B); kkt = np.zeros(B)
+    st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    rc = _EMU.nmpc_emu_solve_poly(C.c_int(N), P(prm), C.c_double(tol), C.c_int(max_iter), C.c_int(PB), C.c_int(B), C.c_int(nc),
+                                  P(state), P(coeffs), P(u0), P(pred), P(obj), st.ctypes.data_as(ip), it.ctypes.data_as(ip), P(kkt))
+    assert rc == 0
+    return dict(u0=u0, pred=pred, obj=obj, status=st, iters=it, kkt=kkt)
+
+
+def higher_order(seed, batch, ncoef):
+    """Mild problems with a path polynomial of order ncoef - 1 (FG_eval takes any order, mpc_planner.cpp:186-190)."""
+    state, c4 = mild(seed, batch)
+    rng = np.random.default_rng(seed + 1000)
+    coeffs = np.zeros((ncoef, batch)); coeffs[:4] = c4
+    coeffs[4:] = rng.uniform(-0.05, 0.05, size=(ncoef - 4, batch))
+    return state, coeffs
+
+
+def test_emu_higher_order_path_polynomial(oracle):
+    pm = dict(YAML_DEFAULT, BOUND=1e19)
+    for ncoef in (5, 6, 8):
+        state, coeffs = higher_order(70 + ncoef, 10, ncoef)
+        r = emu_solve_poly(pm, state, coeffs, PB=3)
+        for i in range(10):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert r["status"][i] == 1 and o["status"] == 1
+            assert r["iters"][i] == o["iters"]
+            assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-9
+            assert abs(r["obj"][i] - o["obj"]) <= 1e-9 * abs(o["obj"])
+            # the higher coefficients matter: the cubic part alone gives another answer
+            o3 = oracle.solve(pm, state[:, i], coeffs[:4, i])
+            assert abs(o3["obj"] - o["obj"]) > 1e-7 * abs(o["obj"])

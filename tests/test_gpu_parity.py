@@ -557,3 +557,37 @@ def test_kkt_conditions_in_the_reference_formulation(oracle):
         assert min(zlw.min(), zla.min(), zuw.min(), zua.min()) > 0.0
         compl = max((zlw * (w + Uw)).max(), (zuw * (Uw - w)).max(), (zla * (a + Ua)).max(), (zua * (Ua - a)).max())
         assert sf * compl <= 1e-8 * s_c * 1.001 + 1e-8 * sf * max(zlw.max(), zla.max(), zuw.max(), zua.max())   # (+ the 1e-8 bound relaxation)
+
+
+def test_higher_order_path_polynomial(oracle):
+    """FG_eval takes a path polynomial of any order (mpc_planner.cpp:186-190: coeffs.size()); orders 4..7 run through
+    the option "poly_coeffs" (cold start, plain weights); the tick entry points and the variants that do not carry
+    it refuse loudly."""
+    from tests.test_emu import higher_order
+    pm = YAML_DEFAULT
+    for ncoef in (5, 8):
+        state, coeffs = higher_order(80 + ncoef, 40, ncoef)
+        sv = _solver(pm, 40)
+        sv.set_option("poly_coeffs", ncoef)
+        out = sv.solve(state, coeffs)
+        for i in range(0, 40, 2):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert out["status"][i] == 1 and o["status"] == 1
+            assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
+            assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+            assert out["kkt"][i] <= KKT_TOL
+        # back to cubics on the same handle: the first four rows alone
+        sv.set_option("poly_coeffs", 4)
+        out3 = sv.solve(state, coeffs[:4])
+        o3 = oracle.solve(pm, state[:, 0], coeffs[:4, 0])
+        assert np.abs(out3["u0"][:, 0] - o3["u0"]).max() <= U_TOL
+        with pytest.raises(capi.MpcError):
+            sv.set_option("poly_coeffs", 9)
+        sv.close()
+    # rate penalties + higher order: refused, not solved as something else
+    sv = _solver(CFG_DEFAULT, 8)
+    sv.set_option("poly_coeffs", 6)
+    state, coeffs = higher_order(90, 8, 6)
+    with pytest.raises(capi.MpcError):
+        sv.solve(state, coeffs)
+    sv.close()

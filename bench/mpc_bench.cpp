@@ -3,6 +3,8 @@
 //   mpc_bench latency [calls]      BASELINE config 1: repeated MPC::Solve through the adapter class
 //                                  (batch of one, host buffers, H2D/D2H included); p50/p99 latency
 //   mpc_bench batch [B] [reps]     config 2: one handle, B problems per call through the C ABI
+//   mpc_bench poly c0 c1 .. cn     one MPC::Solve with a path polynomial of order n (FG_eval takes any order,
+//                                  mpc_planner.cpp:186-190), state (0, 0, 0, 0.3, c0, -0.1), then a cubic again
 // Prints one JSON object per run.
 #include "mpc_planner.h"
 #include "mpc_b200.h"
@@ -63,6 +65,27 @@ static int run_latency(int calls)
     return 0;
 }
 
+static int run_poly(int n, char **c)
+{
+    MPC mpc;
+    std::map<std::string, double> p;
+    p["DT"] = 0.1; p["STEPS"] = 20; p["REF_CTE"] = 0; p["REF_ETHETA"] = 0; p["REF_V"] = 0.5; p["W_CTE"] = 100;
+    p["W_EPSI"] = 0; p["W_V"] = 1000; p["W_ANGVEL"] = 100; p["W_A"] = 50; p["W_DANGVEL"] = 0; p["W_DA"] = 0;
+    p["ANGVEL"] = 1.5; p["MAXTHR"] = 1.0; p["BOUND"] = 1e3;
+    mpc.LoadParams(p);
+    Eigen::VectorXd state(6), coeffs(n), cubic(n < 4 ? n : 4);
+    for (int i = 0; i < n; i++) coeffs[i] = atof(c[i]);
+    for (int i = 0; i < cubic.size(); i++) cubic[i] = coeffs[i];
+    state[0] = 0; state[1] = 0; state[2] = 0; state[3] = 0.3; state[4] = coeffs[0]; state[5] = -0.1;
+    const std::vector<double> r = mpc.Solve(state, coeffs);
+    const int st = mpc.last_status(), it = mpc.last_iterations();
+    const std::vector<double> r3 = mpc.Solve(state, cubic);        // the handle is back on cubics
+    printf("{\"mode\": \"poly\", \"order\": %d, \"w0\": %.12g, \"a0\": %.12g, \"status\": %d, \"iters\": %d, "
+           "\"w0_cubic\": %.12g, \"a0_cubic\": %.12g, \"status_cubic\": %d}\n",
+           n - 1, r[0], r[1], st, it, r3[0], r3[1], mpc.last_status());
+    return 0;
+}
+
 static int run_batch(int B, int reps)
 {
     mpc_b200_params prm; mpc_b200_params_yaml_default(&prm); prm.delay_mode = 0;
@@ -96,6 +119,7 @@ int main(int argc, char **argv)
 {
     if (argc >= 2 && !strcmp(argv[1], "latency")) return run_latency(argc >= 3 ? atoi(argv[2]) : 10000);
     if (argc >= 2 && !strcmp(argv[1], "batch")) return run_batch(argc >= 3 ? atoi(argv[2]) : 4096, argc >= 4 ? atoi(argv[3]) : 20);
-    fprintf(stderr, "usage: mpc_bench latency [calls] | batch [B] [reps]\n");
+    if (argc >= 3 && !strcmp(argv[1], "poly")) return run_poly(argc - 2, argv + 2);
+    fprintf(stderr, "usage: mpc_bench latency [calls] | batch [B] [reps] | poly c0 c1 ..\n");
     return 1;
 }

@@ -39,3 +39,27 @@ def test_config1_single_solve_through_adapter(oracle):
     assert abs(res["w0"] - o["u0"][0]) <= 1e-5 and abs(res["a0"] - o["u0"][1]) <= 1e-5
     assert res["kkt"] <= 1e-8
     assert res["p99_us"] < 1000.0                      # north-star: p99 single-solve latency < 1 ms
+
+
+@pytest.mark.gpu
+def test_higher_order_polynomial_through_adapter(oracle):
+    """MPC::Solve with coeffs.size() == 6 (a quintic): the adapter switches the handle to the higher-order path for
+    that call and back; lower orders are zero-padded."""
+    from oracle.oracle_py import YAML_DEFAULT
+    co = [0.05, -0.1, 0.02, 0.003, 0.04, -0.03]
+    r = subprocess.run([os.path.join(LIBDIR, "mpc_bench"), "poly"] + ["%.17g" % c for c in co], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stderr
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    state = [0.0, 0.0, 0.0, 0.3, co[0], -0.1]
+    o = oracle.solve(YAML_DEFAULT, state, co)
+    o3 = oracle.solve(YAML_DEFAULT, state, co[:4])
+    assert res["status"] == 1 and o["status"] == 1 and res["status_cubic"] == 1
+    assert abs(res["w0"] - o["u0"][0]) <= 1e-5 and abs(res["a0"] - o["u0"][1]) <= 1e-5
+    assert abs(res["w0_cubic"] - o3["u0"][0]) <= 1e-5 and abs(res["a0_cubic"] - o3["u0"][1]) <= 1e-5
+    assert abs(o["u0"][0] - o3["u0"][0]) > 1e-4          # (the two problems differ)
+    # a quadratic: zero-padded
+    r = subprocess.run([os.path.join(LIBDIR, "mpc_bench"), "poly", "0.05", "-0.1", "0.02"], capture_output=True, text=True, timeout=120)
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    o2 = oracle.solve(YAML_DEFAULT, [0.0, 0.0, 0.0, 0.3, 0.05, -0.1], [0.05, -0.1, 0.02, 0.0])
+    assert res["status"] == 1 and abs(res["w0"] - o2["u0"][0]) <= 1e-5

@@ -479,8 +479,9 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, true, false>));
     // rate-penalty variant (w_angvel_d / w_accel_d != 0): 44 slots per stage, lanes per CTA chosen at run time
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true>));
-    // path polynomial of order 4..7 (cold start, no rate penalties)
-    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>));
+    // path polynomial of order 4..7
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS>));
 #undef SET_SMEM
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
     rc = alloc_scratch(h);
@@ -612,7 +613,6 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.batch = batch;
     a.ncoef = h->opt_nc;
     const bool rate = P.w_angvel_d != 0.0 || P.w_accel_d != 0.0;
-    if (a.ncoef > 4 && (rate || d_warm_in)) return MPC_B200_ERR_UNSUPPORTED;     // higher order: cold, plain variant only
     const int nslots = rate ? nmpc::NSLOTS_RATE : nmpc::NSLOTS;
     a.prm.w_angvel_d = P.w_angvel_d; a.prm.w_accel_d = P.w_accel_d;
     a.PB = choose_pb(h, N, batch, nslots);
@@ -640,7 +640,10 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     }
     if (timed) CK(cudaEventRecord(h->ev0, st));
     if (a.ncoef > 4) {
-        nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
+        if (rate && a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
+        else if (rate) nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
+        else if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
+        else nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
     } else if (rate) {
         if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);

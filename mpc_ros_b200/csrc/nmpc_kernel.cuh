@@ -186,9 +186,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             }
             if (WARM && lane && sm.I(PI_MODE, p) == MODE_ROLLOUT) {
                 const size_t i = (size_t)sm.I(PI_PROB, p);
-                double c4[4];
-                for (int q = 0; q < 4; q++) c4[q] = a.coeffs[(size_t)q * batch + i];
-                ctrl_rollout(prm, sm, p, c4);
+                double c4[NC];
+#pragma unroll
+                for (int q = 0; q < NC; q++) c4[q] = q < a.ncoef ? a.coeffs[(size_t)q * batch + i] : 0.0;
+                ctrl_rollout<NC>(prm, sm, p, c4);
                 sm.I(PI_MODE, p) = MODE_EVAL;       // plain evaluation of the start point in P1
                 sm.I(PI_FLAGS, p) = 0;
             }

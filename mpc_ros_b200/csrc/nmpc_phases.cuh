@@ -355,8 +355,25 @@ MPC_HD void stage_init_warm(const Params &prm, const SM &sm, StageRegs &r, int k
     }
 }
 
+// Path polynomial p(x) = sum_i cf[i] x^i (mpc_planner.cpp:186-190; the order is coeffs.size() - 1 there) with its
+// first two derivatives, by Horner's rule.  NC = 4 is the cubic the reference's only caller fits
+// (driving_state.cpp:210); the forms below then reduce to the closed cubic expressions.
+#define NMPC_MAX_COEFFS 8
+template <int NC>
+MPC_HD void path_poly(const double *cf, double x, double &p0, double &p1, double &p2)
+{
+    double a = cf[NC - 1], b = (double)(NC - 1) * cf[NC - 1], c = (double)((NC - 1) * (NC - 2)) * cf[NC - 1];
+#pragma unroll
+    for (int i = NC - 2; i >= 0; i--) a = cf[i] + x * a;
+#pragma unroll
+    for (int i = NC - 2; i >= 1; i--) b = (double)i * cf[i] + x * b;
+#pragma unroll
+    for (int i = NC - 2; i >= 2; i--) c = (double)(i * (i - 1)) * cf[i] + x * c;
+    p0 = a; p1 = b; p2 = c;
+}
+
 // Roll-out of the model from s_0 with the controls left in W_10/W_11 (control thread).
-template <class SM>
+template <int NC = 4, class SM>
 MPC_HD void ctrl_rollout(const Params &prm, const SM &sm, int p, const double *coef4)
 {
     const int N = prm.N;
@@ -367,7 +384,9 @@ MPC_HD void ctrl_rollout(const Params &prm, const SM &sm, int p, const double *c
         double sn, cs, se, ce;
         sincos_d(th, &sn, &cs);
         sincos_d(e, &se, &ce);
-        const double poly = coef4[0] + x * (coef4[1] + x * (coef4[2] + x * coef4[3]));
+        double poly, d1_unused, d2_unused;
+        path_poly<NC>(coef4, x, poly, d1_unused, d2_unused);
+        (void)d1_unused; (void)d2_unused;
         const double nc = (poly - y) + v * se * dt;
         const double nx = x + v * cs * dt, ny = y + v * sn * dt;
         th += uw * dt; e += uw * dt; v += ua * dt; x = nx; y = ny;
@@ -427,23 +446,6 @@ MPC_HD double rate_grad(double wd2, double u, double up, double un, bool has_pre
     if (has_prev) g += wd2 * (u - up);
     if (has_next) g -= wd2 * (un - u);
     return g;
-}
-
-// Path polynomial p(x) = sum_i cf[i] x^i (mpc_planner.cpp:186-190; the order is coeffs.size() - 1 there) with its
-// first two derivatives, by Horner's rule.  NC = 4 is the cubic the reference's only caller fits
-// (driving_state.cpp:210); the forms below then reduce to the closed cubic expressions.
-#define NMPC_MAX_COEFFS 8
-template <int NC>
-MPC_HD void path_poly(const double *cf, double x, double &p0, double &p1, double &p2)
-{
-    double a = cf[NC - 1], b = (double)(NC - 1) * cf[NC - 1], c = (double)((NC - 1) * (NC - 2)) * cf[NC - 1];
-#pragma unroll
-    for (int i = NC - 2; i >= 0; i--) a = cf[i] + x * a;
-#pragma unroll
-    for (int i = NC - 2; i >= 1; i--) b = (double)i * cf[i] + x * b;
-#pragma unroll
-    for (int i = NC - 2; i >= 2; i--) c = (double)(i * (i - 1)) * cf[i] + x * c;
-    p0 = a; p1 = b; p2 = c;
 }
 
 // ---------------------------------------------------------------- P1: evaluate  iterate + alpha * step

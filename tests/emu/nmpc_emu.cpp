@@ -227,12 +227,15 @@ extern "C" int nmpc_emu_solve(int N, const double *prm14, double tol, int max_it
 }
 
 // Path polynomial of order ncoef - 1 in 4 .. NMPC_MAX_COEFFS - 1 (coeffs: ncoef x batch): the instantiation the
-// kernel uses for orders above 3 (cold start, no rate penalties).
+// kernel uses for orders above 3.
 extern "C" int nmpc_emu_solve_poly(int N, const double *prm14, double tol, int max_iter, int PB, int batch, int ncoef,
                                    const double *state, const double *coeffs, double *u0, double *pred, double *obj,
                                    int *status, int *iters, double *kkt)
 {
-    if (ncoef < 4 || ncoef > NMPC_MAX_COEFFS || prm14[11] != 0.0 || prm14[12] != 0.0) return -1;
+    if (ncoef < 4 || ncoef > NMPC_MAX_COEFFS) return -1;
+    if (prm14[11] != 0.0 || prm14[12] != 0.0)
+        return emu_run<true, NMPC_MAX_COEFFS>(N, prm14, tol, max_iter, PB, batch, ncoef, state, coeffs, nullptr, u0, pred, obj,
+                                              status, iters, kkt, nullptr, nullptr);
     return emu_run<false, NMPC_MAX_COEFFS>(N, prm14, tol, max_iter, PB, batch, ncoef, state, coeffs, nullptr, u0, pred, obj,
                                            status, iters, kkt, nullptr, nullptr);
 }

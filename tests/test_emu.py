@@ -154,7 +154,8 @@ def emu_solve_poly(pm, state, coeffs, PB=4, tol=1e-8, max_iter=200):
     dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
     N = int(pm["STEPS"]); B = state.shape[1]; nc = coeffs.shape[0]
     prm = np.array([pm["DT"], pm["REF_CTE"], pm["REF_ETHETA"], pm["REF_V"], pm["W_CTE"], pm["W_EPSI"], pm["W_V"],
-                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], 0.0, 0.0, 0], dtype=np.float64)
+                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], pm.get("W_DANGVEL", 0.0), pm.get("W_DA", 0.0), 0],
+                   dtype=np.float64)
     state = np.ascontiguousarray(state, dtype=np.float64); coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
     u0 = np.zeros((2, B)); pred = np.zeros((3 * N, B)); obj = np.zeros(B); kkt = np.zeros(B)
     st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
@@ -188,3 +189,14 @@ def test_emu_higher_order_path_polynomial(oracle):
             # the higher coefficients matter: the cubic part alone gives another answer
             o3 = oracle.solve(pm, state[:, i], coeffs[:4, i])
             assert abs(o3["obj"] - o["obj"]) > 1e-7 * abs(o["obj"])
+
+
+def test_emu_higher_order_with_rate_penalties(oracle):
+    pm = dict(CFG_DEFAULT, BOUND=1e19)
+    state, coeffs = higher_order(77, 8, 6)
+    r = emu_solve_poly(pm, state, coeffs, PB=3)
+    for i in range(8):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert r["status"][i] == 1 and o["status"] == 1
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-7
+        assert abs(r["obj"][i] - o["obj"]) <= 1e-8 * abs(o["obj"])

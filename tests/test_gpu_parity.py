@@ -561,8 +561,7 @@ def test_kkt_conditions_in_the_reference_formulation(oracle):
 
 def test_higher_order_path_polynomial(oracle):
     """FG_eval takes a path polynomial of any order (mpc_planner.cpp:186-190: coeffs.size()); orders 4..7 run through
-    the option "poly_coeffs" (cold start, plain weights); the tick entry points and the variants that do not carry
-    it refuse loudly."""
+    the option "poly_coeffs" (every variant carries it; the tick entry points, whose pre-step fits a cubic, refuse)."""
     from tests.test_emu import higher_order
     pm = YAML_DEFAULT
     for ncoef in (5, 8):
@@ -584,10 +583,43 @@ def test_higher_order_path_polynomial(oracle):
         with pytest.raises(capi.MpcError):
             sv.set_option("poly_coeffs", 9)
         sv.close()
-    # rate penalties + higher order: refused, not solved as something else
-    sv = _solver(CFG_DEFAULT, 8)
+    # rate penalties (the cfg defaults) + a quintic: the augmented variant carries the higher-order polynomial too
+    pm = dict(CFG_DEFAULT)
+    sv = _solver(pm, 24)
     sv.set_option("poly_coeffs", 6)
-    state, coeffs = higher_order(90, 8, 6)
-    with pytest.raises(capi.MpcError):
-        sv.solve(state, coeffs)
+    state, coeffs = higher_order(90, 24, 6)
+    out = sv.solve(state, coeffs)
     sv.close()
+    for i in range(0, 24, 2):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        assert out["status"][i] == 1 and o["status"] == 1
+        assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
+        assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+
+
+def test_higher_order_warm_start():
+    """Warm start with a quintic path: the roll-out of the model uses the same polynomial; re-solving from the converged
+    record reproduces the cold solution in fewer iterations."""
+    torch = pytest.importorskip("torch")
+    from tests.test_emu import higher_order
+    B = 32; N = 20
+    state, coeffs = higher_order(95, B, 6)
+    dev = torch.device("cuda:0")
+    sv = _solver(YAML_DEFAULT, B)
+    sv.set_option("poly_coeffs", 6)
+    ws = capi.lib().mpc_b200_warm_size(N)
+    f64 = dict(dtype=torch.float64, device=dev)
+    ds = torch.from_numpy(state).to(dev); dc = torch.from_numpy(coeffs).to(dev)
+    u_cold = torch.zeros((2, B), **f64); u_w = torch.zeros((2, B), **f64); pred = torch.zeros((3 * N, B), **f64)
+    it_cold = torch.zeros(B, dtype=torch.int32, device=dev); it_w = torch.zeros(B, dtype=torch.int32, device=dev)
+    st = torch.zeros(B, dtype=torch.int32, device=dev)
+    wo = torch.zeros((ws, B), **f64)
+    sv.solve_raw(B, ds, dc, u_cold, pred, status=st, iters=it_cold, warm_out=wo)
+    torch.cuda.synchronize()
+    assert bool((st == 1).all())
+    sv.solve_raw(B, ds, dc, u_w, pred, warm_in=wo, status=st, iters=it_w)
+    torch.cuda.synchronize()
+    sv.close()
+    assert bool((st == 1).all())
+    assert float((u_w - u_cold).abs().max()) <= U_TOL
+    assert float(it_w.double().mean()) <= 0.7 * float(it_cold.double().mean())

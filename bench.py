@@ -42,11 +42,29 @@ UNIT = "solves/s"
 BATCH = 4096                 # BASELINE config 2
 SEED = 20261018 + 2          # seed = 20261018 + config#
 FLOP_PER_ITER_N20 = 27879.0  # SURVEY 8d algorithmic flops per interior-point iteration, N = 20
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE solve-kernel launch (4,096 problems) from the ncu --set full
-# capture in profiles/r1_solve_kernel_ncu_raw.csv (934,912 + 12,032 B).  Algorithmic: 88 B in + ~520 B out per
-# problem = 2.5 MB per launch; the 2.1 MB of results are still in the 126 MB L2 when the kernel ends, so DRAM
-# sees less than the algorithmic bytes -- nothing is re-read.
-NCU_DRAM_BYTES_PER_LAUNCH = 946944
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE solve-kernel launch (4,096 problems) from the latest ncu --set full
+# capture, profiles/r*_solve_kernel_ncu_raw.csv (read at start; the constant is the round-1 capture: 446,720 + 0 B).
+# Algorithmic: 88 B in + ~520 B out per problem = 2.5 MB per launch; the 2.1 MB of results are still in the 126 MB
+# L2 when the kernel ends, so DRAM sees less than the algorithmic bytes -- nothing is re-read.
+NCU_DRAM_BYTES_PER_LAUNCH = 446720
+
+
+def _ncu_dram_bytes():
+    import csv
+    import glob
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        f = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_solve_kernel_ncu_raw.csv")))[-1]
+        rr = list(csv.reader(open(f)))
+        h, u, v = rr[0], rr[1], rr[2]
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(v[h.index(k)].replace(",", "")) * unit[u[h.index(k)]]
+        return int(round(tot))
+    except Exception:
+        return NCU_DRAM_BYTES_PER_LAUNCH
+
+
 WORKLOAD = ("config2: batch of 4096 independent N=20 diff-drive NMPC problems per GPU, random poses on "
             "infinity/epitrochoid/square tracks, mpc_params.yaml weights, cold start; step = prestep "
             "(transform+polyfit+state) + solve")
@@ -297,7 +315,7 @@ def run_ours(a):
         iso.append(x.elapsed_time(y))
     iso_ms = float(np.median(iso))
     roofline = dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak,
-                    traffic=NCU_DRAM_BYTES_PER_LAUNCH if B == BATCH else None, kernel="nmpc_solve_kernel", kernel_ms=eff_ms,
+                    traffic=_ncu_dram_bytes() if B == BATCH else None, kernel="nmpc_solve_kernel", kernel_ms=eff_ms,
                     kernel_ms_isolated=iso_ms, achieved_isolated=flops_per_launch / (iso_ms * 1e-3) / 1e12,
                     streams=S, flops_per_launch=flops_per_launch,
                     peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak; "

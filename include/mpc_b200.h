@@ -113,8 +113,8 @@ int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p);
  * in descending order of |c1|+|c2|+|c3| so that the slow problems of a batch start first (results do not
  * depend on it).  "poly_coeffs": rows of the coeffs arrays of mpc_b200_solve_batch = order of the path
  * polynomial + 1, 4 (default, the cubic of driving_state.cpp:210) .. 8; FG_eval takes any order
- * (mpc_planner.cpp:186-190: coeffs.size()).  Orders above 3 do not go through the tick entry points, whose
- * pre-step fits a cubic (MPC_B200_ERR_UNSUPPORTED).
+ * (mpc_planner.cpp:186-190: coeffs.size()); the pre-step entry points then fit that order (polyfit(x, y, order),
+ * driving_state.cpp:283-300) and write as many rows (they need M >= poly_coeffs waypoints).
  * Unknown name or value: MPC_B200_ERR_INVALID. */
 int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value);
 

@@ -193,6 +193,7 @@ class Solver:
             self._h = None
             raise MpcError(rc)
         self.N = params.mpc_steps
+        self.nc = 4          # rows of the coeffs arrays (option poly_coeffs)
 
     def close(self):
         if self._h:
@@ -215,6 +216,8 @@ class Solver:
         rc = lib().mpc_b200_set_option(self._h, name.encode(), float(value))
         if rc != 0:
             raise MpcError(rc, name)
+        if name == "poly_coeffs":
+            self.nc = int(value)
 
     def solve_raw(self, batch, state, coeffs, u0, pred, ref_vel=None, warm_in=None, obj=None, status=None,
                   iters=None, kkt=None, warm_out=None, stream=None):
@@ -243,7 +246,7 @@ class Solver:
         wy = np.ascontiguousarray(wy, dtype=np.float64)
         pose = np.ascontiguousarray(pose, dtype=np.float64)
         M, B = wx.shape
-        coeffs = np.zeros((4, B)); ce = np.zeros((2, B))
+        coeffs = np.zeros((self.nc, B)); ce = np.zeros((2, B))
         rc = lib().mpc_b200_polyfit_batch(self._h, B, M, _addr(wx), _addr(wy), _addr(pose), _addr(coeffs), _addr(ce), None)
         if rc != 0:
             raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
@@ -327,7 +330,7 @@ class Solver:
         wx = np.ascontiguousarray(wx, dtype=np.float64); wy = np.ascontiguousarray(wy, dtype=np.float64)
         pose = np.ascontiguousarray(pose, dtype=np.float64); vel = np.ascontiguousarray(vel, dtype=np.float64)
         M, B = wx.shape
-        coeffs = np.zeros((4, B)); state = np.zeros((6, B))
+        coeffs = np.zeros((self.nc, B)); state = np.zeros((6, B))
         self.prestep_raw(B, M, wx, wy, pose, vel, coeffs, state)
         return coeffs, state
 

@@ -23,6 +23,8 @@ using nmpc::SolveArgs;
 // Reference: Tracking::findBestPath, mpc_ros/src/driving_state.cpp:196-235, polyfit :283-300
 // (Vandermonde by running products + unpivoted Householder QR, what Eigen's
 // householderQr().solve() does).  One thread per problem: M ~ 11 waypoints, a 11x4 QR.
+// NC = order + 1 columns (polyfit(x, y, order), driving_state.cpp:283-300, takes any order; the caller fits 3).
+template <int NC>
 __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, const double *__restrict__ wy,
                                const double *__restrict__ pose, double *__restrict__ coeffs_out,
                                double *__restrict__ cte_eth_out, const double *__restrict__ vel,
@@ -33,18 +35,19 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
     const double px = pose[i], py = pose[(size_t)batch + i], th = pose[2 * (size_t)batch + i];
     double st, ct;
     sincos(th, &st, &ct);
-    double A[MAX_WAYPOINTS][4];
+    double A[MAX_WAYPOINTS][NC];
     double b[MAX_WAYPOINTS];
     for (int j = 0; j < M; j++) {
         const double dx = wx[(size_t)j * batch + i] - px, dy = wy[(size_t)j * batch + i] - py;
         const double xv = dx * ct + dy * st;      // driving_state.cpp:205
         b[j] = dy * ct - dx * st;                 // :206
         A[j][0] = 1.0;
-        A[j][1] = A[j][0] * xv; A[j][2] = A[j][1] * xv; A[j][3] = A[j][2] * xv;   // :292-296
+#pragma unroll
+        for (int q = 1; q < NC; q++) A[j][q] = A[j][q - 1] * xv;                  // :292-296
     }
-    double c[4];
+    double c[NC];
     bool ok = true;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NC; k++) {
         double nrm = 0.0;
         for (int r = k; r < M; r++) nrm += A[r][k] * A[r][k];
         nrm = sqrt(nrm);
@@ -54,7 +57,7 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
         double vtv = 0.0;
         for (int r = k; r < M; r++) vtv += A[r][k] * A[r][k];
         const double beta = 2.0 / vtv;
-        for (int j = k + 1; j < 4; j++) {
+        for (int j = k + 1; j < NC; j++) {
             double s = 0.0;
             for (int r = k; r < M; r++) s += A[r][k] * A[r][j];
             s *= beta;
@@ -67,16 +70,16 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
         A[k][k] = alpha;
     }
     if (ok) {
-        for (int k = 3; k >= 0; k--) {
+        for (int k = NC - 1; k >= 0; k--) {
             double s = b[k];
-            for (int j = k + 1; j < 4; j++) s -= A[k][j] * c[j];
+            for (int j = k + 1; j < NC; j++) s -= A[k][j] * c[j];
             c[k] = s / A[k][k];
         }
     } else {
         const double nanv = nan("");
-        c[0] = c[1] = c[2] = c[3] = nanv;
+        for (int k = 0; k < NC; k++) c[k] = nanv;
     }
-    for (int k = 0; k < 4; k++) coeffs_out[(size_t)k * batch + i] = c[k];
+    for (int k = 0; k < NC; k++) coeffs_out[(size_t)k * batch + i] = c[k];
     if (cte_eth_out || state_out) {
         // cte = polyeval(coeffs, 0) = c[0] (:211); etheta by the reference's atan2 rule (:215-235)
         double gx = 0.0, gy = 0.0;
@@ -113,6 +116,20 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
             state_out[5 * (size_t)batch + i] = s5;
         }
     }
+}
+
+// Launch for nc = order + 1 coefficient rows (4 .. NMPC_MAX_COEFFS).
+static void launch_prestep(int nc, cudaStream_t st, int batch, int M, const double *wx, const double *wy, const double *pose,
+                           double *coeffs_out, double *cte_eth_out, const double *vel, double *state_out, int delay_mode,
+                           double dt)
+{
+    const int grid = (batch + 127) / 128;
+#define PRESTEP_CASE(K) case K: prestep_kernel<K><<<grid, 128, 0, st>>>(batch, M, wx, wy, pose, coeffs_out, cte_eth_out, vel, state_out, delay_mode, dt); break
+    switch (nc) {
+        PRESTEP_CASE(5); PRESTEP_CASE(6); PRESTEP_CASE(7); PRESTEP_CASE(8);
+        default: prestep_kernel<4><<<grid, 128, 0, st>>>(batch, M, wx, wy, pose, coeffs_out, cte_eth_out, vel, state_out, delay_mode, dt); break;
+    }
+#undef PRESTEP_CASE
 }
 
 // ================================================================ hard-first queue order
@@ -787,7 +804,7 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
     if (is_device_ptr(wx) || is_device_ptr(u0)) return MPC_B200_ERR_UNSUPPORTED;   // host entry point; device callers chain the
                                                                                  // prestep / solve / poststep calls themselves
     if (h->pending.active) return MPC_B200_ERR_INVALID;                         // one tick in flight per handle
-    if (h->opt_nc != 4) return MPC_B200_ERR_UNSUPPORTED;                        // the pre-step fits a cubic
+    if (M < h->opt_nc) return MPC_B200_ERR_INVALID;                             // fewer waypoints than coefficients
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
     const size_t B = (size_t)batch;
@@ -804,8 +821,8 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
     CK(cudaMemcpyAsync(h->d_pose, sp, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_vel, sv, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
     if (ref_vel) CK(cudaMemcpyAsync(h->d_refv, sr, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, h->d_wx, h->d_wy, h->d_pose, h->d_coeffs, NULL, h->d_vel,
-                                                         h->d_state, h->params.delay_mode, h->params.dt);
+    launch_prestep(h->opt_nc, st, batch, M, h->d_wx, h->d_wy, h->d_pose, h->d_coeffs, NULL, h->d_vel, h->d_state,
+                   h->params.delay_mode, h->params.dt);
     CK(cudaGetLastError());
     h->kernels++;
     int rc = enqueue_solve(h, batch, h->d_state, h->d_coeffs, ref_vel ? h->d_refv : NULL, NULL, h->d_u0, h->d_pred, h->d_obj,
@@ -846,7 +863,7 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                            double *coeffs_out, double *cte_etheta_out, void *stream_v)
 {
     if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !coeffs_out) return MPC_B200_ERR_INVALID;
-    if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;   // polyfit asserts order <= M-1 (driving_state.cpp:286)
+    if (M < h->opt_nc || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;   // polyfit asserts order <= M-1 (driving_state.cpp:286)
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
     const size_t B = (size_t)batch;
@@ -868,17 +885,18 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
     double *dco = dev_out ? coeffs_out : h->d_coeffs;
     double *dce = cte_etheta_out ? (dev_out ? cte_etheta_out : h->d_cte) : NULL;
     CK(cudaEventRecord(h->ev0, st));
-    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, dce, NULL, NULL, 0, 0.0);
+    launch_prestep(h->opt_nc, st, batch, M, dwx, dwy, dpose, dco, dce, NULL, NULL, 0, 0.0);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++; h->kernels++;
     if (!dev_out) {
         double *ho = h->h_out;
-        CK(cudaMemcpyAsync(ho, dco, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
-        if (dce) CK(cudaMemcpyAsync(ho + 4 * B, dce, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
+        const size_t nc = (size_t)h->opt_nc;
+        CK(cudaMemcpyAsync(ho, dco, sizeof(double) * nc * B, cudaMemcpyDeviceToHost, st));
+        if (dce) CK(cudaMemcpyAsync(ho + nc * B, dce, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        memcpy(coeffs_out, ho, sizeof(double) * 4 * B);
-        if (dce) memcpy(cte_etheta_out, ho + 4 * B, sizeof(double) * 2 * B);
+        memcpy(coeffs_out, ho, sizeof(double) * nc * B);
+        if (dce) memcpy(cte_etheta_out, ho + nc * B, sizeof(double) * 2 * B);
     } else if (!(dev_in && stream_v)) {
         CK(cudaStreamSynchronize(st));
     }
@@ -895,7 +913,7 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
 {
     if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !vel || !coeffs_out || !state_out)
         return MPC_B200_ERR_INVALID;
-    if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
+    if (M < h->opt_nc || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
     const size_t B = (size_t)batch;
@@ -919,18 +937,18 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
     double *dco = dev_out ? coeffs_out : h->d_coeffs;
     double *dso = dev_out ? state_out : h->d_state;
     CK(cudaEventRecord(h->ev0, st));
-    prestep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, M, dwx, dwy, dpose, dco, NULL, dvel, dso,
-                                                         h->params.delay_mode, h->params.dt);
+    launch_prestep(h->opt_nc, st, batch, M, dwx, dwy, dpose, dco, NULL, dvel, dso, h->params.delay_mode, h->params.dt);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->launches++; h->kernels++;
     if (!dev_out) {
         double *ho = h->h_out;
-        CK(cudaMemcpyAsync(ho, dco, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ho + 4 * B, dso, sizeof(double) * 6 * B, cudaMemcpyDeviceToHost, st));
+        const size_t nc = (size_t)h->opt_nc;
+        CK(cudaMemcpyAsync(ho, dco, sizeof(double) * nc * B, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ho + nc * B, dso, sizeof(double) * 6 * B, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        memcpy(coeffs_out, ho, sizeof(double) * 4 * B);
-        memcpy(state_out, ho + 4 * B, sizeof(double) * 6 * B);
+        memcpy(coeffs_out, ho, sizeof(double) * nc * B);
+        memcpy(state_out, ho + nc * B, sizeof(double) * 6 * B);
     } else if (!(dev_in && stream_v)) {
         CK(cudaStreamSynchronize(st));
     }

@@ -623,3 +623,38 @@ def test_higher_order_warm_start():
     assert bool((st == 1).all())
     assert float((u_w - u_cold).abs().max()) <= U_TOL
     assert float(it_w.double().mean()) <= 0.7 * float(it_cold.double().mean())
+
+
+def test_prestep_fits_higher_orders(oracle):
+    """polyfit(x, y, order) takes any order (driving_state.cpp:283-300); with the option poly_coeffs the pre-step fits
+    and writes that many coefficients, and the whole tick (pre-step -> solve) then runs on the higher-order path."""
+    from bench import gen_py
+    B = 48
+    g = gen_py.problems(20261031, B)
+    sv = _solver(YAML_DEFAULT, B)
+    sv.set_option("poly_coeffs", 6)
+    coeffs, cte, eth = sv.polyfit(g["wx"], g["wy"], g["pose"])
+    assert coeffs.shape == (6, B)
+    for i in range(B):
+        px, py, th = g["pose"][:, i]
+        dx = g["wx"][:, i] - px; dy = g["wy"][:, i] - py
+        xs = dx * np.cos(th) + dy * np.sin(th); ys = dy * np.cos(th) - dx * np.sin(th)
+        c_o = oracle.polyfit(xs, ys, 5)
+        scale = max(1.0, np.abs(c_o).max())
+        assert np.abs(c_o - coeffs[:, i]).max() <= 1e-7 * scale, (i, c_o, coeffs[:, i])
+        assert cte[i] == coeffs[0, i]
+    # pre-step + solve on the quintic fits = the oracle's solve on them (mild problems only: a quintic through a sharp
+    # corner is as wild as the cubic)
+    state = np.zeros((6, B)); state[3] = g["vel"][0]; state[4] = cte; state[5] = eth
+    out = sv.solve(state, coeffs)
+    sv.close()
+    checked = 0
+    for i in range(B):
+        if np.abs(coeffs[1:, i]).sum() > 2.0:
+            continue
+        o = oracle.solve(YAML_DEFAULT, state[:, i], coeffs[:, i])
+        if o["status"] == 1 and out["status"][i] == 1:
+            checked += 1
+            assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
+            assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+    assert checked >= B // 3

@@ -200,3 +200,17 @@ def test_emu_higher_order_with_rate_penalties(oracle):
         assert r["status"][i] == 1 and o["status"] == 1
         assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-7
         assert abs(r["obj"][i] - o["obj"]) <= 1e-8 * abs(o["obj"])
+
+
+def test_emu_short_and_odd_horizons(oracle):
+    """mpc_steps is a parameter (mpc_planner.cpp:247): horizons that do not fill the stage groups evenly, down to 3."""
+    for N in (3, 5, 7, 21):
+        pm = dict(YAML_DEFAULT, STEPS=N, BOUND=1e19)
+        state, coeffs = mild(30 + N, 6)
+        r = emu_solve(pm, state, coeffs, PB=4)
+        for i in range(6):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert r["status"][i] == 1 and o["status"] == 1, (N, i)
+            assert r["iters"][i] == o["iters"], (N, i)
+            assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-9
+            assert abs(r["obj"][i] - o["obj"]) <= 1e-9 * max(1e-12, abs(o["obj"]))

@@ -658,3 +658,24 @@ def test_prestep_fits_higher_orders(oracle):
             assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
             assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
     assert checked >= B // 3
+
+
+def test_short_and_odd_horizons(oracle):
+    """mpc_steps is a parameter (mpc_planner.cpp:247): horizons that do not fill the stage groups evenly, down to 3
+    (one stage group, the adjoint sweep of all lanes on group 0), with narrow and full-width CTAs."""
+    for N, pb in ((3, 0), (5, 32), (7, 0), (21, 32)):
+        pm = dict(YAML_DEFAULT, STEPS=N)
+        B = 64
+        state, coeffs = mild(30 + N, B)
+        sv = _solver(pm, B)
+        if pb:
+            sv.set_option("problems_per_cta", pb); sv.set_option("max_ctas", 1)
+        out = sv.solve(state, coeffs)
+        sv.close()
+        assert out["pred"].shape == (3 * N, B)
+        for i in range(0, B, 4):
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            assert out["status"][i] == 1 and o["status"] == 1, (N, i)
+            assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
+            assert abs(out["obj"][i] - o["obj"]) <= F_TOL * max(1e-12, abs(o["obj"]))
+            assert np.abs(out["pred"][:, i].reshape(3, N) - o["pred"]).max() <= 1e-6

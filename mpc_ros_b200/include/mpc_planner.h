@@ -20,12 +20,18 @@
 
 struct mpc_b200_handle;
 
+// The reference's header does this at mpc_planner.h:24 and code that includes it may lean on it.
+using namespace std;
+
 class MPC {
 public:
     MPC();
     ~MPC();
-    MPC(const MPC &) = delete;
-    MPC &operator=(const MPC &) = delete;
+    // Copyable like the reference's class (DrivingStateContext::getMpc() returns an MPC by value,
+    // driving_state.h:80-82): a copy takes the parameters, the device and the last prediction, and lazily
+    // creates its OWN solver handle on its first Solve.
+    MPC(const MPC &other);
+    MPC &operator=(const MPC &other);
 
     std::vector<double> Solve(Eigen::VectorXd state, Eigen::VectorXd coeffs);
     std::vector<double> mpc_x;

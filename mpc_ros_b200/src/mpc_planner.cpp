@@ -16,6 +16,24 @@ MPC::~MPC()
     if (handle_) mpc_b200_destroy(handle_);
 }
 
+MPC::MPC(const MPC &o)
+    : mpc_x(o.mpc_x), mpc_y(o.mpc_y), mpc_theta(o.mpc_theta), params_(o.params_), handle_(nullptr), device_(o.device_),
+      handle_steps_(0), dirty_(true), status_(o.status_), iters_(o.iters_), obj_(o.obj_), kkt_(o.kkt_), pred_(o.pred_)
+{
+}
+
+MPC &MPC::operator=(const MPC &o)
+{
+    if (this == &o) return *this;
+    mpc_x = o.mpc_x; mpc_y = o.mpc_y; mpc_theta = o.mpc_theta;
+    params_ = o.params_;
+    if (handle_ && device_ != o.device_) { mpc_b200_destroy(handle_); handle_ = nullptr; handle_steps_ = 0; }
+    device_ = o.device_;
+    dirty_ = true;                 // the own handle (if any) is re-parameterised on the next Solve
+    status_ = o.status_; iters_ = o.iters_; obj_ = o.obj_; kkt_ = o.kkt_; pred_ = o.pred_;
+    return *this;
+}
+
 void MPC::LoadParams(const std::map<std::string, double> &params)
 {
     // merge: the reference re-reads every key on each call and keeps the old value of a key

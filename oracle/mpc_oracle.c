@@ -372,3 +372,76 @@ double mpc_oracle_decel(double px, double py, double gx, double gy, double v,
     }
     return ref_v;
 }
+
+/* State assembly, driving_state.cpp:242-256 */
+void mpc_oracle_state(int delay_mode, double v, double w_prev, double throttle_prev, double dt,
+                      double cte, double etheta, double *state6)
+{
+    if (delay_mode) {
+        const double px_act = v * dt;                                    /* :245 */
+        const double py_act = 0;                                         /* :246 */
+        const double theta_act = w_prev * dt;                            /* :247 */
+        const double v_act = v + throttle_prev * dt;                     /* :248 */
+        const double cte_act = cte + v * sin(etheta) * dt;               /* :250 */
+        const double etheta_act = etheta - theta_act;                    /* :251 */
+        state6[0] = px_act; state6[1] = py_act; state6[2] = theta_act; state6[3] = v_act;
+        state6[4] = cte_act; state6[5] = etheta_act;                     /* :253 */
+    } else {
+        state6[0] = 0; state6[1] = 0; state6[2] = 0; state6[3] = v; state6[4] = cte; state6[5] = etheta;   /* :255 */
+    }
+}
+
+/* driving_state.cpp:266-269 */
+double mpc_oracle_poststep_speed(double v, double throttle, double dt, double ref_v)
+{
+    double speed = v + throttle * dt;
+    if (speed >= ref_v) speed = ref_v;
+    return speed;
+}
+
+/* MPCPlannerROS::getCutOffPlan, mpc_planner_ros.cpp:266-291 */
+int mpc_oracle_cutoff(int n, const double *px, const double *py, int first, int ring, int max_erase,
+                      double rx, double ry)
+{
+    double max_distance_sq = 10e5;                                       /* :273 */
+    int erased = 0;
+    while (erased < max_erase) {                                         /* :276 while (it != end) */
+        int i = first + erased;
+        if (ring) i %= n; else if (i >= n) break;
+        const double x_diff = rx - px[i], y_diff = ry - py[i];           /* :278-279 */
+        const double distance_sq = x_diff * x_diff + y_diff * y_diff;    /* :280 */
+        if (max_distance_sq < distance_sq) break;                        /* :282-284 */
+        erased++;                                                        /* :285 erase(it) */
+        max_distance_sq = distance_sq;                                   /* :286 */
+    }
+    return erased;
+}
+
+/* mpc_planner_ros.cpp:374 */
+int mpc_oracle_downsample_step(double path_length, double waypoints_dist)
+{
+    return (int)(path_length / 10.0 / waypoints_dist);
+}
+
+/* MPCPlannerROS::downSamplePlan, mpc_planner_ros.cpp:365-391 */
+int mpc_oracle_downsample(int n, const double *px, const double *py, int first, int ring, int win, int step,
+                          int cap, double *wx, double *wy)
+{
+    int m = 0;
+    int sampling = step;                                                 /* :376 */
+    int last = first;
+    for (int i = 0; i < win; i++) {                                      /* :379 */
+        int q = first + i;
+        if (ring) q %= n; else if (q >= n) break;
+        last = q;
+        if (sampling == step) {                                          /* :381-386 */
+            if (m < cap) { wx[m] = px[q]; wy[m] = py[q]; }
+            m++;
+            sampling = 0;
+        }
+        sampling += 1;                                                   /* :388 */
+    }
+    if (m < cap) { wx[m] = px[last]; wy[m] = py[last]; }                 /* :390 cutoff_plan.back() */
+    m++;
+    return m;
+}

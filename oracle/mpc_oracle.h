@@ -77,6 +77,29 @@ void mpc_oracle_prestep(const double *wx, const double *wy, int M,
 double mpc_oracle_decel(double px, double py, double gx, double gy, double v,
                         double max_throttle, double max_speed, double min_speed, double ref_v);
 
+/* State handed to MPC::Solve (Tracking::findBestPath, driving_state.cpp:242-256): with delay_mode the kinematic
+ * model predicts the state one dt ahead using the previous w / throttle, else (0, 0, 0, v, cte, etheta). */
+void mpc_oracle_state(int delay_mode, double v, double w_prev, double throttle_prev, double dt,
+                      double cte, double etheta, double *state6);
+
+/* Result post-step (driving_state.cpp:263-269): speed = v + throttle dt, clamped ABOVE at REF_V only. */
+double mpc_oracle_poststep_speed(double v, double throttle, double dt, double ref_v);
+
+/* Plan windowing.
+ * mpc_oracle_cutoff: MPCPlannerROS::getCutOffPlan, mpc_ros/src/mpc_planner_ros.cpp:266-291 -- plan points are erased
+ * from the front while the squared distance to the robot does not grow (start value 10e5); returns how many were
+ * erased, at most max_erase (the reference walks the whole plan: pass n).  Indices wrap modulo n when ring != 0
+ * (closed tracks; the reference's plan is open).
+ * mpc_oracle_downsample: MPCPlannerROS::downSamplePlan, :365-391 -- of a window of `win` points starting at `first`
+ * keep every `step`-th one, beginning with the first, then append the window's last point; the reference derives
+ * step = int(path_length / 10 / waypoints_dist) from the spacing of the first two points (:369-375) -- here the
+ * caller passes it (mpc_oracle_downsample_step).  Returns the number of waypoints written (capacity cap). */
+int mpc_oracle_cutoff(int n, const double *px, const double *py, int first, int ring, int max_erase,
+                      double rx, double ry);
+int mpc_oracle_downsample_step(double path_length, double waypoints_dist);
+int mpc_oracle_downsample(int n, const double *px, const double *py, int first, int ring, int win, int step,
+                          int cap, double *wx, double *wy);
+
 #ifdef __cplusplus
 }
 #endif

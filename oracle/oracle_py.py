@@ -99,6 +99,15 @@ class Oracle:
         L.mpc_oracle_decel.restype = C.c_double
         L.mpc_oracle_prestep.argtypes = [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp]
         L.ipm_default_options.argtypes = [C.POINTER(IpmOptions)]
+        L.mpc_oracle_state.argtypes = [C.c_int] + [C.c_double] * 6 + [_dp]
+        L.mpc_oracle_poststep_speed.argtypes = [C.c_double] * 4
+        L.mpc_oracle_poststep_speed.restype = C.c_double
+        L.mpc_oracle_cutoff.restype = C.c_int
+        L.mpc_oracle_cutoff.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.mpc_oracle_downsample_step.restype = C.c_int
+        L.mpc_oracle_downsample_step.argtypes = [C.c_double, C.c_double]
+        L.mpc_oracle_downsample.restype = C.c_int
+        L.mpc_oracle_downsample.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]
 
     def default_options(self):
         o = IpmOptions()
@@ -149,6 +158,29 @@ class Oracle:
 
     def decel(self, px, py, gx, gy, v, max_throttle, max_speed, min_speed, ref_v):
         return self.lib.mpc_oracle_decel(px, py, gx, gy, v, max_throttle, max_speed, min_speed, ref_v)
+
+    def state(self, delay_mode, v, w_prev, thr_prev, dt, cte, etheta):
+        s6 = np.zeros(6)
+        self.lib.mpc_oracle_state(int(bool(delay_mode)), v, w_prev, thr_prev, dt, cte, etheta, _ptr(s6))
+        return s6
+
+    def poststep_speed(self, v, throttle, dt, ref_v):
+        return self.lib.mpc_oracle_poststep_speed(v, throttle, dt, ref_v)
+
+    def cutoff(self, px, py, first, rx, ry, ring=True, max_erase=None):
+        px = _arr(px); py = _arr(py)
+        return self.lib.mpc_oracle_cutoff(len(px), _ptr(px), _ptr(py), int(first), int(bool(ring)),
+                                          len(px) if max_erase is None else int(max_erase), rx, ry)
+
+    def downsample_step(self, path_length, waypoints_dist):
+        return self.lib.mpc_oracle_downsample_step(path_length, waypoints_dist)
+
+    def downsample(self, px, py, first, win, step, ring=True, cap=64):
+        px = _arr(px); py = _arr(py)
+        wx = np.zeros(cap); wy = np.zeros(cap)
+        m = self.lib.mpc_oracle_downsample(len(px), _ptr(px), _ptr(py), int(first), int(bool(ring)), int(win), int(step),
+                                           cap, _ptr(wx), _ptr(wy))
+        return wx[:min(m, cap)], wy[:min(m, cap)], m
 
 
 def ref_available():
@@ -218,3 +250,55 @@ class Reference:
         x = np.zeros(4); zl = np.zeros(4); zu = np.zeros(4); obj = C.c_double(); it = C.c_int()
         st = self.lib.ref_hs071(tol, _ptr(x), _ptr(zl), _ptr(zu), C.byref(obj), C.byref(it))
         return dict(status=st, x=x, zl=zl, zu=zu, obj=obj.value, iters=it.value)
+
+
+def ros_ref_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libros_ref.so"))
+
+
+class RosReference:
+    """The reference's UNMODIFIED ROS-side sources (driving_state.cpp, mpc_planner_ros.cpp) behind the stand-in ROS
+    headers of oracle/shim/ros_stubs, with the reference's own MPC (oracle/_ref/libros_ref.so, oracle/ros_ref_driver.cpp)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libros_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (build with make -C oracle where /root/reference exists)")
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.ros_ref_window.restype = C.c_int
+        L.ros_ref_window.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp, _ip, _ip]
+        L.ros_ref_tick_new.restype = C.c_void_p
+        L.ros_ref_tick_new.argtypes = [_dp, C.c_int, C.c_double]
+        L.ros_ref_tick.restype = C.c_int
+        L.ros_ref_tick.argtypes = [C.c_void_p] + [C.c_double] * 6 + [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]
+        L.ros_ref_polyfit.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp]
+        L.ros_ref_polyeval.restype = C.c_double
+        L.ros_ref_polyeval.argtypes = [C.c_int, _dp, C.c_double]
+
+    def window(self, px, py, rx, ry, path_length, cap=256):
+        px = _arr(px); py = _arr(py)
+        wx = np.zeros(cap); wy = np.zeros(cap); ne = C.c_int(); ds = C.c_int()
+        m = self.lib.ros_ref_window(len(px), _ptr(px), _ptr(py), rx, ry, path_length, cap, _ptr(wx), _ptr(wy),
+                                    C.byref(ne), C.byref(ds))
+        return dict(m=m, wx=wx[:max(0, min(m, cap))], wy=wy[:max(0, min(m, cap))], erased=ne.value, step=ds.value)
+
+    def tracker(self, pm, delay_mode, max_speed):
+        cfg = _arr([pm[k] for k in PARAM_KEYS])
+        return self.lib.ros_ref_tick_new(_ptr(cfg), int(bool(delay_mode)), float(max_speed))
+
+    def tick(self, h, pose, goal, v, wx, wy, state3, N=20):
+        """state3 = [_w, _throttle, REF_V] in / out.  Returns dict(cmd=(linear.x, angular.z), w, throttle, ref_v, pred)."""
+        wx = _arr(wx); wy = _arr(wy); st = _arr(state3).copy(); out = np.zeros(5); pred = np.zeros(3 * N)
+        ok = self.lib.ros_ref_tick(h, pose[0], pose[1], pose[2], goal[0], goal[1], v, len(wx), _ptr(wx), _ptr(wy),
+                                   _ptr(st), _ptr(out), _ptr(pred), N)
+        return dict(ok=ok, cmd=out[:2].copy(), w=out[2], throttle=out[3], ref_v=out[4], state3=st, pred=pred.reshape(3, N))
+
+    def polyfit(self, xs, ys, order=3):
+        xs = _arr(xs); ys = _arr(ys); c = np.zeros(order + 1)
+        self.lib.ros_ref_polyfit(len(xs), _ptr(xs), _ptr(ys), order, _ptr(c))
+        return c
+
+    def polyeval(self, coeffs, x):
+        coeffs = _arr(coeffs)
+        return self.lib.ros_ref_polyeval(len(coeffs), _ptr(coeffs), x)

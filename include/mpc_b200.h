@@ -15,6 +15,7 @@
 #ifndef MPC_B200_H
 #define MPC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -45,7 +46,14 @@ enum {
     MPC_B200_STATUS_LOCAL_INFEASIBILITY = 5,
     MPC_B200_STATUS_RESTORATION_FAILURE = 9,
     MPC_B200_STATUS_ERROR_IN_STEP_COMPUTATION = 10,
-    MPC_B200_STATUS_INVALID_NUMBER_DETECTED = 11
+    MPC_B200_STATUS_INVALID_NUMBER_DETECTED = 11,
+    /* Not a solve_result value.  The reference bounds every state variable by +-bound_value
+     * (mpc_ros/src/mpc_planner.cpp:303-312, cfg range 0.01 .. 1000, cfg/MPCPlanner.cfg:37).  The GPU path carries
+     * barrier terms for the control bounds only: a point all of whose states lie strictly inside the state bounds
+     * is a KKT point of the bounded problem as well and is returned as SUCCESS; a point with some |state| within
+     * 0.1 % of bound_value (or beyond) would have been shaped by the bounds and is returned with THIS status -- the
+     * iterate is still written out (mpc_planner.cpp:378 ignores the status), but it is never counted as converged. */
+    MPC_B200_STATUS_BOUND_ACTIVE = 64
 };
 
 /*
@@ -129,7 +137,7 @@ int32_t mpc_b200_warm_size(int32_t mpc_steps);
  *   coeffs   4 x batch   cubic reference-path coefficients    (:186-190; driving_state.cpp:210)
  *   ref_vel  batch       optional per-problem REF_V override (NULL = params.ref_vel); the reference
  *                        rewrites REF_V per tick (driving_state.cpp:127-139)
- *   warm_in  warm_size x batch, optional, DEVICE memory (NULL = the reference's cold start, :288-300):
+ *   warm_in  warm_size x batch, optional, device or host memory (NULL = the reference's cold start, :288-300):
  *            controls, equality and bound multipliers are taken from it, the states are re-derived
  *            by a roll-out of the model from `state`
  *   u0       2 x batch   {w_0, throttle_0} = MPC::Solve's return value (:398-401)
@@ -138,7 +146,7 @@ int32_t mpc_b200_warm_size(int32_t mpc_steps);
  *   status   batch       per-problem status (:378), optional
  *   iters    batch       interior-point iterations, optional
  *   kkt_res  batch       final scaled optimality error E_0 (Ipopt's `tol` measure), optional
- *   warm_out warm_size x batch, optional, DEVICE memory
+ *   warm_out warm_size x batch, optional, device or host memory (host records are staged)
  *   stream   cudaStream_t, or NULL for the handle's own stream.  The call returns after the
  *            results are in the caller's buffers (synchronous, like MPC::Solve) unless every
  *            buffer is device memory AND a stream is given, in which case it only enqueues; one handle
@@ -152,7 +160,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
 
 /*
  * Plan windowing for a device-resident closed loop (all pointers DEVICE memory): cut the plan at the
- * nearest point ahead of the robot (MPCPlannerROS::getCutOffPlan, mpc_ros/src/mpc_planner_ros.cpp:266-291)
+ * first plan point past the one nearest to the robot (MPCPlannerROS::getCutOffPlan, mpc_ros/src/mpc_planner_ros.cpp:266-291)
  * and down-sample the next params.path_length metres (downSamplePlan, :365-391; waypoint spacing =
  * params.waypoints_dist, or 0.05 m when that is <= 0).  Plans are closed tracks stored back to back:
  * track t occupies path_x/path_y[track_off[t] .. track_off[t] + track_len[t]).
@@ -254,6 +262,23 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
                           double *obj, int32_t *status, int32_t *iters, double *kkt_res);
 int mpc_b200_track_wait(mpc_b200_handle *h);
 
+/*
+ * The same tick over ONE caller buffer: a single host-to-device and a single device-to-host copy per tick instead
+ * of one per array (the arrays are small; per-copy overhead is what a host thread feeding several GPUs pays).
+ * _layout returns the buffer size in BYTES and the byte offset of each block, in this order:
+ *   0 wx (M x batch)  1 wy  2 pose (3 x batch)  3 ref_vel (batch; -1 when with_ref_vel == 0)
+ *   4 vel (3 x batch, in AND out)  5 u0 (2 x batch)  6 pred (3N x batch)  7 cmd (2 x batch)  8 obj  9 kkt_res
+ *   10 status (int32 x batch)  11 iters (int32 x batch)
+ * Blocks 0-4 are read, blocks 4-11 written; the caller fills the inputs in place, calls _packed_submit, and reads the
+ * outputs in place after mpc_b200_track_wait.  Page-locked buffers (mpc_b200_host_alloc) are copied by DMA directly.
+ */
+int64_t mpc_b200_track_packed_layout(const mpc_b200_handle *h, int32_t batch, int32_t M, int32_t with_ref_vel,
+                                     int64_t *offsets_bytes12);
+int mpc_b200_track_packed_submit(mpc_b200_handle *h, int32_t batch, int32_t M, int32_t with_ref_vel, void *io);
+/* Page-locked host memory for callers that do not link the CUDA runtime (cgo / JNI / ctypes). */
+void *mpc_b200_host_alloc(size_t bytes);
+void mpc_b200_host_free(void *p);
+
 /* Seconds spent on the device by the last solve_batch / polyfit_batch on this handle
  * (CUDA events on the launching stream around the kernel only; no copies). */
 double mpc_b200_last_kernel_seconds(const mpc_b200_handle *h);
@@ -269,6 +294,11 @@ int mpc_b200_device_count(void);
 /* FP64 FMA microbenchmark used to fix the roofline denominator (MEASURED_PEAKS.json has
  * no FP64 entry): independent DFMA chains on every SM.  Returns measured TFLOP/s, <0 on error. */
 double mpc_b200_measure_fp64_peak(int32_t device, int32_t iters);
+/* Diagnostics.  _debug_profile: per-phase SM-cycle counters of the last solve (libraries built with
+ * -DNMPC_PROFILE only; returns 0 otherwise; out = 1024 values, see bench/gpu_sat.py).  _debug_fp64_probe: SM cycles per
+ * warp-level DFMA of a single warp with `ilp` independent chains and `active_lanes` lanes (profiles/r1_fp64_probe.md). */
+int mpc_b200_debug_profile(mpc_b200_handle *h, long long *out1024);
+double mpc_b200_debug_fp64_probe(int32_t device, int32_t ilp, int32_t active_lanes, int32_t iters);
 
 #ifdef __cplusplus
 }

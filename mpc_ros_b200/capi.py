@@ -41,6 +41,8 @@ EXPORTS = [
     "mpc_b200_num_waypoints", "mpc_b200_decel_batch", "mpc_b200_plant_step_batch", "mpc_b200_stream_create", "mpc_b200_stream_destroy", "mpc_b200_stream_synchronize", "mpc_b200_track_batch", "mpc_b200_track_submit", "mpc_b200_track_wait",
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
+    "mpc_b200_track_packed_layout", "mpc_b200_track_packed_submit", "mpc_b200_host_alloc", "mpc_b200_host_free",
+    "mpc_b200_debug_profile", "mpc_b200_debug_fp64_probe",
 ]
 
 _LIB = None
@@ -113,6 +115,13 @@ def lib():
     L.mpc_b200_device_count.restype = C.c_int
     L.mpc_b200_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32]
     L.mpc_b200_measure_fp64_peak.restype = C.c_double
+    L.mpc_b200_track_packed_layout.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+    L.mpc_b200_track_packed_layout.restype = C.c_int64
+    L.mpc_b200_track_packed_submit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.mpc_b200_track_packed_submit.restype = C.c_int
+    L.mpc_b200_host_alloc.argtypes = [C.c_size_t]
+    L.mpc_b200_host_alloc.restype = C.c_void_p
+    L.mpc_b200_host_free.argtypes = [C.c_void_p]
     if hasattr(L, "mpc_b200_debug_profile"):
         L.mpc_b200_debug_profile.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.mpc_b200_debug_profile.restype = C.c_int
@@ -314,6 +323,34 @@ class Solver:
         self.track_raw(B, M, wx, wy, pose, vel, out["u0"], out["pred"], ref_vel=ref_vel, cmd=out["cmd"], obj=out["obj"],
                        status=out["status"], iters=out["iters"], kkt=out["kkt"])
         return out
+
+    def packed_layout(self, batch, M, with_ref_vel=False):
+        """(total bytes, dict name -> byte offset) of the one-buffer tick (mpc_b200_track_packed_submit)."""
+        off = (C.c_int64 * 12)()
+        total = lib().mpc_b200_track_packed_layout(self._h, batch, M, int(with_ref_vel), off)
+        if total < 0:
+            raise MpcError(int(total))
+        names = ["wx", "wy", "pose", "ref_vel", "vel", "u0", "pred", "cmd", "obj", "kkt", "status", "iters"]
+        return int(total), {n: int(o) for n, o in zip(names, off)}
+
+    def packed_views(self, buf, batch, M, with_ref_vel=False):
+        """numpy views of the blocks of a packed tick buffer (`buf`: uint8 array of packed_layout()[0] bytes)."""
+        total, off = self.packed_layout(batch, M, with_ref_vel)
+        N = self.N
+        def f64(name, rows):
+            return np.frombuffer(buf, dtype=np.float64, count=rows * batch, offset=off[name]).reshape(rows, batch)
+        v = dict(wx=f64("wx", M), wy=f64("wy", M), pose=f64("pose", 3), vel=f64("vel", 3), u0=f64("u0", 2),
+                 pred=f64("pred", 3 * N), cmd=f64("cmd", 2), obj=f64("obj", 1)[0], kkt=f64("kkt", 1)[0],
+                 status=np.frombuffer(buf, dtype=np.int32, count=batch, offset=off["status"]),
+                 iters=np.frombuffer(buf, dtype=np.int32, count=batch, offset=off["iters"]))
+        if with_ref_vel:
+            v["ref_vel"] = f64("ref_vel", 1)[0]
+        return v
+
+    def track_packed_submit(self, batch, M, io, with_ref_vel=False):
+        rc = lib().mpc_b200_track_packed_submit(self._h, batch, M, int(with_ref_vel), _addr(io))
+        if rc != 0:
+            raise MpcError(rc, lib().mpc_b200_last_cuda_error(self._h).decode())
 
     def warm_shift(self, batch, prev, nxt, stream=None):
         rc = lib().mpc_b200_warm_shift(self._h, batch, _addr(prev), _addr(nxt), stream)

@@ -3,6 +3,7 @@
 #include "nmpc_kernel.cuh"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -11,6 +12,9 @@
 #include <string>
 
 using nmpc::SolveArgs;
+
+// NVTX range around every batch entry point (tracing): shows up in nsys / ncu timelines
+namespace { struct NvtxRange { explicit NvtxRange(const char *n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } }; }
 
 #define MAX_WAYPOINTS 64
 #define QUEUE_RING 1024
@@ -24,7 +28,9 @@ using nmpc::SolveArgs;
 // (Vandermonde by running products + unpivoted Householder QR, what Eigen's
 // householderQr().solve() does).  One thread per problem: M ~ 11 waypoints, a 11x4 QR.
 // NC = order + 1 columns (polyfit(x, y, order), driving_state.cpp:283-300, takes any order; the caller fits 3).
-template <int NC>
+// MAXM: rows the per-thread scratch is sized for -- 16 covers the reference's ~11 down-sampled waypoints (640 B of stack
+// at NC = 4), 64 is the general case.
+template <int NC, int MAXM>
 __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, const double *__restrict__ wy,
                                const double *__restrict__ pose, double *__restrict__ coeffs_out,
                                double *__restrict__ cte_eth_out, const double *__restrict__ vel,
@@ -35,8 +41,8 @@ __global__ void prestep_kernel(int batch, int M, const double *__restrict__ wx, 
     const double px = pose[i], py = pose[(size_t)batch + i], th = pose[2 * (size_t)batch + i];
     double st, ct;
     sincos(th, &st, &ct);
-    double A[MAX_WAYPOINTS][NC];
-    double b[MAX_WAYPOINTS];
+    double A[MAXM][NC];
+    double b[MAXM];
     for (int j = 0; j < M; j++) {
         const double dx = wx[(size_t)j * batch + i] - px, dy = wy[(size_t)j * batch + i] - py;
         const double xv = dx * ct + dy * st;      // driving_state.cpp:205
@@ -124,12 +130,18 @@ static void launch_prestep(int nc, cudaStream_t st, int batch, int M, const doub
                            double dt)
 {
     const int grid = (batch + 127) / 128;
-#define PRESTEP_CASE(K) case K: prestep_kernel<K><<<grid, 128, 0, st>>>(batch, M, wx, wy, pose, coeffs_out, cte_eth_out, vel, state_out, delay_mode, dt); break
+#define PRESTEP_ARGS batch, M, wx, wy, pose, coeffs_out, cte_eth_out, vel, state_out, delay_mode, dt
+#define PRESTEP_CASE(K) case K: if (M <= 16) prestep_kernel<K, 16><<<grid, 128, 0, st>>>(PRESTEP_ARGS); \
+                                else prestep_kernel<K, MAX_WAYPOINTS><<<grid, 128, 0, st>>>(PRESTEP_ARGS); break
     switch (nc) {
         PRESTEP_CASE(5); PRESTEP_CASE(6); PRESTEP_CASE(7); PRESTEP_CASE(8);
-        default: prestep_kernel<4><<<grid, 128, 0, st>>>(batch, M, wx, wy, pose, coeffs_out, cte_eth_out, vel, state_out, delay_mode, dt); break;
+        default:
+            if (M <= 16) prestep_kernel<4, 16><<<grid, 128, 0, st>>>(PRESTEP_ARGS);
+            else prestep_kernel<4, MAX_WAYPOINTS><<<grid, 128, 0, st>>>(PRESTEP_ARGS);
+            break;
     }
 #undef PRESTEP_CASE
+#undef PRESTEP_ARGS
 }
 
 // ================================================================ hard-first queue order
@@ -169,11 +181,14 @@ __global__ void __launch_bounds__(128) queue_order_kernel(int batch, const doubl
 }
 
 // ================================================================ plan windowing
-// Reference: MPCPlannerROS::getCutOffPlan (mpc_ros/src/mpc_planner_ros.cpp:266-291) drops plan points while
-// the distance to the robot keeps shrinking, i.e. advances to the first local minimum of the distance along
-// the plan; downSamplePlan (:365-391) then keeps every `step`-th point of the window plus its last point
-// (with path_length / waypoints_dist taken from the parameters instead of the reference's uninitialised
-// members).  Closed tracks: indices wrap.  One thread per robot.
+// Reference: MPCPlannerROS::getCutOffPlan (mpc_ros/src/mpc_planner_ros.cpp:266-291) erases plan points from the
+// front while the squared distance to the robot does not grow (start value 10e5, :273): the plan then begins at the
+// first point that is farther away than its predecessor, i.e. one past the nearest point.  downSamplePlan
+// (:365-391) keeps every `step`-th point of the window, beginning with its first, and appends its last point (with
+// path_length / waypoints_dist taken from the parameters instead of the reference's uninitialised members).
+// Closed tracks: indices wrap; at most max_advance points are erased per tick.  One thread per robot.
+// Checked against oracle/mpc_oracle.c (mpc_oracle_cutoff / _downsample), which tests/test_ros_ref.py pins to the
+// reference's own code.
 __global__ void window_kernel(int batch, const double *__restrict__ px, const double *__restrict__ py,
                               const int *__restrict__ track_off, const int *__restrict__ track_len,
                               const int *__restrict__ track_id, int *__restrict__ idx_io,
@@ -185,15 +200,17 @@ __global__ void window_kernel(int batch, const double *__restrict__ px, const do
     const int t = track_id[i], off = track_off[t], n = track_len[t];
     const double rx = pose[i], ry = pose[(size_t)batch + i];
     int j = idx_io[i] % n;
-    double best = 1e300;
-    for (int a = 0; a < max_advance; a++) {
-        const int q = (j + a) % n;
+    double max_distance_sq = 10e5;                          // :273
+    int erased = 0;
+    while (erased < max_advance) {
+        const int q = (j + erased) % n;
         const double dx = rx - px[off + q], dy = ry - py[off + q];
         const double d2 = dx * dx + dy * dy;
-        if (best < d2) { j = (j + a - 1) % n; break; }     // distance started to grow: previous point is the cut
-        best = d2;
-        if (a == max_advance - 1) j = q;
+        if (max_distance_sq < d2) break;                    // :282-284: this point stays, it is the new plan start
+        erased++;                                           // :285
+        max_distance_sq = d2;                               // :286
     }
+    j = (j + erased) % n;
     idx_io[i] = j;
     int m = 0;
     for (int a = 0; a < win; a += step, m++) {
@@ -318,6 +335,8 @@ __global__ void dfma_kernel(double *out, int iters, int active_lanes, long long 
 // host-buffer results of a tick that is still in flight (mpc_b200_track_submit / _wait)
 struct Fetch {
     bool active;
+    bool packed;           // mpc_b200_track_packed_submit: one D2H into `io` (or the staging area)
+    void *io; size_t io_off, io_bytes; bool io_pinned;
     int32_t batch;
     double *u0, *pred, *obj, *kkt, *cmd, *vel;
     int32_t *status, *iters;
@@ -351,6 +370,11 @@ struct mpc_b200_handle {
     int max_ctas;          // option: cap on the persistent grid (0 = one CTA per SM)
     int opt_pb;            // option: problems per CTA (0 = auto)
     int opt_nc;            // option: rows of the coeffs arrays = polynomial order + 1 (4 .. NMPC_MAX_COEFFS; default 4)
+    double *d_io;          // packed tick buffer (mpc_b200_track_packed_*), allocated on first use
+    size_t d_io_doubles;
+    double *d_warm_stage_in, *d_warm_stage_out;   // device staging of HOST warm-start records, allocated on first use
+    const void *pin_ptr[8]; bool pin_val[8]; int pin_next;   // small cache of cudaPointerGetAttributes answers
+    cudaEvent_t *slot_ev;  // one event per queue / order ring slot: a slot is reused only after its launch has finished
     Fetch pending;
     std::string last_err;
 };
@@ -373,6 +397,17 @@ static bool is_pinned_host(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
+// The tick entry points see the same caller buffers every tick: remember the answers (a buffer's kind does not
+// change while it is allocated; a freed-and-reallocated address of another kind would be a caller bug either way).
+static bool is_pinned_cached(mpc_b200_handle *h, const void *p)
+{
+    if (!p) return false;
+    for (int i = 0; i < 8; i++) if (h->pin_ptr[i] == p) return h->pin_val[i];
+    const bool v = is_pinned_host(p);
+    h->pin_ptr[h->pin_next] = p; h->pin_val[h->pin_next] = v; h->pin_next = (h->pin_next + 1) & 7;
+    return v;
+}
+
 static int cuda_fail(mpc_b200_handle *h, cudaError_t e, const char *what)
 {
     if (h) h->last_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -387,17 +422,42 @@ static void free_scratch(mpc_b200_handle *h)
     cudaFree(h->d_obj); cudaFree(h->d_kkt); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_warm_out);
     cudaFree(h->d_wx); cudaFree(h->d_wy); cudaFree(h->d_pose); cudaFree(h->d_cte); cudaFree(h->d_vel);
     cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
-    if (h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
-    if (h->d_queue) { cudaFree(h->d_queue); h->d_queue = NULL; }
-    if (h->d_order) { cudaFree(h->d_order); h->d_order = NULL; }
+    if (h->d_io) { cudaFree(h->d_io); h->d_io = NULL; h->d_io_doubles = 0; }
+    if (h->d_warm_stage_in) { cudaFree(h->d_warm_stage_in); h->d_warm_stage_in = NULL; }
+    if (h->d_warm_stage_out) { cudaFree(h->d_warm_stage_out); h->d_warm_stage_out = NULL; }
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL;
     h->h_in = h->h_out = NULL;
 }
 
-static int alloc_scratch(mpc_b200_handle *h)
+// what does not depend on the horizon: the work-queue heads, the queue orders and their per-slot events
+static void free_rings(mpc_b200_handle *h)
 {
-    const size_t B = (size_t)h->max_batch, N = (size_t)h->params.mpc_steps;
+    if (h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
+    if (h->d_queue) { cudaFree(h->d_queue); h->d_queue = NULL; }
+    if (h->d_order) { cudaFree(h->d_order); h->d_order = NULL; }
+    if (h->slot_ev) {
+        for (int i = 0; i < h->order_ring; i++) if (h->slot_ev[i]) cudaEventDestroy(h->slot_ev[i]);
+        free(h->slot_ev); h->slot_ev = NULL;
+    }
+}
+
+static int alloc_rings(mpc_b200_handle *h)
+{
+    const size_t B = (size_t)h->max_batch;
+    CK(cudaMalloc(&h->d_queue, sizeof(int) * QUEUE_RING));
+    h->order_ring = (int)((size_t)(1 << 22) / B);
+    if (h->order_ring < 16) h->order_ring = 16;
+    if (h->order_ring > QUEUE_RING) h->order_ring = QUEUE_RING;
+    CK(cudaMalloc(&h->d_order, sizeof(int) * (size_t)h->order_ring * B));
+    h->slot_ev = (cudaEvent_t *)calloc((size_t)h->order_ring, sizeof(cudaEvent_t));
+    if (!h->slot_ev) return MPC_B200_ERR_NOMEM;
+    return MPC_B200_OK;
+}
+
+static int alloc_scratch(mpc_b200_handle *h, int steps)
+{
+    const size_t B = (size_t)h->max_batch, N = (size_t)steps;
     h->pred_steps = (int)N;
     CK(cudaMalloc(&h->d_state, sizeof(double) * 6 * B));
     CK(cudaMalloc(&h->d_coeffs, sizeof(double) * NMPC_MAX_COEFFS * B));
@@ -413,11 +473,6 @@ static int alloc_scratch(mpc_b200_handle *h)
     CK(cudaMalloc(&h->d_pose, sizeof(double) * 3 * B));
     CK(cudaMalloc(&h->d_cte, sizeof(double) * 2 * B));
     CK(cudaMalloc(&h->d_vel, sizeof(double) * 3 * B));
-    CK(cudaMalloc(&h->d_queue, sizeof(int) * QUEUE_RING));
-    h->order_ring = (int)((size_t)(1 << 22) / B);
-    if (h->order_ring < 16) h->order_ring = 16;
-    if (h->order_ring > QUEUE_RING) h->order_ring = QUEUE_RING;
-    CK(cudaMalloc(&h->d_order, sizeof(int) * (size_t)h->order_ring * B));
     h->d_warm_out = NULL;
     h->h_in_bytes = sizeof(double) * (2 * MAX_WAYPOINTS + 3 + 11) * B;
     h->h_out_bytes = sizeof(double) * (2 + 3 * N + 2 + 2 + 3 + 1 + 6) * B;   // u0 pred obj kkt cmd vel status/iters + slack
@@ -480,6 +535,10 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
     h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->opt_nc = 4; h->d_order = NULL; h->opt_order = 1;
+    h->d_io = NULL; h->d_io_doubles = 0; h->d_warm_stage_in = h->d_warm_stage_out = NULL; h->slot_ev = NULL; h->order_ring = 0;
+    for (int i = 0; i < 8; i++) { h->pin_ptr[i] = NULL; h->pin_val[i] = false; }
+    h->pin_next = 0;
+    h->pending = Fetch();
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -501,8 +560,9 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS>));
 #undef SET_SMEM
     if (e != cudaSuccess) { cudaGetLastError(); delete h; return MPC_B200_ERR_CUDA; }
-    rc = alloc_scratch(h);
-    if (rc != MPC_B200_OK) { free_scratch(h); delete h; return rc; }
+    rc = alloc_scratch(h, h->params.mpc_steps);
+    if (rc == MPC_B200_OK) rc = alloc_rings(h);
+    if (rc != MPC_B200_OK) { free_scratch(h); free_rings(h); delete h; return rc; }
     *out = h;
     return MPC_B200_OK;
 }
@@ -511,8 +571,9 @@ void mpc_b200_destroy(mpc_b200_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();          // launches given caller streams may still be using the rings
     free_scratch(h);
+    free_rings(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -551,13 +612,22 @@ int mpc_b200_set_params(mpc_b200_handle *h, const mpc_b200_params *p)
     if (rc != MPC_B200_OK) return rc;
     if (h->pending.active) return MPC_B200_ERR_INVALID;      // a submitted tick must be waited for first
     const bool regrow = p->mpc_steps > h->pred_steps;
-    h->params = *p;
     if (regrow) {
+        // A longer horizon needs larger result / staging buffers.  Launches enqueued with CALLER streams may still be
+        // running: wait for the whole device, not just the handle's stream.  The queue / order rings do not depend on
+        // the horizon and are kept.  The new parameters are adopted only once the new scratch exists.
         CK(cudaSetDevice(h->device));
-        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaDeviceSynchronize());
         free_scratch(h);
-        return alloc_scratch(h);
+        rc = alloc_scratch(h, p->mpc_steps);
+        if (rc != MPC_B200_OK) {
+            // back to a usable handle with the OLD parameters
+            free_scratch(h);
+            if (alloc_scratch(h, h->params.mpc_steps) != MPC_B200_OK) free_scratch(h);
+            return rc;
+        }
     }
+    h->params = *p;
     return MPC_B200_OK;
 }
 
@@ -627,6 +697,9 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.prm.idt = 1.0 / P.dt;
     a.prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); a.prm.i_nb = 1.0 / (double)(4 * (N - 1));
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
+    // +-bound_value on the states (mpc_planner.cpp:303-312) carries no barrier term here: a point within 0.1 % of
+    // it is reported as MPC_B200_STATUS_BOUND_ACTIVE instead of success (nmpc_phases.cuh, ctrl_decide)
+    a.prm.bound_chk = (P.bound_value > 0.0 ? P.bound_value : 1e3) * (1.0 - 1e-3);
     a.batch = batch;
     a.ncoef = h->opt_nc;
     const bool rate = P.w_angvel_d != 0.0 || P.w_accel_d != 0.0;
@@ -645,10 +718,23 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     const int cap = h->max_ctas > 0 ? h->max_ctas : h->num_sms;
     if (grid > cap) grid = cap;
     const size_t smem = nmpc::smem_bytes(N, NG, a.PB, nslots);
-    a.queue = h->d_queue + (h->launches % QUEUE_RING);
+    // Ring slot of this launch (work-queue head + queue order).  A slot is reused only when the launch that had it
+    // last has finished: more than order_ring launches in flight is refused, not silently aliased.
+    const int slot = (int)(h->launches % h->order_ring);
+    if (h->slot_ev[slot]) {
+        const cudaError_t q = cudaEventQuery(h->slot_ev[slot]);
+        if (q == cudaErrorNotReady) {
+            h->last_err = "too many launches in flight on this handle (see mpc_b200_solve_batch, `stream`)";
+            return MPC_B200_ERR_INVALID;
+        }
+        if (q != cudaSuccess) return cuda_fail(h, q, "cudaEventQuery(slot)");
+    } else {
+        CK(cudaEventCreateWithFlags(&h->slot_ev[slot], cudaEventDisableTiming));
+    }
+    a.queue = h->d_queue + slot;
     a.order = NULL;
     if (h->opt_order && batch > grid * a.PB) {      // only matters when lanes work through several problems
-        a.order = h->d_order + (size_t)(h->launches % h->order_ring) * h->max_batch;
+        a.order = h->d_order + (size_t)slot * h->max_batch;
         queue_order_kernel<<<1, 128, 0, st>>>(batch, a.coeffs, (int *)a.order, a.queue);
         CK(cudaGetLastError());
         h->kernels++;
@@ -677,6 +763,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     }
     CK(cudaGetLastError());
     if (timed) CK(cudaEventRecord(h->ev1, st));
+    CK(cudaEventRecord(h->slot_ev[slot], st));
     h->launches++; h->kernels++;
     return MPC_B200_OK;
 }
@@ -698,8 +785,8 @@ static int fetch_enqueue(mpc_b200_handle *h, Fetch &f, cudaStream_t st)
     const size_t B = (size_t)f.batch, N = (size_t)h->params.mpc_steps;
     double *ho_u0, *ho_pred, *ho_obj, *ho_kkt, *ho_cmd, *ho_vel; int *ho_status, *ho_iters;
     fetch_layout(h, B, &ho_u0, &ho_pred, &ho_obj, &ho_kkt, &ho_cmd, &ho_vel, &ho_status, &ho_iters);
-    f.pu = is_pinned_host(f.u0); f.pp = is_pinned_host(f.pred); f.po = is_pinned_host(f.obj); f.pk = is_pinned_host(f.kkt);
-    f.ps = is_pinned_host(f.status); f.pi = is_pinned_host(f.iters); f.pc = is_pinned_host(f.cmd); f.pv = is_pinned_host(f.vel);
+    f.pu = is_pinned_cached(h, f.u0); f.pp = is_pinned_cached(h, f.pred); f.po = is_pinned_cached(h, f.obj); f.pk = is_pinned_cached(h, f.kkt);
+    f.ps = is_pinned_cached(h, f.status); f.pi = is_pinned_cached(h, f.iters); f.pc = is_pinned_cached(h, f.cmd); f.pv = is_pinned_cached(h, f.vel);
     CK(cudaMemcpyAsync(f.pu ? f.u0 : ho_u0, h->d_u0, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(f.pp ? f.pred : ho_pred, h->d_pred, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToHost, st));
     if (f.obj) CK(cudaMemcpyAsync(f.po ? f.obj : ho_obj, h->d_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
@@ -716,6 +803,14 @@ static int fetch_finish(mpc_b200_handle *h, Fetch &f, cudaStream_t st)
 {
     if (!f.active) return MPC_B200_OK;
     f.active = false;
+    if (f.packed) {
+        f.packed = false;
+        CK(cudaStreamSynchronize(st));
+        if (!f.io_pinned) memcpy((char *)f.io + f.io_off, h->h_out, f.io_bytes);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
+        return MPC_B200_OK;
+    }
     const size_t B = (size_t)f.batch, N = (size_t)h->params.mpc_steps;
     double *ho_u0, *ho_pred, *ho_obj, *ho_kkt, *ho_cmd, *ho_vel; int *ho_status, *ho_iters;
     fetch_layout(h, B, &ho_u0, &ho_pred, &ho_obj, &ho_kkt, &ho_cmd, &ho_vel, &ho_status, &ho_iters);
@@ -739,6 +834,7 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
                          double *u0, double *pred, double *obj, int32_t *status, int32_t *iters,
                          double *kkt_res, double *warm_out, void *stream_v)
 {
+    NvtxRange nv("mpc_b200_solve_batch");
     if (!h || batch < 0 || batch > h->max_batch || !state || !coeffs || !u0 || !pred) return MPC_B200_ERR_INVALID;
     if (batch == 0) return MPC_B200_OK;
     CK(cudaSetDevice(h->device));
@@ -748,9 +844,20 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
     const bool dev_in = is_device_ptr(state);
     const bool dev_out = is_device_ptr(u0);
     if (is_device_ptr(coeffs) != dev_in || (ref_vel && is_device_ptr(ref_vel) != dev_in)) return MPC_B200_ERR_INVALID;
-    // warm-start records are large and meant to stay on the device between ticks
-    if (warm_in && !is_device_ptr(warm_in)) return MPC_B200_ERR_UNSUPPORTED;
-    if (warm_out && !is_device_ptr(warm_out)) return MPC_B200_ERR_UNSUPPORTED;
+    // Warm-start records are large and meant to stay on the device between ticks; HOST records are accepted too
+    // (SURVEY 8b "ownership": any buffer may be host memory) and staged through device buffers the handle keeps.
+    const size_t wsz = (size_t)mpc_b200_warm_size(h->params.mpc_steps);
+    double *host_warm_out = NULL;
+    if (warm_in && !is_device_ptr(warm_in)) {
+        if (!h->d_warm_stage_in) CK(cudaMalloc(&h->d_warm_stage_in, sizeof(double) * (size_t)mpc_b200_warm_size(h->pred_steps) * h->max_batch));
+        CK(cudaMemcpyAsync(h->d_warm_stage_in, warm_in, sizeof(double) * wsz * B, cudaMemcpyHostToDevice, st));
+        warm_in = h->d_warm_stage_in;
+    }
+    if (warm_out && !is_device_ptr(warm_out)) {
+        if (!h->d_warm_stage_out) CK(cudaMalloc(&h->d_warm_stage_out, sizeof(double) * (size_t)mpc_b200_warm_size(h->pred_steps) * h->max_batch));
+        host_warm_out = warm_out;
+        warm_out = h->d_warm_stage_out;
+    }
     if (is_device_ptr(pred) != dev_out || (obj && is_device_ptr(obj) != dev_out) ||
         (status && is_device_ptr(status) != dev_out) || (iters && is_device_ptr(iters) != dev_out) ||
         (kkt_res && is_device_ptr(kkt_res) != dev_out))
@@ -778,6 +885,10 @@ int mpc_b200_solve_batch(mpc_b200_handle *h, int32_t batch,
         rc = enqueue_solve(h, batch, ds, dc, dr, warm_in, h->d_u0, h->d_pred, h->d_obj, h->d_status, h->d_iters, h->d_kkt,
                            warm_out, st);
     if (rc != MPC_B200_OK) return rc;
+    if (host_warm_out) {
+        CK(cudaMemcpyAsync(host_warm_out, warm_out, sizeof(double) * wsz * B, cudaMemcpyDeviceToHost, st));
+        if (dev_out) CK(cudaStreamSynchronize(st));      // a host buffer is filled when the call returns
+    }
 
     if (!dev_out) {
         Fetch f = {};
@@ -799,6 +910,7 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
                           const double *ref_vel, double *u0, double *pred, double *cmd_out,
                           double *obj, int32_t *status, int32_t *iters, double *kkt_res)
 {
+    NvtxRange nv("mpc_b200_track_submit");
     if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !vel_inout || !u0 || !pred) return MPC_B200_ERR_INVALID;
     if (M < 4 || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;
     if (is_device_ptr(wx) || is_device_ptr(u0)) return MPC_B200_ERR_UNSUPPORTED;   // host entry point; device callers chain the
@@ -811,11 +923,11 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
     cudaStream_t st = h->stream;
     double *hi = h->h_in;
     const double *sx = wx, *sy = wy, *sp = pose, *sv = vel_inout, *sr = ref_vel;
-    if (!is_pinned_host(wx)) { memcpy(hi, wx, sizeof(double) * M * B); sx = hi; }
-    if (!is_pinned_host(wy)) { memcpy(hi + (size_t)M * B, wy, sizeof(double) * M * B); sy = hi + (size_t)M * B; }
-    if (!is_pinned_host(pose)) { memcpy(hi + 2 * (size_t)M * B, pose, sizeof(double) * 3 * B); sp = hi + 2 * (size_t)M * B; }
-    if (!is_pinned_host(vel_inout)) { memcpy(hi + 2 * (size_t)M * B + 3 * B, vel_inout, sizeof(double) * 3 * B); sv = hi + 2 * (size_t)M * B + 3 * B; }
-    if (ref_vel && !is_pinned_host(ref_vel)) { memcpy(hi + 2 * (size_t)M * B + 6 * B, ref_vel, sizeof(double) * B); sr = hi + 2 * (size_t)M * B + 6 * B; }
+    if (!is_pinned_cached(h, wx)) { memcpy(hi, wx, sizeof(double) * M * B); sx = hi; }
+    if (!is_pinned_cached(h, wy)) { memcpy(hi + (size_t)M * B, wy, sizeof(double) * M * B); sy = hi + (size_t)M * B; }
+    if (!is_pinned_cached(h, pose)) { memcpy(hi + 2 * (size_t)M * B, pose, sizeof(double) * 3 * B); sp = hi + 2 * (size_t)M * B; }
+    if (!is_pinned_cached(h, vel_inout)) { memcpy(hi + 2 * (size_t)M * B + 3 * B, vel_inout, sizeof(double) * 3 * B); sv = hi + 2 * (size_t)M * B + 3 * B; }
+    if (ref_vel && !is_pinned_cached(h, ref_vel)) { memcpy(hi + 2 * (size_t)M * B + 6 * B, ref_vel, sizeof(double) * B); sr = hi + 2 * (size_t)M * B + 6 * B; }
     CK(cudaMemcpyAsync(h->d_wx, sx, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_wy, sy, sizeof(double) * M * B, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_pose, sp, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
@@ -837,6 +949,103 @@ int mpc_b200_track_submit(mpc_b200_handle *h, int32_t batch, int32_t M,
     f.batch = batch; f.u0 = u0; f.pred = pred; f.obj = obj; f.kkt = kkt_res; f.status = status; f.iters = iters;
     f.cmd = cmd_out; f.vel = vel_inout;
     return fetch_enqueue(h, f, st);
+}
+
+// ---- packed tick: ONE caller buffer, one H2D and one D2H copy per tick
+// Layout in doubles for (batch B, M waypoints, horizon N), blocks in this order:
+//   wx M*B | wy M*B | pose 3B | [ref_vel B] | vel 3B | u0 2B | pred 3N*B | cmd 2B | obj B | kkt B | status | iters
+// (status, iters: int32 arrays, each padded to a whole number of doubles).  Inputs = [wx .. vel], outputs = [vel .. iters]:
+// the in/out block vel sits where the two ranges meet.
+static size_t packed_layout(int N, size_t B, size_t M, int with_refv, int64_t *off /* 12, doubles */)
+{
+    size_t o = 0;
+    off[0] = (int64_t)o; o += M * B;            // wx
+    off[1] = (int64_t)o; o += M * B;            // wy
+    off[2] = (int64_t)o; o += 3 * B;            // pose
+    if (with_refv) { off[3] = (int64_t)o; o += B; } else off[3] = -1;
+    off[4] = (int64_t)o; o += 3 * B;            // vel (in / out)
+    off[5] = (int64_t)o; o += 2 * B;            // u0
+    off[6] = (int64_t)o; o += 3 * (size_t)N * B;   // pred
+    off[7] = (int64_t)o; o += 2 * B;            // cmd
+    off[8] = (int64_t)o; o += B;                // obj
+    off[9] = (int64_t)o; o += B;                // kkt
+    off[10] = (int64_t)o; o += (B + 1) / 2;     // status (int32)
+    off[11] = (int64_t)o; o += (B + 1) / 2;     // iters (int32)
+    return o;
+}
+
+int64_t mpc_b200_track_packed_layout(const mpc_b200_handle *h, int32_t batch, int32_t M, int32_t with_ref_vel,
+                                     int64_t *offsets_bytes12)
+{
+    if (!h || batch < 1 || M < 1) return MPC_B200_ERR_INVALID;
+    int64_t off[12];
+    const size_t n = packed_layout(h->params.mpc_steps, (size_t)batch, (size_t)M, with_ref_vel, off);
+    if (offsets_bytes12) for (int i = 0; i < 12; i++) offsets_bytes12[i] = off[i] < 0 ? -1 : off[i] * (int64_t)sizeof(double);
+    return (int64_t)(n * sizeof(double));
+}
+
+int mpc_b200_track_packed_submit(mpc_b200_handle *h, int32_t batch, int32_t M, int32_t with_ref_vel, void *io)
+{
+    NvtxRange nv("mpc_b200_track_packed_submit");
+    if (!h || batch < 0 || batch > h->max_batch || !io) return MPC_B200_ERR_INVALID;
+    if (M < 4 || M > MAX_WAYPOINTS || M < h->opt_nc) return MPC_B200_ERR_INVALID;
+    if (h->pending.active) return MPC_B200_ERR_INVALID;
+    if (batch == 0) return MPC_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t B = (size_t)batch;
+    const int N = h->params.mpc_steps;
+    int64_t off[12];
+    const size_t total = packed_layout(N, B, (size_t)M, with_ref_vel, off);
+    if (h->d_io_doubles < total) {
+        // sized for the largest tick this handle can see, so that it is allocated once
+        int64_t o2[12];
+        const size_t cap = packed_layout(h->pred_steps, (size_t)h->max_batch, MAX_WAYPOINTS, 1, o2);
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_io) { cudaFree(h->d_io); h->d_io = NULL; h->d_io_doubles = 0; }
+        CK(cudaMalloc(&h->d_io, sizeof(double) * cap));
+        h->d_io_doubles = cap;
+    }
+    cudaStream_t st = h->stream;
+    double *d = h->d_io;
+    const size_t in_bytes = sizeof(double) * (size_t)off[5], out_off = sizeof(double) * (size_t)off[4],
+                 out_bytes = sizeof(double) * total - out_off;
+    if (is_device_ptr(io)) return MPC_B200_ERR_UNSUPPORTED;
+    const bool pinned = is_pinned_cached(h, io);
+    if (in_bytes > h->h_in_bytes || out_bytes > h->h_out_bytes) return MPC_B200_ERR_INVALID;
+    const void *src = io;
+    if (!pinned) { memcpy(h->h_in, io, in_bytes); src = h->h_in; }
+    CK(cudaMemcpyAsync(d, src, in_bytes, cudaMemcpyHostToDevice, st));
+    double *d_wx = d + off[0], *d_wy = d + off[1], *d_pose = d + off[2], *d_refv = off[3] >= 0 ? d + off[3] : NULL, *d_vel = d + off[4];
+    double *d_u0 = d + off[5], *d_pred = d + off[6], *d_cmd = d + off[7], *d_obj = d + off[8], *d_kkt = d + off[9];
+    int *d_status = reinterpret_cast<int *>(d + off[10]), *d_iters = reinterpret_cast<int *>(d + off[11]);
+    launch_prestep(h->opt_nc, st, batch, M, d_wx, d_wy, d_pose, h->d_coeffs, NULL, d_vel, h->d_state, h->params.delay_mode,
+                   h->params.dt);
+    CK(cudaGetLastError());
+    h->kernels++;
+    int rc = enqueue_solve(h, batch, h->d_state, h->d_coeffs, d_refv, NULL, d_u0, d_pred, d_obj, d_status, d_iters, d_kkt, NULL, st);
+    if (rc != MPC_B200_OK) return rc;
+    poststep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, d_u0, d_vel, d_refv, h->params.ref_vel, h->params.dt, d_cmd);
+    CK(cudaGetLastError());
+    h->kernels++;
+    Fetch &f = h->pending;
+    f = Fetch();
+    f.packed = true; f.io = io; f.io_off = out_off; f.io_bytes = out_bytes; f.io_pinned = pinned; f.batch = batch;
+    CK(cudaMemcpyAsync(pinned ? (void *)((char *)io + out_off) : (void *)h->h_out, (const char *)d + out_off, out_bytes,
+                       cudaMemcpyDeviceToHost, st));
+    f.active = true;
+    return MPC_B200_OK;
+}
+
+void *mpc_b200_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return p;
+}
+
+void mpc_b200_host_free(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
 }
 
 int mpc_b200_track_wait(mpc_b200_handle *h)
@@ -862,6 +1071,7 @@ int mpc_b200_polyfit_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                            const double *wx, const double *wy, const double *pose,
                            double *coeffs_out, double *cte_etheta_out, void *stream_v)
 {
+    NvtxRange nv("mpc_b200_polyfit_batch");
     if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !coeffs_out) return MPC_B200_ERR_INVALID;
     if (M < h->opt_nc || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;   // polyfit asserts order <= M-1 (driving_state.cpp:286)
     if (batch == 0) return MPC_B200_OK;
@@ -911,6 +1121,7 @@ int mpc_b200_prestep_batch(mpc_b200_handle *h, int32_t batch, int32_t M,
                            const double *wx, const double *wy, const double *pose, const double *vel,
                            double *coeffs_out, double *state_out, void *stream_v)
 {
+    NvtxRange nv("mpc_b200_prestep_batch");
     if (!h || batch < 0 || batch > h->max_batch || !wx || !wy || !pose || !vel || !coeffs_out || !state_out)
         return MPC_B200_ERR_INVALID;
     if (M < h->opt_nc || M > MAX_WAYPOINTS) return MPC_B200_ERR_INVALID;

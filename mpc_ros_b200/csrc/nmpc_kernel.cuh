@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             TRACE_C(3);
             PROF_MARK(2);
             // ---- P4: Riccati sweeps
+            int step_lsq = 0;     // sampled here for P6: the lane's adjoint stage thread rewrites PI_FLAGS there
             if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
                 const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                step_lsq = lsq;
                 const double dw = sm.P(PS_DW, p);
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
                 const int okb = riccati_backward<RATE>(prm, sm, p, hd);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             //      which nothing here depends on.  A least-squares lane (FL_LSQ) gets its flags from that thread.
             bool late = false;
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
-                if (!(sm.I(PI_FLAGS, p) & FL_LSQ)) {
+                if (!step_lsq) {
                     ctrl_step(prm, sm, c, p, NG);
                     sm.I(PI_FLAGS, p) = FL_LS;
                     late = true;
@@ -407,6 +409,11 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                         a.pred[((size_t)0 * N + k) * batch + i] = sm.at(k, S_X, p);
                         a.pred[((size_t)1 * N + k) * batch + i] = sm.at(k, S_Y, p);
                         a.pred[((size_t)2 * N + k) * batch + i] = sm.at(k, S_T, p);
+                        if (a.status && stage_bound_hit(prm, sm, k, p)) {
+                            // (the control thread wrote the status before barrier B1b; every stage that hits writes the same value)
+                            const int st = a.status[i];
+                            if (st == 1 || st == 4) a.status[i] = NMPC_STATUS_BOUND_ACTIVE;
+                        }
                         if (k == 0) { a.u0[i] = r[j].uw; a.u0[(size_t)batch + i] = r[j].ua; }
                         if (a.warm_out) {
                             // primal in the reference's variable layout (mpc_planner.cpp:232-239), then equality

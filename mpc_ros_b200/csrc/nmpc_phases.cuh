@@ -103,9 +103,14 @@ struct Params {
     double w_angvel_d, w_accel_d;   // rate penalties (mpc_planner.cpp:144-147); both 0 in the plain variant
     double idt;       // 1 / dt
     double i_mnb, i_nb;   // 1 / (6N + 4(N-1)), 1 / (4(N-1)): reciprocal counts of all / of the bound multipliers
+    double bound_chk;     // a returned point with some |state| >= this would feel the +-bound_value state bounds
+                          // (mpc_planner.cpp:303-312), which this kernel leaves out: flagged NMPC_STATUS_BOUND_ACTIVE
+                          // when the finished problem is written out (stage_bound_hit)
 };
 
 #define NMPC_MAX_FILTER 8
+// per-problem status outside the solve_result::status_type values: see Params::bound_chk (= MPC_B200_STATUS_BOUND_ACTIVE)
+#define NMPC_STATUS_BOUND_ACTIVE 64
 
 // View of the CTA's shared-memory block.  CPB > 0 fixes the lanes-per-CTA at compile time so that
 // every access is base + lane*8 + immediate (no index arithmetic in the sweeps).
@@ -298,6 +303,18 @@ template <class SM> MPC_HD void part_store(const SM &sm, int g, int p, const Eva
 template <class SM> MPC_HD void part_store(const SM &sm, int g, int p, const StepPart &a)
 {
     sm.part(g, PT_0, p) = a.rmax; sm.part(g, PT_1, p) = a.rzmax; sm.part(g, PT_2, p) = a.gd;
+}
+
+// The reference bounds every state by +-bound_value (mpc_planner.cpp:303-312); this solver carries no barrier for those
+// bounds.  A point strictly inside them is a KKT point of the bounded problem as well (zero multipliers); one that is not
+// would have been shaped by them.  Checked per stage when a finished problem is written out: a success / acceptable
+// status is then replaced by NMPC_STATUS_BOUND_ACTIVE -- reported, never passed off as a solution.
+template <class SM>
+MPC_HD bool stage_bound_hit(const Params &prm, const SM &sm, int k, int p)
+{
+    const double m = fmax2(fmax2(fmax2(fabs(sm.at(k, S_X, p)), fabs(sm.at(k, S_Y, p))), fmax2(fabs(sm.at(k, S_T, p)), fabs(sm.at(k, S_V, p)))),
+                           fmax2(fabs(sm.at(k, S_C, p)), fabs(sm.at(k, S_E, p))));
+    return !(m < prm.bound_chk);
 }
 
 // ---------------------------------------------------------------- init (new problem in a lane)

@@ -34,6 +34,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     prm.grp = SPT;
     prm.idt = 1.0 / prm.dt;
     prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); prm.i_nb = 1.0 / (double)(4 * (N - 1));
+    prm.bound_chk = (prm14[13] > 0.0 ? prm14[13] : 1e3) * (1.0 - 1e-3);   // prm14[13]: bound_value (0 = the 1e3 default)
     const int NG = (N + SPT - 1) / SPT;
 
     const int NS = RATE ? NSLOTS_RATE : NSLOTS;
@@ -70,6 +71,9 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 if (fl & FL_APPLY) for (int k = 0; k < N; k++) stage_apply<RATE>(prm, sm, REG(k, p), k, p);
                 if (fl & FL_FLUSH) {
                     const size_t i = (size_t)sm.I(PI_PROB, p);
+                    if (status)
+                        for (int k = 0; k < N; k++)
+                            if (stage_bound_hit(prm, sm, k, p) && (status[i] == 1 || status[i] == 4)) status[i] = NMPC_STATUS_BOUND_ACTIVE;
                     u0[i] = REG(0, p).uw; u0[(size_t)batch + i] = REG(0, p).ua;
                     for (int k = 0; k < N; k++) {
                         pred[((size_t)0 * N + k) * batch + i] = sm.at(k, S_X, p);

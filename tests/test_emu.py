@@ -19,7 +19,8 @@ def emu_solve(pm, state, coeffs, PB=4, tol=1e-8, max_iter=200, ref_vel=None):
     dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
     N = int(pm["STEPS"]); B = state.shape[1]
     prm = np.array([pm["DT"], pm["REF_CTE"], pm["REF_ETHETA"], pm["REF_V"], pm["W_CTE"], pm["W_EPSI"], pm["W_V"],
-                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], pm.get("W_DANGVEL", 0.0), pm.get("W_DA", 0.0), 0],
+                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], pm.get("W_DANGVEL", 0.0), pm.get("W_DA", 0.0),
+                    min(pm.get("BOUND", 1e3), 1e300)],
                    dtype=np.float64)
     state = np.ascontiguousarray(state, dtype=np.float64); coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
     u0 = np.zeros((2, B)); pred = np.zeros((3 * N, B)); obj = np.zeros(B); kkt = np.zeros(B); lam = np.zeros((6 * N, B))
@@ -154,7 +155,8 @@ def emu_solve_poly(pm, state, coeffs, PB=4, tol=1e-8, max_iter=200):
     dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
     N = int(pm["STEPS"]); B = state.shape[1]; nc = coeffs.shape[0]
     prm = np.array([pm["DT"], pm["REF_CTE"], pm["REF_ETHETA"], pm["REF_V"], pm["W_CTE"], pm["W_EPSI"], pm["W_V"],
-                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], pm.get("W_DANGVEL", 0.0), pm.get("W_DA", 0.0), 0],
+                    pm["W_ANGVEL"], pm["W_A"], pm["ANGVEL"], pm["MAXTHR"], pm.get("W_DANGVEL", 0.0), pm.get("W_DA", 0.0),
+                    min(pm.get("BOUND", 1e3), 1e300)],
                    dtype=np.float64)
     state = np.ascontiguousarray(state, dtype=np.float64); coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
     u0 = np.zeros((2, B)); pred = np.zeros((3 * N, B)); obj = np.zeros(B); kkt = np.zeros(B)

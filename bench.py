@@ -4,23 +4,28 @@
     python bench.py --gpus 1 --steps K --warmup W           # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W   # the reference's CPU MPC::Solve
 
-A "step" is one pass of the hot path over one batch of synthetic problems: the reference pre-step
-(waypoint transform + cubic polyfit + state assembly, driving_state.cpp:196-256) followed by the
-batched MPC::Solve, i.e. mpc_b200_prestep_batch + mpc_b200_solve_batch on BASELINE config 2
-(4,096 independent N = 20 problems on random poses along the infinity / epitrochoid / square tracks,
-mpc_params.yaml weights).  For N > 1 every rank owns its own 4,096-problem slice (weak scaling, no
-collective on the solve path); the timed region is bracketed by a barrier + synchronize and the
-slowest rank's device time is used.
+A "step" is one pass of the hot path over 256 independent batches of BASELINE config 2 (4,096 N = 20
+problems each: random poses along the infinity / epitrochoid / square tracks, mpc_params.yaml
+weights), streamed: per batch the reference pre-step (waypoint transform + cubic polyfit + state
+assembly, driving_state.cpp:196-256) followed by the batched MPC::Solve, i.e.
+mpc_b200_prestep_batch + mpc_b200_solve_batch.  K steps are timed back to back (steady state; a
+step is ~1 M solves, so the figure does not depend on K).  For N > 1 every rank streams its own
+batches (weak scaling, no collective on the solve path); the timed region is bracketed by a
+barrier + synchronize and the slowest rank's device time is used.
 
-`value`   : inputs already resident in HBM, device-pointer C-ABI calls on one stream.
-`e2e`     : the same steps through the C ABI with HOST buffers (pinned staging, H2D + D2H inside
-            the timed region).
+`value`   : inputs already resident in HBM, device-pointer C-ABI calls on 128 streams.
+`e2e`     : the same K steps as control ticks through the C ABI with HOST buffers (one packed
+            page-locked buffer per batch: one H2D + one D2H copy inside the timed region).
+`latency` : config 1, p50 / p99 of one MPC::Solve through the C++ adapter (mpc_bench latency).
+`config3` : BASELINE config 3, ONE batch of 65,536 problems split contiguously over the N GPUs,
+            first submit to last host gather, through the C++ harness (mpc_bench multi).
 `roofline`: FP64 pipe.  achieved = algorithmic flops of the solve kernel (SURVEY section 8d:
             27,879 flop per interior-point iteration at N = 20, times the iterations actually
             taken) / its CUDA-event duration on the launching stream; peak = DFMA-chain peak
             measured live (MEASURED_PEAKS.json has no FP64 entry).
-`cpu_baseline`: oracle/_ref (the reference's unmodified mpc_planner.cpp + CppAD; solver inside is
-            the repo's Ipopt stand-in, Ipopt itself is not installed) on all host cores, bounded sample.
+`cpu_baseline`: oracle/_ref/ref_bench (the reference's unmodified mpc_planner.cpp + CppAD, std::thread
+            per core; solver inside is the repo's Ipopt stand-in, Ipopt itself is not installed) on all
+            host cores, bounded sample; `--impl reference` times the same thing.
 """
 import argparse
 import json
@@ -65,9 +70,9 @@ def _ncu_dram_bytes():
         return NCU_DRAM_BYTES_PER_LAUNCH
 
 
-WORKLOAD = ("config2: batch of 4096 independent N=20 diff-drive NMPC problems per GPU, random poses on "
-            "infinity/epitrochoid/square tracks, mpc_params.yaml weights, cold start; step = prestep "
-            "(transform+polyfit+state) + solve")
+WORKLOAD = ("config2 streamed: batches of 4096 independent N=20 diff-drive NMPC problems, random poses on "
+            "infinity/epitrochoid/square tracks, mpc_params.yaml weights, cold start; per batch prestep "
+            "(transform+polyfit+state) + solve; a step = batches_per_step such batches per GPU")
 
 
 # ------------------------------------------------------------------ clocks sampler
@@ -118,53 +123,84 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
-def _ref_worker(args):
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libmpc_ref.so")
+_REF_LOADED = []
+
+
+def _load_ref_in_parent():
+    """The baseline binary (oracle/_ref/ref_bench) is a separate process; the same reference objects are also loaded
+    into THIS process (oracle/_ref/libmpc_ref.so) and called once, so that what runs is visible from here."""
+    if _REF_LOADED or not os.path.exists(REF_LIB):
+        return
+    from oracle.oracle_py import Reference, YAML_DEFAULT
+    r = Reference(YAML_DEFAULT)
+    r.solve(np.array([0.0, 0.0, 0.0, 0.3, 0.05, -0.1]), np.array([0.05, -0.1, 0.02, 0.003]))
+    _REF_LOADED.append(r)
+
+
+def _port_worker(args):
     seed, count, offset = args
-    from oracle.oracle_py import Oracle, Reference, YAML_DEFAULT, ref_available
+    from oracle.oracle_py import Oracle, YAML_DEFAULT
     from bench import gen_py
     g = gen_py.problems(seed, offset + count)
     orc = Oracle()
-    use_ref = ref_available()
-    if use_ref:
-        R = Reference(YAML_DEFAULT)
     conv = 0; iters = 0
     t0 = time.perf_counter()
     for i in range(offset, offset + count):
         c, cte, eth = orc.prestep(g["wx"][:, i], g["wy"][:, i], *g["pose"][:, i])
-        st = np.array([0.0, 0.0, 0.0, g["vel"][0, i], cte, eth])
-        r = R.solve(st, c) if use_ref else orc.solve(YAML_DEFAULT, st, c)
+        r = orc.solve(YAML_DEFAULT, np.array([0.0, 0.0, 0.0, g["vel"][0, i], cte, eth]), c)
         conv += int(r["status"] == 1); iters += r["iters"]
-    return conv, iters, time.perf_counter() - t0, use_ref
+    return conv, iters, time.perf_counter() - t0
 
 
 def cpu_reference_rate(per_core, cores=None):
-    """Times the reference's MPC::Solve (oracle/_ref) on `cores` processes, per_core problems each."""
-    import multiprocessing as mp
+    """The reference's MPC::Solve on the host cores.  kind "reference": oracle/_ref/ref_bench -- the reference's
+    unmodified mpc_planner.cpp + CppAD, std::thread per core (CppAD::thread_alloc::parallel_setup), C++ harness
+    oracle/ref_bench.cpp.  kind "port" (only where oracle/_ref was never built): the C restatement, fork per core."""
     cores = cores or os.cpu_count() or 1
+    if os.path.exists(REF_BENCH):
+        _load_ref_in_parent()
+        T = min(cores, 47)      # CPPAD_MAX_NUM_THREADS
+        r = subprocess.run([REF_BENCH, str(T), str(per_core), str(SEED)], capture_output=True, text=True, timeout=1200)
+        if r.returncode != 0:
+            raise RuntimeError("ref_bench failed: " + r.stderr[-2000:])
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        return dict(value=d["solves_per_s"], unit=UNIT, cores=d["threads"], kind="reference",
+                    sample="%d problems (%d per thread x %d std::threads) of the config-2 generator, seed %d; %d converged; "
+                           "mean %.1f iterations; reference mpc_planner.cpp + CppAD unmodified (oracle/_ref/ref_bench), solver "
+                           "inside: oracle/ipm.c stand-in for Ipopt 3.12.8" % (d["problems"], d["per_thread"], d["threads"], SEED,
+                                                                          d["converged"], d["mean_iters"]),
+                    wall_s=d["wall_s"])
+    import multiprocessing as mp
     ctx = mp.get_context("fork")
     jobs = [(SEED, per_core, k * per_core) for k in range(cores)]
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_ref_worker, jobs)
+        res = pool.map(_port_worker, jobs)
     wall = time.perf_counter() - t0
     conv = sum(r[0] for r in res); iters = sum(r[1] for r in res)
-    busy = max(r[2] for r in res)
-    kind = "reference" if res[0][3] else "port"
-    return dict(value=conv / busy, unit=UNIT, cores=cores, kind=kind,
-                sample="%d problems (%d per core x %d processes) of the config-2 generator, seed %d; %d converged; "
-                       "mean %.1f iterations; solver inside: oracle/ipm.c stand-in for Ipopt 3.12.8"
-                       % (per_core * cores, per_core, cores, SEED, conv, iters / max(1, per_core * cores)),
+    return dict(value=conv / wall, unit=UNIT, cores=cores, kind="port",
+                sample="%d problems (%d per core x %d processes) of the config-2 generator, seed %d; %d converged; mean %.1f "
+                       "iterations; oracle/mpc_oracle.c + oracle/ipm.c" % (per_core * cores, per_core, cores, SEED, conv,
+                                                                          iters / max(1, per_core * cores)),
                 wall_s=wall)
+
+
+def bench_config(a, world):
+    """The `config` object both arms print (the reference arm runs the same workload definition)."""
+    return dict(workload=WORKLOAD, batch_per_gpu=a.batch, batches_per_step=a.batches_per_step, mpc_steps=20,
+                max_iter=a.max_iter, n_gpus=world)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample per step so that the whole run stays within a few minutes whatever K is
-    per_core = max(8, min(a.ref_per_core, 10000 // max(1, a.steps)))
-    for _ in range(a.warmup):
-        cpu_reference_rate(max(1, per_core // 8))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    per_core = a.ref_per_core          # the same bounded sample as the cpu_baseline leg of the CUDA arm
+    for _ in range(min(a.warmup, 2)):
+        cpu_reference_rate(max(8, per_core // 8))
     vals = []; last = None
     t0 = time.perf_counter()
     for _ in range(a.steps):
@@ -173,14 +209,35 @@ def run_reference(a):
     ms = (time.perf_counter() - t0) * 1e3 / max(1, a.steps)
     v = float(np.mean(vals))
     last["value"] = v
+    last["sample"] = "each step: " + last["sample"]
     print(json.dumps(dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps,
                           warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-                          dtype="f64", data="synthetic", config=dict(workload=WORKLOAD),
+                          dtype="f64", data="synthetic", config=bench_config(a, world),
                           cpu_baseline=last,
                           e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
 # ------------------------------------------------------------------ our arm (CUDA)
+def _ncu_executed_flops():
+    """FP64 flops one solve-kernel launch really executes (2 x DFMA + DMUL + DADD thread instructions) from the latest
+    ncu --set full capture under profiles/, or None."""
+    import csv
+    import glob
+    try:
+        f = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_solve_kernel_ncu_raw.csv")))[-1]
+        rr = list(csv.reader(open(f)))
+        h, v = rr[0], rr[2]
+        def g(k):
+            return float(v[h.index(k)].replace(",", ""))
+        cyc = g("smsp__cycles_elapsed.max") if "smsp__cycles_elapsed.max" in h else g("sm__cycles_elapsed.max")
+        fl = 0.0
+        for k, w in (("dfma", 2.0), ("dmul", 1.0), ("dadd", 1.0)):
+            fl += w * g("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k) * cyc
+        return fl, os.path.basename(f)
+    except Exception:
+        return None, None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -195,7 +252,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = a.batch; N = 20
+    B = a.batch; N = 20; NB = a.batches_per_step
     prm = capi.yaml_default_params()
     prm.delay_mode = 0                       # configs 2-4 use the plain state
     prm.max_iter = a.max_iter
@@ -218,42 +275,44 @@ def run_ours(a):
     out_bytes = (2 + 3 * N + 2) * B * 8 + 2 * B * 4
     set_bytes = in_bytes + out_bytes + 10 * B * 8
     flush = torch.empty(256 * 1024 * 1024 // 8, **f64)
-    # Steps are independent batches: they are issued round-robin on S streams so that the tail of one
-    # batch (a few problems need 10-25x the median iteration count) overlaps the next batches.
-    S = max(1, min(a.streams, a.steps))
-    # torch.cuda.Stream() hands out at most 32 distinct streams per device (a pool): the library creates them
-    raw_streams = [capi.stream_create(local) for _ in range(S)]
+    # A step = NB independent batches, issued round-robin on S streams so that the tail of one batch (a few problems
+    # need 10-25x the median iteration count) overlaps the next batches.  Every stream keeps at most DEPTH batches
+    # in flight (the host waits on the batch DEPTH back), which bounds the launches a handle has in flight.
+    S = max(1, min(a.streams, NB))
+    DEPTH = 2
+    raw_streams = [capi.stream_create(local) for _ in range(S)]      # torch hands out only 32 distinct streams
     streams = [torch.cuda.ExternalStream(p, device=dev) for p in raw_streams]
-    # persistent-grid size per launch: with many batches in flight each launch takes a slice of the SMs and
-    # every lane works through several problems; with few steps a launch must cover the machine by itself
     max_ctas = a.max_ctas if a.max_ctas > 0 else max(4, min(128, -(-512 // S)))
     solver.set_option("max_ctas", max_ctas)
-
-    # pre-marshalled C-ABI argument tuples (the timed loop is launches only, ~10 us of host time each)
     pre_f = L.mpc_b200_prestep_batch; sol_f = L.mpc_b200_solve_batch
-    H = max(1, min(a.handles, S))
-    solvers = [solver] + [capi.Solver(prm, B, local) for _ in range(H - 1)]
-    for s_ in solvers:
-        s_.set_option("max_ctas", max_ctas)
-    hs = [s_._h for s_ in solvers]                # stream k always uses handle k % H
     pre_args = [(B, M, d_wx[j].data_ptr(), d_wy[j].data_ptr(), d_pose[j].data_ptr(), d_vel[j].data_ptr(),
                  d_coef[j].data_ptr(), d_state[j].data_ptr()) for j in range(R)]
     sol_args = [(B, d_state[j].data_ptr(), d_coef[j].data_ptr(), None, None, d_u0[j].data_ptr(),
                  d_pred[j].data_ptr(), d_obj[j].data_ptr(), d_stat[j].data_ptr(), d_it[j].data_ptr(),
                  d_kkt[j].data_ptr(), None) for j in range(R)]
-    sptr = raw_streams
+    hh = solver._h
+    done_ev = [[torch.cuda.Event() for _ in range(DEPTH)] for _ in range(S)]
+    issued = [0] * S
+    launch_ev = []            # (start, end) CUDA events around sampled solve launches, on their own streams
 
-    def step_dev(j, ev=None):
-        sp = sptr[j % S]; st = streams[j % S]; hh = hs[(j % S) % H]
-        j %= R
-        rc = pre_f(hh, *pre_args[j], sp)
-        if ev is not None:
-            ev[0].record(st)
-        rc |= sol_f(hh, *sol_args[j], sp)
-        if ev is not None:
-            ev[1].record(st)
+    def batch_dev(j, sample=False):
+        s_ = j % S
+        sp = raw_streams[s_]; st = streams[s_]
+        k = issued[s_]
+        if k >= DEPTH:
+            done_ev[s_][k % DEPTH].synchronize()
+        q = j % R
+        rc = pre_f(hh, *pre_args[q], sp)
+        if sample:
+            x = torch.cuda.Event(enable_timing=True); y = torch.cuda.Event(enable_timing=True)
+            x.record(st)
+        rc |= sol_f(hh, *sol_args[q], sp)
+        if sample:
+            y.record(st); launch_ev.append((x, y))
+        done_ev[s_][k % DEPTH].record(st)
+        issued[s_] = k + 1
         if rc != 0:
-            raise RuntimeError("C ABI call failed: %d" % rc)
+            raise RuntimeError("C ABI call failed: %d %s" % (rc, L.mpc_b200_last_cuda_error(hh).decode()))
 
     def barrier():
         torch.cuda.synchronize()
@@ -262,33 +321,39 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     fp64_peak = L.mpc_b200_measure_fp64_peak(local, 100000)   # also brings the clocks up
-    for j in range(a.warmup):
-        step_dev(j)
+    jb = 0
+    for _ in range(a.warmup):
+        for _ in range(NB):
+            batch_dev(jb); jb += 1
+    torch.cuda.synchronize()
     flush.fill_(1.0)                        # one L2 flush; the timed steps then rotate over > L2 of data
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    n0 = sum(s_.launch_count for s_ in solvers)
+    n0 = solver.launch_count
     main = torch.cuda.current_stream()
     e0.record(main)
     for st in streams:
         st.wait_event(e0)
-    for j in range(a.steps):
-        step_dev(a.warmup + j)
+    j_first = jb
+    for _ in range(a.steps):
+        for b in range(NB):
+            batch_dev(jb, sample=(b % 16 == 0)); jb += 1
     for st in streams:
         main.wait_stream(st)
     e1.record(main)
     barrier()
-    launches = sum(s_.launch_count for s_ in solvers) - n0
+    launches = solver.launch_count - n0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
+    n_batches = a.steps * NB
 
     # converged problems and iterations actually taken in the timed steps (results are deterministic per set)
     conv_steps = 0; iter_steps = 0.0; per_set = {}
-    for j in range(a.steps):
-        s = (a.warmup + j) % R
+    for j in range(j_first, j_first + n_batches):
+        s = j % R
         if s not in per_set:
             st = d_stat[s].cpu().numpy(); kk = d_kkt[s].cpu().numpy(); it = d_it[s].cpu().numpy()
             ok = (st == 1) & (kk <= 1e-8)
@@ -298,56 +363,64 @@ def run_ours(a):
     ms_total, (conv_total, _iters_all) = reduce_over_ranks(ms_total, [conv_steps, iter_steps], device=dev)
     value = conv_total / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (the solve kernel), this rank
-    # With S > 1 launches overlap on the device: the event-to-event time of one launch then includes
-    # waiting for SMs held by its neighbours, so the launch duration that matters for the roofline is the
-    # device time per launch of the timed region (= region / launches; the pre-step kernel is < 1 % of it).
-    # A launch timed ALONE (one stream, synchronised) is reported next to it.
-    flops_per_launch = FLOP_PER_ITER_N20 * iter_steps / a.steps
-    eff_ms = ms_total / a.steps
+    # ---- roofline of the dominant kernel (the solve kernel), this rank.
+    # Launches overlap on the device (S streams, a slice of the SMs each), so the duration that relates one launch's
+    # flops to the machine's peak is the device time per launch of the timed region: region / launches (the pre-step
+    # and queue-order kernels are < 1 % of it).  The CUDA-event duration of single launches on their own streams is
+    # reported beside it (launch_ms_event_avg: it includes the time a launch shares the SMs with its neighbours;
+    # concurrency = launch_ms_event_avg / kernel_ms launches are in flight on average).
+    flops_per_launch = FLOP_PER_ITER_N20 * iter_steps / n_batches
+    eff_ms = ms_total / n_batches
     achieved = flops_per_launch / (eff_ms * 1e-3) / 1e12
+    ev_ms = [x.elapsed_time(y) for x, y in launch_ev]
     iso = []
     for j in range(5):
         x = torch.cuda.Event(enable_timing=True); y = torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        step_dev(j * S, (x, y))
+        st0 = streams[0]
+        pre_f(hh, *pre_args[j % R], raw_streams[0]); x.record(st0); sol_f(hh, *sol_args[j % R], raw_streams[0]); y.record(st0)
         torch.cuda.synchronize()
         iso.append(x.elapsed_time(y))
     iso_ms = float(np.median(iso))
+    exe, exe_src = _ncu_executed_flops()
     roofline = dict(bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s", frac=achieved / fp64_peak,
                     traffic=_ncu_dram_bytes() if B == BATCH else None, kernel="nmpc_solve_kernel", kernel_ms=eff_ms,
+                    launch_ms_event_avg=float(np.mean(ev_ms)) if ev_ms else None,
+                    concurrency=(float(np.mean(ev_ms)) / eff_ms) if ev_ms else None,
                     kernel_ms_isolated=iso_ms, achieved_isolated=flops_per_launch / (iso_ms * 1e-3) / 1e12,
                     streams=S, flops_per_launch=flops_per_launch,
-                    peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak; "
-                                "MEASURED_PEAKS.json has no FP64 entry")
+                    flops="algorithmic: SURVEY 8d count, 27,879 flop per interior-point iteration at N = 20 x iterations taken",
+                    executed_flops_per_launch_ncu=exe, executed_source=exe_src,
+                    frac_executed=(exe / (eff_ms * 1e-3) / 1e12 / fp64_peak) if exe else None,
+                    peak_source="DFMA-chain peak measured live by mpc_b200_measure_fp64_peak (datasheet: 148 SM x 64 FMA/clk "
+                                "x 2 x 1.965 GHz = 37.2); MEASURED_PEAKS.json has no FP64 entry")
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  T host threads, each keeping
-    # K ticks in flight on K handles (a handle owns a stream and its device scratch) through
-    # mpc_b200_track_submit / _wait -- the way a server feeding the solver from request queues would.
-    def pinned(shape, dtype=torch.float64):
-        return torch.zeros(shape, dtype=dtype).pin_memory()
+    # ---- e2e: the same K steps of NB batches through the C ABI with HOST buffers, copies inside the timed region.
+    # T host threads, each keeping several ticks in flight on as many handles (a handle owns a stream and its device
+    # scratch) through the ONE-buffer tick mpc_b200_track_packed_submit / _wait: one H2D and one D2H copy per tick.
     T = max(1, a.e2e_threads)
     K = max(1, a.e2e_inflight // T)
-    sub_f = L.mpc_b200_track_submit; wait_f = L.mpc_b200_track_wait
+    sub_f = L.mpc_b200_track_packed_submit; wait_f = L.mpc_b200_track_wait
 
     class Slot:
         def __init__(self, q):
             self.solver = capi.Solver(prm, B, local)
             self.solver.set_option("max_ctas", a.e2e_max_ctas if a.e2e_max_ctas > 0 else max(8, min(128, -(-512 // (T * K)))))
-            self.wx = pinned((M, B)); self.wy = pinned((M, B)); self.pose = pinned((3, B)); self.vel = pinned((3, B))
-            self.wx.copy_(d_wx[q]); self.wy.copy_(d_wy[q]); self.pose.copy_(d_pose[q]); self.vel.copy_(d_vel[q])
-            self.cmd = pinned((2, B)); self.u0 = pinned((2, B)); self.pred = pinned((3 * N, B))
-            self.obj = pinned(B); self.kkt = pinned(B); self.stat = pinned(B, torch.int32); self.it = pinned(B, torch.int32)
-            self.stat_np = self.stat.numpy(); self.kkt_np = self.kkt.numpy()
-            # one control tick per robot: pre-step -> solve -> post-step, host buffers in and out
-            self.args = (self.solver._h, B, M, self.wx.data_ptr(), self.wy.data_ptr(), self.pose.data_ptr(),
-                         self.vel.data_ptr(), None, self.u0.data_ptr(), self.pred.data_ptr(), self.cmd.data_ptr(),
-                         self.obj.data_ptr(), self.stat.data_ptr(), self.it.data_ptr(), self.kkt.data_ptr())
+            total, self.off = self.solver.packed_layout(B, M)
+            self.ptr = L.mpc_b200_host_alloc(total)
+            if not self.ptr:
+                raise RuntimeError("mpc_b200_host_alloc failed")
+            self.buf = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(total,))
+            self.v = self.solver.packed_views(self.buf, B, M)
+            self.v["wx"][:] = d_wx[q].cpu().numpy(); self.v["wy"][:] = d_wy[q].cpu().numpy()
+            self.v["pose"][:] = d_pose[q].cpu().numpy(); self.v["vel"][:] = d_vel[q].cpu().numpy()
+            self.h2d = self.off["u0"]; self.d2h = total - self.off["vel"]
+            self.args = (self.solver._h, B, M, 0, self.ptr)
             self.busy = False
 
         def submit(self):
             if sub_f(*self.args) != 0:
-                raise RuntimeError("mpc_b200_track_submit failed")
+                raise RuntimeError("mpc_b200_track_packed_submit failed")
             self.busy = True
 
         def wait(self):
@@ -356,7 +429,13 @@ def run_ours(a):
             if wait_f(self.solver._h) != 0:
                 raise RuntimeError("mpc_b200_track_wait failed")
             self.busy = False
-            return int(((self.stat_np == 1) & (self.kkt_np <= 1e-8)).sum())
+            return int(((self.v["status"] == 1) & (self.v["kkt"] <= 1e-8)).sum())
+
+        def close(self):
+            self.solver.close()
+            L.mpc_b200_host_free(self.ptr)
+
+    import ctypes as C
 
     class Worker:
         def __init__(self, t):
@@ -373,7 +452,8 @@ def run_ours(a):
                 self.conv += s.wait()
 
     workers = [Worker(t) for t in range(T)]
-    per_thread = max(2, a.e2e_steps // T)
+    e2e_ticks = a.steps * NB
+    per_thread = max(2, e2e_ticks // T)
     for w in workers:
         w.run(K)
     barrier()
@@ -386,55 +466,76 @@ def run_ours(a):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     conv_h = sum(w.conv for w in workers)
-    e2e_steps = per_thread * T
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev); ce = torch.tensor([float(conv_h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce, op=dist.ReduceOp.SUM)
-    h2d = (2 * M + 6) * B * 8                       # waypoints, pose, (v, previous w, previous throttle)
-    d2h = (3 + 2 + 3 * N + 2 + 2) * B * 8 + 2 * B * 4   # vel, u0, pred, cmd, obj, kkt, status, iters
-    e2e = dict(value=float(ce.item()) / float(te.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-               steps=e2e_steps, threads=T, in_flight=T * K,
-               note="mpc_b200_track_submit/_wait with page-locked host buffers (H2D and D2H inside the timed region), "
-                    "%d host thread(s) x %d handles in flight each; host wall clock" % (T, K))
+    s0 = workers[0].slots[0]
+    e2e = dict(value=float(ce.item()) / float(te.item()), unit=UNIT, h2d_bytes_per_step=s0.h2d * NB, d2h_bytes_per_step=s0.d2h * NB,
+               h2d_bytes_per_batch=s0.h2d, d2h_bytes_per_batch=s0.d2h,
+               steps=a.steps, batches=per_thread * T, threads=T, in_flight=T * K, seconds=float(te.item()),
+               note="the same %d steps x %d batches as control ticks (pre-step + solve + post-step) through "
+                    "mpc_b200_track_packed_submit/_wait with page-locked host buffers: one H2D + one D2H copy per batch "
+                    "inside the timed region; %d host thread(s) x %d handles in flight each; host wall clock, max over ranks"
+                    % (a.steps, NB, T, K))
     for w in workers:
         for s in w.slots:
-            s.solver.close()
+            s.close()
 
+    # ---- the rest of the line (rank 0): config-1 latency through the C++ MPC adapter, config-3 one-shot through the
+    # C++ multi-GPU harness (mpc_bench multi: std::thread per GPU, contiguous slices, host gather), CPU baseline
+    latency = None; config3 = None; cpu = None
+    bench_bin = os.path.join(ROOT, "mpc_ros_b200", "lib", "mpc_bench")
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and os.path.exists(bench_bin) and not a.no_extras:
+        def run_json(args, timeout=600):
+            r = subprocess.run([bench_bin] + args, capture_output=True, text=True, timeout=timeout)
+            if r.returncode != 0:
+                return dict(error=r.stderr[-500:])
+            return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        if world == 1:
+            lt = run_json(["latency", "3000"])
+            latency = dict(p50_us=lt.get("p50_us"), p99_us=lt.get("p99_us"), calls=lt.get("calls"),
+                           what="config 1: one MPC::Solve through the C++ adapter (batch of one, host buffers, H2D/D2H inside)") \
+                if "error" not in lt else lt
+        config3 = run_json(["multi", str(world), "65536", "5"])
+    if world > 1:
+        dist.barrier()
     if rank == 0:
-        cpu = None
         if world == 1 and not a.no_cpu_baseline:
             cpu = cpu_reference_rate(a.ref_per_core)
         it_mean = float(np.mean([v[2] for v in per_set.values()])); it_max = int(max(v[3] for v in per_set.values()))
+        cfg = bench_config(a, world)
+        cfg.update(streams=S, max_ctas=max_ctas, in_flight_per_stream=DEPTH,
+                   step="one step = %d independent config-2 batches of %d problems, streamed on %d streams "
+                        "(prestep + solve each); %d steps are timed back to back" % (NB, B, S, a.steps),
+                   l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one L2 flush"
+                      % (R, R * set_bytes / 1e6),
+                   converged_fraction=conv_total / (B * n_batches * world), mean_iters_converged=it_mean, max_iters=it_max)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_total / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f64", data="synthetic",
-                    config=dict(workload=WORKLOAD, batch_per_gpu=B, mpc_steps=N, max_iter=a.max_iter, streams=S,
-                                max_ctas=max_ctas,
-                                l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one "
-                                   "L2 flush" % (R, R * set_bytes / 1e6),
-                                converged_fraction=conv_total / (B * a.steps * world), mean_iters_converged=it_mean,
-                                max_iters=it_max),
-                    clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
+                    dtype="f64", data="synthetic", config=cfg,
+                    clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, latency=latency,
+                    config3=config3, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    for s_ in solvers:
-        s_.close()
+    solver.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batches-per-step", type=int, default=256, help="independent 4,096-problem batches per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--sets", type=int, default=48)
     ap.add_argument("--max-iter", type=int, default=100)
     ap.add_argument("--streams", type=int, default=128)
     ap.add_argument("--max-ctas", type=int, default=0)
-    ap.add_argument("--handles", type=int, default=1, help="solver handles the device-resident loop spreads its streams over")
-    ap.add_argument("--e2e-steps", type=int, default=8192)
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-1 latency and config-3 one-shot legs")
     ap.add_argument("--e2e-threads", type=int, default=2)
     ap.add_argument("--e2e-max-ctas", type=int, default=0)
     ap.add_argument("--e2e-inflight", type=int, default=96, help="ticks in flight over all e2e threads")

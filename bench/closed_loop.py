@@ -51,17 +51,20 @@ class Fleet:
         self.M = gen_py._lib().mpcgen_num_waypoints(path_length)
 
     def window(self):
-        """Cut the plan at the nearest point ahead and down-sample (mpc_planner_ros.cpp:266-291, :365-391)."""
+        """Cut the plan and down-sample it (mpc_planner_ros.cpp:266-291, :365-391), host side of run_gpu.  The rule is
+        the reference's: plan points are erased from the front while the squared distance to the robot does not grow
+        (start value 10e5), so the plan begins at the first point that is farther away than its predecessor; at most 64
+        points per tick (the kernel's cap)."""
         R, M = self.R, self.M
         wx = np.zeros((M, R)); wy = np.zeros((M, R))
         for i in range(R):
             px, py = self.paths[self.kind[i]]
             n = len(px)
-            # getCutOffPlan: drop plan points while the distance to the robot keeps shrinking
-            cand = (self.idx[i] + np.arange(0, 64)) % n
+            cand = (self.idx[i] + np.arange(0, 65)) % n
             d2 = (px[cand] - self.pose[0, i]) ** 2 + (py[cand] - self.pose[1, i]) ** 2
-            grow = np.nonzero(d2[1:] > d2[:-1])[0]
-            self.idx[i] = cand[int(grow[0])] if len(grow) else cand[-1]
+            prev = np.concatenate([[10e5], d2[:-1]])
+            grow = np.nonzero(prev[:64] < d2[:64])[0]
+            self.idx[i] = cand[int(grow[0])] if len(grow) else cand[64]
             sel = list(range(0, self.win, self.step)) + [self.win - 1]
             q = (self.idx[i] + np.array(sel)) % n
             wx[:, i] = px[q]; wy[:, i] = py[q]
@@ -69,6 +72,15 @@ class Fleet:
 
     def vel(self):
         return np.stack([self.v, self.w, self.thr])
+
+    def track_distance(self):
+        """True distance of every robot to its track (the logged cte is c[0] of the cubic fit, which is meaningless
+        where a 5 m window wraps around a sharp corner)."""
+        d = np.zeros(self.R)
+        for i in range(self.R):
+            px, py = self.paths[self.kind[i]]
+            d[i] = np.sqrt(((px - self.pose[0, i]) ** 2 + (py - self.pose[1, i]) ** 2).min())
+        return d
 
     def actuate(self, w, thr, dt, ref_v):
         """driving_state.cpp:263-269 then a unicycle plant."""
@@ -96,7 +108,7 @@ def run_gpu(R, T, warm=True, seed=20261018 + 5, record_solver=False):
     d_state = torch.zeros((6, R), **f64); d_coef = torch.zeros((4, R), **f64)
     d_u0 = torch.zeros((2, R), **f64); d_pred = torch.zeros((3 * N, R), **f64)
     d_it = torch.zeros(R, dtype=torch.int32, device=dev); d_st = torch.zeros(R, dtype=torch.int32, device=dev)
-    trace = dict(cte=[], eth=[], iters=[], conv=[], w=[], thr=[])
+    trace = dict(cte=[], eth=[], iters=[], conv=[], w=[], thr=[], dist=[])
     t_solve = 0.0
     for t in range(T):
         wx, wy = fleet.window()
@@ -120,10 +132,30 @@ def run_gpu(R, T, warm=True, seed=20261018 + 5, record_solver=False):
         trace["cte"].append(ce[0].copy()); trace["eth"].append(ce[1].copy())
         trace["iters"].append(d_it.cpu().numpy().copy()); trace["conv"].append((d_st.cpu().numpy() == 1))
         trace["w"].append(u0[0].copy()); trace["thr"].append(u0[1].copy())
+        trace["dist"].append(fleet.track_distance())
         fleet.actuate(u0[0], u0[1], dt, prm.ref_vel)
     sv.close()
     out = {k: np.array(v) for k, v in trace.items()}
     out["solve_s"] = t_solve
+    out["kind"] = fleet.kind.copy()
+    return out
+
+
+TRACKS = ("infinity", "epitrochoid", "square")
+
+
+def per_track(kind, cte, dist):
+    """Tracking statistics per track: |cte| as the reference logs it (c[0] of the fit) and the true distance to the track."""
+    out = {}
+    for k, name in enumerate(TRACKS):
+        m = kind == k
+        if not m.any():
+            continue
+        a = np.abs(cte[:, m]); d = dist[:, m]
+        out[name] = dict(robots=int(m.sum()), mean_abs_cte=float(a.mean()), median_abs_cte=float(np.median(a)), max_abs_cte=float(a.max()),
+                         frac_ticks_abs_cte_gt_1m=float((a > 1.0).mean()), mean_dist=float(d.mean()), median_dist=float(np.median(d)),
+                         max_dist=float(d.max()), frac_ticks_dist_gt_1m=float((d > 1.0).mean()),
+                         frac_robots_ever_dist_gt_1m=float((d.max(axis=0) > 1.0).mean()))
     return out
 
 
@@ -200,28 +232,6 @@ def run_gpu_device(R, T, groups=8, seed=20261018 + 5, max_iter=100, trace=True):
     return out
 
 
-def run_oracle(R, T, seed=20261018 + 5):
-    """The reference loop: cold-started CPU solve every tick (oracle restatement of MPC::Solve)."""
-    from oracle.oracle_py import Oracle, YAML_DEFAULT
-    orc = Oracle()
-    dt = YAML_DEFAULT["DT"]
-    fleet = Fleet(R, seed)
-    trace = dict(cte=[], eth=[], w=[], thr=[], iters=[])
-    for t in range(T):
-        wx, wy = fleet.window()
-        w = np.zeros(R); thr = np.zeros(R); cte = np.zeros(R); eth = np.zeros(R); its = np.zeros(R)
-        for i in range(R):
-            c, ct, e = orc.prestep(wx[:, i], wy[:, i], *fleet.pose[:, i])
-            v, pw, pt = fleet.v[i], fleet.w[i], fleet.thr[i]
-            st = np.array([v * dt, 0.0, pw * dt, v + pt * dt, ct + v * np.sin(e) * dt, e - pw * dt])   # delay mode
-            r = orc.solve(YAML_DEFAULT, st, c)
-            w[i], thr[i] = r["u0"]; cte[i] = ct; eth[i] = e; its[i] = r["iters"]
-        trace["cte"].append(cte); trace["eth"].append(eth); trace["w"].append(w.copy()); trace["thr"].append(thr.copy())
-        trace["iters"].append(its)
-        fleet.actuate(w, thr, dt, YAML_DEFAULT["REF_V"])
-    return {k: np.array(v) for k, v in trace.items()}
-
-
 def main():
     R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 500
@@ -243,9 +253,14 @@ def main():
                mean_abs_etheta=float(np.abs(g["eth"]).mean()), mean_iters=float(g["iters"].mean()),
                converged_fraction=float(g["conv"].mean()),
                mean_abs_cte_last100=float(np.abs(g["cte"][-100:]).mean()))
+    res["per_track"] = per_track(g["kind"], g["cte"], g["dist"])
     if K > 0:
+        # the checker (cold-started oracle loop = the reference loop) lives with the tests
+        from tests.closed_loop_ref import run_oracle
         o = run_oracle(K, T)
         gk = run_gpu(K, T, warm=not cold)
+        res["per_track_subset_gpu"] = per_track(gk["kind"], gk["cte"], gk["dist"])
+        res["per_track_subset_oracle"] = per_track(o["kind"], o["cte"], o["dist"])
         res["oracle_subset"] = dict(robots=K, mean_abs_cte_oracle=float(np.abs(o["cte"]).mean()),
                                     mean_abs_cte_gpu=float(np.abs(gk["cte"]).mean()),
                                     max_trace_gap_cte=float(np.abs(np.abs(o["cte"]).mean(1) - np.abs(gk["cte"]).mean(1)).max()),

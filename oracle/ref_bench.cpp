@@ -39,16 +39,10 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 struct Out { long conv; long iters; double busy; };
 
-void worker(size_t tn, int per, int B, int M, const double *wx, const double *wy, const double *pose, const double *vel, Out *out)
+void worker(MPC *mpc_ptr, size_t tn, int per, int B, int M, const double *wx, const double *wy, const double *pose, const double *vel, Out *out)
 {
     t_thread_num = tn;
-    // MPC::MPC prints "init mpc" (mpc_planner.cpp:225); harmless here
-    MPC mpc;
-    std::map<std::string, double> p;   // mpc_params.yaml:9-25 through the LoadParams keys
-    p["DT"] = 0.1; p["STEPS"] = 20; p["REF_CTE"] = 0; p["REF_ETHETA"] = 0; p["REF_V"] = 0.5; p["W_CTE"] = 100;
-    p["W_EPSI"] = 0; p["W_V"] = 1000; p["W_ANGVEL"] = 100; p["W_A"] = 50; p["W_DANGVEL"] = 0; p["W_DA"] = 0;
-    p["ANGVEL"] = 1.5; p["MAXTHR"] = 1.0; p["BOUND"] = 1e3;
-    mpc.LoadParams(p);
+    MPC &mpc = *mpc_ptr;           // one MPC object per thread, built by main (MPC::MPC writes to std::cout)
     std::vector<double> x(M), y(M);
     const double t0 = now_s();
     long conv = 0, iters = 0;
@@ -85,21 +79,29 @@ int main(int argc, char **argv)
     CppAD::thread_alloc::parallel_setup((size_t)T + 1, in_parallel, thread_num);
     CppAD::thread_alloc::hold_memory(true);
     CppAD::parallel_ad<double>();
-    g_parallel.store(true);
 
     std::vector<Out> outs(T);
     std::vector<std::thread> ths;
-    // keep the reference's "init mpc" lines off the JSON output
-    std::streambuf *old = std::cout.rdbuf();
-    std::ostringstream sink;
-    std::cout.rdbuf(sink.rdbuf());
+    // one MPC per thread, constructed here: MPC::MPC prints "init mpc" (mpc_planner.cpp:225), kept off the JSON output
+    std::vector<MPC *> mpcs;
+    {
+        std::streambuf *old = std::cout.rdbuf();
+        std::ostringstream sink;
+        std::cout.rdbuf(sink.rdbuf());
+        std::map<std::string, double> p;   // mpc_params.yaml:9-25 through the LoadParams keys
+        p["DT"] = 0.1; p["STEPS"] = 20; p["REF_CTE"] = 0; p["REF_ETHETA"] = 0; p["REF_V"] = 0.5; p["W_CTE"] = 100;
+        p["W_EPSI"] = 0; p["W_V"] = 1000; p["W_ANGVEL"] = 100; p["W_A"] = 50; p["W_DANGVEL"] = 0; p["W_DA"] = 0;
+        p["ANGVEL"] = 1.5; p["MAXTHR"] = 1.0; p["BOUND"] = 1e3;
+        for (int t = 0; t < T; t++) { mpcs.push_back(new MPC()); mpcs.back()->LoadParams(p); }
+        std::cout.rdbuf(old);
+    }
+    g_parallel.store(true);
     const double t0 = now_s();
     for (int t = 0; t < T; t++)
-        ths.emplace_back(worker, (size_t)t + 1, per, B, M, wx.data(), wy.data(), pose.data(), vel.data(), &outs[t]);
+        ths.emplace_back(worker, mpcs[t], (size_t)t + 1, per, B, M, wx.data(), wy.data(), pose.data(), vel.data(), &outs[t]);
     for (auto &th : ths) th.join();
     const double wall = now_s() - t0;
     g_parallel.store(false);
-    std::cout.rdbuf(old);
     long conv = 0, iters = 0; double busy = 0;
     for (int t = 0; t < T; t++) { conv += outs[t].conv; iters += outs[t].iters; if (outs[t].busy > busy) busy = outs[t].busy; }
     printf("{\"threads\": %d, \"per_thread\": %d, \"problems\": %d, \"seed\": %llu, \"converged\": %ld, \"mean_iters\": %.3f, "

@@ -85,6 +85,10 @@ struct RosRefTracker {
 // REF_V, W_CTE, W_EPSI, W_V, W_ANGVEL, W_A, W_DANGVEL, W_DA, ANGVEL, MAXTHR, BOUND.
 void *ros_ref_tick_new(const double *cfg15, int delay_mode, double max_speed)
 {
+    // the reference announces itself on std::cout ("init mpc", the context's parameter dump): kept off the harness output
+    std::streambuf *old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
     RosRefTracker *t = new RosRefTracker();
     t->ctx = new DrivingStateContext();
     t->tracking = new Tracking(t->ctx);
@@ -98,6 +102,7 @@ void *ros_ref_tick_new(const double *cfg15, int delay_mode, double max_speed)
     c.bound_value = cfg15[14];
     t->ctx->updateMpcConfigs(c);
     t->ctx->_max_speed = max_speed;
+    std::cout.rdbuf(old);
     return t;
 }
 

@@ -286,9 +286,10 @@ def test_closed_loop_tracks_like_the_reference_loop():
     """BASELINE config 5 in small: warm-started GPU loop vs the cold-started oracle loop (the reference
     cold-starts every tick), same robots, same plant."""
     from bench import closed_loop
+    from tests.closed_loop_ref import run_oracle
     R, T = 12, 40
     g = closed_loop.run_gpu(R, T, warm=True)
-    o = closed_loop.run_oracle(R, T)
+    o = run_oracle(R, T)
     assert g["conv"].mean() >= 0.99
     # same commands tick by tick while the two loops see the same states (they do until round-off grows)
     assert np.abs(g["w"][:5] - o["w"][:5]).max() <= 1e-4
@@ -679,3 +680,140 @@ def test_short_and_odd_horizons(oracle):
             assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
             assert abs(out["obj"][i] - o["obj"]) <= F_TOL * max(1e-12, abs(o["obj"]))
             assert np.abs(out["pred"][:, i].reshape(3, N) - o["pred"]).max() <= 1e-6
+
+
+# ---------------------------------------------------------------- round 2: windowing, state bounds, large sweeps
+def test_window_kernel_matches_oracle(oracle):
+    """SURVEY 8f-2: window_kernel against the oracle's restatement of MPCPlannerROS::getCutOffPlan (:266-291) and
+    downSamplePlan (:365-391) (mpc_oracle_cutoff / _downsample, pinned to the reference's own code by
+    tests/test_ros_ref.py), over several ticks so that the persistent plan index is exercised."""
+    import torch
+    from bench import gen_py
+    from bench.closed_loop import Fleet
+    R = 240
+    fleet = Fleet(R, seed=99)
+    prm = capi.yaml_default_params()
+    sv = capi.Solver(prm, R, 0)
+    M = capi.lib().mpc_b200_num_waypoints(prm)
+    dev = torch.device("cuda:0")
+    lens = [len(p[0]) for p in fleet.paths]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    d_px = torch.from_numpy(np.concatenate([p[0] for p in fleet.paths])).to(dev)
+    d_py = torch.from_numpy(np.concatenate([p[1] for p in fleet.paths])).to(dev)
+    d_off = torch.from_numpy(offs).to(dev); d_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+    d_tid = torch.from_numpy(fleet.kind.astype(np.int32)).to(dev)
+    d_idx = torch.from_numpy(fleet.idx.astype(np.int32)).to(dev)
+    d_wx = torch.zeros((M, R), dtype=torch.float64, device=dev); d_wy = torch.zeros_like(d_wx)
+    rng = np.random.default_rng(4)
+    idx = fleet.idx.copy()
+    for tick in range(6):
+        d_pose = torch.from_numpy(np.ascontiguousarray(fleet.pose)).to(dev)
+        sv.window_raw(R, d_px, d_py, d_off, d_len, d_tid, d_idx, d_pose, d_wx, d_wy)
+        torch.cuda.synchronize()
+        wx = d_wx.cpu().numpy(); wy = d_wy.cpu().numpy(); gi = d_idx.cpu().numpy()
+        for i in range(R):
+            px, py = fleet.paths[fleet.kind[i]]
+            e = oracle.cutoff(px, py, int(idx[i]), fleet.pose[0, i], fleet.pose[1, i], ring=True, max_erase=64)
+            idx[i] = (int(idx[i]) + e) % len(px)
+            ox, oy, m = oracle.downsample(px, py, int(idx[i]), fleet.win, fleet.step, ring=True)
+            assert m == M and gi[i] == idx[i], (tick, i, gi[i], idx[i])
+            assert np.array_equal(wx[:, i], ox) and np.array_equal(wy[:, i], oy)
+        # move the robots along (and a little off) their tracks, up to ~2.5 m per tick: cuts of 0 .. 50 points
+        for i in range(R):
+            px, py = fleet.paths[fleet.kind[i]]
+            j = (int(idx[i]) + int(rng.integers(0, 50))) % len(px)
+            fleet.pose[0, i] = px[j] + rng.uniform(-0.2, 0.2); fleet.pose[1, i] = py[j] + rng.uniform(-0.2, 0.2)
+    sv.close()
+
+
+@pytest.mark.parametrize("bound", [0.5, 2.0, 1e3])
+def test_state_bounds_honoured_or_refused(oracle, bound):
+    """mpc_planner.cpp:303-312: every state variable is bounded by +-bound_value (cfg range 0.01 .. 1000).  The GPU path
+    has no barrier for these bounds: where the returned point lies strictly inside them it must be the oracle's solution
+    of the BOUNDED problem (within the north-star tolerances); everywhere else it must say MPC_B200_STATUS_BOUND_ACTIVE
+    and never SUCCESS."""
+    pm = dict(YAML_DEFAULT, BOUND=bound)
+    state, coeffs = mild(41, 64)
+    sv = _solver(pm, 64)
+    out = sv.solve(state, coeffs)
+    sv.close()
+    n_inside = n_flag = 0
+    for i in range(64):
+        o = oracle.solve(pm, state[:, i], coeffs[:, i])
+        smax_gpu = max(np.abs(out["pred"][:, i]).max(), np.abs(state[:, i]).max())
+        if out["status"][i] == 1:
+            n_inside += 1
+            assert smax_gpu < bound
+            assert o["status"] == 1
+            assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL, (i, out["u0"][:, i], o["u0"])
+            assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+        else:
+            assert out["status"][i] == 64, out["status"][i]
+            n_flag += 1
+            # the oracle's bounded solution does lean on a bound (or the unbounded one would leave the box)
+            s_o = np.abs(o["sol"][:6 * 20]).max()
+            assert s_o >= bound * (1.0 - 2e-3) or smax_gpu >= bound * (1.0 - 1e-3)
+    if bound >= 1e3:
+        assert n_flag == 0
+    if bound <= 0.5:
+        assert n_flag > 0          # x reaches ~1 m within the horizon: the bound would bind for most problems
+    assert n_inside + n_flag == 64
+
+
+def _oracle_many(pm, state, coeffs, max_iter=100):
+    import multiprocessing as mp
+    from tests.parity_sweep import _oracle_chunk
+    import tests.parity_sweep as ps
+    ps.MAX_ITER = max_iter
+    n = state.shape[1]
+    P = os.cpu_count() or 1
+    cuts = np.linspace(0, n, 4 * P + 1).astype(int)
+    with mp.get_context("fork").Pool(P) as pool:
+        parts = pool.map(_oracle_chunk, [(pm, state[:, a:b].copy(), coeffs[:, a:b].copy()) for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
+    return {k: np.concatenate([p[k] for p in parts], axis=-1) for k in parts[0]}
+
+
+def _sweep_check(name, pm, seed, n, max_both_miss, max_conv_gap):
+    """GPU through the C ABI vs the oracle on all host cores, both capped at 100 iterations; returns the statistics."""
+    from bench import gen_py
+    g = gen_py.problems(seed, n)
+    prm = capi.params_from_map(pm, capi.yaml_default_params()); prm.delay_mode = 0; prm.max_iter = 100
+    sv = capi.Solver(prm, n, 0)
+    coeffs, state = sv.prestep(g["wx"], g["wy"], g["pose"], g["vel"])
+    gpu = sv.solve(state, coeffs)
+    sv.close()
+    orc = _oracle_many(pm, state, coeffs)
+    okg = (gpu["status"] == 1) & (gpu["kkt"] <= KKT_TOL); oko = orc["status"] == 1
+    both = okg & oko
+    du = np.abs(gpu["u0"] - orc["u0"]).max(axis=0)
+    dobj = np.abs(gpu["obj"] - orc["obj"]) / np.maximum(1.0, np.abs(orc["obj"]))
+    miss = int((both & ((du > U_TOL) | (dobj > F_TOL))).sum())
+    stats = dict(sweep=name, problems=n, gpu_converged=int(okg.sum()), oracle_converged=int(oko.sum()), both=int(both.sum()),
+                 miss=miss, only_oracle=int((~okg & oko).sum()), only_gpu=int((okg & ~oko).sum()),
+                 gpu_status={int(k): int(v) for k, v in zip(*np.unique(gpu["status"], return_counts=True))})
+    print(json.dumps(stats))
+    assert miss <= max_both_miss, stats
+    assert abs(stats["gpu_converged"] - stats["oracle_converged"]) <= max_conv_gap, stats
+    assert both.sum() >= 0.995 * n, stats
+    return stats
+
+
+def test_sweep_config2_yaml_weights():
+    """4,096 problems of BASELINE config 2's generator (mpc_params.yaml weights) against the oracle, miss count asserted:
+    a both-converged problem may differ only where the non-convex NLP has a second local minimum (<= 2 per 16k)."""
+    _sweep_check("config2 yaml", YAML_DEFAULT, 20261018 + 2, 4096, max_both_miss=1, max_conv_gap=3)
+
+
+def test_sweep_config2_cfg_weights():
+    """The same with the MPCPlanner.cfg defaults (rate penalties: the augmented-Riccati variant)."""
+    _sweep_check("config2 cfg", CFG_DEFAULT, 20261018 + 12, 4096, max_both_miss=1, max_conv_gap=3)
+
+
+def test_sweep_config3_seed():
+    """BASELINE config 3's problem set (seed 20261018 + 3), first 4,096 problems."""
+    _sweep_check("config3 seed", YAML_DEFAULT, 20261018 + 3, 4096, max_both_miss=1, max_conv_gap=3)
+
+
+def test_sweep_config4_real_generator_N100():
+    """BASELINE config 4 as benchmarked: the REAL generator (seed 20261018 + 4) at N = 100, 1,024 problems."""
+    _sweep_check("config4 N=100", dict(YAML_DEFAULT, STEPS=100), 20261018 + 4, 1024, max_both_miss=1, max_conv_gap=8)

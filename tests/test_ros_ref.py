@@ -102,6 +102,15 @@ def test_cutoff_and_downsample_match_reference(oracle, ros):
             assert np.array_equal(wx, r["wx"]) and np.array_equal(wy, r["wy"])
 
 
+def test_oracle_loop_equals_the_reference_code_loop():
+    """BASELINE config 5's checker: the oracle loop (restatements + oracle solve) and the loop through the reference's own
+    getCutOffPlan / downSamplePlan / Tracking tick / MPC::Solve command the same robots identically."""
+    from tests.closed_loop_ref import run_oracle, run_reference_ros
+    o = run_oracle(6, 30); r = run_reference_ros(6, 30)
+    assert np.abs(o["w"] - r["w"]).max() <= 1e-9 and np.abs(o["thr"] - r["thr"]).max() <= 1e-9
+    assert np.abs(o["dist"] - r["dist"]).max() <= 1e-9
+
+
 def test_reference_ros_sources_compile_against_the_adapter_header():
     """SURVEY 8f-3 / INTEGRATION section 1: the reference's two ROS sources compile UNMODIFIED against this repository's
     mpc_planner.h (the MPC adapter) -- stand-in ROS / Eigen headers, real reference headers; the maintainer's swap is

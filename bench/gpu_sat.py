@@ -44,8 +44,14 @@ def main():
     e0.record()
     for s in streams: s.wait_event(e0)
     t0 = time.perf_counter()
+    # at most 2 launches in flight per stream (the handle refuses more launches in flight than it has ring slots)
+    ev = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
     for j in range(K):
-        f(*args[j % R], sp[j % S])
+        s_ = j % S; k_ = j // S
+        if k_ >= 2: ev[s_][k_ % 2].synchronize()
+        rc = f(*args[j % R], sp[s_])
+        if rc != 0: raise RuntimeError("solve_batch failed: %d" % rc)
+        ev[s_][k_ % 2].record(streams[s_])
     t1 = time.perf_counter()
     for s in streams: torch.cuda.current_stream().wait_stream(s)
     e1.record(); torch.cuda.synchronize()

@@ -275,6 +275,18 @@ int mpc_b200_track_wait(mpc_b200_handle *h);
 int64_t mpc_b200_track_packed_layout(const mpc_b200_handle *h, int32_t batch, int32_t M, int32_t with_ref_vel,
                                      int64_t *offsets_bytes12);
 int mpc_b200_track_packed_submit(mpc_b200_handle *h, int32_t batch, int32_t M, int32_t with_ref_vel, void *io);
+/*
+ * Multi-GPU sharding of ONE batch (contiguous slices, no collective, host gather): the caller's SoA arrays
+ * hold the whole batch (`ld` columns); the handle -- one per GPU and host thread -- takes columns
+ * [offset, offset + batch).  Arrays must be page-locked (mpc_b200_host_alloc; else MPC_B200_ERR_UNSUPPORTED): every
+ * array moves by one strided DMA copy straight between the caller's memory and the device, and each slice's results
+ * land in their own sub-range of the caller's output arrays -- that is the whole "gather".  Arguments as
+ * mpc_b200_track_submit; finish with mpc_b200_track_wait.
+ */
+int mpc_b200_track_slice_submit(mpc_b200_handle *h, int32_t ld, int32_t offset, int32_t batch, int32_t M,
+                                const double *wx, const double *wy, const double *pose, double *vel_inout,
+                                const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                                double *obj, int32_t *status, int32_t *iters, double *kkt_res);
 /* Page-locked host memory for callers that do not link the CUDA runtime (cgo / JNI / ctypes). */
 void *mpc_b200_host_alloc(size_t bytes);
 void mpc_b200_host_free(void *p);

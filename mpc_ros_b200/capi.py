@@ -42,6 +42,7 @@ EXPORTS = [
     "mpc_b200_last_kernel_seconds", "mpc_b200_launch_count", "mpc_b200_strerror",
     "mpc_b200_last_cuda_error", "mpc_b200_version", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
     "mpc_b200_track_packed_layout", "mpc_b200_track_packed_submit", "mpc_b200_host_alloc", "mpc_b200_host_free",
+    "mpc_b200_track_slice_submit",
     "mpc_b200_debug_profile", "mpc_b200_debug_fp64_probe",
 ]
 
@@ -119,6 +120,8 @@ def lib():
     L.mpc_b200_track_packed_layout.restype = C.c_int64
     L.mpc_b200_track_packed_submit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.mpc_b200_track_packed_submit.restype = C.c_int
+    L.mpc_b200_track_slice_submit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 12
+    L.mpc_b200_track_slice_submit.restype = C.c_int
     L.mpc_b200_host_alloc.argtypes = [C.c_size_t]
     L.mpc_b200_host_alloc.restype = C.c_void_p
     L.mpc_b200_host_free.argtypes = [C.c_void_p]

@@ -335,6 +335,7 @@ __global__ void dfma_kernel(double *out, int iters, int active_lanes, long long 
 // host-buffer results of a tick that is still in flight (mpc_b200_track_submit / _wait)
 struct Fetch {
     bool active;
+    bool sliced;           // mpc_b200_track_slice_submit: results went straight into the caller's (page-locked) arrays
     bool packed;           // mpc_b200_track_packed_submit: one D2H into `io` (or the staging area)
     void *io; size_t io_off, io_bytes; bool io_pinned;
     int32_t batch;
@@ -803,6 +804,13 @@ static int fetch_finish(mpc_b200_handle *h, Fetch &f, cudaStream_t st)
 {
     if (!f.active) return MPC_B200_OK;
     f.active = false;
+    if (f.sliced) {
+        f.sliced = false;
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_kernel_s = 1e-3 * ms; else cudaGetLastError();
+        return MPC_B200_OK;
+    }
     if (f.packed) {
         f.packed = false;
         CK(cudaStreamSynchronize(st));
@@ -1033,6 +1041,60 @@ int mpc_b200_track_packed_submit(mpc_b200_handle *h, int32_t batch, int32_t M, i
     CK(cudaMemcpyAsync(pinned ? (void *)((char *)io + out_off) : (void *)h->h_out, (const char *)d + out_off, out_bytes,
                        cudaMemcpyDeviceToHost, st));
     f.active = true;
+    return MPC_B200_OK;
+}
+
+// ---- one GPU's contiguous slice of a batch held in the caller's SoA arrays
+// The arrays have `ld` columns (the whole batch); this handle takes columns [offset, offset + batch).  Every array
+// is moved by ONE strided copy (cudaMemcpy2DAsync: `rows` rows of batch doubles, pitch ld doubles) straight between
+// the caller's page-locked arrays and the device: no staging, no host-side scatter / gather.
+int mpc_b200_track_slice_submit(mpc_b200_handle *h, int32_t ld, int32_t offset, int32_t batch, int32_t M,
+                                const double *wx, const double *wy, const double *pose, double *vel_inout,
+                                const double *ref_vel, double *u0, double *pred, double *cmd_out,
+                                double *obj, int32_t *status, int32_t *iters, double *kkt_res)
+{
+    NvtxRange nv("mpc_b200_track_slice_submit");
+    if (!h || batch < 0 || batch > h->max_batch || ld < batch || offset < 0 || offset + batch > ld) return MPC_B200_ERR_INVALID;
+    if (!wx || !wy || !pose || !vel_inout || !u0 || !pred) return MPC_B200_ERR_INVALID;
+    if (M < 4 || M > MAX_WAYPOINTS || M < h->opt_nc) return MPC_B200_ERR_INVALID;
+    if (h->pending.active) return MPC_B200_ERR_INVALID;
+    if (batch == 0) return MPC_B200_OK;
+    // DMA needs page-locked memory on both ends of a tick that is in flight
+    if (!is_pinned_cached(h, wx) || !is_pinned_cached(h, wy) || !is_pinned_cached(h, pose) || !is_pinned_cached(h, vel_inout) ||
+        !is_pinned_cached(h, u0) || !is_pinned_cached(h, pred) || (ref_vel && !is_pinned_cached(h, ref_vel)) ||
+        (cmd_out && !is_pinned_cached(h, cmd_out)) || (obj && !is_pinned_cached(h, obj)) || (status && !is_pinned_cached(h, status)) ||
+        (iters && !is_pinned_cached(h, iters)) || (kkt_res && !is_pinned_cached(h, kkt_res)))
+        return MPC_B200_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t B = (size_t)batch, N = (size_t)h->params.mpc_steps;
+    const size_t hp = sizeof(double) * (size_t)ld, dp = sizeof(double) * B, w = sizeof(double) * B;
+#define H2D2(dst, src, rows) CK(cudaMemcpy2DAsync(dst, dp, (src) + offset, hp, w, (size_t)(rows), cudaMemcpyHostToDevice, st))
+#define D2H2(dst, src, rows) CK(cudaMemcpy2DAsync((dst) + offset, hp, src, dp, w, (size_t)(rows), cudaMemcpyDeviceToHost, st))
+    H2D2(h->d_wx, wx, M); H2D2(h->d_wy, wy, M); H2D2(h->d_pose, pose, 3); H2D2(h->d_vel, vel_inout, 3);
+    if (ref_vel) H2D2(h->d_refv, ref_vel, 1);
+    launch_prestep(h->opt_nc, st, batch, M, h->d_wx, h->d_wy, h->d_pose, h->d_coeffs, NULL, h->d_vel, h->d_state,
+                   h->params.delay_mode, h->params.dt);
+    CK(cudaGetLastError());
+    h->kernels++;
+    int rc = enqueue_solve(h, batch, h->d_state, h->d_coeffs, ref_vel ? h->d_refv : NULL, NULL, h->d_u0, h->d_pred, h->d_obj,
+                           h->d_status, h->d_iters, h->d_kkt, NULL, st);
+    if (rc != MPC_B200_OK) return rc;
+    poststep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(batch, h->d_u0, h->d_vel, ref_vel ? h->d_refv : NULL, h->params.ref_vel,
+                                                          h->params.dt, h->d_cte);
+    CK(cudaGetLastError());
+    h->kernels++;
+    D2H2(u0, h->d_u0, 2); D2H2(pred, h->d_pred, 3 * N); D2H2(vel_inout, h->d_vel, 3);
+    if (cmd_out) D2H2(cmd_out, h->d_cte, 2);
+    if (obj) D2H2(obj, h->d_obj, 1);
+    if (kkt_res) D2H2(kkt_res, h->d_kkt, 1);
+    if (status) CK(cudaMemcpyAsync(status + offset, h->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters + offset, h->d_iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+#undef H2D2
+#undef D2H2
+    Fetch &f = h->pending;
+    f = Fetch();
+    f.sliced = true; f.batch = batch; f.active = true;
     return MPC_B200_OK;
 }
 

@@ -296,7 +296,10 @@ def test_closed_loop_tracks_like_the_reference_loop():
     assert np.abs(g["thr"][:5] - o["thr"][:5]).max() <= 1e-4
     # and the same tracking quality over the run
     assert abs(np.abs(g["cte"]).mean() - np.abs(o["cte"]).mean()) <= 0.01
-    assert np.abs(g["cte"][-10:]).mean() <= 0.12          # the order of the reference's own trace (assets/mpc.csv)
+    # (the reference's own trace, assets/mpc.csv, has mean |cte| 0.05 m on an unknown path with unknown parameters; with the
+    #  mpc_params.yaml weights on these tracks the reference LOOP itself settles at 0.13 .. 0.15 m: DESIGN section "config 5")
+    assert abs(np.abs(g["cte"][-10:]).mean() - np.abs(o["cte"][-10:]).mean()) <= 0.02
+    assert np.abs(g["cte"][-10:]).mean() <= 0.2
     assert g["iters"][1:].mean() < o["iters"][1:].mean()  # warm start pays
 
 
@@ -817,3 +820,71 @@ def test_sweep_config3_seed():
 def test_sweep_config4_real_generator_N100():
     """BASELINE config 4 as benchmarked: the REAL generator (seed 20261018 + 4) at N = 100, 1,024 problems."""
     _sweep_check("config4 N=100", dict(YAML_DEFAULT, STEPS=100), 20261018 + 4, 1024, max_both_miss=1, max_conv_gap=8)
+
+
+def test_packed_and_sliced_ticks_equal_the_plain_tick():
+    """mpc_b200_track_packed_submit (one buffer, one copy each way) and mpc_b200_track_slice_submit (contiguous slices of
+    the caller's SoA arrays) return bit for bit what mpc_b200_track_batch returns."""
+    import ctypes as C
+    from bench import gen_py
+    B = 500
+    g = gen_py.problems(20261018 + 3, B)
+    M = g["M"]
+    prm = capi.yaml_default_params()
+    sv = capi.Solver(prm, B, 0)
+    vel = np.ascontiguousarray(g["vel"]).copy()
+    ref = sv.track(g["wx"], g["wy"], g["pose"], vel)
+    # ---- packed
+    total, off = sv.packed_layout(B, M)
+    L = capi.lib()
+    ptr = L.mpc_b200_host_alloc(total)
+    buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(total,))
+    v = sv.packed_views(buf, B, M)
+    v["wx"][:] = g["wx"]; v["wy"][:] = g["wy"]; v["pose"][:] = g["pose"]; v["vel"][:] = g["vel"]
+    sv.track_packed_submit(B, M, ptr)
+    sv.track_wait()
+    for k in ("u0", "pred", "cmd", "obj", "kkt", "status", "iters"):
+        assert np.array_equal(v[k], ref[k]), k
+    assert np.array_equal(v["vel"], vel)
+    L.mpc_b200_host_free(ptr)
+    # ---- sliced: two handles on the same device share the batch 200 / 300
+    import torch
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    N = prm.mpc_steps
+    t = dict(wx=pin(g["wx"]), wy=pin(g["wy"]), pose=pin(g["pose"]), vel=pin(g["vel"]), u0=pin(np.zeros((2, B))),
+             pred=pin(np.zeros((3 * N, B))), cmd=pin(np.zeros((2, B))), obj=pin(np.zeros(B)), kkt=pin(np.zeros(B)),
+             status=pin(np.zeros(B, dtype=np.int32)), iters=pin(np.zeros(B, dtype=np.int32)))
+    hs = [capi.Solver(prm, 200, 0), capi.Solver(prm, 300, 0)]
+    for s_, (lo, n) in zip(hs, ((0, 200), (200, 300))):
+        rc = L.mpc_b200_track_slice_submit(s_._h, B, lo, n, M, t["wx"].data_ptr(), t["wy"].data_ptr(), t["pose"].data_ptr(),
+                                           t["vel"].data_ptr(), None, t["u0"].data_ptr(), t["pred"].data_ptr(), t["cmd"].data_ptr(),
+                                           t["obj"].data_ptr(), t["status"].data_ptr(), t["iters"].data_ptr(), t["kkt"].data_ptr())
+        assert rc == 0
+    for s_ in hs:
+        s_.track_wait(); s_.close()
+    for k in ("u0", "pred", "cmd", "obj", "kkt", "status", "iters"):
+        assert np.array_equal(t[k].numpy(), ref[k]), k
+    assert np.array_equal(t["vel"].numpy(), vel)
+    # pageable arrays are refused, not silently staged
+    rc = L.mpc_b200_track_slice_submit(sv._h, B, 0, B, M, g["wx"].ctypes.data, g["wy"].ctypes.data, g["pose"].ctypes.data,
+                                       vel.ctypes.data, None, ref["u0"].ctypes.data, ref["pred"].ctypes.data, None, None, None, None, None)
+    assert rc == -3
+    sv.close()
+
+
+def test_host_warm_records_are_staged(oracle):
+    """SURVEY 8b ownership: warm-start records may live in host memory too."""
+    state, coeffs = mild(7, 16)
+    sv = _solver(YAML_DEFAULT, 16)
+    N = 20; ws = capi.lib().mpc_b200_warm_size(N)
+    w = np.zeros((ws, 16))
+    out = dict(u0=np.zeros((2, 16)), pred=np.zeros((3 * N, 16)), status=np.zeros(16, dtype=np.int32), iters=np.zeros(16, dtype=np.int32))
+    sv.solve_raw(16, state, coeffs, out["u0"], out["pred"], status=out["status"], iters=out["iters"], warm_out=w)
+    assert np.all(out["status"] == 1) and np.abs(w).max() > 0
+    out2 = dict(u0=np.zeros((2, 16)), pred=np.zeros((3 * N, 16)), status=np.zeros(16, dtype=np.int32), iters=np.zeros(16, dtype=np.int32))
+    sv.solve_raw(16, state, coeffs, out2["u0"], out2["pred"], status=out2["status"], iters=out2["iters"], warm_in=w)
+    sv.close()
+    assert np.all(out2["status"] == 1)
+    assert np.abs(out2["u0"] - out["u0"]).max() <= U_TOL
+    assert out2["iters"].mean() < out["iters"].mean()

@@ -191,6 +191,8 @@ def _addr(x):
         return None
     if isinstance(x, np.ndarray):
         return x.ctypes.data
+    if isinstance(x, int):          # a raw address (mpc_b200_host_alloc)
+        return x
     return x.data_ptr()
 
 

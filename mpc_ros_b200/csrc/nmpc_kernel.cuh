@@ -159,8 +159,9 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             // ---- P3a: stage threads apply / flush / init
             __syncthreads();  // B3
             TRACE_C(2);
-            if (lane) {   // apply / flush / init are done
-                sm.I(PI_FLAGS, p) &= ~(FL_APPLY | FL_FLUSH | FL_WARM);
+            if (lane) {   // apply / flush / init are done (FL_SOC next to FL_APPLY: the applied step was a correction)
+                const int f0 = sm.I(PI_FLAGS, p);
+                sm.I(PI_FLAGS, p) = f0 & ~(FL_APPLY | FL_FLUSH | FL_WARM | ((f0 & FL_APPLY) ? FL_SOC : 0));
                 if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
             }
             // ---- P3b: stage threads write coefficients
@@ -169,9 +170,11 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             PROF_MARK(2);
             // ---- P4: Riccati sweeps
             int step_lsq = 0;     // sampled here for P6: the lane's adjoint stage thread rewrites PI_FLAGS there
+            int step_mode = 0;    // FL_SOC / FL_RESUME of the system being solved
             if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
                 const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
                 step_lsq = lsq;
+                step_mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME);
                 const double dw = sm.P(PS_DW, p);
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
                 const int okb = riccati_backward<RATE>(prm, sm, p, hd);
@@ -208,8 +211,8 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             bool late = false;
             if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
                 if (!step_lsq) {
-                    ctrl_step(prm, sm, c, p, NG);
-                    sm.I(PI_FLAGS, p) = FL_LS;
+                    ctrl_step(prm, sm, c, p, NG, step_mode);
+                    sm.I(PI_FLAGS, p) = FL_LS | (step_mode & FL_SOC);
                     late = true;
                 }
                 sm.I(PI_MODE, p) = MODE_EVAL;
@@ -233,6 +236,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                     PROF_MARK(10);
                     if (r == 0) {
                         sm.I(PI_FLAGS, p) = FL_LS;
+                    } else if (r >= 3) {
+                        // second-order correction (3) / resume after failed corrections (4): the same Newton system again
+                        // (PS_DW kept), no step applied
+                        sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = (r == 3) ? FL_SOC : FL_RESUME;
                     } else {
                         int nf = 0;
                         // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
@@ -322,6 +329,12 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
                         for (int j = 0; j < SPT; j++)
                             if (k0 + j < N) stage_init<RATE>(prm, sm, r[j], k0 + j, p, s6, c4);
                     }
+                } else if ((fl & (FL_SOC | FL_APPLY)) == FL_SOC && sm.I(PI_MODE, p) == MODE_NEWTON) {
+                    // second-order correction: the next right-hand side from the rejected trial point, before the
+                    // coefficients of any stage overwrite the step slots
+#pragma unroll
+                    for (int j = 0; j < SPT; j++)
+                        if (k0 + j < N) stage_soc_rhs<NC>(prm, sm, r[j], k0 + j, p, cf);
                 }
             }
             TRACE_S(2);
@@ -330,10 +343,10 @@ __global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(con
             // ---- P3b: Newton-system coefficients
             if (mine) {
                 if (sm.I(PI_MODE, p) == MODE_NEWTON) {
-                    const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                    const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ, soc = sm.I(PI_FLAGS, p) & FL_SOC;
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
-                        if (k0 + j < N) stage_coeffs<RATE, NC>(prm, sm, r[j], k0 + j, p, lsq, cf);
+                        if (k0 + j < N) stage_coeffs<RATE, NC>(prm, sm, r[j], k0 + j, p, lsq, cf, soc);
                 }
             }
             TRACE_S(4);

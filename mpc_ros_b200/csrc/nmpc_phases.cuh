@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define MPC_HD __host__ __device__ __forceinline__
+#define MPC_HD_RARE __host__ __device__ __noinline__     /* rare paths: kept out of the hot phases' register allocation */
 #else
 #define MPC_HD inline
+#define MPC_HD_RARE inline
 #endif
 
 namespace nmpc {
@@ -62,6 +64,8 @@ enum PSlot {
     PS_NX0, PS_NX1, PS_NX2, PS_NX3, PS_NX4, PS_NX5,       // staged inputs of the lane's next problem: state (6),
     PS_NX6, PS_NX7, PS_NX8, PS_NX9, PS_NX10,              // coeffs (4), ref_vel -- written at refill, read in P3a
     PS_NXC4, PS_NXC5, PS_NXC6, PS_NXC7,                   // coefficients 4..7 of a path polynomial of order > 3
+    PS_ALPHA_LS,   // second-order correction: length of the rejected first trial step (Armijo / switching tests, resume)
+    PS_SOC_THETA,  // second-order correction: constraint violation of the previous attempt (kappa_soc test)
     NPS
 };
 enum PISlot {
@@ -69,6 +73,8 @@ enum PISlot {
     PI_FLAGS,      // enum Flag bits
     PI_PROB,       // index of the problem in this lane
     PI_NEXT,       // refill: index of the problem the lane takes over in P3, or -1
+    PI_SOC,        // line search of the pending step: 0 = first trial not yet judged, k >= 1 = k-th second-order
+                   // correction in progress, -1 = plain backtracking (no correction any more)
     NPI
 };
 
@@ -88,7 +94,10 @@ enum Flag {
     FL_LS = 8,       // the point evaluated in P1 is a line-search trial (else it is accepted as is)
     FL_FLUSH = 16,   // P3 must write this lane's finished problem out
     FL_KEEP = 32,    // with FL_ADOPT: keep the least-squares multipliers (else reset to zero)
-    FL_WARM = 64     // P3a initialises the lane from a warm-start record instead of the cold start
+    FL_WARM = 64,    // P3a initialises the lane from a warm-start record instead of the cold start
+    FL_SOC = 128,    // the Newton system / the trial point is a second-order correction (W&B A-5.5 .. A-5.9): same matrix,
+                     // constraint right-hand side c_soc kept in the stage threads' trial sin/cos registers
+    FL_RESUME = 256  // the Newton step is recomputed after a failed correction: the line search resumes at alpha / 2
 };
 
 struct Params {
@@ -166,6 +175,8 @@ MPC_HD size_t smem_bytes(int N, int NG, int PB, int nslots = NSLOTS)
 #define NMPC_KW_PLUS 8.0
 #define NMPC_KW_PLUS_BAR 100.0
 #define NMPC_EPS_MACH 2.220446049250313e-16
+#define NMPC_MAX_SOC 4
+#define NMPC_KAPPA_SOC 0.99
 
 // Roles of the work slots between the sweeps and the next coefficient phase:
 //   W_LAM..+5  g_k (P5), then lambda_{k+1}^+ (adjoint sweep, in place);
@@ -610,6 +621,41 @@ MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, in
     r.sn = r.tsn; r.cs = r.tcs; r.se = r.tse; r.ce = r.tce;
 }
 
+// Second-order correction (W&B A-5.5 .. A-5.9; Ipopt TrySecondOrderCorrection): the rejected trial point
+// iterate + a * step (a = PS_ALPHA; the step is still in the D / W_DU slots) gives the next right-hand side
+//   c_soc <- a * c_soc + c(trial),   first attempt: c_soc = c(iterate).
+// The right-hand side the pending step was computed with is recovered from the step itself, which satisfies the
+// linearised dynamics:  c_old = A_k ds_k + B du_k - ds_{k+1}  (A_k is still in its slots: the iterate has not moved).
+// The rows of theta, v, etheta are linear, so their c_soc equals c(iterate) at every attempt (stage_coeffs writes
+// them as usual); the rows of x, y, cte are handed to stage_coeffs in r.tsn, r.tcs, r.tse (free until the next
+// evaluation).  Runs in P3a, before stage_coeffs of any stage overwrites the step slots.
+template <int NC = 4, class SM>
+MPC_HD void stage_soc_rhs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, const double *cf)
+{
+    if (k >= prm.N - 1) return;
+    const double a = sm.P(PS_ALPHA, p), dt = prm.dt;
+    double dsx = 0, dsy = 0, dst = 0, dsv = 0, dse = 0;
+    if (k > 0) {
+        dsx = sm.at(k - 1, D_X, p); dsy = sm.at(k - 1, D_Y, p); dst = sm.at(k - 1, D_T, p);
+        dsv = sm.at(k - 1, D_V, p); dse = sm.at(k - 1, D_E, p);
+    }
+    const double nsx = sm.at(k, D_X, p), nsy = sm.at(k, D_Y, p), nsc = sm.at(k, D_C, p);
+    const double bx = (dsx + sm.at(k, A_13, p) * dst + sm.at(k, A_14, p) * dsv) - nsx;
+    const double by = (dsy + sm.at(k, A_23, p) * dst + sm.at(k, A_24, p) * dsv) - nsy;
+    const double bc = (sm.at(k, A_51, p) * dsx - dsy + sm.at(k, A_54, p) * dsv + sm.at(k, A_56, p) * dse) - nsc;
+    const double x = sm.at(k, S_X, p) + a * dsx, y = sm.at(k, S_Y, p) + a * dsy;
+    const double th = sm.at(k, S_T, p) + a * dst, v = sm.at(k, S_V, p) + a * dsv, e = sm.at(k, S_E, p) + a * dse;
+    const double nx = sm.at(k + 1, S_X, p) + a * nsx, ny = sm.at(k + 1, S_Y, p) + a * nsy, nc = sm.at(k + 1, S_C, p) + a * nsc;
+    double sn, cs, se, ce, poly, d1, d2;
+    sincos_d(th, &sn, &cs);
+    sincos_d(e, &se, &ce);
+    path_poly<NC>(cf, x, poly, d1, d2);
+    (void)ce; (void)d1; (void)d2;
+    r.tsn = a * bx + (nx - (x + v * cs * dt));
+    r.tcs = a * by + (ny - (y + v * sn * dt));
+    r.tse = a * bc + (nc - ((poly - y) + v * se * dt));
+}
+
 // Diagonal of the stage Hessian that is constant over the horizon: {x, y, theta, v, cte, etheta}, u.
 struct HessDiag { double dx, dy, dt_, dv, dc, de, du; double rw, ra; /* 2 sf w_angvel_d, 2 sf w_accel_d */ };
 MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
@@ -626,7 +672,7 @@ MPC_HD HessDiag hess_diag(const Params &prm, double sf, double dw, int lsq)
 }
 
 template <bool RATE = false, int NC = 4, class SM>
-MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq, const double *cf)
+MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, int p, int lsq, const double *cf, int soc = 0)
 {
     const int N = prm.N;
     const double sf = sm.P(PS_SF, p), mu = sm.P(PS_MU, p), refv = sm.P(PS_REFV, p), dt = prm.dt;
@@ -673,6 +719,7 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
             sm.at(k, D_V, p) = (v + r.ua * dt) - sm.at(k + 1, S_V, p);
             sm.at(k, D_C, p) = ((poly - y) + v * r.se * dt) - sm.at(k + 1, S_C, p);
             sm.at(k, D_E, p) = (e + r.uw * dt) - sm.at(k + 1, S_E, p);
+            if (soc) { sm.at(k, D_X, p) = -r.tsn; sm.at(k, D_Y, p) = -r.tcs; sm.at(k, D_C, p) = -r.tse; }   // -c_soc (stage_soc_rhs)
             const double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mc = sm.at(k, L_C, p);
             // second derivatives of the constraint rows weighted by lambda_{k+1}
             // (stage_step recomputes these five instead of keeping them in registers across the cycle)
@@ -1102,7 +1149,9 @@ MPC_HD void filter_add(const SM &sm, Ctrl &c, int p, double theta, double phi)
 // halves alpha and is evaluated again next cycle.  An accepted point (or a plain evaluation) becomes the
 // iterate: convergence test (W&B eq. (5), (6)) and monotone barrier update (eq. (7)).
 // Returns: 0 = evaluate again (alpha halved), 1 = iterate accepted, continue with a Newton step,
-//          2 = terminated (c.status set; the step, if any, still has to be applied before flushing).
+//          2 = terminated (c.status set; the step, if any, still has to be applied before flushing),
+//          3 = solve the same Newton system for a second-order correction (FL_SOC),
+//          4 = the corrections failed: recompute the Newton step and resume the backtracking (FL_RESUME).
 #if defined(NMPC_PROFILE) && defined(__CUDACC__)
 __device__ long long nmpc_dec_acc[8];
 #endif
@@ -1137,7 +1186,11 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
     // reconverge after every block instead of running the common tail once per path.
     int ret = -1;
     if (flags & FL_LS) {
+        const int soc = flags & FL_SOC;
         const double alpha = sm.P(PS_ALPHA, p);
+        // a second-order correction is judged with the step length of the rejected first trial (Ipopt:
+        // CheckAcceptabilityOfTrialPoint(alpha_primal) inside TrySecondOrderCorrection)
+        const double alpha_t = soc ? sm.P(PS_ALPHA_LS, p) : alpha;
         const double phi_t = f - mu * lnsum;
         const double th = c.theta, phi = c.phi, gd = c.gd;
         const int ok = inside && (pr1 == pr1) && (phi_t == phi_t);
@@ -1145,17 +1198,31 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
         if (ok && filter_acceptable(sm, c, p, pr1, phi_t)) {
             // switching condition (W&B eq. (19)): alpha (-gd)^s_phi > theta^s_theta, with the right-hand side
             // brought over in ctrl_step_late (c.sw_alpha)
-            if (th <= c.theta_min && gd < 0.0 && alpha > c.sw_alpha) {
-                if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha * gd) { acc = 1; armijo = 1; }
+            if (th <= c.theta_min && gd < 0.0 && alpha_t > c.sw_alpha) {
+                if (phi_t - phi - 10.0 * NMPC_EPS_MACH * fabs(phi) <= NMPC_ETA_PHI * alpha_t * gd) { acc = 1; armijo = 1; }
             } else {
                 if (pr1 <= (1.0 - NMPC_GAMMA_THETA) * th ||
                     phi_t - 10.0 * NMPC_EPS_MACH * fabs(phi) <= phi - NMPC_GAMMA_PHI * th) acc = 1;
             }
         }
         if (!acc) {
-            const double a2 = 0.5 * alpha;
+            // second-order correction (W&B A-5.5 .. A-5.9): only after the first trial of a step, and only if it did not
+            // reduce the constraint violation; up to NMPC_MAX_SOC corrections while theta keeps shrinking by kappa_soc
+            const int st = sm.I(PI_SOC, p);
+            int again = 0;      // 1: solve for a(nother) correction, 2: corrections given up, resume the backtracking
+            if (soc) {
+                if (ok && st < NMPC_MAX_SOC && !(pr1 > NMPC_KAPPA_SOC * sm.P(PS_SOC_THETA, p))) {
+                    again = 1; sm.I(PI_SOC, p) = st + 1; sm.P(PS_SOC_THETA, p) = pr1;
+                } else again = 2;
+            } else if (st == 0 && ok && pr1 >= th) {
+                again = 1; sm.I(PI_SOC, p) = 1; sm.P(PS_SOC_THETA, p) = th; sm.P(PS_ALPHA_LS, p) = alpha;
+            }
+            if (again != 1) sm.I(PI_SOC, p) = -1;
+            const double a2 = 0.5 * alpha_t;
+            if (again == 1) ret = 3;
             // (alpha_min can be 0 or NaN in degenerate cases: the absolute floor bounds the number of halvings)
-            if (a2 < c.alpha_min || !(a2 > 1e-40)) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; ret = 2; }
+            else if (a2 < c.alpha_min || !(a2 > 1e-40)) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; ret = 2; }
+            else if (again == 2) ret = 4;
             else { sm.P(PS_ALPHA, p) = a2; ret = 0; }
         } else {
             if (!armijo) filter_add(sm, c, p, th, phi);
@@ -1223,7 +1290,7 @@ MPC_HD double next_dw(const Ctrl &c, double dw)
 // P6: after the step is known and adjoint_sweep has run.  Reduces the step partials and leaves PS_ALPHA
 // (first trial), PS_ALPHA_Z and PS_MU_STEP: all the evaluation in P1 needs.
 template <class SM>
-MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
+MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG, int mode = 0)
 {
     double rmax = 0.0, rzmax = 0.0, gd = 0.0;
     for (int g = 0; g < NG; g++) {
@@ -1232,8 +1299,12 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG)
     const double tau = sm.P(PS_TAU, p);
     const double amax = (rmax > tau) ? tau / rmax : 1.0;      // fraction to the boundary, W&B eq. (15)
     const double az = (rzmax > tau) ? tau / rzmax : 1.0;
-    c.gd = gd;
-    sm.P(PS_ALPHA, p) = amax;
+    // mode & FL_SOC: the step is a second-order correction -- tried at its own fraction-to-the-boundary length, judged with
+    // the original step's directional derivative; FL_RESUME: the original step again, its first trial is already rejected
+    if (!(mode & FL_SOC)) c.gd = gd;
+    if (mode & FL_RESUME) sm.P(PS_ALPHA, p) = 0.5 * sm.P(PS_ALPHA_LS, p);
+    else sm.P(PS_ALPHA, p) = amax;
+    if (!(mode & (FL_SOC | FL_RESUME))) sm.I(PI_SOC, p) = 0;
     sm.P(PS_ALPHA_Z, p) = az;
     sm.P(PS_MU_STEP, p) = sm.P(PS_MU, p);
 }

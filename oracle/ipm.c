@@ -620,6 +620,17 @@ int ipm_solve(const ipm_nlp *nlp, const ipm_options *opt, ipm_result *res)
         }
 
         /* ---- accept (A-6, A-7) ---- */
+        if (dacc == dxs) {
+            /* Ipopt replaces the whole primal-dual step by the corrected one (actual_delta = delta_soc in
+             * TrySecondOrderCorrection) before it computes the dual step size: dz and alpha_z follow dxs. */
+            a_z = 1.0;
+            for (int i = 0; i < N; i++) {
+                dzL[i] = w->hasL[i] ? mu / (X[i] - w->XL[i]) - zL[i] - zL[i] / (X[i] - w->XL[i]) * dxs[i] : 0.0;
+                dzU[i] = w->hasU[i] ? mu / (w->XU[i] - X[i]) - zU[i] + zU[i] / (w->XU[i] - X[i]) * dxs[i] : 0.0;
+                if (w->hasL[i] && dzL[i] < 0.0) a_z = fmin(a_z, -tau * zL[i] / dzL[i]);
+                if (w->hasU[i] && dzU[i] < 0.0) a_z = fmin(a_z, -tau * zU[i] / dzU[i]);
+            }
+        }
         if (!armijo_step) {
             if (nfilt == filt_cap) { filt_cap *= 2; filt = (filt_entry *)realloc(filt, sizeof(filt_entry) * filt_cap); }
             filt[nfilt].theta = (1.0 - gamma_theta) * theta; filt[nfilt].phi = phi - gamma_phi * theta; nfilt++;

@@ -93,17 +93,25 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     for (int c = 0; c < 6; c++) s6[c] = state[(size_t)c * batch + idx];
                     for (int c = 0; c < 4; c++) c4[c] = coeffs[(size_t)c * batch + idx];
                     for (int c = 0; c < NC; c++) cfs[(size_t)NC * p + c] = c < ncoef ? coeffs[(size_t)c * batch + idx] : 0.0;
+                    for (int c = 0; c < 4; c++) sm.P(PS_NX6 + c, p) = c4[c];        // (the kernel's refill stages them here)
+                    for (int c = 4; c < NC; c++) sm.P(PS_NXC4 + (c - 4), p) = c < ncoef ? coeffs[(size_t)c * batch + idx] : 0.0;
                     for (int k = 0; k < N; k++) stage_init<RATE>(prm, sm, REG(k, p), k, p, s6, c4);
                 }
             }
+            // second-order correction: next right-hand side from the rejected trial point, before any stage's coefficients
+            // overwrite the step slots
+            for (int p = 0; p < np; p++)
+                if (sm.I(PI_MODE, p) == MODE_NEWTON && (sm.I(PI_FLAGS, p) & (FL_SOC | FL_APPLY)) == FL_SOC)
+                    for (int k = 0; k < N; k++) stage_soc_rhs<NC>(prm, sm, REG(k, p), k, p, &cfs[(size_t)NC * p]);
             for (int p = 0; p < np; p++) {
+                if (sm.I(PI_FLAGS, p) & FL_APPLY) sm.I(PI_FLAGS, p) &= ~FL_SOC;
                 sm.I(PI_FLAGS, p) &= ~(FL_APPLY | FL_FLUSH);
                 if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
             }
             // ---- P3b
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_NEWTON)
-                    for (int k = 0; k < N; k++) stage_coeffs<RATE, NC>(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)NC * p]);
+                    for (int k = 0; k < N; k++) stage_coeffs<RATE, NC>(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)NC * p], sm.I(PI_FLAGS, p) & FL_SOC);
             // ---- P4
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_NEWTON) continue;
@@ -144,9 +152,10 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     const int keep = ctrl_lsq_finish(prm, sm, p, big);
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
                 } else {
-                    ctrl_step(prm, sm, ctrl[p], p, NG);
+                    const int mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME);
+                    ctrl_step(prm, sm, ctrl[p], p, NG, mode);
                     ctrl_step_late(ctrl[p]);
-                    sm.I(PI_FLAGS, p) = FL_LS;
+                    sm.I(PI_FLAGS, p) = FL_LS | (mode & FL_SOC);
                 }
                 sm.I(PI_MODE, p) = MODE_EVAL;
             }
@@ -172,6 +181,8 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     const int fl = sm.I(PI_FLAGS, p);
                     const int r = ctrl_decide(prm, sm, c, p, fl, NG);
                     if (r == 0) sm.I(PI_FLAGS, p) = FL_LS;
+                    else if (r == 3) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_SOC; }
+                    else if (r == 4) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_RESUME; }
                     else {
                         int nf = 0;
                         // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is

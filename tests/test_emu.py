@@ -216,3 +216,38 @@ def test_emu_short_and_odd_horizons(oracle):
             assert r["iters"][i] == o["iters"], (N, i)
             assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-9
             assert abs(r["obj"][i] - o["obj"]) <= 1e-9 * max(1e-12, abs(o["obj"]))
+
+
+def test_emu_second_order_correction_matches_oracle_iterates(oracle):
+    """The kernel's second-order correction (W&B A-5.5 .. A-5.9) against the oracle's: on the real config-4 generator at
+    N = 100 (where the correction triggers in several per cent of the problems and decides which local minimum is
+    reached) the emulated kernel and the oracle without the +-1e3 state bounds end in the same point with the same
+    status, and take the same number of iterations in > 98 % of the problems."""
+    from bench import gen_py
+    n, N = 72, 100
+    g = gen_py.problems(20261018 + 4, n)
+    coeffs = np.zeros((4, n)); state = np.zeros((6, n))
+    for i in range(n):
+        c, cte, eth = oracle.prestep(g["wx"][:, i], g["wy"][:, i], *g["pose"][:, i])
+        coeffs[:, i] = c; state[3, i] = g["vel"][0, i]; state[4, i] = cte; state[5, i] = eth
+    pm = dict(YAML_DEFAULT, STEPS=N)
+    r = emu_solve(pm, state, coeffs, PB=32, max_iter=100)
+    opt = oracle.default_options(); opt.max_iter = 100
+    nob = dict(pm, BOUND=1e19)
+    same_iters = 0; both = 0; nsoc_matter = 0
+    opt0 = oracle.default_options(); opt0.max_iter = 100; opt0.max_soc = 0
+    for i in range(n):
+        o = oracle.solve(nob, state[:, i], coeffs[:, i], opt)
+        assert (r["status"][i] == 1) == (o["status"] == 1), (i, r["status"][i], o["status"])
+        if o["status"] != 1:
+            continue
+        both += 1
+        assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5, i
+        assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"]), i
+        same_iters += int(r["iters"][i] == o["iters"])
+        if o["iters"] > 12:        # (the easy problems never reject a first trial)
+            o0 = oracle.solve(nob, state[:, i], coeffs[:, i], opt0)
+            nsoc_matter += int(o0["iters"] != o["iters"] or o0["status"] != o["status"])
+    assert both >= n - 2
+    assert same_iters >= 0.97 * both, (same_iters, both)
+    assert nsoc_matter >= 2, nsoc_matter       # the correction does make a difference on this set

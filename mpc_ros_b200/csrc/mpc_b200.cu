@@ -556,6 +556,8 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 32, true, false>));
     // rate-penalty variant (w_angvel_d / w_accel_d != 0): 44 slots per stage, lanes per CTA chosen at run time
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 28, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 28, true, true>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 6, false, false>));
     // path polynomial of order 4..7
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS>));
@@ -749,8 +751,14 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         else if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
     } else if (rate) {
-        if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);
-        else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);
+        // (28 lanes: what the 44-slot stages of the rate-penalty variant leave room for at N = 20, the cfg defaults)
+        if (a.warm_in) {
+            if (a.PB == 28) nmpc::nmpc_solve_kernel<SPT, 28, true, true><<<grid, threads, smem, st>>>(a);
+            else nmpc::nmpc_solve_kernel<SPT, 0, true, true><<<grid, threads, smem, st>>>(a);
+        } else {
+            if (a.PB == 28) nmpc::nmpc_solve_kernel<SPT, 28, false, true><<<grid, threads, smem, st>>>(a);
+            else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);
+        }
     } else if (a.warm_in) {
         if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32, true, false><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, true, false><<<grid, threads, smem, st>>>(a);
@@ -758,6 +766,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         case 32: nmpc::nmpc_solve_kernel<SPT, 32, false, false><<<grid, threads, smem, st>>>(a); break;
         case 16: nmpc::nmpc_solve_kernel<SPT, 16, false, false><<<grid, threads, smem, st>>>(a); break;
         case 8: nmpc::nmpc_solve_kernel<SPT, 8, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 6: nmpc::nmpc_solve_kernel<SPT, 6, false, false><<<grid, threads, smem, st>>>(a); break;   // N = 100 (BASELINE config 4)
         case 4: nmpc::nmpc_solve_kernel<SPT, 4, false, false><<<grid, threads, smem, st>>>(a); break;
         case 1: nmpc::nmpc_solve_kernel<SPT, 1, false, false><<<grid, threads, smem, st>>>(a); break;
         default: nmpc::nmpc_solve_kernel<SPT, 0, false, false><<<grid, threads, smem, st>>>(a); break;

@@ -72,8 +72,9 @@ struct SolveArgs {
 #define NMPC_CTRL_THREADS (32 * NMPC_CTRL_WARPS)
 // NC: coefficients of the path polynomial the instantiation carries (4 = the cubic of the reference's only caller;
 // 8 serves orders 4..7, rows beyond a.ncoef read as zero).
+#define NMPC_MAX_THREADS(SPT, CPB) ((SPT) >= 3 ? 256 : 384)
 template <int SPT, int CPB, bool WARM, bool RATE, int NC = 4>
-__global__ void __launch_bounds__(SPT >= 3 ? 256 : 384, 1) nmpc_solve_kernel(const SolveArgs a)
+__global__ void __launch_bounds__(NMPC_MAX_THREADS(SPT, CPB), 1) nmpc_solve_kernel(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;

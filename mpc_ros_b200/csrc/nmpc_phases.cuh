@@ -775,7 +775,7 @@ MPC_HD void load_coef(const SM &sm, int k, int p, StageCoef &c)
 // so stage k needs K, R~^{-1} and kff of stage k+1 (kept in registers) and contributes
 //   R~ += B'M + M'B + N,   S~ += M'A,   r~_u += M'd + n;   forward: du_k += R~^{-1} D du_{k-1}.
 template <bool RATE = false, class SM>
-MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
+MPC_HD int riccati_backward5(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
     const int N = prm.N;
     const double dt = prm.dt, dt2 = dt * dt;
@@ -919,7 +919,7 @@ MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDi
 // Forward sweep: ds_0 = 0 (the initial-condition rows stay satisfied).  Leaves du_k in
 // W_10/W_11 of stage k and ds_{k+1} in the D slots of stage k.
 template <bool RATE = false, class SM>
-MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
+MPC_HD void riccati_forward5(const Params &prm, const SM &sm, int p, const HessDiag &hd)
 {
     const int N = prm.N;
     const double dt = prm.dt, idt = prm.idt;
@@ -956,6 +956,156 @@ MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDi
         sm.at(k, D_V, p) = nv; sm.at(k, D_C, p) = nc; sm.at(k, D_E, p) = ne;
         sx = nx; sy = ny; st = nt; sv = nv; sc = nc; se = ne;
     }
+}
+
+
+// ---------------------------------------------------------------- Riccati sweeps, plain variant: 4 x 4
+// theta and etheta obey the same linearised dynamics (both advance by dt du_w), so with ds_0 = 0
+//   ds_e,k = ds_theta,k + eps_k,    eps_0 = 0,  eps_{k+1} = eps_k + (d_e,k - d_theta,k)
+// is known before the sweep: etheta is eliminated like cte.  The value matrix is 4 x 4 over (x, y, theta, v)
+// (10 entries instead of 15, 8 gains instead of 10): the stage cost's etheta terms fold into the theta row / column
+//   Q_tt += Q_ee, Q_tv += Q_ev, q_t += q_e + Q_ee eps_k, q_v += Q_ev eps_k,
+// and the cte row reads  a_c = [a51, -1, a56, a54],  d_c += a56 eps_k.  About 140 FP64 instructions per stage
+// instead of 170.  Gains: W_0..W_3 = K_w (x, y, theta, v), W_4..W_7 = K_a, W_10 / W_11 = k_ff (of the step scaled by dt).
+template <class SM>
+MPC_HD int riccati_backward4(const Params &prm, const SM &sm, int p, const HessDiag &hd)
+{
+    const int N = prm.N;
+    // eps_{N-1}: the sum of all defect differences (a short serial pre-pass)
+    double eps = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < N - 1; k++) eps += sm.at(k, D_E, p) - sm.at(k, D_T, p);
+    // terminal stage (cost diagonal; e = theta + eps)
+    double Pxx = hd.dx, Pxy = 0, Pxt = 0, Pxv = 0, Pyy = hd.dy, Pyt = 0, Pyv = 0;
+    double Ptt = hd.dt_ + hd.de, Ptv = 0, Pvv = hd.dv;
+    double px = 0, py = 0, pt = fma(hd.de, eps, sm.at(N - 1, W_2, p)), pv = sm.at(N - 1, W_0, p);
+    double qc_next = sm.at(N - 1, W_1, p);
+    const double gam = hd.dc, gdy = gam + hd.dy;
+    int ok = 1;
+    StageCoef c;
+#pragma unroll 1
+    for (int k = N - 2; k >= 0; k--) {
+        load_coef(sm, k, p, c);
+        // ---- R~ = R + B^T P B and its inverse: the head of the critical chain (unit B: the step is scaled by dt)
+        const double Rww = c.rw + Ptt, Rwa = Ptv, Raa = c.ra + Pvv;
+        const double det = Rww * Raa - Rwa * Rwa;
+        if (!(Rww > 0.0) || !(det > 0.0)) ok = 0;
+        const double idet = fast_rcp(det);
+        const double i11 = Raa * idet, i12 = -Rwa * idet, i22 = Rww * idet;
+        // ---- etheta folded into theta
+        const double ek = eps - (c.de - c.dth);                  // eps_k
+        const double Qtt = c.htt + c.hee, Qtv = c.htv + c.hev;
+        const double qt = fma(c.hee, ek, c.qe), qv = fma(c.hev, ek, c.qv);
+        const double dc = fma(c.a56, ek, c.dc);
+        // ---- W = P A4 (columns theta, v change), M = A4^T W
+        const double Mxt = Pxt + c.a13 * Pxx + c.a23 * Pxy;
+        const double Myt = Pyt + c.a13 * Pxy + c.a23 * Pyy;
+        const double Mxv = Pxv + c.a14 * Pxx + c.a24 * Pxy;
+        const double Myv = Pyv + c.a14 * Pxy + c.a24 * Pyy;
+        const double Wtt = Ptt + c.a13 * Pxt + c.a23 * Pyt;
+        const double Wtv = Ptv + c.a14 * Pxt + c.a24 * Pyt;   // W[theta][v]
+        const double Wvt = Ptv + c.a13 * Pxv + c.a23 * Pyv;   // W[v][theta]
+        const double Wvv = Pvv + c.a14 * Pxv + c.a24 * Pyv;
+        const double Mtt = Wtt + c.a13 * Mxt + c.a23 * Myt;
+        const double Mtv = Wtv + c.a13 * Mxv + c.a23 * Myv;
+        const double Mvv = Wvv + c.a14 * Mxv + c.a24 * Myv;
+        // ---- S~ = B^T W: rows theta and v of W
+        const double Swx = Pxt, Swy = Pyt, Swt = Wtt, Swv = Wtv;
+        const double Sax = Pxv, Say = Pyv, Sat = Wvt, Sav = Wvv;
+        // ---- vector part:  p~ = P d + p,  pi_c = gam d_c + q_c,k+1
+        const double tx = fma(Pxx, c.dx, fma(Pxy, c.dy, fma(Pxt, c.dth, fma(Pxv, c.dv, px))));
+        const double ty = fma(Pxy, c.dx, fma(Pyy, c.dy, fma(Pyt, c.dth, fma(Pyv, c.dv, py))));
+        const double tt = fma(Pxt, c.dx, fma(Pyt, c.dy, fma(Ptt, c.dth, fma(Ptv, c.dv, pt))));
+        const double tv = fma(Pxv, c.dx, fma(Pyv, c.dy, fma(Ptv, c.dth, fma(Pvv, c.dv, pv))));
+        const double pic = fma(gam, dc, qc_next);
+        // ---- Q~ = Q + M + gam a_c a_c^T   (a_c = [a51, -1, a56, a54] over x, y, theta, v)
+        const double g1 = gam * c.a51, g4 = gam * c.a54, g6 = gam * c.a56;
+        const double Qxx = Pxx + fma(g1, c.a51, c.hxx);
+        const double Qxy = Pxy - g1;
+        const double Qxt = fma(g1, c.a56, Mxt);
+        const double Qxv = fma(g1, c.a54, Mxv);
+        const double Qyy = Pyy + gdy;
+        const double Qyt = Myt - g6;
+        const double Qyv = Myv - g4;
+        const double Qtt_ = Mtt + fma(g6, c.a56, Qtt);
+        const double Qtv_ = Mtv + fma(g6, c.a54, Qtv);
+        const double Qvv = Mvv + fma(g4, c.a54, hd.dv);
+        // ---- gains  K = -R~^{-1} S~,  feed-forward
+        const double Kwx = -(i11 * Swx + i12 * Sax), Kax = -(i12 * Swx + i22 * Sax);
+        const double Kwy = -(i11 * Swy + i12 * Say), Kay = -(i12 * Swy + i22 * Say);
+        const double Kwt = -(i11 * Swt + i12 * Sat), Kat = -(i12 * Swt + i22 * Sat);
+        const double Kwv = -(i11 * Swv + i12 * Sav), Kav = -(i12 * Swv + i22 * Sav);
+        const double ruw = c.qw + tt, rua = c.qa + tv;
+        const double kfw = -(i11 * ruw + i12 * rua), kfa = -(i12 * ruw + i22 * rua);
+        sm.at(k, W_0, p) = Kwx; sm.at(k, W_1, p) = Kwy; sm.at(k, W_2, p) = Kwt; sm.at(k, W_3, p) = Kwv;
+        sm.at(k, W_4, p) = Kax; sm.at(k, W_5, p) = Kay; sm.at(k, W_6, p) = Kat; sm.at(k, W_7, p) = Kav;
+        sm.at(k, W_10, p) = kfw; sm.at(k, W_11, p) = kfa;
+        // ---- P_k = Q~ + S~^T K
+        Pxx = fma(Swx, Kwx, fma(Sax, Kax, Qxx));
+        Pxy = fma(Swx, Kwy, fma(Sax, Kay, Qxy));
+        Pxt = fma(Swx, Kwt, fma(Sax, Kat, Qxt));
+        Pxv = fma(Swx, Kwv, fma(Sax, Kav, Qxv));
+        Pyy = fma(Swy, Kwy, fma(Say, Kay, Qyy));
+        Pyt = fma(Swy, Kwt, fma(Say, Kat, Qyt));
+        Pyv = fma(Swy, Kwv, fma(Say, Kav, Qyv));
+        Ptt = fma(Swt, Kwt, fma(Sat, Kat, Qtt_));
+        Ptv = fma(Swt, Kwv, fma(Sat, Kav, Qtv_));
+        Pvv = fma(Swv, Kwv, fma(Sav, Kav, Qvv));
+        // ---- p_k = q_s + A^T p~ + a_c pi_c + S~^T k_ff
+        px = fma(Swx, kfw, fma(Sax, kfa, fma(c.a51, pic, tx)));
+        py = fma(Swy, kfw, fma(Say, kfa, ty - pic));
+        pt = fma(Swt, kfw, fma(Sat, kfa, fma(c.a56, pic, fma(c.a23, ty, fma(c.a13, tx, qt + tt)))));
+        pv = fma(Swv, kfw, fma(Sav, kfa, fma(c.a54, pic, fma(c.a24, ty, fma(c.a14, tx, qv + tv)))));
+        qc_next = c.qc;
+        eps = ek;
+    }
+    return ok;
+}
+
+// Forward sweep of the 4 x 4 form: ds_0 = 0; leaves du_k in W_10 / W_11 of stage k and ds_{k+1} (all six
+// components) in the D slots of stage k.
+template <class SM>
+MPC_HD void riccati_forward4(const Params &prm, const SM &sm, int p)
+{
+    const int N = prm.N;
+    const double idt = prm.idt;
+    double sx = 0, sy = 0, st = 0, sv = 0, eps = 0;
+#pragma unroll 4
+    for (int k = 0; k < N - 1; k++) {
+        // du_k = K ds_k + k_ff as a depth-3 tree (this is the loop-carried chain)
+        const double duw = fma(sm.at(k, W_0, p), sx, sm.at(k, W_1, p) * sy) + fma(sm.at(k, W_2, p), st, fma(sm.at(k, W_3, p), sv, sm.at(k, W_10, p)));
+        const double dua = fma(sm.at(k, W_4, p), sx, sm.at(k, W_5, p) * sy) + fma(sm.at(k, W_6, p), st, fma(sm.at(k, W_7, p), sv, sm.at(k, W_11, p)));
+        const double a13 = sm.at(k, A_13, p), a14 = sm.at(k, A_14, p), a23 = sm.at(k, A_23, p),
+                     a24 = sm.at(k, A_24, p), a51 = sm.at(k, A_51, p), a54 = sm.at(k, A_54, p),
+                     a56 = sm.at(k, A_56, p);
+        const double dth = sm.at(k, D_T, p), de = sm.at(k, D_E, p);
+        const double nx = sx + a13 * st + a14 * sv + sm.at(k, D_X, p);
+        const double ny = sy + a23 * st + a24 * sv + sm.at(k, D_Y, p);
+        const double nt = st + duw + dth;
+        const double nv = sv + dua + sm.at(k, D_V, p);
+        const double nc = a51 * sx - sy + a54 * sv + a56 * (st + eps) + sm.at(k, D_C, p);
+        eps += de - dth;
+        const double ne = nt + eps;
+        // (duw, dua are the scaled steps dt du; the true step is stored for the stage threads)
+        sm.at(k, W_10, p) = duw * idt; sm.at(k, W_11, p) = dua * idt;
+        sm.at(k, D_X, p) = nx; sm.at(k, D_Y, p) = ny; sm.at(k, D_T, p) = nt;
+        sm.at(k, D_V, p) = nv; sm.at(k, D_C, p) = nc; sm.at(k, D_E, p) = ne;
+        sx = nx; sy = ny; st = nt; sv = nv;
+    }
+}
+
+// The sweeps of a variant: rate penalties keep the 5 x 5 + augmented form, the plain variant runs the 4 x 4 one.
+template <bool RATE = false, class SM>
+MPC_HD int riccati_backward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
+{
+    if (RATE) return riccati_backward5<RATE>(prm, sm, p, hd);
+    return riccati_backward4(prm, sm, p, hd);
+}
+template <bool RATE = false, class SM>
+MPC_HD void riccati_forward(const Params &prm, const SM &sm, int p, const HessDiag &hd)
+{
+    if (RATE) riccati_forward5<RATE>(prm, sm, p, hd);
+    else riccati_forward4(prm, sm, p);
 }
 
 // ---------------------------------------------------------------- P5: step-dependent stage work

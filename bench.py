@@ -13,7 +13,7 @@ step is ~1 M solves, so the figure does not depend on K).  For N > 1 every rank 
 batches (weak scaling, no collective on the solve path); the timed region is bracketed by a
 barrier + synchronize and the slowest rank's device time is used.
 
-`value`   : inputs already resident in HBM, device-pointer C-ABI calls on 128 streams.
+`value`   : inputs already resident in HBM, device-pointer C-ABI calls on 64 streams.
 `e2e`     : the same K steps as control ticks through the C ABI with HOST buffers (one packed
             page-locked buffer per batch: one H2D + one D2H copy inside the timed region).
 `latency` : config 1, p50 / p99 of one MPC::Solve through the C++ adapter (mpc_bench latency).
@@ -238,6 +238,35 @@ def _ncu_executed_flops():
         return None, None
 
 
+def _pin_to_gpu_numa_node(torch, local):
+    """Several ranks share one host: keep this rank's threads (and, by first touch, its page-locked buffers) on the NUMA
+    node its GPU hangs off, so that the H2D / D2H traffic of the e2e leg does not cross sockets.  Returns what was done."""
+    try:
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bdf is None:
+            import subprocess as sp
+            bdf = sp.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                         capture_output=True, text=True).stdout.strip()
+        if isinstance(bdf, int):
+            return None
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                      # nvidia-smi prints an 8-digit PCI domain, sysfs a 4-digit one
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return dict(numa_node=node, cpus=len(cpus))
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -250,6 +279,7 @@ def run_ours(a):
         raise RuntimeError("bench.py: no CUDA device; the solver has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _pin_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch; N = 20; NB = a.batches_per_step
@@ -485,8 +515,16 @@ def run_ours(a):
     # C++ multi-GPU harness (mpc_bench multi: std::thread per GPU, contiguous slices, host gather), CPU baseline
     latency = None; config3 = None; cpu = None
     bench_bin = os.path.join(ROOT, "mpc_ros_b200", "lib", "mpc_bench")
+    # (the other ranks leave first: a rank waiting in an NCCL barrier keeps a kernel spinning on its GPU, which is one of
+    #  the GPUs mpc_bench multi is about to time)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        if rank != 0:
+            solver.close()
+            return
+        time.sleep(1.0)
     if rank == 0 and os.path.exists(bench_bin) and not a.no_extras:
         def run_json(args, timeout=600):
             r = subprocess.run([bench_bin] + args, capture_output=True, text=True, timeout=timeout)
@@ -499,14 +537,12 @@ def run_ours(a):
                            what="config 1: one MPC::Solve through the C++ adapter (batch of one, host buffers, H2D/D2H inside)") \
                 if "error" not in lt else lt
         config3 = run_json(["multi", str(world), "65536", "5"])
-    if world > 1:
-        dist.barrier()
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             cpu = cpu_reference_rate(a.ref_per_core)
         it_mean = float(np.mean([v[2] for v in per_set.values()])); it_max = int(max(v[3] for v in per_set.values()))
         cfg = bench_config(a, world)
-        cfg.update(streams=S, max_ctas=max_ctas, in_flight_per_stream=DEPTH,
+        cfg.update(streams=S, max_ctas=max_ctas, in_flight_per_stream=DEPTH, host_affinity=numa,
                    step="one step = %d independent config-2 batches of %d problems, streamed on %d streams "
                         "(prestep + solve each); %d steps are timed back to back" % (NB, B, S, a.steps),
                    l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one L2 flush"
@@ -518,8 +554,6 @@ def run_ours(a):
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, latency=latency,
                     config3=config3, cpu_baseline=cpu)
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
     solver.close()
 
 
@@ -533,7 +567,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--sets", type=int, default=48)
     ap.add_argument("--max-iter", type=int, default=100)
-    ap.add_argument("--streams", type=int, default=128)
+    ap.add_argument("--streams", type=int, default=64,
+                    help="streams the batches of a step are issued on (64 x 8-CTA launches: measured best, profiles/r2_harness_sweep.txt)")
     ap.add_argument("--max-ctas", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip the config-1 latency and config-3 one-shot legs")
     ap.add_argument("--e2e-threads", type=int, default=2)

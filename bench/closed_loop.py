@@ -202,7 +202,17 @@ def run_gpu_device(R, T, groups=8, seed=20261018 + 5, max_iter=100, trace=True):
     e0.record()
     for g in grp:
         g["st"].wait_event(e0)
+    # the host runs ahead of the device, but not without bound: a handle refuses more launches in flight than its
+    # queue ring has slots (1,024), so every 32 ticks the host waits for the ticks issued 64 ticks ago
+    marks = []
     for t in range(T):
+        if t % 32 == 0:
+            ev = torch.cuda.Event()
+            for g in grp:
+                ev2 = torch.cuda.Event(); ev2.record(g["st"]); marks.append(ev2)
+            del ev
+            while len(marks) > 2 * len(grp):
+                marks.pop(0).synchronize()
         for g in grp:
             B, sp = g["B"], g["sp"]
             with torch.cuda.stream(g["st"]):

@@ -16,6 +16,7 @@ def main():
     pbo = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     if pbo: sv.set_option("problems_per_cta", pbo)
     if len(sys.argv) > 6: sv.set_option("hard_first", int(sys.argv[6]))
+    if len(sys.argv) > 7: sv.set_option("dual_groups", int(sys.argv[7]))
     R = 8
     g = gen_py.problems(20261020, B * R)
     M = g["M"]

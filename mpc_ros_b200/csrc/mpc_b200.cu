@@ -1,6 +1,7 @@
 // mpc_b200.cu -- C ABI (include/mpc_b200.h) + kernel launches.  sm_100a only; no CPU path.
 #include "../../include/mpc_b200.h"
 #include "nmpc_kernel.cuh"
+#include "nmpc_kernel_dual.cuh"
 
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
@@ -364,6 +365,7 @@ struct mpc_b200_handle {
     long long launches;    // API calls that launched work (also drives the queue / order rings)
     long long kernels;     // kernels launched by this handle
     long long *d_prof;
+    int opt_dual;
     int *d_queue;          // ring of work-queue heads, one per in-flight launch
     int *d_order;          // ring of hard-first queue orders (order_ring x max_batch)
     int order_ring;        // launches that may be in flight on this handle at once (16 .. 1024)
@@ -535,7 +537,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0; h->kernels = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
-    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->opt_nc = 4; h->d_order = NULL; h->opt_order = 1;
+    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->opt_nc = 4; h->d_order = NULL; h->opt_order = 1; h->opt_dual = 1;
     h->d_io = NULL; h->d_io_doubles = 0; h->d_warm_stage_in = h->d_warm_stage_out = NULL; h->slot_ev = NULL; h->order_ring = 0;
     for (int i = 0; i < 8; i++) { h->pin_ptr[i] = NULL; h->pin_val[i] = false; }
     h->pin_next = 0;
@@ -558,6 +560,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 28, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 28, true, true>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 6, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel_dual<false>)); SET_SMEM((nmpc::nmpc_solve_kernel_dual<true>));
     // path polynomial of order 4..7
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS>));
@@ -647,6 +650,7 @@ int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value)
     if (!strcmp(name, "max_ctas")) h->max_ctas = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "problems_per_cta")) h->opt_pb = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "hard_first")) h->opt_order = value != 0.0;
+    else if (!strcmp(name, "dual_groups")) h->opt_dual = value != 0.0;   // full CTAs as two lane groups out of phase (nmpc_kernel_dual.cuh)
     else if (!strcmp(name, "poly_coeffs")) {
         // rows of the coeffs arrays of mpc_b200_solve_batch: order of the path polynomial + 1 (mpc_planner.cpp:186-190
         // takes any order; the pre-step entry points always fit and write a cubic, 4 rows)
@@ -745,7 +749,12 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     }
     if (timed) CK(cudaEventRecord(h->ev0, st));
-    if (a.ncoef > 4) {
+    if (h->opt_dual && !rate && a.ncoef <= 4 && a.PB == 32 && N > 10 && N <= NMPC_DUAL_MAX_N) {
+        // full CTAs of the plain variant: two groups of 16 lanes out of phase, one stage per stage thread and group
+        const int dthreads = NMPC_CTRL_THREADS + ((16 * N + 31) / 32) * 32;
+        if (a.warm_in) nmpc::nmpc_solve_kernel_dual<true><<<grid, dthreads, smem, st>>>(a);
+        else nmpc::nmpc_solve_kernel_dual<false><<<grid, dthreads, smem, st>>>(a);
+    } else if (a.ncoef > 4) {
         if (rate && a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
         else if (rate) nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);
         else if (a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);

@@ -70,6 +70,232 @@ struct SolveArgs {
 #define NMPC_CTRL_WARPS 2
 #define NMPC_CTRL_LANES 16
 #define NMPC_CTRL_THREADS (32 * NMPC_CTRL_WARPS)
+// Barriers.  The single-group kernel synchronises the whole CTA; the dual-group kernel (nmpc_kernel_dual.cuh) runs two
+// lane groups out of phase and synchronises each group's control warp with the stage warps on a named barrier of its own.
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ int named_vote(int pred, int id, int count)
+{
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(pred), "r"(id), "r"(count) : "memory");
+    return r;
+}
+template <bool DUAL> __device__ __forceinline__ void cta_sync(int id, int count) { if (DUAL) named_sync(id, count); else __syncthreads(); }
+template <bool DUAL> __device__ __forceinline__ int cta_vote(int pred, int id, int count) { return DUAL ? named_vote(pred, id, count) : __syncthreads_or(pred); }
+
+// The control warps' loop (one thread per problem lane, 16 lanes per warp): refill, Riccati sweeps, step sizes, decision.
+// DUAL: the barriers are the named barrier `bar_id` over `bar_count` threads (this warp + the stage warps).
+template <int CPB, bool WARM, bool RATE, int NC, bool DUAL, class SM>
+__device__ __forceinline__ void control_loop(const SolveArgs &a, const SM &sm, const int N, const int PB, const int NG, const int batch,
+                                             const int tid, const int bar_id, const int bar_count)
+{
+    const Params &prm = a.prm;
+    (void)N; (void)bar_id; (void)bar_count;
+    const int p = (tid & 31) % NMPC_CTRL_LANES + NMPC_CTRL_LANES * (tid >> 5);
+    const int wl = tid & 31;      // lane within the warp (ballots, shuffles)
+    const bool lane = wl < NMPC_CTRL_LANES && p < PB;
+    Ctrl c;
+    c.status = 0; c.iter = 0; c.E0 = 0.0; c.obj = 0.0;
+    if (lane) { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_FLAGS, p) = 0; sm.I(PI_PROB, p) = -1; sm.I(PI_NEXT, p) = -1; }
+    bool fin = lane;          // every lane starts by popping a problem
+    PROF_DECL;
+#ifdef NMPC_PROFILE
+    const long long prof_t0 = clock64();
+#endif
+    int trace_cyc = -1; (void)trace_cyc;
+    for (;;) {
+        trace_cyc++;
+        TRACE_C(0);
+        // ---- refill the lanes that finished (fin): one warp-aggregated pop from the work queue; the new
+        //      problem's inputs are staged in shared memory for the stage threads (P3a).
+        //      (Prefetching the next problem during the sweeps was measured: no gain.)
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, fin);
+            int nb = 0;
+            if (wl == 0 && m) nb = atomicAdd(a.queue, __popc(m));
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+            if (fin) {
+                int nidx = nb + __popc(m & ((1u << wl) - 1u));
+                if (nidx >= batch) nidx = -1;
+                else {
+                    if (a.order) nidx = a.order[nidx];
+                    for (int i = 0; i < 6; i++) sm.P(PS_NX0 + i, p) = a.state[(size_t)i * batch + nidx];
+                    for (int i = 0; i < 4; i++) sm.P(PS_NX6 + i, p) = a.coeffs[(size_t)i * batch + nidx];
+                    if (NC > 4)
+                        for (int i = 4; i < NC; i++)
+                            sm.P(PS_NXC4 + (i - 4), p) = i < a.ncoef ? a.coeffs[(size_t)i * batch + nidx] : 0.0;
+                    sm.P(PS_NX10, p) = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
+                }
+                sm.I(PI_NEXT, p) = nidx;
+                if (nidx >= 0) {
+                    double s6[6];
+                    for (int i = 0; i < 6; i++) s6[i] = sm.P(PS_NX0 + i, p);
+                    ctrl_init(prm, sm, c, p, s6, sm.P(PS_NX10, p));
+                    if (WARM) {
+                        sm.P(PS_MU, p) = prm.warm_mu; sm.P(PS_MU_STEP, p) = prm.warm_mu;
+                        sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - prm.warm_mu);
+                        const size_t offl = (size_t)(8 * N - 2);
+                        for (int i = 0; i < 6; i++)
+                            sm.P(PS_L0X + i, p) = sm.P(PS_SF, p) * a.warm_in[(offl + (size_t)i * N) * batch + nidx];
+                        sm.I(PI_MODE, p) = MODE_ROLLOUT;
+                        sm.I(PI_FLAGS, p) |= FL_WARM;
+                    } else {
+                        sm.I(PI_MODE, p) = MODE_NEWTON;
+                        sm.I(PI_FLAGS, p) |= FL_LSQ;
+                    }
+                } else {
+                    sm.I(PI_MODE, p) = MODE_IDLE;
+                }
+            }
+            fin = false;
+        }
+        PROF_MARK(1);
+        int active = 0;
+        if (lane) active = (sm.I(PI_MODE, p) != MODE_IDLE) || (sm.I(PI_FLAGS, p) & FL_FLUSH);
+#ifdef NMPC_PROFILE
+        {   // busy lanes of this cycle
+            const unsigned bz = __ballot_sync(0xffffffffu, lane && sm.I(PI_MODE, p) != MODE_IDLE);
+            if (a.prof && wl == 0) atomicAdd((unsigned long long *)&a.prof[1002], (unsigned long long)__popc(bz));
+        }
+#endif
+        if (!cta_vote<DUAL>(active, bar_id, bar_count)) break;   // B2 (vote)
+        TRACE_C(1);
+        // ---- P3a: stage threads apply / flush / init
+        cta_sync<DUAL>(bar_id, bar_count);  // B3
+        TRACE_C(2);
+        if (lane) {   // apply / flush / init are done (FL_SOC next to FL_APPLY: the applied step was a correction)
+            const int f0 = sm.I(PI_FLAGS, p);
+            sm.I(PI_FLAGS, p) = f0 & ~(FL_APPLY | FL_FLUSH | FL_WARM | ((f0 & FL_APPLY) ? FL_SOC : 0));
+            if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
+        }
+        // ---- P3b: stage threads write coefficients
+        cta_sync<DUAL>(bar_id, bar_count);  // B4
+        TRACE_C(3);
+        PROF_MARK(2);
+        // ---- P4: Riccati sweeps
+        int step_lsq = 0;     // sampled here for P6: the lane's adjoint stage thread rewrites PI_FLAGS there
+        int step_mode = 0;    // FL_SOC / FL_RESUME of the system being solved
+        if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
+            const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+            step_lsq = lsq;
+            step_mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME);
+            const double dw = sm.P(PS_DW, p);
+            const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
+            const int okb = riccati_backward<RATE>(prm, sm, p, hd);
+            PROF_MARK(3);
+            if (okb || lsq) {
+                riccati_forward<RATE>(prm, sm, p, hd);
+                if (dw > 0.0) c.dw_last = dw;
+                sm.I(PI_MODE, p) = MODE_STEP;
+            } else {
+                const double nd = next_dw(c, dw);
+                if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_MODE, p) = MODE_FAIL; }
+                else sm.P(PS_DW, p) = nd;       // stays MODE_NEWTON: coefficients are rewritten next cycle
+            }
+        }
+        if (WARM && lane && sm.I(PI_MODE, p) == MODE_ROLLOUT) {
+            const size_t i = (size_t)sm.I(PI_PROB, p);
+            double c4[NC];
+#pragma unroll
+            for (int q = 0; q < NC; q++) c4[q] = q < a.ncoef ? a.coeffs[(size_t)q * batch + i] : 0.0;
+            ctrl_rollout<NC>(prm, sm, p, c4);
+            sm.I(PI_MODE, p) = MODE_EVAL;       // plain evaluation of the start point in P1
+            sm.I(PI_FLAGS, p) = 0;
+        }
+        PROF_MARK(4);
+        TRACE_C(4);
+        cta_sync<DUAL>(bar_id, bar_count);  // B5
+        TRACE_C(5);
+        // ---- P5: stage threads, step-dependent work
+        cta_sync<DUAL>(bar_id, bar_count);  // B6
+        TRACE_C(6);
+        PROF_MARK(5);
+        // ---- P6: step sizes; meanwhile the lane's stage thread of group 0 runs the adjoint sweep (multipliers),
+        //      which nothing here depends on.  A least-squares lane (FL_LSQ) gets its flags from that thread.
+        bool late = false;
+        if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
+            if (!step_lsq) {
+                ctrl_step(prm, sm, c, p, NG, step_mode);
+                sm.I(PI_FLAGS, p) = FL_LS | (step_mode & FL_SOC);
+                late = true;
+            }
+            sm.I(PI_MODE, p) = MODE_EVAL;
+        }
+        PROF_MARK(6);
+        TRACE_C(7);
+        cta_sync<DUAL>(bar_id, bar_count);  // B7
+        TRACE_C(8);
+        // ---- P1: stage threads evaluate; meanwhile the part of the line-search set-up only P2 needs
+        if (late) ctrl_step_late(c);
+        cta_sync<DUAL>(bar_id, bar_count);  // B1
+        TRACE_C(9);
+        PROF_MARK(7);
+        // ---- P2: decide
+        if (lane) {
+            const int md = sm.I(PI_MODE, p);
+            int term = 0;
+            if (md == MODE_EVAL) {
+                const int fl = sm.I(PI_FLAGS, p);
+                const int r = ctrl_decide(prm, sm, c, p, fl, NG);
+                PROF_MARK(10);
+                if (r == 0) {
+                    sm.I(PI_FLAGS, p) = FL_LS;
+                } else if (r >= 3) {
+                    // second-order correction (3) / resume after failed corrections (4): the same Newton system again
+                    // (PS_DW kept), no step applied
+                    sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = (r == 3) ? FL_SOC : FL_RESUME;
+                } else {
+                    int nf = 0;
+                    // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
+                    // a step of length 0 -- it still adopts the sin/cos computed at the evaluated point)
+                    nf = FL_APPLY;
+                    if (fl & FL_LS) {
+                        sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
+                        ctrl_apply(sm, p);
+                    } else {
+                        sm.P(PS_AP_ALPHA, p) = 0.0; sm.P(PS_AP_AZ, p) = 0.0;
+                    }
+                    sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
+                    if (r == 1) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.P(PS_DW, p) = 0.0; sm.I(PI_FLAGS, p) = nf; }
+                    else { term = 1; sm.I(PI_FLAGS, p) = nf | FL_FLUSH; }
+                }
+            } else if (md == MODE_FAIL) {
+                term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
+            }
+            // watchdog: retries and backtracks are bounded, this only guards against the unforeseen
+            if (!term && md != MODE_IDLE && ++c.age > 8 * prm.max_iter + 64) {
+                if (c.status == 0) c.status = 2;
+                term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
+            }
+            if (term) {
+                const size_t i = (size_t)sm.I(PI_PROB, p);
+                if (a.obj) a.obj[i] = c.obj;
+                if (a.status) a.status[i] = c.status;
+                if (a.iters) a.iters[i] = c.iter;
+                if (a.kkt) a.kkt[i] = c.E0;
+                sm.P(PS_AP_SF, p) = sm.P(PS_SF, p);
+                if (a.warm_out) {
+                    const size_t offl = (size_t)(8 * N - 2);
+                    for (int cc = 0; cc < 6; cc++)
+                        a.warm_out[(offl + (size_t)cc * N) * batch + i] = sm.P(PS_L0X + cc, p) / sm.P(PS_SF, p);
+                }
+                sm.I(PI_MODE, p) = MODE_IDLE;
+                fin = true;
+            }
+        }
+        PROF_MARK(8);
+        TRACE_C(10);
+        cta_sync<DUAL>(bar_id, bar_count);  // B1b: the stage threads apply / flush while the lanes are refilled
+    }
+    PROF_FLUSH();
+#ifdef NMPC_PROFILE
+    if (a.prof && tid == 0) {   // all CTAs: number of global cycles and their total duration
+        atomicAdd((unsigned long long *)&a.prof[1000], (unsigned long long)(trace_cyc));
+        atomicAdd((unsigned long long *)&a.prof[1001], (unsigned long long)(clock64() - prof_t0));
+    }
+#endif
+}
+
 // NC: coefficients of the path polynomial the instantiation carries (4 = the cubic of the reference's only caller;
 // 8 serves orders 4..7, rows beyond a.ncoef read as zero).
 #define NMPC_MAX_THREADS(SPT, CPB) ((SPT) >= 3 ? 256 : 384)
@@ -87,210 +313,7 @@ __global__ void __launch_bounds__(NMPC_MAX_THREADS(SPT, CPB), 1) nmpc_solve_kern
     const int tid = threadIdx.x;
 
     if (tid < NMPC_CTRL_THREADS) {
-        // ------------------------------------------------------------ control warps
-        const int p = (tid & 31) % NMPC_CTRL_LANES + NMPC_CTRL_LANES * (tid >> 5);
-        const int wl = tid & 31;      // lane within the warp (ballots, shuffles)
-        const bool lane = wl < NMPC_CTRL_LANES && p < PB;
-        Ctrl c;
-        c.status = 0; c.iter = 0; c.E0 = 0.0; c.obj = 0.0;
-        if (lane) { sm.I(PI_MODE, p) = MODE_IDLE; sm.I(PI_FLAGS, p) = 0; sm.I(PI_PROB, p) = -1; sm.I(PI_NEXT, p) = -1; }
-        bool fin = lane;          // every lane starts by popping a problem
-        PROF_DECL;
-#ifdef NMPC_PROFILE
-        const long long prof_t0 = clock64();
-#endif
-        int trace_cyc = -1; (void)trace_cyc;
-        for (;;) {
-            trace_cyc++;
-            TRACE_C(0);
-            // ---- refill the lanes that finished (fin): one warp-aggregated pop from the work queue; the new
-            //      problem's inputs are staged in shared memory for the stage threads (P3a).
-            //      (Prefetching the next problem during the sweeps was measured: no gain.)
-            {
-                const unsigned m = __ballot_sync(0xffffffffu, fin);
-                int nb = 0;
-                if (wl == 0 && m) nb = atomicAdd(a.queue, __popc(m));
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-                if (fin) {
-                    int nidx = nb + __popc(m & ((1u << wl) - 1u));
-                    if (nidx >= batch) nidx = -1;
-                    else {
-                        if (a.order) nidx = a.order[nidx];
-                        for (int i = 0; i < 6; i++) sm.P(PS_NX0 + i, p) = a.state[(size_t)i * batch + nidx];
-                        for (int i = 0; i < 4; i++) sm.P(PS_NX6 + i, p) = a.coeffs[(size_t)i * batch + nidx];
-                        if (NC > 4)
-                            for (int i = 4; i < NC; i++)
-                                sm.P(PS_NXC4 + (i - 4), p) = i < a.ncoef ? a.coeffs[(size_t)i * batch + nidx] : 0.0;
-                        sm.P(PS_NX10, p) = a.ref_vel ? a.ref_vel[nidx] : prm.ref_vel;
-                    }
-                    sm.I(PI_NEXT, p) = nidx;
-                    if (nidx >= 0) {
-                        double s6[6];
-                        for (int i = 0; i < 6; i++) s6[i] = sm.P(PS_NX0 + i, p);
-                        ctrl_init(prm, sm, c, p, s6, sm.P(PS_NX10, p));
-                        if (WARM) {
-                            sm.P(PS_MU, p) = prm.warm_mu; sm.P(PS_MU_STEP, p) = prm.warm_mu;
-                            sm.P(PS_TAU, p) = fmax2(NMPC_TAU_MIN, 1.0 - prm.warm_mu);
-                            const size_t offl = (size_t)(8 * N - 2);
-                            for (int i = 0; i < 6; i++)
-                                sm.P(PS_L0X + i, p) = sm.P(PS_SF, p) * a.warm_in[(offl + (size_t)i * N) * batch + nidx];
-                            sm.I(PI_MODE, p) = MODE_ROLLOUT;
-                            sm.I(PI_FLAGS, p) |= FL_WARM;
-                        } else {
-                            sm.I(PI_MODE, p) = MODE_NEWTON;
-                            sm.I(PI_FLAGS, p) |= FL_LSQ;
-                        }
-                    } else {
-                        sm.I(PI_MODE, p) = MODE_IDLE;
-                    }
-                }
-                fin = false;
-            }
-            PROF_MARK(1);
-            int active = 0;
-            if (lane) active = (sm.I(PI_MODE, p) != MODE_IDLE) || (sm.I(PI_FLAGS, p) & FL_FLUSH);
-#ifdef NMPC_PROFILE
-            {   // busy lanes of this cycle
-                const unsigned bz = __ballot_sync(0xffffffffu, lane && sm.I(PI_MODE, p) != MODE_IDLE);
-                if (a.prof && wl == 0) atomicAdd((unsigned long long *)&a.prof[1002], (unsigned long long)__popc(bz));
-            }
-#endif
-            if (!__syncthreads_or(active)) break;   // B2 (vote)
-            TRACE_C(1);
-            // ---- P3a: stage threads apply / flush / init
-            __syncthreads();  // B3
-            TRACE_C(2);
-            if (lane) {   // apply / flush / init are done (FL_SOC next to FL_APPLY: the applied step was a correction)
-                const int f0 = sm.I(PI_FLAGS, p);
-                sm.I(PI_FLAGS, p) = f0 & ~(FL_APPLY | FL_FLUSH | FL_WARM | ((f0 & FL_APPLY) ? FL_SOC : 0));
-                if (sm.I(PI_NEXT, p) >= 0) { sm.I(PI_PROB, p) = sm.I(PI_NEXT, p); sm.I(PI_NEXT, p) = -1; }
-            }
-            // ---- P3b: stage threads write coefficients
-            __syncthreads();  // B4
-            TRACE_C(3);
-            PROF_MARK(2);
-            // ---- P4: Riccati sweeps
-            int step_lsq = 0;     // sampled here for P6: the lane's adjoint stage thread rewrites PI_FLAGS there
-            int step_mode = 0;    // FL_SOC / FL_RESUME of the system being solved
-            if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
-                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
-                step_lsq = lsq;
-                step_mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME);
-                const double dw = sm.P(PS_DW, p);
-                const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
-                const int okb = riccati_backward<RATE>(prm, sm, p, hd);
-                PROF_MARK(3);
-                if (okb || lsq) {
-                    riccati_forward<RATE>(prm, sm, p, hd);
-                    if (dw > 0.0) c.dw_last = dw;
-                    sm.I(PI_MODE, p) = MODE_STEP;
-                } else {
-                    const double nd = next_dw(c, dw);
-                    if (nd > NMPC_DW_MAX) { c.status = 10; sm.I(PI_MODE, p) = MODE_FAIL; }
-                    else sm.P(PS_DW, p) = nd;       // stays MODE_NEWTON: coefficients are rewritten next cycle
-                }
-            }
-            if (WARM && lane && sm.I(PI_MODE, p) == MODE_ROLLOUT) {
-                const size_t i = (size_t)sm.I(PI_PROB, p);
-                double c4[NC];
-#pragma unroll
-                for (int q = 0; q < NC; q++) c4[q] = q < a.ncoef ? a.coeffs[(size_t)q * batch + i] : 0.0;
-                ctrl_rollout<NC>(prm, sm, p, c4);
-                sm.I(PI_MODE, p) = MODE_EVAL;       // plain evaluation of the start point in P1
-                sm.I(PI_FLAGS, p) = 0;
-            }
-            PROF_MARK(4);
-            TRACE_C(4);
-            __syncthreads();  // B5
-            TRACE_C(5);
-            // ---- P5: stage threads, step-dependent work
-            __syncthreads();  // B6
-            TRACE_C(6);
-            PROF_MARK(5);
-            // ---- P6: step sizes; meanwhile the lane's stage thread of group 0 runs the adjoint sweep (multipliers),
-            //      which nothing here depends on.  A least-squares lane (FL_LSQ) gets its flags from that thread.
-            bool late = false;
-            if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
-                if (!step_lsq) {
-                    ctrl_step(prm, sm, c, p, NG, step_mode);
-                    sm.I(PI_FLAGS, p) = FL_LS | (step_mode & FL_SOC);
-                    late = true;
-                }
-                sm.I(PI_MODE, p) = MODE_EVAL;
-            }
-            PROF_MARK(6);
-            TRACE_C(7);
-            __syncthreads();  // B7
-            TRACE_C(8);
-            // ---- P1: stage threads evaluate; meanwhile the part of the line-search set-up only P2 needs
-            if (late) ctrl_step_late(c);
-            __syncthreads();  // B1
-            TRACE_C(9);
-            PROF_MARK(7);
-            // ---- P2: decide
-            if (lane) {
-                const int md = sm.I(PI_MODE, p);
-                int term = 0;
-                if (md == MODE_EVAL) {
-                    const int fl = sm.I(PI_FLAGS, p);
-                    const int r = ctrl_decide(prm, sm, c, p, fl, NG);
-                    PROF_MARK(10);
-                    if (r == 0) {
-                        sm.I(PI_FLAGS, p) = FL_LS;
-                    } else if (r >= 3) {
-                        // second-order correction (3) / resume after failed corrections (4): the same Newton system again
-                        // (PS_DW kept), no step applied
-                        sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = (r == 3) ? FL_SOC : FL_RESUME;
-                    } else {
-                        int nf = 0;
-                        // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
-                        // a step of length 0 -- it still adopts the sin/cos computed at the evaluated point)
-                        nf = FL_APPLY;
-                        if (fl & FL_LS) {
-                            sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
-                            ctrl_apply(sm, p);
-                        } else {
-                            sm.P(PS_AP_ALPHA, p) = 0.0; sm.P(PS_AP_AZ, p) = 0.0;
-                        }
-                        sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
-                        if (r == 1) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.P(PS_DW, p) = 0.0; sm.I(PI_FLAGS, p) = nf; }
-                        else { term = 1; sm.I(PI_FLAGS, p) = nf | FL_FLUSH; }
-                    }
-                } else if (md == MODE_FAIL) {
-                    term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
-                }
-                // watchdog: retries and backtracks are bounded, this only guards against the unforeseen
-                if (!term && md != MODE_IDLE && ++c.age > 8 * prm.max_iter + 64) {
-                    if (c.status == 0) c.status = 2;
-                    term = 1; sm.I(PI_FLAGS, p) = FL_FLUSH;
-                }
-                if (term) {
-                    const size_t i = (size_t)sm.I(PI_PROB, p);
-                    if (a.obj) a.obj[i] = c.obj;
-                    if (a.status) a.status[i] = c.status;
-                    if (a.iters) a.iters[i] = c.iter;
-                    if (a.kkt) a.kkt[i] = c.E0;
-                    sm.P(PS_AP_SF, p) = sm.P(PS_SF, p);
-                    if (a.warm_out) {
-                        const size_t offl = (size_t)(8 * N - 2);
-                        for (int cc = 0; cc < 6; cc++)
-                            a.warm_out[(offl + (size_t)cc * N) * batch + i] = sm.P(PS_L0X + cc, p) / sm.P(PS_SF, p);
-                    }
-                    sm.I(PI_MODE, p) = MODE_IDLE;
-                    fin = true;
-                }
-            }
-            PROF_MARK(8);
-            TRACE_C(10);
-            __syncthreads();  // B1b: the stage threads apply / flush while the lanes are refilled
-        }
-        PROF_FLUSH();
-#ifdef NMPC_PROFILE
-        if (a.prof && tid == 0) {   // all CTAs: number of global cycles and their total duration
-            atomicAdd((unsigned long long *)&a.prof[1000], (unsigned long long)(trace_cyc));
-            atomicAdd((unsigned long long *)&a.prof[1001], (unsigned long long)(clock64() - prof_t0));
-        }
-#endif
+        control_loop<CPB, WARM, RATE, NC, false>(a, sm, N, PB, NG, batch, tid, 0, 0);
     } else {
         // ------------------------------------------------------------ stage threads
         const int t = tid - NMPC_CTRL_THREADS;

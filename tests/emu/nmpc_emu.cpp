@@ -15,6 +15,9 @@
 using namespace nmpc;
 
 static long long g_lane_cycles = 0;
+static std::vector<int> g_ages, g_kinds;   // g_kinds: 4 per problem: backtracks, corrections, resumes, inertia retries
+static std::vector<int> g_kind_lane;
+static std::vector<int> g_ages_unused;      // global cycles each problem of the last run took (tail studies)
 
 template <bool RATE, int NC = 4>
 static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB, int batch, int ncoef,
@@ -36,6 +39,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); prm.i_nb = 1.0 / (double)(4 * (N - 1));
     prm.bound_chk = (prm14[13] > 0.0 ? prm14[13] : 1e3) * (1.0 - 1e-3);   // prm14[13]: bound_value (0 = the 1e3 default)
     const int NG = (N + SPT - 1) / SPT;
+    g_ages.assign((size_t)batch, 0); g_kinds.assign((size_t)4 * batch, 0); g_kind_lane.assign((size_t)4 * PB, 0);
 
     const int NS = RATE ? NSLOTS_RATE : NSLOTS;
     std::vector<double> mem(smem_bytes(N, NG, PB, NS) / sizeof(double) + 8);
@@ -58,7 +62,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
             ctrl_init(prm, sm, ctrl[p], p, s6, rv);
             sm.I(PI_NEXT, p) = base + p;
             sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_LSQ;
-            nreg[p] = 0;
+            nreg[p] = 0; for (int q = 0; q < 4; q++) g_kind_lane[4 * p + q] = 0;
         }
         for (;;) {
             int active = 0;
@@ -180,6 +184,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                 if (md == MODE_EVAL) {
                     const int fl = sm.I(PI_FLAGS, p);
                     const int r = ctrl_decide(prm, sm, c, p, fl, NG);
+                    if (r == 0) g_kind_lane[4 * p]++; else if (r == 3) g_kind_lane[4 * p + 1]++; else if (r == 4) g_kind_lane[4 * p + 2]++;
                     if (r == 0) sm.I(PI_FLAGS, p) = FL_LS;
                     else if (r == 3) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_SOC; }
                     else if (r == 4) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_RESUME; }
@@ -213,6 +218,8 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     if (iters) iters[i] = c.iter;
                     if (kkt) kkt[i] = c.E0;
                     if (n_reg) n_reg[i] = nreg[p];
+                    g_ages[i] = c.age + 1; g_kind_lane[4 * p + 3] = nreg[p];
+                    for (int q = 0; q < 4; q++) g_kinds[4 * i + q] = g_kind_lane[4 * p + q];
                     sm.P(PS_AP_SF, p) = sm.P(PS_SF, p);
                     if (lam_out)
                         for (int cc = 0; cc < 6; cc++)
@@ -224,6 +231,10 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
     }
     return 0;
 }
+
+extern "C" int nmpc_emu_last_ages(int *out, int n) { int m = (int)g_ages.size() < n ? (int)g_ages.size() : n; for (int i = 0; i < m; i++) out[i] = g_ages[i]; return m; }
+
+extern "C" int nmpc_emu_last_kinds(int *out, int n) { int m = (int)g_kinds.size() < 4 * n ? (int)g_kinds.size() : 4 * n; for (int i = 0; i < m; i++) out[i] = g_kinds[i]; return m; }
 
 // lane-cycles (one lane busy for one global cycle) spent since the last reset: utilisation studies
 extern "C" long long nmpc_emu_lane_cycles(int reset) { const long long v = g_lane_cycles; if (reset) g_lane_cycles = 0; return v; }

@@ -341,6 +341,58 @@ def test_all_kernel_specialisations_agree(oracle):
             np.testing.assert_allclose(out["obj"][ok], ref["obj"][ok], rtol=1e-10, err_msg=tag + "obj")
 
 
+def test_dual_group_kernel_equals_single_group_kernel(oracle):
+    """Full CTAs of the plain variant run as two groups of 16 lanes out of phase (nmpc_kernel_dual.cuh, one stage per
+    stage thread and group; option dual_groups).  Same phase functions, partial sums added in the same order: status
+    and iteration counts are identical to the single-group kernel's, controls and predicted states equal to rounding, cold and warm, for
+    even and odd horizons (an odd horizon leaves the upper half of the last stage warp without a stage)."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    g, state, coeffs = generated(20261018 + 3, 4500, oracle)
+    B = state.shape[1]
+    for N in (20, 15, 11):
+        pm = dict(YAML_DEFAULT, STEPS=N)
+        res = {}
+        for dual in (1, 0):
+            sv = _solver(pm, B)
+            sv.set_option("dual_groups", dual); sv.set_option("problems_per_cta", 32); sv.set_option("max_ctas", 6)
+            ws = capi.lib().mpc_b200_warm_size(N)
+            f64 = dict(dtype=torch.float64, device=dev)
+            ds = torch.from_numpy(state).to(dev); dc = torch.from_numpy(coeffs).to(dev)
+            u = torch.zeros((2, B), **f64); pred = torch.zeros((3 * N, B), **f64); wo = torch.zeros((ws, B), **f64)
+            st = torch.zeros(B, dtype=torch.int32, device=dev); it = torch.zeros(B, dtype=torch.int32, device=dev)
+            sv.solve_raw(B, ds, dc, u, pred, status=st, iters=it, warm_out=wo)
+            torch.cuda.synchronize()
+            cold = (u.cpu().numpy().copy(), pred.cpu().numpy().copy(), st.cpu().numpy().copy(), it.cpu().numpy().copy(), wo.cpu().numpy().copy())
+            # warm re-solve of a slightly moved problem from the cold record
+            ds2 = ds.clone(); ds2[3] += 0.02; ds2[4] -= 0.01
+            sv.solve_raw(B, ds2, dc, u, pred, warm_in=wo, status=st, iters=it)
+            torch.cuda.synchronize()
+            warm = (u.cpu().numpy().copy(), pred.cpu().numpy().copy(), st.cpu().numpy().copy(), it.cpu().numpy().copy())
+            sv.close()
+            res[dual] = (cold, warm)
+        tag = "N=%d " % N
+        assert (res[1][0][2] == 1).mean() >= 0.99, tag
+        for which in (0, 1):
+            a, b = res[1][which], res[0][which]
+            assert np.array_equal(a[2], b[2]), tag + "status"
+            assert np.array_equal(a[3], b[3]), tag + "iterations"
+            # (values equal to rounding: the two kernels are separate compilations of the same phase functions, FMA
+            #  contraction may differ -- as between the lanes-per-CTA specialisations)
+            ok = a[2] == 1
+            np.testing.assert_allclose(a[0][:, ok], b[0][:, ok], rtol=0, atol=1e-9, err_msg=tag + "u0")
+            np.testing.assert_allclose(a[1][:, ok], b[1][:, ok], rtol=0, atol=1e-8, err_msg=tag + "pred")
+        okc = res[1][0][2] == 1
+        np.testing.assert_allclose(res[1][0][4][:, okc], res[0][0][4][:, okc], rtol=1e-7, atol=1e-8, err_msg=tag + "warm record")
+        # and both are the oracle's answer
+        for i in range(0, B, 450):
+            if res[1][0][2][i] != 1:
+                continue
+            o = oracle.solve(pm, state[:, i], coeffs[:, i])
+            if o["status"] == 1:
+                assert np.abs(res[1][0][0][:, i] - o["u0"]).max() <= U_TOL, tag
+
+
 def test_prestep_ragged_windows_and_delay_mode(oracle):
     """K1 at the edges: the shortest (M = 4: cubic through 4 points) and longest (M = 64) windows, refused
     sizes, and the delay-compensated state of driving_state.cpp:243-254."""

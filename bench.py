@@ -507,6 +507,34 @@ def run_ours(a):
                     "mpc_b200_track_packed_submit/_wait with page-locked host buffers: one H2D + one D2H copy per batch "
                     "inside the timed region; %d host thread(s) x %d handles in flight each; host wall clock, max over ranks"
                     % (a.steps, NB, T, K))
+    # the same copies WITHOUT any solve (all ranks at once, 8 streams each, ~0.3 s): what the host's memory / PCIe fabric
+    # can feed.  Where e2e sits at this ceiling the end-to-end rate is bound by the box, not by the solver or its host code.
+    try:
+        cs = 8; n_copy = max(256, min(4000, per_thread * T))
+        hin = [torch.empty(s0.h2d, dtype=torch.uint8).pin_memory() for _ in range(cs)]
+        hout = [torch.empty(s0.d2h, dtype=torch.uint8).pin_memory() for _ in range(cs)]
+        din = [torch.empty(s0.h2d, dtype=torch.uint8, device=dev) for _ in range(cs)]
+        dout = [torch.empty(s0.d2h, dtype=torch.uint8, device=dev) for _ in range(cs)]
+        cst = [torch.cuda.Stream() for _ in range(cs)]
+
+        def copies(n):
+            for j in range(n):
+                with torch.cuda.stream(cst[j % cs]):
+                    din[j % cs].copy_(hin[j % cs], non_blocking=True)
+                    hout[j % cs].copy_(dout[j % cs], non_blocking=True)
+            torch.cuda.synchronize()
+        copies(64)
+        barrier()
+        t0 = time.perf_counter(); copies(n_copy); tc = time.perf_counter() - t0
+        tct = torch.tensor([tc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tct, op=dist.ReduceOp.MAX)
+        e2e["copies_alone"] = dict(value=world * n_copy * B / float(tct.item()), unit=UNIT,
+                                   gbytes_per_s=world * n_copy * (s0.h2d + s0.d2h) / float(tct.item()) / 1e9,
+                                   note="the e2e leg's H2D + D2H copies with no solve in between, all ranks at once")
+        del hin, hout, din, dout
+    except Exception as ex:      # (a probe: never fails the bench)
+        e2e["copies_alone"] = dict(error=str(ex))
     for w in workers:
         for s in w.slots:
             s.close()

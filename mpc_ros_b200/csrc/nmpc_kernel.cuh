@@ -230,13 +230,27 @@ __device__ __forceinline__ void control_loop(const SolveArgs &a, const SM &sm, c
         cta_sync<DUAL>(bar_id, bar_count);  // B1
         TRACE_C(9);
         PROF_MARK(7);
-        // ---- P2: decide
+        // ---- P2: decide.  First the partial sums of the stage groups: the two half-warps take half of the groups each
+        //      (lanes l and l + 16 work for the problem of lane l), one exchange, lower half (+) upper half.
+        EvalPart sums;
+        {
+            const int hs = reduce_split(NG), up = wl >> 4;
+            if (p < PB) ctrl_reduce(sm, p, up ? hs : 0, up ? NG : hs, sums);
+            else ctrl_reduce(sm, 0, 0, 0, sums);
+            EvalPart o;
+            o.prinf = __shfl_xor_sync(0xffffffffu, sums.prinf, 16); o.pr1 = __shfl_xor_sync(0xffffffffu, sums.pr1, 16);
+            o.duinf = __shfl_xor_sync(0xffffffffu, sums.duinf, 16); o.vmax = __shfl_xor_sync(0xffffffffu, sums.vmax, 16);
+            o.vmin = __shfl_xor_sync(0xffffffffu, sums.vmin, 16); o.l1 = __shfl_xor_sync(0xffffffffu, sums.l1, 16);
+            o.z1 = __shfl_xor_sync(0xffffffffu, sums.z1, 16); o.f = __shfl_xor_sync(0xffffffffu, sums.f, 16);
+            o.lnsum = __shfl_xor_sync(0xffffffffu, sums.lnsum, 16); o.inside = __shfl_xor_sync(0xffffffffu, sums.inside, 16);
+            eval_combine(sums, o);      // (meaningful in the lower half-warp, the lanes that decide)
+        }
         if (lane) {
             const int md = sm.I(PI_MODE, p);
             int term = 0;
             if (md == MODE_EVAL) {
                 const int fl = sm.I(PI_FLAGS, p);
-                const int r = ctrl_decide(prm, sm, c, p, fl, NG);
+                const int r = ctrl_decide_sums(prm, sm, c, p, fl, sums);
                 PROF_MARK(10);
                 if (r == 0) {
                     sm.I(PI_FLAGS, p) = FL_LS;

@@ -258,7 +258,6 @@ MPC_HD double log_pos(double x)
     double inv; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(sden));
     double e_ = fma(-sden, inv, 1.0); inv = fma(inv, e_, inv);
     e_ = fma(-sden, inv, 1.0); inv = fma(inv, e_, inv);
-    e_ = fma(-sden, inv, 1.0); inv = fma(inv, e_, inv);
 #else
     const double inv = 1.0 / sden;
 #endif
@@ -281,9 +280,9 @@ MPC_HD double fast_rcp(double x)
 {
 #if defined(__CUDA_ARCH__)
     double y;
+    // (the seed is good to ~2^-20: two Newton steps reach 2^-80, i.e. the last bit; a third one was measured to change nothing)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0); y = fma(y, e, y);
-    e = fma(-x, y, 1.0); y = fma(y, e, y);
     e = fma(-x, y, 1.0); y = fma(y, e, y);
     return y;
 #else
@@ -1315,20 +1314,37 @@ __device__ long long nmpc_dec_acc[8];
 #define DEC_MARK(i)
 #define DEC_START()
 #endif
+// Partial sums of the stage groups [g0, g1) of lane p, added up in group order.
 template <class SM>
-MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flags, int NG)
+MPC_HD void ctrl_reduce(const SM &sm, int p, int g0, int g1, EvalPart &s)
+{
+    s.prinf = 0; s.pr1 = 0; s.duinf = 0; s.vmax = -1e300; s.vmin = 1e300; s.l1 = 0; s.z1 = 0; s.f = 0; s.lnsum = 0; s.inside = 1;
+    for (int g = g0; g < g1; g++) {
+        s.prinf = fmax2(s.prinf, sm.part(g, PT_0, p)); s.pr1 += sm.part(g, PT_1, p);
+        s.duinf = fmax2(s.duinf, sm.part(g, PT_2, p));
+        s.vmax = fmax2(s.vmax, sm.part(g, PT_3, p)); s.vmin = fmin2(s.vmin, sm.part(g, PT_4, p));
+        s.l1 += sm.part(g, PT_5, p); s.z1 += sm.part(g, PT_6, p); s.f += sm.part(g, PT_7, p);
+        const double l = sm.part(g, PT_8, p);
+        if (l <= -1e299) s.inside = 0; else s.lnsum += l;
+    }
+}
+// lower half of the groups (+) upper half: the order every build adds them in (the kernel reduces the halves on the two
+// half-warps of a control warp, nmpc_kernel.cuh; the host emulator one after the other)
+MPC_HD void eval_combine(EvalPart &lo, const EvalPart &hi)
+{
+    lo.prinf = fmax2(lo.prinf, hi.prinf); lo.pr1 += hi.pr1; lo.duinf = fmax2(lo.duinf, hi.duinf);
+    lo.vmax = fmax2(lo.vmax, hi.vmax); lo.vmin = fmin2(lo.vmin, hi.vmin); lo.l1 += hi.l1; lo.z1 += hi.z1; lo.f += hi.f;
+    lo.lnsum += hi.lnsum; lo.inside &= hi.inside;
+}
+MPC_HD int reduce_split(int NG) { return (NG + 1) / 2; }
+
+template <class SM>
+MPC_HD int ctrl_decide_sums(const Params &prm, const SM &sm, Ctrl &c, int p, int flags, const EvalPart &sums)
 {
     DEC_START();
-    double prinf = 0, pr1 = 0, duinf = 0, vmax = -1e300, vmin = 1e300, l1 = 0, z1 = 0, f = 0, lnsum = 0;
-    int inside = 1;
-    for (int g = 0; g < NG; g++) {
-        prinf = fmax2(prinf, sm.part(g, PT_0, p)); pr1 += sm.part(g, PT_1, p);
-        duinf = fmax2(duinf, sm.part(g, PT_2, p));
-        vmax = fmax2(vmax, sm.part(g, PT_3, p)); vmin = fmin2(vmin, sm.part(g, PT_4, p));
-        l1 += sm.part(g, PT_5, p); z1 += sm.part(g, PT_6, p); f += sm.part(g, PT_7, p);
-        const double l = sm.part(g, PT_8, p);
-        if (l <= -1e299) inside = 0; else lnsum += l;
-    }
+    const double prinf = sums.prinf, pr1 = sums.pr1, duinf = sums.duinf, vmax = sums.vmax, vmin = sums.vmin, l1 = sums.l1, z1 = sums.z1,
+                 f = sums.f, lnsum = sums.lnsum;
+    const int inside = sums.inside;
     double mu = sm.P(PS_MU, p);
     const double sf = sm.P(PS_SF, p);
     DEC_MARK(0);
@@ -1428,6 +1444,16 @@ MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flag
     }
     DEC_MARK(3);
     return ret;
+}
+
+template <class SM>
+MPC_HD int ctrl_decide(const Params &prm, const SM &sm, Ctrl &c, int p, int flags, int NG)
+{
+    EvalPart lo, hi;
+    ctrl_reduce(sm, p, 0, reduce_split(NG), lo);
+    ctrl_reduce(sm, p, reduce_split(NG), NG, hi);
+    eval_combine(lo, hi);
+    return ctrl_decide_sums(prm, sm, c, p, flags, lo);
 }
 
 // Next regularisation value of the inertia-correction sequence (W&B Algorithm IC).

@@ -97,6 +97,7 @@ static int run_batch(int B, int reps)
     mpc_b200_params prm; mpc_b200_params_yaml_default(&prm); prm.delay_mode = 0;
     mpc_b200_handle *h = nullptr;
     if (mpc_b200_create(&h, &prm, B, 0) != MPC_B200_OK) { fprintf(stderr, "no CUDA device\n"); return 2; }
+    if (getenv("MPC_BENCH_TWO_STAGES")) mpc_b200_set_option(h, "narrow_one_stage", 0.0);      // A/B of the latency mode
     const int M = mpcgen_num_waypoints(5.0), N = prm.mpc_steps;
     std::vector<double> wx((size_t)M * B), wy((size_t)M * B), pose(3 * (size_t)B), vel(3 * (size_t)B);
     mpcgen_problems(20261018ULL + 2, B, 5.0, wx.data(), wy.data(), pose.data(), vel.data(), nullptr);

@@ -366,6 +366,7 @@ struct mpc_b200_handle {
     long long kernels;     // kernels launched by this handle
     long long *d_prof;
     int opt_dual;
+    int opt_spt1;
     int *d_queue;          // ring of work-queue heads, one per in-flight launch
     int *d_order;          // ring of hard-first queue orders (order_ring x max_batch)
     int order_ring;        // launches that may be in flight on this handle at once (16 .. 1024)
@@ -537,7 +538,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     h->params = *p; h->device = device; h->max_batch = max_batch; h->last_kernel_s = 0.0; h->launches = 0; h->kernels = 0;
     h->d_state = h->d_coeffs = h->d_refv = h->d_u0 = h->d_pred = h->d_obj = h->d_kkt = h->d_warm_out = NULL;
     h->d_status = h->d_iters = NULL; h->d_wx = h->d_wy = h->d_pose = h->d_cte = h->d_vel = NULL; h->h_in = h->h_out = NULL;
-    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->opt_nc = 4; h->d_order = NULL; h->opt_order = 1; h->opt_dual = 1;
+    h->stream = NULL; h->ev0 = h->ev1 = NULL; h->d_prof = NULL; h->d_queue = NULL; h->max_ctas = 0; h->opt_pb = 0; h->opt_nc = 4; h->d_order = NULL; h->opt_order = 1; h->opt_dual = 1; h->opt_spt1 = 1;
     h->d_io = NULL; h->d_io_doubles = 0; h->d_warm_stage_in = h->d_warm_stage_out = NULL; h->slot_ev = NULL; h->order_ring = 0;
     for (int i = 0; i < 8; i++) { h->pin_ptr[i] = NULL; h->pin_val[i] = false; }
     h->pin_next = 0;
@@ -560,6 +561,8 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 28, false, true>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 28, true, true>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 6, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<1, 16, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 8, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<1, 4, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 1, false, false>));
     SET_SMEM((nmpc::nmpc_solve_kernel_dual<false>)); SET_SMEM((nmpc::nmpc_solve_kernel_dual<true>));
     // path polynomial of order 4..7
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS>));
@@ -650,6 +653,7 @@ int mpc_b200_set_option(mpc_b200_handle *h, const char *name, double value)
     if (!strcmp(name, "max_ctas")) h->max_ctas = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "problems_per_cta")) h->opt_pb = value > 0 ? (int)value : 0;
     else if (!strcmp(name, "hard_first")) h->opt_order = value != 0.0;
+    else if (!strcmp(name, "narrow_one_stage")) h->opt_spt1 = value != 0.0;   // narrow CTAs: one stage per stage thread (latency mode)
     else if (!strcmp(name, "dual_groups")) h->opt_dual = value != 0.0;   // full CTAs as two lane groups out of phase (nmpc_kernel_dual.cuh)
     else if (!strcmp(name, "poly_coeffs")) {
         // rows of the coeffs arrays of mpc_b200_solve_batch: order of the path polynomial + 1 (mpc_planner.cpp:186-190
@@ -700,7 +704,7 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.prm.w_accel = P.w_accel; a.prm.max_angvel = P.max_angvel; a.prm.max_throttle = P.max_throttle;
     a.prm.tol = P.tol > 0.0 ? P.tol : 1e-8;
     a.prm.max_iter = P.max_iter > 0 ? P.max_iter : 100;
-    a.prm.grp = SPT;
+    a.prm.grp = SPT;     // (adjusted below once the lanes per CTA are known)
     a.prm.idt = 1.0 / P.dt;
     a.prm.i_mnb = 1.0 / (double)(6 * N + 4 * (N - 1)); a.prm.i_nb = 1.0 / (double)(4 * (N - 1));
     a.prm.warm_mu = P.warm_mu_init > 0.0 ? P.warm_mu_init : 1e-3;
@@ -717,7 +721,13 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.state = d_state; a.coeffs = d_coeffs; a.ref_vel = d_refv; a.warm_in = d_warm_in;
     a.u0 = d_u0; a.pred = d_pred; a.obj = d_obj; a.status = d_status; a.iters = d_iters; a.kkt = d_kkt; a.warm_out = d_warm_out;
 
-    const int NG = (N + SPT - 1) / SPT;
+    // Narrow CTAs (small batches spread over the SMs, a single MPC::Solve) are latency-bound: one stage per stage thread
+    // instead of two halves the stage phases (plain variant, cold start, the compiled lane counts).
+    const int spt1_threads = NMPC_CTRL_THREADS + ((N * a.PB + 31) / 32) * 32;
+    const int spt = (h->opt_spt1 && !rate && a.ncoef <= 4 && !a.warm_in && (a.PB == 16 || a.PB == 8 || a.PB == 4 || a.PB == 1) &&
+                     spt1_threads <= NMPC_MAX_THREADS(1, a.PB)) ? 1 : SPT;
+    a.prm.grp = spt;
+    const int NG = (N + spt - 1) / spt;
     const int stage_threads = ((NG * a.PB + 31) / 32) * 32;
     const int threads = NMPC_CTRL_THREADS + stage_threads;
     // persistent grid: at most one CTA per SM (or the max_ctas option); lanes refill from the queue
@@ -771,6 +781,11 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     } else if (a.warm_in) {
         if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32, true, false><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, true, false><<<grid, threads, smem, st>>>(a);
+    } else if (spt == 1) switch (a.PB) {
+        case 16: nmpc::nmpc_solve_kernel<1, 16, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 8: nmpc::nmpc_solve_kernel<1, 8, false, false><<<grid, threads, smem, st>>>(a); break;
+        case 4: nmpc::nmpc_solve_kernel<1, 4, false, false><<<grid, threads, smem, st>>>(a); break;
+        default: nmpc::nmpc_solve_kernel<1, 1, false, false><<<grid, threads, smem, st>>>(a); break;
     } else switch (a.PB) {
         case 32: nmpc::nmpc_solve_kernel<SPT, 32, false, false><<<grid, threads, smem, st>>>(a); break;
         case 16: nmpc::nmpc_solve_kernel<SPT, 16, false, false><<<grid, threads, smem, st>>>(a); break;

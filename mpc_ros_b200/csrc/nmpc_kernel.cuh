@@ -312,7 +312,9 @@ __device__ __forceinline__ void control_loop(const SolveArgs &a, const SM &sm, c
 
 // NC: coefficients of the path polynomial the instantiation carries (4 = the cubic of the reference's only caller;
 // 8 serves orders 4..7, rows beyond a.ncoef read as zero).
-#define NMPC_MAX_THREADS(SPT, CPB) ((SPT) >= 3 ? 256 : 384)
+// (one stage per thread is the latency mode of narrow CTAs at short horizons: 8 / 4 / 1 lanes need fewer threads, so the
+//  compiler may use more registers -- no spills; the host checks the thread count against these bounds)
+#define NMPC_MAX_THREADS(SPT, CPB) ((SPT) >= 3 ? 256 : (SPT) == 1 ? ((CPB) == 8 ? 256 : (CPB) == 4 ? 160 : (CPB) == 1 ? 128 : 384) : 384)
 template <int SPT, int CPB, bool WARM, bool RATE, int NC = 4>
 __global__ void __launch_bounds__(NMPC_MAX_THREADS(SPT, CPB), 1) nmpc_solve_kernel(const SolveArgs a)
 {

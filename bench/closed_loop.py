@@ -203,16 +203,18 @@ def run_gpu_device(R, T, groups=8, seed=20261018 + 5, max_iter=100, trace=True):
     for g in grp:
         g["st"].wait_event(e0)
     # the host runs ahead of the device, but not without bound: a handle refuses more launches in flight than its
-    # queue ring has slots (1,024), so every 32 ticks the host waits for the ticks issued 64 ticks ago
+    # queue ring has slots (1,024; here 8 launches per tick), so every 16 ticks the host marks the streams and waits
+    # for the marks set 32 ticks earlier: at most 48 ticks = 384 launches are in flight
     marks = []
     for t in range(T):
-        if t % 32 == 0:
-            ev = torch.cuda.Event()
+        if t % 16 == 0:
+            cur = []
             for g in grp:
-                ev2 = torch.cuda.Event(); ev2.record(g["st"]); marks.append(ev2)
-            del ev
-            while len(marks) > 2 * len(grp):
-                marks.pop(0).synchronize()
+                ev = torch.cuda.Event(); ev.record(g["st"]); cur.append(ev)
+            marks.append(cur)
+            while len(marks) > 2:
+                for ev in marks.pop(0):
+                    ev.synchronize()
         for g in grp:
             B, sp = g["B"], g["sp"]
             with torch.cuda.stream(g["st"]):

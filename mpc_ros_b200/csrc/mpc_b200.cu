@@ -563,6 +563,8 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 6, false, false>));
     SET_SMEM((nmpc::nmpc_solve_kernel<1, 16, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 8, false, false>));
     SET_SMEM((nmpc::nmpc_solve_kernel<1, 4, false, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 1, false, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<1, 16, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 8, true, false>));
+    SET_SMEM((nmpc::nmpc_solve_kernel<1, 4, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 1, true, false>));
     SET_SMEM((nmpc::nmpc_solve_kernel_dual<false>)); SET_SMEM((nmpc::nmpc_solve_kernel_dual<true>));
     // path polynomial of order 4..7
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS>));
@@ -722,9 +724,9 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
     a.u0 = d_u0; a.pred = d_pred; a.obj = d_obj; a.status = d_status; a.iters = d_iters; a.kkt = d_kkt; a.warm_out = d_warm_out;
 
     // Narrow CTAs (small batches spread over the SMs, a single MPC::Solve) are latency-bound: one stage per stage thread
-    // instead of two halves the stage phases (plain variant, cold start, the compiled lane counts).
+    // instead of two halves the stage phases (plain variant, the compiled lane counts).
     const int spt1_threads = NMPC_CTRL_THREADS + ((N * a.PB + 31) / 32) * 32;
-    const int spt = (h->opt_spt1 && !rate && a.ncoef <= 4 && !a.warm_in && (a.PB == 16 || a.PB == 8 || a.PB == 4 || a.PB == 1) &&
+    const int spt = (h->opt_spt1 && !rate && a.ncoef <= 4 && (a.PB == 16 || a.PB == 8 || a.PB == 4 || a.PB == 1) &&
                      spt1_threads <= NMPC_MAX_THREADS(1, a.PB)) ? 1 : SPT;
     a.prm.grp = spt;
     const int NG = (N + spt - 1) / spt;
@@ -778,9 +780,14 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
             if (a.PB == 28) nmpc::nmpc_solve_kernel<SPT, 28, false, true><<<grid, threads, smem, st>>>(a);
             else nmpc::nmpc_solve_kernel<SPT, 0, false, true><<<grid, threads, smem, st>>>(a);
         }
-    } else if (a.warm_in) {
+    } else if (a.warm_in && spt != 1) {
         if (a.PB == 32) nmpc::nmpc_solve_kernel<SPT, 32, true, false><<<grid, threads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel<SPT, 0, true, false><<<grid, threads, smem, st>>>(a);
+    } else if (spt == 1 && a.warm_in) switch (a.PB) {      // (the closed loop of BASELINE config 5: 1,024 robots = 8 lanes per CTA)
+        case 16: nmpc::nmpc_solve_kernel<1, 16, true, false><<<grid, threads, smem, st>>>(a); break;
+        case 8: nmpc::nmpc_solve_kernel<1, 8, true, false><<<grid, threads, smem, st>>>(a); break;
+        case 4: nmpc::nmpc_solve_kernel<1, 4, true, false><<<grid, threads, smem, st>>>(a); break;
+        default: nmpc::nmpc_solve_kernel<1, 1, true, false><<<grid, threads, smem, st>>>(a); break;
     } else if (spt == 1) switch (a.PB) {
         case 16: nmpc::nmpc_solve_kernel<1, 16, false, false><<<grid, threads, smem, st>>>(a); break;
         case 8: nmpc::nmpc_solve_kernel<1, 8, false, false><<<grid, threads, smem, st>>>(a); break;

@@ -2,7 +2,7 @@
 # profiles/r2_evidence.sh -- round-2 evidence in one gpurun call (1 GPU):
 #   gpurun --timeout 2400 -- 'bash profiles/r2_evidence.sh'
 # (ncu passes run only after the same command has exited 0 without ncu; numbers printed under ncu are not used.)
-T=r2; O=gpurun_out; mkdir -p $O
+T=r2f; O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader; nproc
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5 > $O/${T}_pytest.log; cat $O/${T}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee $O/${T}_smoke.txt

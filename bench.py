@@ -309,7 +309,7 @@ def run_ours(a):
     # need 10-25x the median iteration count) overlaps the next batches.  Every stream keeps at most DEPTH batches
     # in flight (the host waits on the batch DEPTH back), which bounds the launches a handle has in flight.
     S = max(1, min(a.streams, NB))
-    DEPTH = 2
+    DEPTH = max(1, a.depth)
     raw_streams = [capi.stream_create(local) for _ in range(S)]      # torch hands out only 32 distinct streams
     streams = [torch.cuda.ExternalStream(p, device=dev) for p in raw_streams]
     max_ctas = a.max_ctas if a.max_ctas > 0 else max(4, min(128, -(-512 // S)))
@@ -350,11 +350,42 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The issue loop in C++ (bench/issue_loop.cpp: the same two C-ABI calls per batch, the same depth control): a Python
+    # loop costs about as much per batch as the device needs for it.  --python-issue keeps the Python loop.
+    import ctypes as C
+    IL = None; ictx = None
+    iss_path = os.path.join(ROOT, "bench", "libmpc_issue.so")
+    if not a.python_issue:
+        if not os.path.exists(iss_path):
+            raise RuntimeError("bench/libmpc_issue.so is missing: run __graft_entry__.build() (or pass --python-issue)")
+        IL = C.CDLL(iss_path)
+        IL.mpcb_issue_create.restype = C.c_void_p; IL.mpcb_issue_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        IL.mpcb_issue_run.restype = C.c_int
+        IL.mpcb_issue_run.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        IL.mpcb_issue_samples.restype = C.c_int; IL.mpcb_issue_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        IL.mpcb_issue_destroy.argtypes = [C.c_void_p]
+        ictx = IL.mpcb_issue_create(local, S, DEPTH, 4096)
+        if not ictx:
+            raise RuntimeError("mpcb_issue_create failed")
+        stream_arr = (C.c_void_p * S)(*raw_streams)
+        ptr_arr = (C.c_size_t * (12 * R))()
+        for q in range(R):
+            for i_, t_ in enumerate((d_wx[q], d_wy[q], d_pose[q], d_vel[q], d_coef[q], d_state[q], d_u0[q], d_pred[q], d_obj[q],
+                                     d_stat[q], d_it[q], d_kkt[q])):
+                ptr_arr[12 * q + i_] = t_.data_ptr()
+
+    def issue(j0, n, sample_every=0):
+        if IL is None:
+            for j in range(j0, j0 + n):
+                batch_dev(j, sample=(sample_every > 0 and (j - j0) % sample_every == 0))
+            return
+        rc = IL.mpcb_issue_run(ictx, hh, j0, n, stream_arr, R, ptr_arr, B, M, sample_every)
+        if rc != 0:
+            raise RuntimeError("issue loop failed: %d %s" % (rc, L.mpc_b200_last_cuda_error(hh).decode()))
+
     fp64_peak = L.mpc_b200_measure_fp64_peak(local, 100000)   # also brings the clocks up
     jb = 0
-    for _ in range(a.warmup):
-        for _ in range(NB):
-            batch_dev(jb); jb += 1
+    issue(jb, a.warmup * NB); jb += a.warmup * NB
     torch.cuda.synchronize()
     flush.fill_(1.0)                        # one L2 flush; the timed steps then rotate over > L2 of data
     barrier()
@@ -368,9 +399,7 @@ def run_ours(a):
     for st in streams:
         st.wait_event(e0)
     j_first = jb
-    for _ in range(a.steps):
-        for b in range(NB):
-            batch_dev(jb, sample=(b % 16 == 0)); jb += 1
+    issue(jb, a.steps * NB, sample_every=16); jb += a.steps * NB
     for st in streams:
         main.wait_stream(st)
     e1.record(main)
@@ -403,6 +432,9 @@ def run_ours(a):
     eff_ms = ms_total / n_batches
     achieved = flops_per_launch / (eff_ms * 1e-3) / 1e12
     ev_ms = [x.elapsed_time(y) for x, y in launch_ev]
+    if IL is not None:
+        buf = (C.c_float * 4096)()
+        ev_ms = list(buf[:IL.mpcb_issue_samples(ictx, buf, 4096)])
     iso = []
     for j in range(5):
         x = torch.cuda.Event(enable_timing=True); y = torch.cuda.Event(enable_timing=True)
@@ -571,6 +603,7 @@ def run_ours(a):
         it_mean = float(np.mean([v[2] for v in per_set.values()])); it_max = int(max(v[3] for v in per_set.values()))
         cfg = bench_config(a, world)
         cfg.update(streams=S, max_ctas=max_ctas, in_flight_per_stream=DEPTH, host_affinity=numa,
+                   issue_loop="python" if IL is None else "C++ (bench/issue_loop.cpp) over the C ABI",
                    step="one step = %d independent config-2 batches of %d problems, streamed on %d streams "
                         "(prestep + solve each); %d steps are timed back to back" % (NB, B, S, a.steps),
                    l2="inputs+outputs rotate over %d distinct batches (%.0f MB > 126 MB L2) after one L2 flush"
@@ -598,6 +631,8 @@ def main():
     ap.add_argument("--streams", type=int, default=64,
                     help="streams the batches of a step are issued on (64 x 8-CTA launches: measured best, profiles/r2_harness_sweep.txt)")
     ap.add_argument("--max-ctas", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight per stream")
+    ap.add_argument("--python-issue", action="store_true", help="issue the device-resident leg from Python instead of bench/issue_loop.cpp")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-1 latency and config-3 one-shot legs")
     ap.add_argument("--e2e-threads", type=int, default=2)
     ap.add_argument("--e2e-max-ctas", type=int, default=0)

@@ -17,7 +17,7 @@ def main():
     if pbo: sv.set_option("problems_per_cta", pbo)
     if len(sys.argv) > 6: sv.set_option("hard_first", int(sys.argv[6]))
     if len(sys.argv) > 7: sv.set_option("dual_groups", int(sys.argv[7]))
-    R = 8
+    R = int(sys.argv[9]) if len(sys.argv) > 9 else 8       # distinct input / output sets the launches rotate over (48: larger than L2, as bench.py)
     g = gen_py.problems(20261020, B * R)
     M = g["M"]
     def split(x): return [torch.from_numpy(np.ascontiguousarray(x[:, j*B:(j+1)*B])).to(dev) for j in range(R)]
@@ -39,6 +39,8 @@ def main():
         args.append((sv._h, B, state[j].data_ptr(), coef[j].data_ptr(), None, None, u0[j].data_ptr(), pred[j].data_ptr(),
                      None, stat[j].data_ptr(), None, None, None))
     sp = raw
+    with_pre = len(sys.argv) > 8 and int(sys.argv[8]) != 0       # also the pre-step kernel in front of every solve (as bench.py)
+    pre_args = [(sv._h, B, M, wx[j].data_ptr(), wy[j].data_ptr(), pose[j].data_ptr(), vel[j].data_ptr(), coef[j].data_ptr(), state[j].data_ptr()) for j in range(R)]
     f = L.mpc_b200_solve_batch
     for j in range(S):
         f(*args[j % R], sp[j % S])
@@ -53,6 +55,7 @@ def main():
         s_ = j % S; k_ = j // S
         if k_ >= 2: ev[s_][k_ % 2].synchronize()
         a_ = list(args[j % R]); a_[9] = stat_all[j].data_ptr()
+        if with_pre: L.mpc_b200_prestep_batch(*pre_args[j % R], sp[s_])
         rc = f(*a_, sp[s_])
         if rc != 0: raise RuntimeError("solve_batch failed: %d" % rc)
         ev[s_][k_ % 2].record(streams[s_])

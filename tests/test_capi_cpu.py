@@ -113,3 +113,17 @@ def test_product_library_has_no_oracle_or_emulator_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     for bad in ("ipm_solve", "mpc_oracle", "nmpc_emu", "ldl_factor"):
         assert bad not in out
+
+
+def test_bench_issue_loop_library_loads():
+    """bench.py's device-resident leg is issued by bench/libmpc_issue.so (C++ over the C ABI): it loads without a GPU and
+    exports its four entry points; it links the product library, not a copy of it."""
+    path = os.path.join(ROOT, "bench", "libmpc_issue.so")
+    if not os.path.exists(path):
+        pytest.skip("bench/libmpc_issue.so not built (run __graft_entry__.build())")
+    L = C.CDLL(path)
+    for name in ("mpcb_issue_create", "mpcb_issue_run", "mpcb_issue_samples", "mpcb_issue_destroy"):
+        assert hasattr(L, name)
+    import subprocess
+    deps = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+    assert "libmpc_b200.so" in deps

@@ -393,6 +393,26 @@ def test_dual_group_kernel_equals_single_group_kernel(oracle):
                 assert np.abs(res[1][0][0][:, i] - o["u0"]).max() <= U_TOL, tag
 
 
+def test_kernel_choice_options():
+    """The launch-shaping options are accepted by name, unknown names refused; the latency mode (one stage per stage thread in
+    narrow CTAs) returns what the two-stage kernels return."""
+    state, coeffs = mild(77, 96)
+    res = {}
+    for one in (1, 0):
+        sv = _solver(YAML_DEFAULT, 96)
+        for name in ("dual_groups", "narrow_one_stage", "hard_first", "max_ctas", "problems_per_cta"):
+            sv.set_option(name, 1 if name != "max_ctas" else 0)
+        sv.set_option("problems_per_cta", 0); sv.set_option("narrow_one_stage", one)
+        with pytest.raises(capi.MpcError):
+            sv.set_option("no_such_option", 1)
+        res[one] = sv.solve(state, coeffs)
+        sv.close()
+    assert np.all(res[1]["status"] == 1) and np.array_equal(res[1]["status"], res[0]["status"])
+    assert np.array_equal(res[1]["iters"], res[0]["iters"])
+    np.testing.assert_allclose(res[1]["u0"], res[0]["u0"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(res[1]["pred"], res[0]["pred"], rtol=0, atol=1e-8)
+
+
 def test_prestep_ragged_windows_and_delay_mode(oracle):
     """K1 at the edges: the shortest (M = 4: cubic through 4 points) and longest (M = 64) windows, refused
     sizes, and the delay-compensated state of driving_state.cpp:243-254."""

@@ -32,7 +32,7 @@ def main():
     print("global cycles per problem: mean %.2f, quantiles 50/90/99/99.9/99.99/100 %%: %s" %
           (ages.mean(), np.quantile(ages, [.5, .9, .99, .999, .9999, 1]).tolist()))
     print("all cycles %d = iterations %d + least-squares starts %d + backtracking trials %d + second-order corrections %d"
-          " + resumed line searches %d + inertia retries %d" %
+          " + resumed line searches %d + inertia retries %d   (restoration steps are counted with the corrections)" %
           (ages.sum(), r["iters"].sum(), n, k[:, 0].sum(), k[:, 1].sum(), k[:, 2].sum(), k[:, 3].sum()))
     for thr in (24, 50, 100):
         m = ages > thr

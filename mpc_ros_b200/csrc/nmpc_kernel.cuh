@@ -176,9 +176,9 @@ __device__ __forceinline__ void control_loop(const SolveArgs &a, const SM &sm, c
         int step_lsq = 0;     // sampled here for P6: the lane's adjoint stage thread rewrites PI_FLAGS there
         int step_mode = 0;    // FL_SOC / FL_RESUME of the system being solved
         if (lane && sm.I(PI_MODE, p) == MODE_NEWTON) {
-            const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
-            step_lsq = lsq;
-            step_mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME);
+            const int lsq = sys_kind(sm.I(PI_FLAGS, p));      // 0 Newton step, 1 least-squares start, 2 restoration step
+            step_lsq = lsq == 1;
+            step_mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME | FL_RESTO);
             const double dw = sm.P(PS_DW, p);
             const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
             const int okb = riccati_backward<RATE>(prm, sm, p, hd);
@@ -216,7 +216,7 @@ __device__ __forceinline__ void control_loop(const SolveArgs &a, const SM &sm, c
         if (lane && sm.I(PI_MODE, p) == MODE_STEP) {
             if (!step_lsq) {
                 ctrl_step(prm, sm, c, p, NG, step_mode);
-                sm.I(PI_FLAGS, p) = FL_LS | (step_mode & FL_SOC);
+                sm.I(PI_FLAGS, p) = FL_LS | (step_mode & (FL_SOC | FL_RESTO));
                 late = true;
             }
             sm.I(PI_MODE, p) = MODE_EVAL;
@@ -253,17 +253,27 @@ __device__ __forceinline__ void control_loop(const SolveArgs &a, const SM &sm, c
                 const int r = ctrl_decide_sums(prm, sm, c, p, fl, sums);
                 PROF_MARK(10);
                 if (r == 0) {
-                    sm.I(PI_FLAGS, p) = FL_LS;
-                } else if (r >= 3) {
+                    sm.I(PI_FLAGS, p) = FL_LS | (fl & FL_RESTO);
+                } else if (r == 3 || r == 4) {
                     // second-order correction (3) / resume after failed corrections (4): the same Newton system again
                     // (PS_DW kept), no step applied
                     sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = (r == 3) ? FL_SOC : FL_RESUME;
+                } else if (r == 5) {
+                    // the line search failed: feasibility restoration from the iterate (nothing applied)
+                    sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_RESTO; sm.P(PS_DW, p) = 0.0;
+                } else if (r == 6) {
+                    // restoration step taken (primal only), the next restoration system from the new point
+                    sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = NMPC_AZ_RESTO; sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
+                    sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_APPLY | FL_RESTO; sm.P(PS_DW, p) = 0.0;
                 } else {
                     int nf = 0;
                     // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
                     // a step of length 0 -- it still adopts the sin/cos computed at the evaluated point)
                     nf = FL_APPLY;
-                    if (fl & FL_LS) {
+                    if ((fl & (FL_LS | FL_RESTO)) == (FL_LS | FL_RESTO)) {
+                        // restoration ends here (or the problem does): primal step, multipliers kept, z reset
+                        sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = NMPC_AZ_RESTO_END;
+                    } else if (fl & FL_LS) {
                         sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
                         ctrl_apply(sm, p);
                     } else {
@@ -383,7 +393,7 @@ __global__ void __launch_bounds__(NMPC_MAX_THREADS(SPT, CPB), 1) nmpc_solve_kern
             // ---- P3b: Newton-system coefficients
             if (mine) {
                 if (sm.I(PI_MODE, p) == MODE_NEWTON) {
-                    const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ, soc = sm.I(PI_FLAGS, p) & FL_SOC;
+                    const int lsq = sys_kind(sm.I(PI_FLAGS, p)), soc = sm.I(PI_FLAGS, p) & FL_SOC;
 #pragma unroll
                     for (int j = 0; j < SPT; j++)
                         if (k0 + j < N) stage_coeffs<RATE, NC>(prm, sm, r[j], k0 + j, p, lsq, cf, soc);
@@ -396,9 +406,10 @@ __global__ void __launch_bounds__(NMPC_MAX_THREADS(SPT, CPB), 1) nmpc_solve_kern
             TRACE_S(5);
             // ---- P5: step-dependent work
             const bool stepping = mine && sm.I(PI_MODE, p) == MODE_STEP;     // (sampled before B6: the control thread
-            const int step_lsq = stepping ? (sm.I(PI_FLAGS, p) & FL_LSQ) : 0;  //  rewrites mode and flags in P6)
+            const int step_kind = stepping ? sys_kind(sm.I(PI_FLAGS, p)) : 0;  //  rewrites mode and flags in P6)
+            const int step_lsq = step_kind == 1;
             if (stepping) {
-                const int lsq = step_lsq;
+                const int lsq = step_kind;
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
                 StepPart acc;
                 part_reset(acc);

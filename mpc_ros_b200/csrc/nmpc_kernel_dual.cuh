@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
                 named_sync(bid, bar_count);   // B3
                 // ---- P3b: Newton-system coefficients
                 if (mine && sm.I(PI_MODE, p) == MODE_NEWTON) {
-                    const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ, soc = sm.I(PI_FLAGS, p) & FL_SOC;
+                    const int lsq = sys_kind(sm.I(PI_FLAGS, p)), soc = sm.I(PI_FLAGS, p) & FL_SOC;
                     stage_coeffs<false, NC>(prm, sm, r, k, p, lsq, cf, soc);
                 }
                 named_sync(bid, bar_count);   // B4: the group's control warp starts its sweeps
@@ -174,14 +174,15 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
             named_sync(bid, bar_count);       // B5: the sweeps are done
             // ---- P5: step-dependent work
             const bool stepping = mine && sm.I(PI_MODE, p) == MODE_STEP;       // (sampled before B6: the control thread
-            const int step_lsq = stepping ? (sm.I(PI_FLAGS, p) & FL_LSQ) : 0;  //  rewrites mode and flags in P6)
+            const int step_kind = stepping ? sys_kind(sm.I(PI_FLAGS, p)) : 0;  //  rewrites mode and flags in P6)
+            const int step_lsq = step_kind == 1;
             {
                 StepPart acc;
                 part_reset(acc);
                 if (stepping) {
-                    const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), step_lsq);
+                    const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), step_kind);
                     double gk[6];
-                    stage_step<false, NC>(prm, sm, r, k, p, hd, step_lsq, acc, gk, cf);
+                    stage_step<false, NC>(prm, sm, r, k, p, hd, step_kind, acc, gk, cf);
                     for (int q = 0; q < 6; q++) sm.at(k, W_0 + q, p) = gk[q];
                 }
                 part_pair(acc);

@@ -97,8 +97,13 @@ enum Flag {
     FL_WARM = 64,    // P3a initialises the lane from a warm-start record instead of the cold start
     FL_SOC = 128,    // the Newton system / the trial point is a second-order correction (W&B A-5.5 .. A-5.9): same matrix,
                      // constraint right-hand side c_soc kept in the stage threads' trial sin/cos registers
-    FL_RESUME = 256  // the Newton step is recomputed after a failed correction: the line search resumes at alpha / 2
+    FL_RESUME = 256, // the Newton step is recomputed after a failed correction: the line search resumes at alpha / 2
+    FL_RESTO = 512   // feasibility restoration (stand-in for Ipopt's restoration phase, as in the oracle: min-norm Gauss-Newton
+                     // steps on the constraint violation): the system is  [I J'; J 0] (dx, .) = (0, -c),  only the primal moves
 };
+// What the Newton machinery is asked to solve: 0 = the primal-dual Newton step, 1 = the least-squares multiplier start
+// (identity Hessian, right-hand side (grad, 0)), 2 = a restoration step (identity Hessian, right-hand side (0, -c)).
+MPC_HD int sys_kind(int flags) { return (flags & FL_LSQ) ? 1 : ((flags & FL_RESTO) ? 2 : 0); }
 
 struct Params {
     int N;
@@ -494,7 +499,8 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
     const bool adopt = (flags & FL_ADOPT) != 0;
     const double alpha = ls ? sm.P(PS_ALPHA, p) : 0.0;
     const double az = ls ? sm.P(PS_ALPHA_Z, p) : 0.0;
-    const double lcoef = adopt ? (((flags & FL_KEEP) != 0) ? 1.0 : 0.0) : alpha;   // step length of lambda_k
+    const double al = (flags & FL_RESTO) ? 0.0 : alpha;      // step length of the equality multipliers (restoration: primal only)
+    const double lcoef = adopt ? (((flags & FL_KEEP) != 0) ? 1.0 : 0.0) : al;   // step length of lambda_k
     const double mu = sm.P(PS_MU_STEP, p);
     const int km = k > 0 ? k - 1 : 0;
     const double dmask = k > 0 ? alpha : 0.0;        // ds_0 = 0
@@ -543,9 +549,9 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
         // trial lambda_{k+1} (after an adoption stage_adopt has already put it into L)
         double mx = sm.at(k, L_X, p), my = sm.at(k, L_Y, p), mt = sm.at(k, L_T, p);
         double mv = sm.at(k, L_V, p), mc = sm.at(k, L_C, p), me = sm.at(k, L_E, p);
-        mx += alpha * (sm.at(k, W_LAM, p) - mx); my += alpha * (sm.at(k, W_LAM + 1, p) - my);
-        mt += alpha * (sm.at(k, W_LAM + 2, p) - mt); mv += alpha * (sm.at(k, W_LAM + 3, p) - mv);
-        mc += alpha * (sm.at(k, W_LAM + 4, p) - mc); me += alpha * (sm.at(k, W_LAM + 5, p) - me);
+        mx += al * (sm.at(k, W_LAM, p) - mx); my += al * (sm.at(k, W_LAM + 1, p) - my);
+        mt += al * (sm.at(k, W_LAM + 2, p) - mt); mv += al * (sm.at(k, W_LAM + 3, p) - mv);
+        mc += al * (sm.at(k, W_LAM + 4, p) - mc); me += al * (sm.at(k, W_LAM + 5, p) - me);
         // stationarity wrt s_k:  grad f + lambda_k - A_k^T lambda_{k+1}
         const double a13 = -v * r.tsn * dt, a14 = r.tcs * dt, a23 = v * r.tcs * dt, a24 = r.tsn * dt;
         const double a51 = dpoly, a54 = r.tse * dt, a56 = v * r.tce * dt;
@@ -591,6 +597,11 @@ MPC_HD void stage_eval(const Params &prm, const SM &sm, StageRegs &r, int k, int
     acc.z1 += z1; acc.f += sf * f; acc.lnsum += lnsum;
 }
 
+#define NMPC_AZ_RESTO (-1.0)
+#define NMPC_AZ_RESTO_END (-2.0)
+#define NMPC_RESTO_MAX_IT 50
+#define NMPC_RESTO_MAX_BT 30
+
 // ---------------------------------------------------------------- P3: apply the accepted step, write coefficients
 // With FL_APPLY: s += alpha ds, lambda += alpha (lambda^+ - lambda), u, z updated (W&B A-6); the sin/cos of
 // the point evaluated in P1 become the iterate's.  Then writes A_k, d_k and the work slots
@@ -603,17 +614,26 @@ template <bool RATE = false, class SM>
 MPC_HD void stage_apply(const Params &prm, const SM &sm, StageRegs &r, int k, int p)
 {
     const int N = prm.N;
-    const double alpha = sm.P(PS_AP_ALPHA, p), az = sm.P(PS_AP_AZ, p), mu = sm.P(PS_AP_MU, p);
+    // PS_AP_AZ < 0 marks a restoration step: only the primal moves (NMPC_AZ_RESTO), and when restoration ends the bound
+    // multipliers are brought back within kappa_Sigma of mu / slack as Ipopt does (NMPC_AZ_RESTO_END)
+    const double alpha = sm.P(PS_AP_ALPHA, p), azm = sm.P(PS_AP_AZ, p), mu = sm.P(PS_AP_MU, p);
+    const bool resto = azm < 0.0;
+    const double az = resto ? 0.0 : azm, al = resto ? 0.0 : alpha;
     if (k > 0)
         for (int c = 0; c < 6; c++) sm.at(k, S_X + c, p) += alpha * sm.at(k - 1, D_X + c, p);
     if (k < N - 1) {
         for (int c = 0; c < 6; c++) {
             const double l = sm.at(k, L_X + c, p);
-            sm.at(k, L_X + c, p) = l + alpha * (sm.at(k, W_LAM + c, p) - l);
+            sm.at(k, L_X + c, p) = l + al * (sm.at(k, W_LAM + c, p) - l);
         }
         const double uw = r.uw + alpha * sm.at(k, W_DU, p), ua = r.ua + alpha * sm.at(k, W_DU + 1, p);
         double zlw, zuw, zla, zua;
         trial_z(prm, sm, r, k, p, az, mu, uw, ua, zlw, zuw, zla, zua);
+        if (azm == NMPC_AZ_RESTO_END) {
+            const double Uw = relaxed(prm.max_angvel), Ua = relaxed(prm.max_throttle);
+            zlw = zclamp(zlw, mu, 1.0 / (uw + Uw)); zuw = zclamp(zuw, mu, 1.0 / (Uw - uw));
+            zla = zclamp(zla, mu, 1.0 / (ua + Ua)); zua = zclamp(zua, mu, 1.0 / (Ua - ua));
+        }
         r.uw = uw; r.ua = ua; r.zlw = zlw; r.zuw = zuw; r.zla = zla; r.zua = zua;
         if (RATE) { sm.at(k, U_W, p) = uw; sm.at(k, U_A, p) = ua; }
     }
@@ -706,10 +726,20 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
         // plain variant: the sweeps work with the control step scaled by dt (riccati_backward): q_u / dt, R / dt^2
         const double su = RATE ? 1.0 : prm.idt, su2 = su * su;
         if (lsq) {
-            sm.at(k, W_3, p) = (gw - r.zlw + r.zuw) * su;
-            sm.at(k, W_4, p) = (ga - r.zla + r.zua) * su;
+            // least-squares multipliers (1): right-hand side (gradient, 0); restoration step (2): right-hand side (0, defect)
+            sm.at(k, W_3, p) = lsq == 2 ? 0.0 : (gw - r.zlw + r.zuw) * su;
+            sm.at(k, W_4, p) = lsq == 2 ? 0.0 : (ga - r.zla + r.zua) * su;
             sm.at(k, W_10, p) = (1.0 + hd.du) * su2; sm.at(k, W_11, p) = (1.0 + hd.du) * su2;
-            for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
+            if (lsq == 2) {
+                sm.at(k, D_X, p) = (x + v * r.cs * dt) - sm.at(k + 1, S_X, p);
+                sm.at(k, D_Y, p) = (y + v * r.sn * dt) - sm.at(k + 1, S_Y, p);
+                sm.at(k, D_T, p) = (th + r.uw * dt) - sm.at(k + 1, S_T, p);
+                sm.at(k, D_V, p) = (v + r.ua * dt) - sm.at(k + 1, S_V, p);
+                sm.at(k, D_C, p) = ((poly - y) + v * r.se * dt) - sm.at(k + 1, S_C, p);
+                sm.at(k, D_E, p) = (e + r.uw * dt) - sm.at(k + 1, S_E, p);
+            } else {
+                for (int c = 0; c < 6; c++) sm.at(k, D_X + c, p) = 0.0;
+            }
         } else {
             // d_k = -(s_{k+1} - phi(s_k, u_k))  (mpc_planner.cpp:208-215)
             sm.at(k, D_X, p) = (x + v * r.cs * dt) - sm.at(k + 1, S_X, p);
@@ -736,6 +766,7 @@ MPC_HD void stage_coeffs(const Params &prm, const SM &sm, StageRegs &r, int k, i
         sm.at(k, W_8, p) = hee + hd.de; sm.at(k, W_9, p) = hev;
     }
     sm.at(k, W_0, p) = qv; sm.at(k, W_1, p) = qc; sm.at(k, W_2, p) = qe;
+    if (lsq == 2) { sm.at(k, W_0, p) = 0.0; sm.at(k, W_1, p) = 0.0; sm.at(k, W_2, p) = 0.0; }      // (rare: restoration step)
 }
 
 // ---------------------------------------------------------------- Riccati sweeps (control thread)
@@ -1137,8 +1168,8 @@ MPC_HD void stage_step(const Params &prm, const SM &sm, StageRegs &r, int k, int
         const double ilw = fast_rcp(r.uw + Uw), iuw = fast_rcp(Uw - r.uw);
         const double ila = fast_rcp(r.ua + Ua), iua = fast_rcp(Ua - r.ua);
         sm.at(k, W_ISL, p) = ilw; sm.at(k, W_ISL + 1, p) = iuw; sm.at(k, W_ISL + 2, p) = ila; sm.at(k, W_ISL + 3, p) = iua;
+        if (lsq != 1) rmax = fmax2(fmax2(-duw * ilw, duw * iuw), fmax2(-dua * ila, dua * iua));
         if (!lsq) {
-            rmax = fmax2(fmax2(-duw * ilw, duw * iuw), fmax2(-dua * ila, dua * iua));
             const double mlw = mu * ilw, muw = mu * iuw, mla = mu * ila, mua = mu * iua;
             const double dzlw = mlw - r.zlw - r.zlw * ilw * duw;
             const double dzuw = muw - r.zuw + r.zuw * iuw * duw;
@@ -1294,13 +1325,60 @@ MPC_HD void filter_add(const SM &sm, Ctrl &c, int p, double theta, double phi)
     sm.F(2 * j, p) = th; sm.F(2 * j + 1, p) = ph;
 }
 
+// ---- feasibility restoration (rare path).  Ipopt switches to its restoration phase when the backtracking line search
+// runs below alpha_min.  As in the oracle (oracle/ipm.c: the stand-in for that phase) the violation theta = ||c||_1 is
+// reduced by min-norm Gauss-Newton steps  [I J'; J 0] (dx, .) = (0, -c)  with a backtracking test on theta alone, until
+// theta has dropped to 90 % of its value at entry (kappa_resto) and the point is acceptable to the filter; then the bound
+// multipliers are reset and the regular iteration continues.  State: theta at entry in PS_ALPHA_LS, current theta_r in
+// PS_SOC_THETA, 64 * steps + backtracks in PI_SOC (the second-order-correction slots, idle while restoring).
+// Entry (line search failed at the iterate with violation th, barrier objective phi): returns 5 = solve a restoration
+// step, or 2 = terminate (status set).
+// (Both helpers are kept out of line and take / return plain values -- packed result: low byte = the return code, the
+//  rest = the new filter size / iteration count -- so that the control thread's state stays in registers on the hot path.)
+template <class SM>
+MPC_HD_RARE int ctrl_enter_resto(const SM &sm, int p, double th, double phi, double theta_min, int nfilt)
+{
+    sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0;           // (nothing to apply if this terminates)
+    if (th <= 1e-13 * (1e4 * theta_min)) return 2 | (3 << 8);      // 1e4 theta_min = max(1, theta_0): tiny step, status 3
+    Ctrl t; t.nfilt = nfilt;
+    filter_add(sm, t, p, th, phi);                                  // W&B A-9
+    sm.P(PS_ALPHA_LS, p) = th; sm.P(PS_SOC_THETA, p) = th; sm.I(PI_SOC, p) = 0;
+    return 5 | (t.nfilt << 8);
+}
+// A restoration trial point (step length PS_ALPHA) has been evaluated: th_t = its violation, phi_t its barrier objective.
+// Returns (low byte) 0 = shorter step, same direction; 6 = step taken, another restoration step; 7 = restoration finished,
+// the trial point is the new iterate (the caller goes on as for an accepted line-search trial); 2 = terminate with the
+// status in the upper bits.
+template <class SM>
+MPC_HD_RARE int ctrl_decide_resto(const SM &sm, int p, int ok, double th_t, double phi_t, double theta_max, int nfilt)
+{
+    const double a = sm.P(PS_ALPHA, p), thr = sm.P(PS_SOC_THETA, p);
+    const int st = sm.I(PI_SOC, p), steps = st >> 6, bts = st & 63;
+    if (ok && th_t < (1.0 - 1e-4 * a) * thr) {
+        sm.P(PS_SOC_THETA, p) = th_t;
+        Ctrl t; t.theta_max = theta_max; t.nfilt = nfilt;
+        if (th_t <= 0.9 * sm.P(PS_ALPHA_LS, p) && filter_acceptable(sm, t, p, th_t, phi_t)) return 7;
+        if (steps + 1 >= NMPC_RESTO_MAX_IT) return 2 | ((th_t > 1e-6 ? 5 : 9) << 8);
+        sm.I(PI_SOC, p) = (steps + 1) << 6;
+        return 6;
+    }
+    if (bts + 1 >= NMPC_RESTO_MAX_BT) {
+        sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0;
+        return 2 | ((thr > 1e-6 ? 5 : 9) << 8);                      // local infeasibility / restoration failure
+    }
+    sm.I(PI_SOC, p) = (steps << 6) | (bts + 1);
+    sm.P(PS_ALPHA, p) = 0.5 * a;
+    return 0;
+}
+
 // P2: the point evaluated in P1.  Line-search trial (FL_LS): filter test (W&B A-5); a rejected trial
 // halves alpha and is evaluated again next cycle.  An accepted point (or a plain evaluation) becomes the
 // iterate: convergence test (W&B eq. (5), (6)) and monotone barrier update (eq. (7)).
 // Returns: 0 = evaluate again (alpha halved), 1 = iterate accepted, continue with a Newton step,
 //          2 = terminated (c.status set; the step, if any, still has to be applied before flushing),
 //          3 = solve the same Newton system for a second-order correction (FL_SOC),
-//          4 = the corrections failed: recompute the Newton step and resume the backtracking (FL_RESUME).
+//          4 = the corrections failed: recompute the Newton step and resume the backtracking (FL_RESUME),
+//          5 = the line search failed: solve a restoration step (FL_RESTO), 6 = restoration step taken, solve another.
 #if defined(NMPC_PROFILE) && defined(__CUDACC__)
 __device__ long long nmpc_dec_acc[8];
 #endif
@@ -1351,7 +1429,13 @@ MPC_HD int ctrl_decide_sums(const Params &prm, const SM &sm, Ctrl &c, int p, int
     // The function is written without early returns (ret < 0 = still undecided) so that the lanes of the warp
     // reconverge after every block instead of running the common tail once per path.
     int ret = -1;
-    if (flags & FL_LS) {
+    if ((flags & (FL_LS | FL_RESTO)) == (FL_LS | FL_RESTO)) {
+        const int ok = inside && (pr1 == pr1) && (f == f);
+        const int rr = ctrl_decide_resto(sm, p, ok, pr1, f - mu * lnsum, c.theta_max, c.nfilt);
+        ret = rr & 255;
+        if (ret == 2) c.status = rr >> 8;
+        if (ret == 7) { c.iter++; ret = -1; }
+    } else if (flags & FL_LS) {
         const int soc = flags & FL_SOC;
         const double alpha = sm.P(PS_ALPHA, p);
         // a second-order correction is judged with the step length of the rejected first trial (Ipopt:
@@ -1387,7 +1471,11 @@ MPC_HD int ctrl_decide_sums(const Params &prm, const SM &sm, Ctrl &c, int p, int
             const double a2 = 0.5 * alpha_t;
             if (again == 1) ret = 3;
             // (alpha_min can be 0 or NaN in degenerate cases: the absolute floor bounds the number of halvings)
-            else if (a2 < c.alpha_min || !(a2 > 1e-40)) { c.status = 9; sm.P(PS_ALPHA, p) = 0.0; sm.P(PS_ALPHA_Z, p) = 0.0; ret = 2; }
+            else if (a2 < c.alpha_min || !(a2 > 1e-40)) {
+                const int rr = ctrl_enter_resto(sm, p, th, phi, c.theta_min, c.nfilt);
+                ret = rr & 255;
+                if (ret == 2) c.status = rr >> 8; else c.nfilt = rr >> 8;
+            }
             else if (again == 2) ret = 4;
             else { sm.P(PS_ALPHA, p) = a2; ret = 0; }
         } else {
@@ -1477,6 +1565,12 @@ MPC_HD void ctrl_step(const Params &prm, const SM &sm, Ctrl &c, int p, int NG, i
     const double az = (rzmax > tau) ? tau / rzmax : 1.0;
     // mode & FL_SOC: the step is a second-order correction -- tried at its own fraction-to-the-boundary length, judged with
     // the original step's directional derivative; FL_RESUME: the original step again, its first trial is already rejected
+    if (mode & FL_RESTO) {
+        // restoration step: the fraction-to-the-boundary length, bound multipliers untouched; line-search state kept
+        sm.P(PS_ALPHA, p) = amax; sm.P(PS_ALPHA_Z, p) = 0.0;
+        sm.P(PS_MU_STEP, p) = sm.P(PS_MU, p);
+        return;
+    }
     if (!(mode & FL_SOC)) c.gd = gd;
     if (mode & FL_RESUME) sm.P(PS_ALPHA, p) = 0.5 * sm.P(PS_ALPHA_LS, p);
     else sm.P(PS_ALPHA, p) = amax;

@@ -115,12 +115,12 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
             // ---- P3b
             for (int p = 0; p < np; p++)
                 if (sm.I(PI_MODE, p) == MODE_NEWTON)
-                    for (int k = 0; k < N; k++) stage_coeffs<RATE, NC>(prm, sm, REG(k, p), k, p, sm.I(PI_FLAGS, p) & FL_LSQ, &cfs[(size_t)NC * p], sm.I(PI_FLAGS, p) & FL_SOC);
+                    for (int k = 0; k < N; k++) stage_coeffs<RATE, NC>(prm, sm, REG(k, p), k, p, sys_kind(sm.I(PI_FLAGS, p)), &cfs[(size_t)NC * p], sm.I(PI_FLAGS, p) & FL_SOC);
             // ---- P4
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_NEWTON) continue;
                 Ctrl &c = ctrl[p];
-                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                const int lsq = sys_kind(sm.I(PI_FLAGS, p));
                 const double dw = sm.P(PS_DW, p);
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), dw, lsq);
                 if (riccati_backward<RATE>(prm, sm, p, hd) || lsq) {
@@ -137,7 +137,7 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
             // ---- P5
             for (int p = 0; p < np; p++) {
                 if (sm.I(PI_MODE, p) != MODE_STEP) continue;
-                const int lsq = sm.I(PI_FLAGS, p) & FL_LSQ;
+                const int lsq = sys_kind(sm.I(PI_FLAGS, p));
                 const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), lsq);
                 for (int g = 0; g < NG; g++) {
                     StepPart acc; part_reset(acc);
@@ -156,10 +156,10 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     const int keep = ctrl_lsq_finish(prm, sm, p, big);
                     sm.I(PI_FLAGS, p) = FL_ADOPT | keep;
                 } else {
-                    const int mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME);
+                    const int mode = sm.I(PI_FLAGS, p) & (FL_SOC | FL_RESUME | FL_RESTO);
                     ctrl_step(prm, sm, ctrl[p], p, NG, mode);
                     ctrl_step_late(ctrl[p]);
-                    sm.I(PI_FLAGS, p) = FL_LS | (mode & FL_SOC);
+                    sm.I(PI_FLAGS, p) = FL_LS | (mode & (FL_SOC | FL_RESTO));
                 }
                 sm.I(PI_MODE, p) = MODE_EVAL;
             }
@@ -185,15 +185,22 @@ static int emu_run(int N, const double *prm14, double tol, int max_iter, int PB,
                     const int fl = sm.I(PI_FLAGS, p);
                     const int r = ctrl_decide(prm, sm, c, p, fl, NG);
                     if (r == 0) g_kind_lane[4 * p]++; else if (r == 3) g_kind_lane[4 * p + 1]++; else if (r == 4) g_kind_lane[4 * p + 2]++;
-                    if (r == 0) sm.I(PI_FLAGS, p) = FL_LS;
+                    if (r == 5 || r == 6) g_kind_lane[4 * p + 1]++;      // (restoration steps are counted with the corrections)
+                    if (r == 0) sm.I(PI_FLAGS, p) = FL_LS | (fl & FL_RESTO);
                     else if (r == 3) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_SOC; }
                     else if (r == 4) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_RESUME; }
-                    else {
+                    else if (r == 5) { sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_RESTO; sm.P(PS_DW, p) = 0.0; }
+                    else if (r == 6) {
+                        sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = NMPC_AZ_RESTO; sm.P(PS_AP_MU, p) = sm.P(PS_MU_STEP, p);
+                        sm.I(PI_MODE, p) = MODE_NEWTON; sm.I(PI_FLAGS, p) = FL_APPLY | FL_RESTO; sm.P(PS_DW, p) = 0.0;
+                    } else {
                         int nf = 0;
                         // the evaluated point becomes the iterate: P3a applies the step (a plain evaluation is
                         // a step of length 0 -- it still adopts the sin/cos computed at the evaluated point)
                         nf = FL_APPLY;
-                        if (fl & FL_LS) {
+                        if ((fl & (FL_LS | FL_RESTO)) == (FL_LS | FL_RESTO)) {
+                            sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = NMPC_AZ_RESTO_END;
+                        } else if (fl & FL_LS) {
                             sm.P(PS_AP_ALPHA, p) = sm.P(PS_ALPHA, p); sm.P(PS_AP_AZ, p) = sm.P(PS_ALPHA_Z, p);
                             ctrl_apply(sm, p);
                         } else {

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from oracle.oracle_py import YAML_DEFAULT, CFG_DEFAULT
-from tests.problems import mild, generated
+from tests.problems import mild, generated, restoration_cases
 
 _EMU = None
 
@@ -251,3 +251,25 @@ def test_emu_second_order_correction_matches_oracle_iterates(oracle):
     assert both >= n - 2
     assert same_iters >= 0.97 * both, (same_iters, both)
     assert nsoc_matter >= 2, nsoc_matter       # the correction does make a difference on this set
+
+
+def test_emu_restoration_matches_oracle(oracle):
+    """Line search below alpha_min: the kernel logic runs the same feasibility restoration as the oracle (min-norm steps on
+    the constraint violation, kappa_resto = 0.9, filter test, bound multipliers reset) instead of giving up with status 9:
+    problems the oracle rescues converge to the same point in the same number of iterations, the others end with the
+    oracle's status (5 = locally infeasible)."""
+    state, coeffs = restoration_cases(oracle)
+    opt = oracle.default_options(); opt.max_iter = 100
+    r = emu_solve(YAML_DEFAULT, state, coeffs, PB=3, max_iter=100)
+    rescued = 0
+    for i in range(state.shape[1]):
+        o = oracle.solve(YAML_DEFAULT, state[:, i], coeffs[:, i], opt)
+        assert o["n_resto"] >= 1
+        assert r["status"][i] == o["status"], (i, r["status"][i], o["status"])
+        if o["status"] == 1:
+            rescued += 1
+            assert r["iters"][i] == o["iters"]
+            assert np.abs(r["u0"][:, i] - o["u0"]).max() <= 1e-5
+            assert abs(r["obj"][i] - o["obj"]) <= 1e-6 * abs(o["obj"])
+            assert r["kkt"][i] <= 1e-8
+    assert rescued == 3

@@ -10,7 +10,7 @@ import pytest
 
 from mpc_ros_b200 import capi
 from oracle.oracle_py import YAML_DEFAULT, CFG_DEFAULT
-from tests.problems import mild, generated
+from tests.problems import mild, generated, restoration_cases
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -391,6 +391,30 @@ def test_dual_group_kernel_equals_single_group_kernel(oracle):
             o = oracle.solve(pm, state[:, i], coeffs[:, i])
             if o["status"] == 1:
                 assert np.abs(res[1][0][0][:, i] - o["u0"]).max() <= U_TOL, tag
+
+
+def test_restoration_phase(oracle):
+    """The same on the GPU, in a full CTA of the dual-group kernel (the cases are mixed into a batch of ordinary problems)
+    and in the single-solve kernel."""
+    rs, rc = restoration_cases(oracle)
+    g, state, coeffs = generated(20261018 + 2, 40, oracle)
+    nr = rs.shape[1]
+    st = np.concatenate([state, rs], axis=1); co = np.concatenate([coeffs, rc], axis=1)
+    opt = oracle.default_options(); opt.max_iter = 100
+    for pb in (32, 1):
+        sv = _solver(YAML_DEFAULT, st.shape[1])
+        sv.set_option("problems_per_cta", pb)
+        out = sv.solve(st, co)
+        sv.close()
+        for j in range(nr):
+            i = 40 + j
+            o = oracle.solve(YAML_DEFAULT, rs[:, j], rc[:, j], opt)
+            assert out["status"][i] == o["status"], (pb, j, out["status"][i], o["status"])
+            if o["status"] == 1:
+                assert out["iters"][i] == o["iters"]
+                assert np.abs(out["u0"][:, i] - o["u0"]).max() <= U_TOL
+                assert abs(out["obj"][i] - o["obj"]) <= F_TOL * abs(o["obj"])
+                assert out["kkt"][i] <= KKT_TOL
 
 
 def test_kernel_choice_options():

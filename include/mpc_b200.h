@@ -123,7 +123,7 @@ int mpc_b200_get_params(const mpc_b200_handle *h, mpc_b200_params *p);
  * polynomial + 1, 4 (default, the cubic of driving_state.cpp:210) .. 8; FG_eval takes any order
  * (mpc_planner.cpp:186-190: coeffs.size()); the pre-step entry points then fit that order (polyfit(x, y, order),
  * driving_state.cpp:283-300) and write as many rows (they need M >= poly_coeffs waypoints).
- * "dual_groups": 1 (default) runs full CTAs of the plain variant (32 lanes, horizons 11..20) as two groups of 16 lanes
+ * "dual_groups": 1 (default) runs full CTAs (32 lanes, 28 with rate penalties; horizons 11..20) as two lane groups
  * out of phase on shared stage threads (nmpc_kernel_dual.cuh); "narrow_one_stage": 1 (default) gives every stage thread
  * of a narrow CTA (16 / 8 / 4 / 1 lanes: small batches, a single MPC::Solve) one stage instead of two (latency mode).
  * Both only choose between kernels that run the same phase functions; results agree to rounding.

@@ -566,6 +566,7 @@ int mpc_b200_create(mpc_b200_handle **out, const mpc_b200_params *p, int32_t max
     SET_SMEM((nmpc::nmpc_solve_kernel<1, 16, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 8, true, false>));
     SET_SMEM((nmpc::nmpc_solve_kernel<1, 4, true, false>)); SET_SMEM((nmpc::nmpc_solve_kernel<1, 1, true, false>));
     SET_SMEM((nmpc::nmpc_solve_kernel_dual<false>)); SET_SMEM((nmpc::nmpc_solve_kernel_dual<true>));
+    SET_SMEM((nmpc::nmpc_solve_kernel_dual<false, 4, true>)); SET_SMEM((nmpc::nmpc_solve_kernel_dual<true, 4, true>));
     // path polynomial of order 4..7
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, false, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, false, NMPC_MAX_COEFFS>));
     SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, false, true, NMPC_MAX_COEFFS>)); SET_SMEM((nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS>));
@@ -761,10 +762,12 @@ static int enqueue_solve(mpc_b200_handle *h, int32_t batch, const double *d_stat
         CK(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
     }
     if (timed) CK(cudaEventRecord(h->ev0, st));
-    if (h->opt_dual && !rate && a.ncoef <= 4 && a.PB == 32 && N > 10 && N <= NMPC_DUAL_MAX_N) {
-        // full CTAs of the plain variant: two groups of 16 lanes out of phase, one stage per stage thread and group
+    if (h->opt_dual && a.ncoef <= 4 && a.PB == (rate ? 28 : 32) && N > 10 && N <= NMPC_DUAL_MAX_N) {
+        // full CTAs: two lane groups out of phase, one stage per stage thread and group
         const int dthreads = NMPC_CTRL_THREADS + ((16 * N + 31) / 32) * 32;
-        if (a.warm_in) nmpc::nmpc_solve_kernel_dual<true><<<grid, dthreads, smem, st>>>(a);
+        if (rate && a.warm_in) nmpc::nmpc_solve_kernel_dual<true, 4, true><<<grid, dthreads, smem, st>>>(a);
+        else if (rate) nmpc::nmpc_solve_kernel_dual<false, 4, true><<<grid, dthreads, smem, st>>>(a);
+        else if (a.warm_in) nmpc::nmpc_solve_kernel_dual<true><<<grid, dthreads, smem, st>>>(a);
         else nmpc::nmpc_solve_kernel_dual<false><<<grid, dthreads, smem, st>>>(a);
     } else if (a.ncoef > 4) {
         if (rate && a.warm_in) nmpc::nmpc_solve_kernel<SPT, 0, true, true, NMPC_MAX_COEFFS><<<grid, threads, smem, st>>>(a);

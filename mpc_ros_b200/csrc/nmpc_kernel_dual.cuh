@@ -1,5 +1,5 @@
-// nmpc_kernel_dual.cuh -- the solve kernel for full CTAs (32 lanes, horizons up to 20 stages, plain variant): two lane
-// groups of 16 run OUT OF PHASE on one set of stage threads.
+// nmpc_kernel_dual.cuh -- the solve kernel for full CTAs (32 lanes, or 28 in the rate-penalty variant; horizons up to 20
+// stages): two lane groups run OUT OF PHASE on one set of stage threads.
 //
 // Why.  A global cycle of nmpc_solve_kernel alternates between the control warps (Riccati sweeps, decisions: ~20 k SM
 // cycles during which the ten stage warps wait) and the stage warps (~16 k cycles during which the control warps wait),
@@ -44,22 +44,23 @@ __device__ __forceinline__ void part_pair(StepPart &a)
     a.rmax = fmax2(a.rmax, rmax); a.rzmax = fmax2(a.rzmax, rzmax); a.gd += gd;
 }
 
-template <bool WARM, int NC = 4>
+// RATE: the rate-penalty variant (44 slots per stage: 28 lanes = group A with 16 lanes, group B with 12).
+template <bool WARM, int NC = 4, bool RATE = false>
 __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs a)
 {
     extern __shared__ double smem_raw[];
     const Params &prm = a.prm;
     const int N = prm.N, batch = a.batch;
-    constexpr int PB = 32;
+    constexpr int PB = RATE ? 28 : 32;
     const int NG = (N + 1) / 2;            // partial sums per pair of stages, as in the single-group kernel (SPT = 2)
-    SmemT<PB, NSLOTS> sm;
+    SmemT<PB, RATE ? NSLOTS_RATE : NSLOTS> sm;
     sm.PB = PB;
     sm.carve(smem_raw, N, NG);
     const int tid = threadIdx.x;
     const int bar_count = blockDim.x - 32;         // one control warp + the stage warps
 
     if (tid < NMPC_CTRL_THREADS) {
-        control_loop<PB, WARM, false, NC, true>(a, sm, N, PB, NG, batch, tid, 1 + (tid >> 5), bar_count);
+        control_loop<PB, WARM, RATE, NC, true>(a, sm, N, PB, NG, batch, tid, 1 + (tid >> 5), bar_count);
         return;
     }
 
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
     const int t = tid - NMPC_CTRL_THREADS;
     const int k = t >> 4;                  // the thread's stage (both groups)
     const int p16 = t & 15;
-    const bool mine = k < N;
+    const bool mine_k = k < N;
     const bool lower = (tid & 16) == 0;    // holds the even stage of the warp's pair
     const int g = k >> 1;
     StageRegs r, ro;                       // current / other group
@@ -89,12 +90,13 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
         // ================================================= X(G)
         if (alive & (1 << G)) {
             const int p = p16 + 16 * G, bid = 1 + G;
+            const bool mine = mine_k && p < PB;
             if (started & (1 << G)) {
                 named_sync(bid, bar_count);   // B1b
                 // ---- P3a0: apply the accepted step, flush a finished problem (the control warp refills meanwhile)
                 if (mine) {
                     const int fl = sm.I(PI_FLAGS, p);
-                    if (fl & FL_APPLY) stage_apply<false>(prm, sm, r, k, p);
+                    if (fl & FL_APPLY) stage_apply<RATE>(prm, sm, r, k, p);
                     if (fl & FL_FLUSH) {
                         // the last iterate whatever the status (mpc_planner.cpp:378-401)
                         const size_t i = (size_t)sm.I(PI_PROB, p);
@@ -145,8 +147,8 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
 #pragma unroll
                             for (int i = 4; i < NC; i++) cf[i] = sm.P(PS_NXC4 + (i - 4), p);
                         }
-                        if (WARM && (fl & FL_WARM)) stage_init_warm<false>(prm, sm, r, k, p, s6, c4, a.warm_in, (size_t)batch, (size_t)idx);
-                        else stage_init<false>(prm, sm, r, k, p, s6, c4);
+                        if (WARM && (fl & FL_WARM)) stage_init_warm<RATE>(prm, sm, r, k, p, s6, c4, a.warm_in, (size_t)batch, (size_t)idx);
+                        else stage_init<RATE>(prm, sm, r, k, p, s6, c4);
                     } else if ((fl & (FL_SOC | FL_APPLY)) == FL_SOC && sm.I(PI_MODE, p) == MODE_NEWTON) {
                         stage_soc_rhs<NC>(prm, sm, r, k, p, cf);
                     }
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
                 // ---- P3b: Newton-system coefficients
                 if (mine && sm.I(PI_MODE, p) == MODE_NEWTON) {
                     const int lsq = sys_kind(sm.I(PI_FLAGS, p)), soc = sm.I(PI_FLAGS, p) & FL_SOC;
-                    stage_coeffs<false, NC>(prm, sm, r, k, p, lsq, cf, soc);
+                    stage_coeffs<RATE, NC>(prm, sm, r, k, p, lsq, cf, soc);
                 }
                 named_sync(bid, bar_count);   // B4: the group's control warp starts its sweeps
             }
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
         // ================================================= Y(G)
         if ((alive & started) & (1 << G)) {
             const int p = p16 + 16 * G, bid = 1 + G;
+            const bool mine = mine_k && p < PB;
             named_sync(bid, bar_count);       // B5: the sweeps are done
             // ---- P5: step-dependent work
             const bool stepping = mine && sm.I(PI_MODE, p) == MODE_STEP;       // (sampled before B6: the control thread
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
                 if (stepping) {
                     const HessDiag hd = hess_diag(prm, sm.P(PS_SF, p), sm.P(PS_DW, p), step_kind);
                     double gk[6];
-                    stage_step<false, NC>(prm, sm, r, k, p, hd, step_kind, acc, gk, cf);
+                    stage_step<RATE, NC>(prm, sm, r, k, p, hd, step_kind, acc, gk, cf);
                     for (int q = 0; q < 6; q++) sm.at(k, W_0 + q, p) = gk[q];
                 }
                 part_pair(acc);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(384, 1) nmpc_solve_kernel_dual(const SolveArgs
                 if (ev) {
                     const int fl = sm.I(PI_FLAGS, p);
                     if (fl & FL_ADOPT) stage_adopt(prm, sm, k, p, fl);
-                    stage_eval<false, NC>(prm, sm, r, k, p, fl, acc, cf);
+                    stage_eval<RATE, NC>(prm, sm, r, k, p, fl, acc, cf);
                 }
                 part_pair(acc);
                 if (ev && lower) part_store(sm, g, p, acc);

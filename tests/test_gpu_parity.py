@@ -350,12 +350,13 @@ def test_dual_group_kernel_equals_single_group_kernel(oracle):
     dev = torch.device("cuda:0")
     g, state, coeffs = generated(20261018 + 3, 4500, oracle)
     B = state.shape[1]
-    for N in (20, 15, 11):
-        pm = dict(YAML_DEFAULT, STEPS=N)
+    for base, N, lanes in ((YAML_DEFAULT, 20, 32), (YAML_DEFAULT, 15, 32), (YAML_DEFAULT, 11, 32), (CFG_DEFAULT, 20, 28)):
+        # (the last one: the rate-penalty variant, 28 lanes per CTA = a group of 16 and a group of 12)
+        pm = dict(base, STEPS=N)
         res = {}
         for dual in (1, 0):
             sv = _solver(pm, B)
-            sv.set_option("dual_groups", dual); sv.set_option("problems_per_cta", 32); sv.set_option("max_ctas", 6)
+            sv.set_option("dual_groups", dual); sv.set_option("problems_per_cta", lanes); sv.set_option("max_ctas", 6)
             ws = capi.lib().mpc_b200_warm_size(N)
             f64 = dict(dtype=torch.float64, device=dev)
             ds = torch.from_numpy(state).to(dev); dc = torch.from_numpy(coeffs).to(dev)
@@ -371,7 +372,7 @@ def test_dual_group_kernel_equals_single_group_kernel(oracle):
             warm = (u.cpu().numpy().copy(), pred.cpu().numpy().copy(), st.cpu().numpy().copy(), it.cpu().numpy().copy())
             sv.close()
             res[dual] = (cold, warm)
-        tag = "N=%d " % N
+        tag = "N=%d lanes=%d " % (N, lanes)
         assert (res[1][0][2] == 1).mean() >= 0.99, tag
         for which in (0, 1):
             a, b = res[1][which], res[0][which]

@@ -80,13 +80,13 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index = index; self.rows = []; self.proc = None; self.thr = None
+    def __init__(self, index, period_ms=50):
+        self.index = index; self.rows = []; self.proc = None; self.thr = None; self.period_ms = int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -387,7 +387,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     flush.fill_(1.0)                        # one L2 flush; the timed steps then rotate over > L2 of data
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, a.clock_period_ms)
     if rank == 0:
         sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -630,6 +630,7 @@ def main():
                     help="streams the batches of a step are issued on (64 x 8-CTA launches: measured best, profiles/r2_harness_sweep.txt)")
     ap.add_argument("--max-ctas", type=int, default=0)
     ap.add_argument("--depth", type=int, default=2, help="batches in flight per stream")
+    ap.add_argument("--clock-period-ms", type=int, default=50, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--python-issue", action="store_true", help="issue the device-resident leg from Python instead of bench/issue_loop.cpp")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-1 latency and config-3 one-shot legs")
     ap.add_argument("--e2e-threads", type=int, default=2)

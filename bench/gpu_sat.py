@@ -10,6 +10,7 @@ def main():
     B = int(sys.argv[1]); S = int(sys.argv[2]); K = int(sys.argv[3]); maxc = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     L = capi.lib(); dev = torch.device("cuda:0")
     prm = capi.yaml_default_params(); prm.delay_mode = 0
+    if len(sys.argv) > 11: prm.max_iter = int(sys.argv[11])
     sv = capi.Solver(prm, B, 0)
     if hasattr(L, 'mpc_b200_debug_profile'): L.mpc_b200_debug_profile(sv._h, None)
     if maxc: sv.set_option("max_ctas", maxc)
@@ -35,9 +36,13 @@ def main():
         sv.prestep_raw(B, M, wx[j], wy[j], pose[j], vel[j], coef[j], state[j])
     torch.cuda.synchronize()
     args = []
+    full_out = len(sys.argv) > 10 and int(sys.argv[10]) != 0     # also obj / iters / kkt per problem (as bench.py)
+    obj = [torch.zeros(B, **f64) for _ in range(R)]; kkt = [torch.zeros(B, **f64) for _ in range(R)]
+    its = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(R)]
     for j in range(R):
         args.append((sv._h, B, state[j].data_ptr(), coef[j].data_ptr(), None, None, u0[j].data_ptr(), pred[j].data_ptr(),
-                     None, stat[j].data_ptr(), None, None, None))
+                     obj[j].data_ptr() if full_out else None, stat[j].data_ptr(), its[j].data_ptr() if full_out else None,
+                     kkt[j].data_ptr() if full_out else None, None))
     sp = raw
     with_pre = len(sys.argv) > 8 and int(sys.argv[8]) != 0       # also the pre-step kernel in front of every solve (as bench.py)
     pre_args = [(sv._h, B, M, wx[j].data_ptr(), wy[j].data_ptr(), pose[j].data_ptr(), vel[j].data_ptr(), coef[j].data_ptr(), state[j].data_ptr()) for j in range(R)]
